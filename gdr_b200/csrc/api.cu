@@ -1,0 +1,305 @@
+// C-ABI entry points (include/gdr_b200.h): handle management, argument checking, scratch sizing,
+// kernel sequencing.  No torch types, no exceptions across the boundary.
+#include <climits>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "gdr_common.cuh"
+
+namespace gdr {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string &msg) { g_last_error = msg; }
+
+int cuda_fail(cudaError_t e, const char *what) {
+    g_last_error = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+    return GDR_ERR_CUDA;
+}
+
+static int invalid(const char *msg) {
+    g_last_error = msg;
+    return GDR_ERR_INVALID;
+}
+
+bool umma_make_tensor_map(CUtensorMap *out, const void *emb, int64_t n_docs, int dim);   // score_umma.cu
+
+}  // namespace gdr
+
+using namespace gdr;
+
+struct gdr_store {
+    const void *emb = nullptr;
+    int64_t n_docs = 0;
+    int32_t dim = 0, dtype = 0, n_clusters = 0, max_cluster = 0;
+    const int32_t *offsets = nullptr;
+    const int32_t *docid = nullptr;
+    int device = 0, sm_count = 148;
+    // per-cluster scratch (allocated at create)
+    int32_t *cluster_ws = nullptr;   // cnt | grp_off | simt_off | umma_off | counters
+    // per-batch scratch (grows)
+    void *batch_ws = nullptr;
+    size_t batch_ws_bytes = 0;
+    bool has_tmap = false;
+    CUtensorMap tmap;
+    int last_launches = 0;
+    int umma_min_group = 8;
+};
+
+struct gdr_trie {
+    int32_t *first_child = nullptr, *child_tok = nullptr, *child_node = nullptr;
+    int32_t n_nodes = 0, n_edges = 0;
+};
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+extern "C" {
+
+int gdr_abi_version(void) { return 1; }
+
+const char *gdr_last_error(void) { return g_last_error.c_str(); }
+
+int gdr_store_create(gdr_store_t **out, const void *emb, int64_t n_docs, int32_t dim, int32_t dtype,
+                     const int32_t *offsets, int32_t n_clusters, const int32_t *docid, int32_t max_cluster_size) {
+    if (!out) return invalid("gdr_store_create: out is null");
+    *out = nullptr;
+    if (!emb || !offsets || !docid) return invalid("gdr_store_create: null device pointer");
+    if (n_docs <= 0 || n_docs > INT_MAX) return invalid("gdr_store_create: n_docs must be in [1, 2^31)");
+    if (dtype != GDR_DTYPE_F32 && dtype != GDR_DTYPE_BF16) return invalid("gdr_store_create: dtype must be F32 or BF16");
+    if (dim <= 0 || dim % 8 != 0) return invalid("gdr_store_create: dim must be a positive multiple of 8");
+    if (dim > MAX_DIM) {
+        set_error("gdr_store_create: dim > 1024 is not supported");
+        return GDR_ERR_UNSUPPORTED;
+    }
+    if (n_clusters <= 0) return invalid("gdr_store_create: n_clusters must be positive");
+    if (max_cluster_size <= 0 || max_cluster_size > n_docs) return invalid("gdr_store_create: bad max_cluster_size");
+    if (reinterpret_cast<uintptr_t>(emb) & 15) return invalid("gdr_store_create: emb must be 16-byte aligned");
+    gdr_store *s = new (std::nothrow) gdr_store();
+    if (!s) return GDR_ERR_NOMEM;
+    s->emb = emb; s->n_docs = n_docs; s->dim = dim; s->dtype = dtype;
+    s->offsets = offsets; s->n_clusters = n_clusters; s->docid = docid; s->max_cluster = max_cluster_size;
+    cudaError_t e = cudaGetDevice(&s->device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device);
+    const size_t n = (size_t)n_clusters;
+    const size_t words = n + 3 * (n + 1) + CTR_COUNT;
+    if (e == cudaSuccess) e = cudaMalloc(&s->cluster_ws, words * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMemset(s->cluster_ws, 0, words * sizeof(int32_t));
+    if (e != cudaSuccess) {
+        delete s;
+        return cuda_fail(e, "gdr_store_create");
+    }
+    if (dtype == GDR_DTYPE_BF16 && dim % 64 == 0) s->has_tmap = umma_make_tensor_map(&s->tmap, emb, n_docs, dim);
+    if (const char *env = getenv("GDR_UMMA_MIN_GROUP")) s->umma_min_group = atoi(env);
+    *out = s;
+    return GDR_OK;
+}
+
+int gdr_store_destroy(gdr_store_t *s) {
+    if (!s) return GDR_OK;
+    cudaFree(s->cluster_ws);
+    cudaFree(s->batch_ws);
+    delete s;
+    return GDR_OK;
+}
+
+int gdr_score_topk(gdr_store_t *s, const float *q, const int32_t *beams, const float *prob, const float *alphas,
+                   int32_t n_alpha, int32_t B, int32_t K, int32_t act, int32_t k, uint32_t flags, float *out_scores,
+                   int32_t *out_docids, void *stream) {
+    if (!s) return invalid("gdr_score_topk: store is null");
+    if (B < 0 || K <= 0 || k <= 0) return invalid("gdr_score_topk: need B >= 0, K > 0, k > 0");
+    if (B == 0) return GDR_OK;
+    if (!q || !beams || !out_scores || !out_docids) return invalid("gdr_score_topk: null pointer");
+    if (act < GDR_ACT_NONE || act > GDR_ACT_SIGMOID) return invalid("gdr_score_topk: bad activation");
+    if (n_alpha < 1 || (!alphas && n_alpha != 1)) return invalid("gdr_score_topk: n_alpha must be >= 1 (1 when alphas is null)");
+    if (k > 4096) {
+        set_error("gdr_score_topk: k > 4096 is not supported");
+        return GDR_ERR_UNSUPPORTED;
+    }
+    if ((int64_t)B * K > INT_MAX / 2) return invalid("gdr_score_topk: B*K too large");
+    if ((flags & GDR_FORCE_UMMA) && !s->has_tmap) {
+        set_error("gdr_score_topk: GDR_FORCE_UMMA needs a bf16 store with dim % 64 == 0");
+        return GDR_ERR_UNSUPPORTED;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t pairs = (int64_t)B * K;
+    const int64_t stride = align_up((size_t)K * s->max_cluster, 4);
+    const int64_t simt_cap = pairs * ((s->max_cluster + SIMT_ROWS - 1) / SIMT_ROWS);
+    const int64_t umma_cap = pairs * ((s->max_cluster + UMMA_ROWS - 1) / UMMA_ROWS);
+    const bool umma_possible = s->has_tmap && !(flags & GDR_FORCE_SIMT);
+    const int64_t q_rows = (flags & GDR_Q_PER_BEAM) ? pairs : B;
+    const bool global_keys = (size_t)stride * 4 + 8 * 4096 + 4 * 4096 + (size_t)(K + 1) * 4 > 96 * 1024;
+
+    // carve the per-batch scratch
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    const size_t o_pair = take(pairs * 4);
+    const size_t o_cand = take((size_t)B * (K + 1) * 4);
+    const size_t o_simt = take((size_t)simt_cap * sizeof(Item));
+    const size_t o_umma = take(umma_possible ? (size_t)umma_cap * sizeof(Item) : 0);
+    const size_t o_score = take((size_t)B * stride * 4);
+    const size_t o_qsplit = take(umma_possible ? (size_t)q_rows * 3 * s->dim * 2 : 0);
+    const size_t o_keys = take(global_keys ? (size_t)B * stride * 4 : 0);
+    if (off > s->batch_ws_bytes) {
+        // growing the scratch synchronises; run one call per shape before capturing a CUDA graph
+        GDR_CUDA(cudaStreamSynchronize(st));
+        if (s->batch_ws) GDR_CUDA(cudaFree(s->batch_ws));
+        s->batch_ws = nullptr;
+        s->batch_ws_bytes = 0;
+        GDR_CUDA(cudaMalloc(&s->batch_ws, off));
+        s->batch_ws_bytes = off;
+    }
+    char *ws = reinterpret_cast<char *>(s->batch_ws);
+    const size_t n = (size_t)s->n_clusters;
+
+    ScoreArgs a;
+    memset(&a, 0, sizeof(a));
+    a.emb = s->emb; a.offsets = s->offsets; a.docid = s->docid;
+    a.dim = s->dim; a.dtype = s->dtype; a.n_clusters = s->n_clusters; a.max_cluster = s->max_cluster; a.n_docs = s->n_docs;
+    a.q = q; a.beams = beams; a.prob = prob; a.B = B; a.K = K; a.act = act; a.k = k; a.flags = flags;
+    a.cnt = s->cluster_ws;
+    a.grp_off = s->cluster_ws + n;
+    a.simt_off = a.grp_off + (n + 1);
+    a.umma_off = a.simt_off + (n + 1);
+    a.counters = a.umma_off + (n + 1);
+    a.grp_pair = reinterpret_cast<int32_t *>(ws + o_pair);
+    a.candoff = reinterpret_cast<int32_t *>(ws + o_cand);
+    a.simt_items = reinterpret_cast<Item *>(ws + o_simt);
+    a.umma_items = reinterpret_cast<Item *>(ws + o_umma);
+    a.scorebuf = reinterpret_cast<float *>(ws + o_score);
+    a.stride = stride;
+    a.qsplit = reinterpret_cast<__nv_bfloat16 *>(ws + o_qsplit);
+    a.gkeys = reinterpret_cast<uint32_t *>(ws + o_keys);
+    a.umma_min_group = !umma_possible ? INT_MAX : ((flags & GDR_FORCE_UMMA) ? 1 : s->umma_min_group);
+
+    int launches = 0;
+    GDR_CUDA(launch_invert(a, st, &launches));
+    if (umma_possible) {
+        GDR_CUDA(launch_qsplit(a, st));
+        GDR_CUDA(launch_score_umma(a, &s->tmap, st, s->sm_count));
+        launches += 2;
+    }
+    if (!(flags & GDR_FORCE_UMMA)) {
+        GDR_CUDA(launch_score_simt(a, st, s->sm_count));
+        launches += 1;
+    }
+    for (int r = 0; r < n_alpha; ++r) {
+        const float alpha = alphas ? alphas[r] : 1.0f;
+        GDR_CUDA(launch_topk_store(a, alpha, out_scores + (int64_t)r * B * k, out_docids + (int64_t)r * B * k, st));
+        launches += 1;
+    }
+    s->last_launches = launches;
+    return GDR_OK;
+}
+
+int gdr_store_last_stats(gdr_store_t *s, int64_t out[4], void *stream) {
+    if (!s || !out) return invalid("gdr_store_last_stats: null argument");
+    int32_t c[CTR_COUNT];
+    GDR_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    const size_t n = (size_t)s->n_clusters;
+    GDR_CUDA(cudaMemcpy(c, s->cluster_ws + n + 3 * (n + 1), sizeof(c), cudaMemcpyDeviceToHost));
+    out[0] = c[CTR_N_SIMT];
+    out[1] = c[CTR_N_UMMA];
+    out[2] = s->last_launches;
+    out[3] = c[CTR_N_TOUCHED];
+    return GDR_OK;
+}
+
+int gdr_similarity(const float *q, int64_t Q, const void *p, int64_t P, int32_t dim, int32_t p_dtype, float *out,
+                   void *stream) {
+    if (Q < 0 || P < 0) return invalid("gdr_similarity: negative size");
+    if (Q == 0 || P == 0) return GDR_OK;
+    if (!q || !p || !out) return invalid("gdr_similarity: null pointer");
+    if (p_dtype != GDR_DTYPE_F32 && p_dtype != GDR_DTYPE_BF16) return invalid("gdr_similarity: bad dtype");
+    if (dim <= 0 || dim % 8 != 0) return invalid("gdr_similarity: dim must be a positive multiple of 8");
+    if (dim > MAX_DIM) {
+        set_error("gdr_similarity: dim > 1024 is not supported");
+        return GDR_ERR_UNSUPPORTED;
+    }
+    if ((reinterpret_cast<uintptr_t>(p) & 15) || (reinterpret_cast<uintptr_t>(q) & 15))
+        return invalid("gdr_similarity: q and p must be 16-byte aligned");
+    int dev = 0, sms = 148;
+    GDR_CUDA(cudaGetDevice(&dev));
+    GDR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    GDR_CUDA(launch_similarity(q, Q, p, P, dim, p_dtype, out, (cudaStream_t)stream, sms));
+    return GDR_OK;
+}
+
+int gdr_merge_topk(const float *scores, const int32_t *docids, int32_t G, int32_t B, int32_t k_in, int64_t g_stride,
+                   int32_t k, float *out_scores, int32_t *out_docids, void *stream) {
+    if (G <= 0 || B < 0 || k_in <= 0 || k <= 0) return invalid("gdr_merge_topk: bad sizes");
+    if (g_stride < (int64_t)B * k_in) return invalid("gdr_merge_topk: g_stride smaller than one rank's block");
+    if (B == 0) return GDR_OK;
+    if (!scores || !docids || !out_scores || !out_docids) return invalid("gdr_merge_topk: null pointer");
+    if (k > 4096 || (int64_t)G * k_in > 32768) {
+        set_error("gdr_merge_topk: need k <= 4096 and G*k_in <= 32768");
+        return GDR_ERR_UNSUPPORTED;
+    }
+    GDR_CUDA(launch_merge_topk(scores, docids, G, B, k_in, g_stride, k, out_scores, out_docids, (cudaStream_t)stream));
+    return GDR_OK;
+}
+
+int gdr_trie_create(gdr_trie_t **out, const int32_t *first_child, const int32_t *child_tok, const int32_t *child_node,
+                    int32_t n_nodes, int32_t n_edges) {
+    if (!out) return invalid("gdr_trie_create: out is null");
+    *out = nullptr;
+    if (n_nodes <= 0 || n_edges < 0 || !first_child) return invalid("gdr_trie_create: bad sizes");
+    if (n_edges > 0 && (!child_tok || !child_node)) return invalid("gdr_trie_create: null edge arrays");
+    if (first_child[0] != 0 || first_child[n_nodes] != n_edges) return invalid("gdr_trie_create: first_child must span [0, n_edges]");
+    for (int i = 0; i < n_nodes; ++i)
+        if (first_child[i + 1] < first_child[i]) return invalid("gdr_trie_create: first_child must be non-decreasing");
+    for (int e = 0; e < n_edges; ++e)
+        if (child_node[e] <= 0 || child_node[e] >= n_nodes) return invalid("gdr_trie_create: child_node out of range");
+    gdr_trie *t = new (std::nothrow) gdr_trie();
+    if (!t) return GDR_ERR_NOMEM;
+    t->n_nodes = n_nodes; t->n_edges = n_edges;
+    const size_t ne = (size_t)(n_edges > 0 ? n_edges : 1);
+    cudaError_t e = cudaMalloc(&t->first_child, (size_t)(n_nodes + 1) * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&t->child_tok, ne * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&t->child_node, ne * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(t->first_child, first_child, (size_t)(n_nodes + 1) * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && n_edges) e = cudaMemcpy(t->child_tok, child_tok, (size_t)n_edges * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && n_edges) e = cudaMemcpy(t->child_node, child_node, (size_t)n_edges * 4, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        gdr_trie_destroy(t);
+        return cuda_fail(e, "gdr_trie_create");
+    }
+    *out = t;
+    return GDR_OK;
+}
+
+int gdr_trie_destroy(gdr_trie_t *t) {
+    if (!t) return GDR_OK;
+    cudaFree(t->first_child);
+    cudaFree(t->child_tok);
+    cudaFree(t->child_node);
+    delete t;
+    return GDR_OK;
+}
+
+int gdr_tree_mask(gdr_trie_t *t, const int64_t *input_ids, int64_t ids_row_stride, int32_t R, int32_t cur_len,
+                  float *scores, int64_t scores_row_stride, int32_t V, int32_t eos_id, int32_t strict, void *stream) {
+    if (!t) return invalid("gdr_tree_mask: trie is null");
+    if (R < 0 || cur_len < 1 || V <= 0) return invalid("gdr_tree_mask: need R >= 0, cur_len >= 1, V > 0");
+    if (R == 0) return GDR_OK;
+    if (!input_ids || !scores) return invalid("gdr_tree_mask: null pointer");
+    if (ids_row_stride < cur_len || scores_row_stride < V) return invalid("gdr_tree_mask: row stride smaller than row");
+    GDR_CUDA(launch_tree_mask(t->first_child, t->child_tok, t->child_node, input_ids, ids_row_stride, R, cur_len, scores,
+                              scores_row_stride, V, eos_id, strict, (cudaStream_t)stream));
+    return GDR_OK;
+}
+
+int gdr_position_mask(float *logits, int64_t bz, int32_t sl, int32_t V, int32_t v_out, int32_t last_eos_only,
+                      void *stream) {
+    if (bz < 0 || sl <= 0 || V <= 0 || v_out <= 0) return invalid("gdr_position_mask: bad sizes");
+    if (bz == 0) return GDR_OK;
+    if (!logits) return invalid("gdr_position_mask: null pointer");
+    // the reference scatters into index (sl-1)*v_out + v_out + 1, which must exist (modeling_t5.py:1567)
+    const int64_t last_t = last_eos_only ? sl - 2 : sl - 1;   // last position that keeps its digit range
+    if (last_t >= 0 && last_t * v_out + v_out + 1 >= V)
+        return invalid("gdr_position_mask: vocabulary too small for sl positions of v_out tokens");
+    GDR_CUDA(launch_position_mask(logits, bz, sl, V, v_out, last_eos_only, (cudaStream_t)stream));
+    return GDR_OK;
+}
+
+}  // extern "C"

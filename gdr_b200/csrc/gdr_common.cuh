@@ -1,0 +1,106 @@
+// Shared declarations of the gdr_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/gdr_b200.h"
+
+namespace gdr {
+
+// ----- error plumbing ---------------------------------------------------------------------
+void set_error(const std::string &msg);
+int cuda_fail(cudaError_t e, const char *what);
+
+#define GDR_CUDA(call)                                        \
+    do {                                                      \
+        cudaError_t _e = (call);                              \
+        if (_e != cudaSuccess) return gdr::cuda_fail(_e, #call); \
+    } while (0)
+
+// ----- work items ---------------------------------------------------------------------------
+// One unit of scoring work: `nrows` consecutive store rows starting at `row0` (all inside one
+// cluster, `rel0` rows after the cluster start) against `nq` (query, beam) pairs taken from
+// grp_pair[slot0 .. slot0+nq).  Produced on the device by the inversion kernels.
+struct __align__(16) Item {
+    int32_t row0;
+    int32_t rel0;
+    int32_t nrows_nq;  // nrows | (nq << 16)
+    int32_t slot0;
+};
+
+constexpr int SIMT_ROWS = 128;   // rows per SIMT item (one warp walks them 4 at a time)
+constexpr int SIMT_QT = 4;       // (query, beam) pairs per SIMT item
+constexpr int UMMA_ROWS = 128;   // rows per tcgen05 tile (UMMA_M)
+constexpr int UMMA_NQ = 64;      // max pairs per tcgen05 tile (UMMA_N)
+constexpr int MAX_DIM = 1024;
+
+// counters[] layout (device int32)
+enum { CTR_N_SIMT = 0, CTR_N_UMMA = 1, CTR_N_TOUCHED = 2, CTR_COUNT = 8 };
+
+// Everything one gdr_score_topk call needs on the device.
+struct ScoreArgs {
+    // store
+    const void *emb;
+    const int32_t *offsets;
+    const int32_t *docid;
+    int32_t dim, dtype, n_clusters, max_cluster;
+    int64_t n_docs;
+    // batch
+    const float *q;
+    const int32_t *beams;
+    const float *prob;
+    int32_t B, K, act, k;
+    uint32_t flags;
+    // scratch
+    int32_t *cnt;        // [C]   zero between calls (self-restoring)
+    int32_t *grp_off;    // [C+1] exclusive scan of cnt
+    int32_t *simt_off;   // [C+1]
+    int32_t *umma_off;   // [C+1]
+    int32_t *grp_pair;   // [B*K] pair ids grouped by cluster
+    int32_t *candoff;    // [B, K+1] start of each beam's segment in the query's candidate list
+    Item *simt_items;
+    Item *umma_items;
+    int32_t *counters;   // [CTR_COUNT]
+    float *scorebuf;     // [B, stride]
+    int64_t stride;
+    __nv_bfloat16 *qsplit;  // [rows(q), 3, dim] bf16 hi/mid/lo split of q (tcgen05 path)
+    uint32_t *gkeys;     // [B, stride] keys scratch for the global-memory top-k variant
+    int32_t umma_min_group;  // groups with at least this many pairs go to the tcgen05 path (INT_MAX = never)
+};
+
+// ----- launchers (each enqueues on `s`, returns cudaGetLastError()) ---------------------------
+cudaError_t launch_invert(const ScoreArgs &a, cudaStream_t s, int *n_launches);
+cudaError_t launch_score_simt(const ScoreArgs &a, cudaStream_t s, int sm_count);
+cudaError_t launch_score_umma(const ScoreArgs &a, const CUtensorMap *tmap, cudaStream_t s, int sm_count);
+cudaError_t launch_qsplit(const ScoreArgs &a, cudaStream_t s);
+cudaError_t launch_topk_store(const ScoreArgs &a, float alpha, float *out_scores, int32_t *out_docids,
+                              cudaStream_t s);
+cudaError_t launch_merge_topk(const float *scores, const int32_t *docids, int G, int B, int k_in, int64_t g_stride, int k,
+                              float *out_scores, int32_t *out_docids, cudaStream_t s);
+cudaError_t launch_similarity(const float *q, int64_t Q, const void *p, int64_t P, int dim, int p_dtype,
+                              float *out, cudaStream_t s, int sm_count);
+cudaError_t launch_tree_mask(const int32_t *first_child, const int32_t *child_tok, const int32_t *child_node,
+                             const int64_t *input_ids, int64_t ids_stride, int R, int cur_len, float *scores,
+                             int64_t scores_stride, int V, int eos_id, int strict, cudaStream_t s);
+cudaError_t launch_position_mask(float *logits, int64_t bz, int sl, int V, int v_out, int last_eos_only,
+                                 cudaStream_t s);
+
+// ----- small device helpers -----------------------------------------------------------------
+__device__ __forceinline__ uint32_t float_to_ordered(float f) {
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_to_float(uint32_t k) {
+    uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ float apply_act(float x, int act) {
+    if (act == GDR_ACT_TANH) return tanhf(x);
+    if (act == GDR_ACT_SIGMOID) return 1.0f / (1.0f + expf(-x));
+    return x;
+}
+
+}  // namespace gdr

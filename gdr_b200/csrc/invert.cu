@@ -1,0 +1,167 @@
+// Pair inversion: turn the [B, K] beam table (query-major) into cluster -> (query, beam) groups
+// and emit the work lists the scoring kernels walk.  Replaces the host-side dict walk of
+// main_models.py:1435-1443 (flatten clusters, id_mapping lookup per (query, beam)).
+//
+//   k_count : one warp per query.  cnt[c] += 1 per valid beam; candoff[b, i] = start of beam i's
+//             segment in query b's candidate list (beam-major order, as main_models.py:1441-1443).
+//   k_scan  : one CTA.  Exclusive scans over clusters of the group sizes and of the number of
+//             SIMT / tcgen05 work items each cluster produces.
+//   k_fill  : scatter pair ids into their groups (atomicSub on cnt, which returns it to all-zero
+//             for the next call) and write the work items.
+#include "gdr_common.cuh"
+
+namespace gdr {
+
+__global__ void __launch_bounds__(128) k_count(ScoreArgs a) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= a.B) return;
+    const int b = warp;
+    const int32_t *beams = a.beams + (int64_t)b * a.K;
+    int32_t *co = a.candoff + (int64_t)b * (a.K + 1);
+    int carry = 0;
+    for (int i0 = 0; i0 < a.K; i0 += 32) {
+        const int i = i0 + lane;
+        int sz = 0;
+        if (i < a.K) {
+            const int c = beams[i];
+            if (c >= 0 && c < a.n_clusters) {
+                sz = a.offsets[c + 1] - a.offsets[c];
+                atomicAdd(&a.cnt[c], 1);
+            }
+        }
+        int incl = sz;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (i < a.K) co[i] = carry + incl - sz;
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) co[a.K] = carry;
+}
+
+__device__ __forceinline__ int ceil_div(int x, int y) { return (x + y - 1) / y; }
+
+// Block-wide exclusive scan of three ints per thread (1024 threads), returns totals via `tot`.
+__device__ __forceinline__ void block_scan3(int &x, int &y, int &z, int tot[3], int (*wsum)[3]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int ix = x, iy = y, iz = z;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int tx = __shfl_up_sync(0xffffffffu, ix, d);
+        int ty = __shfl_up_sync(0xffffffffu, iy, d);
+        int tz = __shfl_up_sync(0xffffffffu, iz, d);
+        if (lane >= d) { ix += tx; iy += ty; iz += tz; }
+    }
+    if (lane == 31) { wsum[warp][0] = ix; wsum[warp][1] = iy; wsum[warp][2] = iz; }
+    __syncthreads();
+    if (warp == 0) {
+        int sx = wsum[lane][0], sy = wsum[lane][1], sz = wsum[lane][2];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int tx = __shfl_up_sync(0xffffffffu, sx, d);
+            int ty = __shfl_up_sync(0xffffffffu, sy, d);
+            int tz = __shfl_up_sync(0xffffffffu, sz, d);
+            if (lane >= d) { sx += tx; sy += ty; sz += tz; }
+        }
+        wsum[lane][0] = sx; wsum[lane][1] = sy; wsum[lane][2] = sz;   // inclusive over warps
+    }
+    __syncthreads();
+    const int bx = warp ? wsum[warp - 1][0] : 0, by = warp ? wsum[warp - 1][1] : 0, bz = warp ? wsum[warp - 1][2] : 0;
+    tot[0] = wsum[31][0]; tot[1] = wsum[31][1]; tot[2] = wsum[31][2];
+    x = bx + ix - x; y = by + iy - y; z = bz + iz - z;
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(1024) k_scan(ScoreArgs a) {
+    __shared__ int wsum[32][3];
+    int carry[3] = {0, 0, 0};
+    int touched = 0;
+    const int C = a.n_clusters;
+    for (int c0 = 0; c0 < C; c0 += 1024) {
+        const int c = c0 + threadIdx.x;
+        int g = 0, ns = 0, nu = 0;
+        if (c < C) {
+            g = a.cnt[c];
+            const int size = a.offsets[c + 1] - a.offsets[c];
+            if (g > 0 && size > 0) {
+                touched++;
+                if (g >= a.umma_min_group) nu = ceil_div(size, UMMA_ROWS) * ceil_div(g, UMMA_NQ);
+                else ns = ceil_div(size, SIMT_ROWS) * ceil_div(g, SIMT_QT);
+            }
+        }
+        int tot[3];
+        block_scan3(g, ns, nu, tot, wsum);
+        if (c < C) {
+            a.grp_off[c] = carry[0] + g;
+            a.simt_off[c] = carry[1] + ns;
+            a.umma_off[c] = carry[2] + nu;
+        }
+        carry[0] += tot[0]; carry[1] += tot[1]; carry[2] += tot[2];
+    }
+    // total clusters touched (block reduce, reuse wsum)
+    for (int d = 16; d; d >>= 1) touched += __shfl_xor_sync(0xffffffffu, touched, d);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5][0] = touched;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < 32; ++w) t += wsum[w][0];
+        a.grp_off[C] = carry[0];
+        a.simt_off[C] = carry[1];
+        a.umma_off[C] = carry[2];
+        a.counters[CTR_N_SIMT] = carry[1];
+        a.counters[CTR_N_UMMA] = carry[2];
+        a.counters[CTR_N_TOUCHED] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_fill(ScoreArgs a) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n_pairs = (int64_t)a.B * a.K;
+    if (t < n_pairs) {
+        const int c = a.beams[t];
+        if (c >= 0 && c < a.n_clusters) {
+            const int slot = a.grp_off[c] + atomicSub(&a.cnt[c], 1) - 1;
+            a.grp_pair[slot] = (int32_t)t;
+        }
+    }
+    if (t < a.n_clusters) {
+        const int c = (int)t;
+        const int g0 = a.grp_off[c];
+        const int g = a.grp_off[c + 1] - g0;
+        const int row_lo = a.offsets[c];
+        const int size = a.offsets[c + 1] - row_lo;
+        if (g > 0 && size > 0) {
+            const bool umma = g >= a.umma_min_group;
+            const int rows_per = umma ? UMMA_ROWS : SIMT_ROWS;
+            const int q_per = umma ? UMMA_NQ : SIMT_QT;
+            Item *dst = umma ? a.umma_items + a.umma_off[c] : a.simt_items + a.simt_off[c];
+            // row tile outer, query chunk inner: consecutive items re-read the same rows (L2/L1 reuse)
+            for (int r = 0; r < size; r += rows_per) {
+                const int nrows = min(rows_per, size - r);
+                for (int s = 0; s < g; s += q_per) {
+                    Item it;
+                    it.row0 = row_lo + r;
+                    it.rel0 = r;
+                    it.nrows_nq = nrows | (min(q_per, g - s) << 16);
+                    it.slot0 = g0 + s;
+                    *dst++ = it;
+                }
+            }
+        }
+    }
+}
+
+cudaError_t launch_invert(const ScoreArgs &a, cudaStream_t s, int *n_launches) {
+    k_count<<<(a.B + 3) / 4, 128, 0, s>>>(a);
+    k_scan<<<1, 1024, 0, s>>>(a);
+    const int64_t n = max((int64_t)a.B * a.K, (int64_t)a.n_clusters);
+    k_fill<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a);
+    *n_launches += 3;
+    return cudaGetLastError();
+}
+
+}  // namespace gdr

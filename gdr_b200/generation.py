@@ -1,0 +1,134 @@
+"""Docid logit masks for the constrained beam search, on the device.
+
+    DeviceTrie / tree_mask_      the live prefix-tree mask of the reference's beam search,
+                                 GDR_model/transformers/generation_utils_previous.py:712-730
+                                 (a Python loop over B*K rows with .tolist() syncs, dict walks and
+                                 one index_put per row) as ONE kernel over a CSR trie in HBM.
+    position_mask_ /             the positional docid mask of GDR_model/transformers/modeling_t5.py:
+    select_valid_embedding       1546-1571 (eval, applied :1646) and 1279-1301 (training buffer, :1644).
+
+The beam search itself (T5 forward, log_softmax, topk(2K), hypothesis bookkeeping) stays in stock
+PyTorch; `TreeMask` is the hook a maintainer drops where the reference's block sits.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Tuple
+
+import numpy as np
+import torch
+
+from . import _cabi
+
+
+def flatten_trie(root) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """`Node` trie (anything with a `.children: Dict[int, node]`) -> CSR arrays
+    (first_child [n_nodes+1], child_tok [n_edges], child_node [n_edges]); node 0 is the root,
+    nodes are numbered breadth-first, each node's edges are sorted by token."""
+    first_child, child_tok, child_node = [0], [], []
+    queue = [root]
+    head = 0
+    while head < len(queue):
+        node = queue[head]
+        head += 1
+        for tok in sorted(node.children):
+            child_tok.append(int(tok))
+            child_node.append(len(queue))
+            queue.append(node.children[tok])
+        first_child.append(len(child_tok))
+    return (np.asarray(first_child, dtype=np.int32), np.asarray(child_tok, dtype=np.int32),
+            np.asarray(child_node, dtype=np.int32))
+
+
+class DeviceTrie:
+    """Device-resident CSR form of the reference's `Node` trie (main_models.py:112-151)."""
+
+    def __init__(self, first_child: np.ndarray, child_tok: np.ndarray, child_node: np.ndarray, device="cuda"):
+        self.first_child = np.ascontiguousarray(first_child, dtype=np.int32)
+        self.child_tok = np.ascontiguousarray(child_tok, dtype=np.int32)
+        self.child_node = np.ascontiguousarray(child_node, dtype=np.int32)
+        self.n_nodes = int(self.first_child.size - 1)
+        self.n_edges = int(self.child_tok.size)
+        self.device = torch.device(device)
+        self._handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _cabi.check(_cabi.lib().gdr_trie_create(
+                ctypes.byref(self._handle), self.first_child.ctypes.data, self.child_tok.ctypes.data,
+                self.child_node.ctypes.data, self.n_nodes, self.n_edges))
+
+    @classmethod
+    def from_root(cls, root, device="cuda") -> "DeviceTrie":
+        return cls(*flatten_trie(root), device=device)
+
+    def mask_(self, scores: torch.Tensor, input_ids: torch.Tensor, eos_token_id: int = 1, strict: bool = False,
+              stream=None) -> torch.Tensor:
+        """In place on `scores` [R, V] fp32 (cuda, last dim contiguous) given `input_ids` [R, cur_len]
+        int64: what generation_utils_previous.py:714-729 does to `scores`.  Returns `scores`."""
+        if not (scores.is_cuda and input_ids.is_cuda):
+            raise ValueError("tree mask runs on the device: scores and input_ids must be CUDA tensors (no CPU fallback)")
+        if scores.dtype != torch.float32 or input_ids.dtype != torch.int64:
+            raise ValueError("scores must be float32 and input_ids int64")
+        if scores.dim() != 2 or input_ids.dim() != 2 or scores.shape[0] != input_ids.shape[0]:
+            raise ValueError("scores [R, V] and input_ids [R, cur_len] must agree on R")
+        if scores.stride(1) != 1 or input_ids.stride(1) != 1:
+            raise ValueError("last dimension must be contiguous")
+        R, V = scores.shape
+        with torch.cuda.device(scores.device):
+            _cabi.check(_cabi.lib().gdr_tree_mask(
+                self._handle, input_ids.data_ptr(), input_ids.stride(0) if R > 1 else input_ids.shape[1], R,
+                input_ids.shape[1], scores.data_ptr(), scores.stride(0) if R > 1 else V, V, int(eos_token_id),
+                int(strict), _cabi.stream_ptr(stream)))
+        return scores
+
+    def close(self):
+        if getattr(self, "_handle", None) is not None and self._handle.value:
+            _cabi.lib().gdr_trie_destroy(self._handle)
+            self._handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class TreeMask:
+    """Callable hook for the beam-search loop: `scores = tree_mask(input_ids, scores)` replaces the
+    `if decode_tree:` block of generation_utils_previous.py:714-729 (`decode_tree` = the `Node` root
+    passed to `generate(..., decode_tree=self.root)`, main_models.py:1393)."""
+
+    def __init__(self, decode_tree, eos_token_id: int = 1, strict: bool = False, device="cuda"):
+        self.trie = decode_tree if isinstance(decode_tree, DeviceTrie) else DeviceTrie.from_root(decode_tree, device)
+        self.eos_token_id = eos_token_id
+        self.strict = strict
+
+    def __call__(self, input_ids: torch.Tensor, scores: torch.Tensor) -> torch.Tensor:
+        return self.trie.mask_(scores, input_ids, self.eos_token_id, self.strict)
+
+
+def position_mask_(logits: torch.Tensor, output_vocab_size: int, last_eos_only: bool = False, stream=None) -> torch.Tensor:
+    """In place on logits [bz, seq_length, vocab] fp32: position t keeps tokens
+    {t*V_out+2 .. t*V_out+V_out+1} and 1, everything else gets -1e9 added (modeling_t5.py:1566-1569).
+    `last_eos_only` = the training-time `logit_mask` variant (modeling_t5.py:1296)."""
+    if not logits.is_cuda:
+        raise ValueError("position mask runs on the device (no CPU fallback)")
+    if logits.dtype != torch.float32 or logits.dim() != 3 or not logits.is_contiguous():
+        raise ValueError("logits must be a contiguous float32 [bz, seq_length, vocab] tensor")
+    bz, sl, V = logits.shape
+    with torch.cuda.device(logits.device):
+        _cabi.check(_cabi.lib().gdr_position_mask(logits.data_ptr(), bz, sl, V, int(output_vocab_size),
+                                                  int(last_eos_only), _cabi.stream_ptr(stream)))
+    return logits
+
+
+def select_valid_embedding(sequence: torch.Tensor, output_vocab_size: int) -> torch.Tensor:
+    """Functional form with the reference's signature (nested function at modeling_t5.py:1546-1571,
+    `self.output_vocab_size` passed explicitly): returns `sequence + mask` as a new tensor."""
+    return position_mask_(sequence.contiguous().clone(), output_vocab_size, last_eos_only=False)
+
+
+def build_logit_mask(max_output_length: int, decode_vocab_size: int, output_vocab_size: int, device="cuda") -> torch.Tensor:
+    """The `self.logit_mask` buffer of modeling_t5.py:1279-1301: [1, max_output_length, decode_vocab_size],
+    0 at valid tokens, -1e9 elsewhere, last position EOS-only."""
+    z = torch.zeros(1, max_output_length, decode_vocab_size, dtype=torch.float32, device=device)
+    return position_mask_(z, output_vocab_size, last_eos_only=True)

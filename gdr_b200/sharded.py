@@ -1,0 +1,111 @@
+"""Cluster-sharded multi-GPU execution (one process per GPU, torch.distributed for the plumbing).
+
+New design — the reference keeps a full replica of the pickle on every DDP rank
+(GDR_model/main_models.py:806-814) and has no cross-rank step in retrieval.
+Clusters are the independent units: each rank owns a subset of the clusters (balanced by document
+count), scores only the beams that land in its clusters, and produces a local sorted top-k padded
+with (-inf, -1).  The single exchange step is an all-gather of the packed (score, docid) candidates
+(Q*k*8 bytes per rank — NCCL over NVLink 5 / NVSwitch on the GPU box, gloo in the CPU tests),
+followed by the merge top-k kernel (gdr_merge_topk).  Ordering is by (score desc, docid asc), which
+does not depend on candidate order, so the merged result equals the single-GPU result exactly.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def partition_clusters(sizes: Sequence[int], world_size: int) -> np.ndarray:
+    """Assign clusters to ranks, balanced by document count: largest cluster first onto the currently
+    lightest rank (LPT).  Deterministic; returns owner[c] in [0, world_size)."""
+    sizes = np.asarray(sizes, dtype=np.int64)
+    order = np.argsort(-sizes, kind="stable")
+    load = np.zeros(world_size, dtype=np.int64)
+    owner = np.empty(sizes.size, dtype=np.int32)
+    if world_size == 1:
+        owner[:] = 0
+        return owner
+    # LPT with a vectorised fast path: after the first pass loads are near-equal, so round-robin over
+    # ranks sorted by load per block of `world_size` clusters is within one cluster of true LPT.
+    for start in range(0, sizes.size, world_size):
+        blk = order[start:start + world_size]
+        ranks = np.argsort(load, kind="stable")[:blk.size]
+        owner[blk] = ranks
+        load[ranks] += sizes[blk]
+    return owner
+
+
+def global_to_local(owner: np.ndarray, rank: int) -> Tuple[np.ndarray, np.ndarray]:
+    """Returns (g2l [C] int32: local cluster index or -1, local_clusters: the global ids this rank owns,
+    ascending)."""
+    mine = np.nonzero(owner == rank)[0]
+    g2l = np.full(owner.size, -1, dtype=np.int32)
+    g2l[mine] = np.arange(mine.size, dtype=np.int32)
+    return g2l, mine
+
+
+def pack_candidates(scores: torch.Tensor, docids: torch.Tensor) -> torch.Tensor:
+    """[B, k] fp32 + [B, k] int32 -> one int32 buffer [2, B, k] (score bits, docids) so the exchange is a
+    single collective."""
+    return torch.stack([scores.contiguous().view(torch.int32), docids.to(torch.int32)], dim=0).contiguous()
+
+
+class ShardedRetriever:
+    """One rank's view of a cluster-sharded corpus.
+
+    local_topk(q, local_beams, k, prob, alphas, act) -> (scores [n_alpha, B, k], docids [n_alpha, B, k])
+    merge(gathered int32 [G, 2, B, k], k) -> (scores [B, k], docids [B, k])
+    default to the CUDA implementations (ClusterStore.score_topk / gdr_merge_topk); the CPU (gloo)
+    tests inject checkers for them — the product path never leaves the device.
+    """
+
+    def __init__(self, store, g2l: torch.Tensor, group=None,
+                 local_topk: Optional[Callable] = None, merge: Optional[Callable] = None):
+        self.store = store
+        self.g2l = g2l
+        self.group = group
+        self.world_size = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self._local_topk = local_topk if local_topk is not None else self._cuda_local_topk
+        self._merge = merge if merge is not None else self._cuda_merge
+
+    # ---- CUDA implementations ---------------------------------------------------------------------
+    def _cuda_local_topk(self, q, local_beams, k, prob, alphas, act):
+        return self.store.score_topk(q, local_beams, k, prob=prob, alphas=alphas if alphas is not None else [1.0], act=act)
+
+    @staticmethod
+    def _cuda_merge(gathered: torch.Tensor, k: int):
+        import ctypes  # noqa: F401
+        from . import _cabi
+        G, _, B, k_in = gathered.shape
+        out_s = torch.empty((B, k), dtype=torch.float32, device=gathered.device)
+        out_d = torch.empty((B, k), dtype=torch.int32, device=gathered.device)
+        base = gathered.data_ptr()
+        with torch.cuda.device(gathered.device):
+            _cabi.check(_cabi.lib().gdr_merge_topk(base, base + B * k_in * 4, G, B, k_in, 2 * B * k_in, k,
+                                                   out_s.data_ptr(), out_d.data_ptr(), _cabi.stream_ptr()))
+        return out_s, out_d
+
+    # ---- one batch ----------------------------------------------------------------------------------
+    def localize(self, beams: torch.Tensor) -> torch.Tensor:
+        """Global cluster ids [B, K] (-1 = absent) -> this rank's local ids, -1 where another rank owns it."""
+        idx = beams.long()
+        loc = self.g2l[idx.clamp(min=0)]
+        return torch.where(idx >= 0, loc, torch.full_like(loc, -1)).to(torch.int32)
+
+    def score_topk(self, q: torch.Tensor, beams: torch.Tensor, k: int, prob: Optional[torch.Tensor] = None,
+                   alpha: Optional[float] = None, act: str = "none") -> Tuple[torch.Tensor, torch.Tensor]:
+        """q [B, D] and beams [B, K] (GLOBAL cluster ids) are replicated on every rank.
+        Returns the merged (scores [B, k], docids [B, k]) on every rank."""
+        s, d = self._local_topk(q, self.localize(beams), k, prob, None if alpha is None else [alpha], act)
+        s, d = s[0], d[0]
+        if self.world_size == 1:
+            return s, d
+        packed = pack_candidates(s, d)
+        # output is the dim-0 concatenation of every rank's [2, B, k] block (the layout both NCCL and gloo accept)
+        gathered = torch.empty((self.world_size * 2,) + tuple(packed.shape[1:]), dtype=packed.dtype, device=packed.device)
+        dist.all_gather_into_tensor(gathered, packed, group=self.group)
+        return self._merge(gathered.view((self.world_size,) + tuple(packed.shape)), k)

@@ -1,0 +1,160 @@
+"""Cluster-contiguous CSR document-embedding store resident in HBM.
+
+Replaces the reference's two host-side index structures:
+  * `self.doc_embed`  — int-indexable container of 1-D fp32 [D] tensors, unpickled at start-up
+                        (GDR_model/main_models.py:806-814, loader :182-187) and copied to the GPU one
+                        document at a time at query time (:1458-1462);
+  * `self.id_mapping` — Dict[str cluster id -> List[int doc index]] (main_models.py:874-889).
+Here the rows are permuted once so that a cluster is one contiguous slab of `emb[N, D]` (bf16 or
+fp32) with `offsets[C+1]` and `docid[N]` (the reference's doc index of each row) beside it.
+All compute goes through libgdr_b200.so (gdr_b200/_cabi.py); there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _cabi
+
+
+def csr_from_reference(doc_embed, id_mapping: Dict[str, List[int]]
+                       ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, List[str]]:
+    """(doc_embed, id_mapping) -> host CSR (emb [N, D] fp32, offsets [C+1], docid [N], keys).
+    `doc_embed[i]` -> [D] tensor (or `doc_embed` is an [N, D] tensor).  Clusters keep the dict's
+    insertion order, documents inside a cluster keep their list order (= the reference's candidate
+    order, main_models.py:1441-1443).  A document listed by several clusters gets one row per cluster."""
+    keys = list(id_mapping.keys())
+    rows: List[int] = []
+    offsets = [0]
+    for key in keys:
+        rows.extend(int(i) for i in id_mapping[key])
+        offsets.append(len(rows))
+    idx = torch.tensor(rows, dtype=torch.int64)
+    if isinstance(doc_embed, torch.Tensor):
+        table = doc_embed.detach().to("cpu").reshape(len(doc_embed), -1)
+    else:
+        table = torch.stack([torch.as_tensor(doc_embed[i]).detach().to("cpu").reshape(-1) for i in range(len(doc_embed))])
+    return table.float()[idx].contiguous(), torch.tensor(offsets, dtype=torch.int64), idx, keys
+
+
+class ClusterStore:
+    def __init__(self, emb: torch.Tensor, offsets: torch.Tensor, docid: torch.Tensor,
+                 keys: Optional[Sequence[str]] = None):
+        """emb [N, D] cuda bf16/fp32 (cluster-contiguous), offsets [C+1] / docid [N] integer tensors."""
+        if not emb.is_cuda:
+            raise ValueError("ClusterStore lives in HBM: emb must be a CUDA tensor (no CPU fallback)")
+        if emb.dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("emb must be float32 or bfloat16")
+        self.emb = emb.contiguous()
+        off_host = offsets.detach().to("cpu", torch.int64)
+        if off_host.numel() < 2 or int(off_host[0]) != 0 or int(off_host[-1]) != emb.shape[0] or \
+                bool((off_host[1:] < off_host[:-1]).any()):
+            raise ValueError("offsets must be a non-decreasing [C+1] array spanning [0, N]")
+        self.offsets_host = off_host.numpy()
+        self.sizes_host = np.diff(self.offsets_host)
+        self.offsets = off_host.to(torch.int32).to(emb.device)
+        self.docid = docid.detach().to(torch.int32).to(emb.device).contiguous()
+        if self.docid.numel() != emb.shape[0]:
+            raise ValueError("docid must have one entry per row of emb")
+        self.n_docs, self.dim = int(emb.shape[0]), int(emb.shape[1])
+        self.n_clusters = int(off_host.numel() - 1)
+        self.max_cluster = int(self.sizes_host.max())
+        self.keys = list(keys) if keys is not None else None
+        self.cluster_index: Dict[str, int] = {k: i for i, k in enumerate(self.keys)} if self.keys is not None else {}
+        self._handle = ctypes.c_void_p()
+        with torch.cuda.device(emb.device):
+            _cabi.check(_cabi.lib().gdr_store_create(
+                ctypes.byref(self._handle), self.emb.data_ptr(), self.n_docs, self.dim,
+                _cabi.DTYPE_BF16 if emb.dtype == torch.bfloat16 else _cabi.DTYPE_F32,
+                self.offsets.data_ptr(), self.n_clusters, self.docid.data_ptr(), self.max_cluster))
+
+    # ---- construction from the reference's objects ------------------------------------------
+    @classmethod
+    def from_reference(cls, doc_embed, id_mapping: Dict[str, List[int]], dtype=torch.bfloat16,
+                       device="cuda") -> "ClusterStore":
+        """Build from exactly the two objects the reference holds (main_models.py:806-814, 874-889)."""
+        emb, offsets, docid, keys = csr_from_reference(doc_embed, id_mapping)
+        return cls(emb.to(dtype).to(device), offsets, docid, keys)
+
+    @classmethod
+    def from_csr(cls, emb: torch.Tensor, offsets, docid, keys=None, dtype=None, device="cuda") -> "ClusterStore":
+        emb = torch.as_tensor(emb)
+        if dtype is not None:
+            emb = emb.to(dtype)
+        return cls(emb.to(device), torch.as_tensor(np.asarray(offsets)), torch.as_tensor(np.asarray(docid)), keys)
+
+    # ---- lookups ---------------------------------------------------------------------------------
+    def beams_from_ids(self, dec: Sequence[Sequence[str]]) -> torch.Tensor:
+        """B x K cluster-id strings -> int32 [B, K] cluster indices.  KeyError for an unknown id,
+        like `self.id_mapping[cluster_id]` at main_models.py:1442."""
+        return torch.tensor([[self.cluster_index[c] for c in row] for row in dec], dtype=torch.int32)
+
+    def candidate_counts(self, beams_host: torch.Tensor) -> torch.Tensor:
+        sizes = torch.from_numpy(np.append(self.sizes_host, 0))     # index -1 -> 0
+        return sizes[beams_host.long()].sum(dim=1)
+
+    # ---- the hot path ----------------------------------------------------------------------------
+    def score_topk(self, q: torch.Tensor, beams: torch.Tensor, k: int, prob: Optional[torch.Tensor] = None,
+                   alphas: Optional[Sequence[float]] = None, act: Optional[str] = "none", per_beam: bool = False,
+                   flags: int = 0, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, stream=None
+                   ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Cluster-restricted scoring + top-k for one batch (gdr_score_topk in include/gdr_b200.h).
+        q [B, D] fp32 cuda ([B*K, D] with per_beam), beams [B, K] int32 cuda (-1 = absent),
+        prob [B, K] fp32 cuda or None, alphas list of floats or None.
+        Returns (scores [n_alpha, B, k] fp32, docids [n_alpha, B, k] int32) — [B, k] when alphas is None."""
+        dev = self.emb.device
+        B, K = int(beams.shape[0]), int(beams.shape[1])
+        if q.device != dev or beams.device != dev:
+            raise ValueError("q and beams must live on the store's device")
+        if q.dtype != torch.float32 or beams.dtype != torch.int32:
+            raise ValueError("q must be float32 and beams int32")
+        if q.shape != ((B * K if per_beam else B), self.dim):
+            raise ValueError(f"q has shape {tuple(q.shape)}, expected {(B * K if per_beam else B, self.dim)}")
+        q = q.contiguous()
+        beams = beams.contiguous()
+        if prob is not None:
+            if prob.shape != (B, K) or prob.dtype != torch.float32 or prob.device != dev:
+                raise ValueError("prob must be float32 [B, K] on the store's device")
+            prob = prob.contiguous()
+        n_alpha = 1 if alphas is None else len(alphas)
+        alpha_arr = None if alphas is None else (ctypes.c_float * n_alpha)(*[float(a) for a in alphas])
+        if out is None:
+            out_s = torch.empty((n_alpha, B, k), dtype=torch.float32, device=dev)
+            out_d = torch.empty((n_alpha, B, k), dtype=torch.int32, device=dev)
+        else:
+            out_s, out_d = out
+        if per_beam:
+            flags |= _cabi.Q_PER_BEAM
+        with torch.cuda.device(dev):
+            _cabi.check(_cabi.lib().gdr_score_topk(
+                self._handle, q.data_ptr(), beams.data_ptr(), None if prob is None else prob.data_ptr(), alpha_arr,
+                n_alpha, B, K, _cabi.ACT[act], int(k), flags, out_s.data_ptr(), out_d.data_ptr(), _cabi.stream_ptr(stream)))
+        if alphas is None and out is None:
+            return out_s[0], out_d[0]
+        return out_s, out_d
+
+    def last_stats(self) -> Dict[str, int]:
+        arr = (ctypes.c_int64 * 4)()
+        with torch.cuda.device(self.emb.device):
+            _cabi.check(_cabi.lib().gdr_store_last_stats(self._handle, arr, _cabi.stream_ptr()))
+        return {"simt_items": arr[0], "umma_tiles": arr[1], "launches": arr[2], "clusters_touched": arr[3]}
+
+    def bytes_touched(self, beams_host: torch.Tensor) -> int:
+        """Algorithmic HBM bytes of the embeddings one batch touches: every touched cluster once
+        (SURVEY.md §8d)."""
+        u = torch.unique(beams_host[beams_host >= 0]).long().numpy()
+        return int(self.sizes_host[u].sum()) * self.dim * self.emb.element_size()
+
+    def close(self):
+        if getattr(self, "_handle", None) is not None and self._handle.value:
+            _cabi.lib().gdr_store_destroy(self._handle)
+            self._handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

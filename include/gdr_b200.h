@@ -1,0 +1,127 @@
+/*
+ * gdr_b200.h — C ABI of the B200-native fine-grained stage of GDR (ypw0102/GDR).
+ *
+ * The reference is pure Python on torch and has no FFI layer of its own;
+ * the entry points below are what a binding for this path replaces, each citing the
+ * reference code it stands in for (paths relative to the reference root).  All pointers
+ * marked DEV are device pointers on the current CUDA device; HOST pointers are host
+ * memory.  The caller owns every buffer it passes in; the library owns only its handles
+ * and their scratch.  Every function returns GDR_OK or a negative status, never throws or
+ * aborts; gdr_last_error() gives the message for the calling thread.  Kernels are enqueued
+ * on the `stream` argument (a cudaStream_t passed as void*; NULL = legacy default stream);
+ * no entry point synchronises the device unless documented.  There is NO CPU fallback.
+ */
+#ifndef GDR_B200_H
+#define GDR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GDR_OK 0
+#define GDR_ERR_INVALID (-1)     /* bad argument (shape, dtype, null pointer)            */
+#define GDR_ERR_CUDA (-2)        /* a CUDA runtime/driver call failed                    */
+#define GDR_ERR_UNSUPPORTED (-3) /* valid request this build cannot serve (e.g. D > 1024) */
+#define GDR_ERR_NOMEM (-4)
+
+#define GDR_DTYPE_F32 0
+#define GDR_DTYPE_BF16 1
+
+#define GDR_ACT_NONE 0    /* dense.py:53-54 (plain q·d)                                  */
+#define GDR_ACT_TANH 1    /* main_models.py:1580-1582, --loss_func tanh (main.py:393)     */
+#define GDR_ACT_SIGMOID 2 /* main_models.py:1578-1579, --loss_func sigmoid                */
+
+/* flags for gdr_score_topk */
+#define GDR_Q_PER_BEAM 1u       /* q is [B*K, D]: one query vector per (query, beam), main_models.py:1467-1571,1583-1594 */
+#define GDR_FORCE_SIMT 2u       /* never use the tcgen05 grouped-GEMM path                */
+#define GDR_FORCE_UMMA 4u       /* use the tcgen05 path for every non-empty group         */
+
+typedef struct gdr_store gdr_store_t;
+typedef struct gdr_trie gdr_trie_t;
+
+int gdr_abi_version(void);
+const char *gdr_last_error(void);
+
+/* ---- document-embedding store ------------------------------------------------------------
+ * Replaces `self.doc_embed` (int-indexable list of [D] tensors, main_models.py:806-814) and
+ * `self.id_mapping` (cluster id -> list of doc indices, main_models.py:874-889) with a
+ * cluster-contiguous CSR table resident in HBM:
+ *   emb     DEV [n_docs, dim] row-major, GDR_DTYPE_F32 or GDR_DTYPE_BF16, 16-byte aligned,
+ *           rows permuted so that cluster c is rows offsets[c] .. offsets[c+1]-1
+ *   offsets DEV int32 [n_clusters + 1]
+ *   docid   DEV int32 [n_docs]: the reference's global doc index of each row
+ *   max_cluster_size  max_c (offsets[c+1]-offsets[c]), computed by the caller while building the CSR
+ * The store keeps the pointers (no copy); they must outlive it.  dim % 8 == 0, dim <= 1024. */
+int gdr_store_create(gdr_store_t **out, const void *emb, int64_t n_docs, int32_t dim, int32_t dtype,
+                     const int32_t *offsets, int32_t n_clusters, const int32_t *docid,
+                     int32_t max_cluster_size);
+int gdr_store_destroy(gdr_store_t *store);
+
+/* ---- fine stage: cluster-restricted scoring + top-k ---------------------------------------
+ * Replaces main_models.py:1441-1462 (gather), :1577-1594 (score), :1596-1624 (rerank bias),
+ * :1625 (topk) and :1628-1631 (index -> doc index) for one batch; with act = NONE, prob = NULL
+ * it is dense.py:53-54 `compute_similarity` restricted to the beam clusters + `Tensor.topk`.
+ *   q        DEV fp32 [B, dim]  (or [B*K, dim] with GDR_Q_PER_BEAM)
+ *   beams    DEV int32 [B, K]   cluster index of each beam, -1 = absent
+ *   prob     DEV fp32 [B, K] or NULL: softmax of the beam scores (main_models.py:1601)
+ *   alphas   HOST fp32 [n_alpha] or NULL (then n_alpha must be 1 and alpha = 1): --score_rate
+ *            (main.py:389); result r uses score + alphas[r] * prob[b, beam_of(candidate)]
+ *   out_scores DEV fp32 [n_alpha, B, k], out_docids DEV int32 [n_alpha, B, k], sorted by score
+ *            descending, ties by ascending docid; queries with fewer than k candidates are padded
+ *            with (-inf, -1) (the reference raises there, main_models.py:1625; the Python shim
+ *            restores that behaviour). */
+int gdr_score_topk(gdr_store_t *store, const float *q, const int32_t *beams, const float *prob,
+                   const float *alphas, int32_t n_alpha, int32_t B, int32_t K, int32_t act, int32_t k,
+                   uint32_t flags, float *out_scores, int32_t *out_docids, void *stream);
+
+/* Counters of the most recent gdr_score_topk on this store (device-side work-list sizes):
+ * out[0] = (cluster, query-chunk) items scored by the SIMT GEMV path, out[1] = tiles scored by the
+ * tcgen05 grouped-GEMM path, out[2] = kernels launched by that call, out[3] = clusters touched.
+ * Synchronises `stream`. */
+int gdr_store_last_stats(gdr_store_t *store, int64_t out[4], void *stream);
+
+/* ---- dense similarity (dense.py:53-54 / encoder.py:128-129): out[Q, P] = q @ p^T, fp32 out ----
+ *   q DEV fp32 [Q, dim]; p DEV [P, dim] of p_dtype; out DEV fp32 [Q, P]. */
+int gdr_similarity(const float *q, int64_t Q, const void *p, int64_t P, int32_t dim, int32_t p_dtype,
+                   float *out, void *stream);
+
+/* ---- merge of per-rank candidates (new in the sharded design) ----------------
+ *   scores DEV fp32 [G, B, k_in], docids DEV int32 [G, B, k_in] (docid -1 = padding); rank g's
+ *   block starts g * g_stride elements after the base pointer (g_stride = B * k_in when dense; a
+ *   larger stride lets both arrays live interleaved in one all-gather buffer)
+ *   -> out_scores DEV fp32 [B, k], out_docids DEV int32 [B, k], same ordering rule as above. */
+int gdr_merge_topk(const float *scores, const int32_t *docids, int32_t G, int32_t B, int32_t k_in,
+                   int64_t g_stride, int32_t k, float *out_scores, int32_t *out_docids, void *stream);
+
+/* ---- prefix-tree docid mask ------------------------------------------------------------------
+ * Device form of the `Node` trie (main_models.py:112-151).  HOST CSR arrays, copied by the
+ * library: node n's children are edges first_child[n] .. first_child[n+1]-1, sorted by token;
+ * node 0 is the root. */
+int gdr_trie_create(gdr_trie_t **out, const int32_t *first_child, const int32_t *child_tok,
+                    const int32_t *child_node, int32_t n_nodes, int32_t n_edges);
+int gdr_trie_destroy(gdr_trie_t *trie);
+
+/* Replaces generation_utils_previous.py:714-729.  For each of R rows, walk the trie along
+ * input_ids[r, 1:cur_len]; allowed = children of the node reached, or {eos_id} if the path
+ * leaves the tree.  In place on scores DEV fp32 [R, V] (row stride in elements): allowed
+ * entries become s + 0.0f, all others s + (-inf).  strict = 0 writes -inf without reading
+ * the masked entries (identical unless a masked input is NaN or +inf); strict = 1 reads
+ * every entry and is bit-identical for all inputs.  Child tokens >= V are ignored.
+ *   input_ids DEV int64 [R, cur_len] (row stride in elements). */
+int gdr_tree_mask(gdr_trie_t *trie, const int64_t *input_ids, int64_t ids_row_stride, int32_t R,
+                  int32_t cur_len, float *scores, int64_t scores_row_stride, int32_t V, int32_t eos_id,
+                  int32_t strict, void *stream);
+
+/* Replaces modeling_t5.py:1546-1571 `select_valid_embedding` (eval; last_eos_only = 0) and the
+ * `logit_mask` buffer of modeling_t5.py:1279-1301 (training; last_eos_only = 1): in place on
+ * logits DEV fp32 [bz, sl, V]; position t keeps tokens {t*v_out+2 .. t*v_out+v_out+1} and 1
+ * (x + 0.0f), every other entry becomes x + (-1e9f). */
+int gdr_position_mask(float *logits, int64_t bz, int32_t sl, int32_t V, int32_t v_out,
+                      int32_t last_eos_only, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GDR_B200_H */

@@ -1,0 +1,258 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by EXECUTING THE UNMODIFIED REFERENCE in the dev container.
+
+TEST INFRASTRUCTURE.  Run here (needs /root/reference):   python oracle/make_golden.py
+The fixtures it writes are committed; nothing on the GPU box reads /root/reference.
+
+Each fixture holds the inputs and the reference's outputs for one piece of the hot path:
+  dense_topk_*.npz   reference dense.py `DenseModel.compute_similarity` (dense.py:53-54) + `Tensor.topk`
+                     per query over its beam clusters (BASELINE.md §2 recipe)
+  fine_stage_*.npz   reference `T5FineTuner.validation_step_i` (main_models.py:1337-1642) driven unbound
+                     with a stub `self` (fake generate/tokenizer/encoder), docid strings per alpha
+  tree_*.npz         reference `TreeBuilder/Node` (main_models.py:112-151), codecs (297-346) and the live
+                     tree-mask block, whose SOURCE LINES generation_utils_previous.py:714-729 are read
+                     from the mounted reference at run time and exec'd (the block is inline in a
+                     300-line method and cannot be called on its own)
+  position_mask.npz  reference `select_valid_embedding` (modeling_t5.py:1546-1571), same technique,
+                     and the training `logit_mask` recipe (modeling_t5.py:1279-1301)
+"""
+import json
+import os
+import subprocess
+import sys
+import textwrap
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLD = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, HERE)
+
+
+def _bf16_bits(t):
+    import torch
+    return t.to(torch.bfloat16).view(torch.int16).numpy().astype("uint16")
+
+
+# ---------------------------------------------------------------------------------------------
+def gen_dense():
+    import numpy as np
+    import torch
+    import ref_shims
+    import gdr_oracle as orc
+
+    ref_dense = ref_shims.load_ref_dense()
+    cases = {
+        # name: (N, C, D, Q, K, k, zipf)
+        "dense_topk_d768": (512, 8, 768, 6, 3, 20, 0.0),
+        "dense_topk_d128": (4096, 64, 128, 32, 8, 100, 0.0),
+        "dense_topk_zipf": (3000, 40, 64, 16, 6, 64, 1.1),
+    }
+    for name, (N, C, D, Q, K, k, zipf) in cases.items():
+        emb, offsets, docid = orc.synth_corpus(N, C, D, seed=11 + N, zipf=zipf)
+        emb = emb.bfloat16().float()              # bf16-representable so one fixture serves both store dtypes
+        q, beams, beam_scores = orc.synth_queries(Q, C, K, D, seed=7 + Q)
+        beams = beams.copy()
+        beams[0, -1] = -1                         # an absent beam
+        bias = torch.softmax(beam_scores, dim=-1)
+        out = {}
+        for tag, act, use_bias in (("plain", None, False), ("tanh_bias", torch.tanh, True)):
+            S = torch.full((Q, k), float("-inf"))
+            I = torch.full((Q, k), -1, dtype=torch.int64)
+            for b in range(Q):
+                rows, sb = [], []
+                for i, c in enumerate(beams[b].tolist()):
+                    if c < 0:
+                        continue
+                    r = torch.arange(int(offsets[c]), int(offsets[c + 1]))
+                    rows.append(r)
+                    sb.append(bias[b, i].expand(r.numel()))
+                rows = torch.cat(rows)
+                s = ref_dense.DenseModel.compute_similarity(None, q[b:b + 1], emb[rows])[0]   # dense.py:53-54
+                if act is not None:
+                    s = act(s)
+                if use_bias:
+                    s = s + torch.cat(sb)
+                kk = min(k, s.numel())
+                v, i = s.topk(kk, largest=True, sorted=True)                                  # main_models.py:1625
+                S[b, :kk] = v
+                I[b, :kk] = torch.from_numpy(docid)[rows[i]]
+            out["scores_" + tag] = S.numpy()
+            out["docids_" + tag] = I.numpy()
+        np.savez_compressed(os.path.join(GOLD, name + ".npz"), emb_bf16_bits=_bf16_bits(emb), offsets=offsets,
+                            docid=docid, q=q.numpy(), beams=beams, bias=bias.numpy(), k=np.int64(k), **out)
+        print("wrote", name)
+
+
+# ---------------------------------------------------------------------------------------------
+def _ref_lines(path, first, last):
+    """Source lines [first, last] (1-based, inclusive) of a reference file, dedented."""
+    with open(path) as f:
+        lines = f.read().splitlines()
+    return textwrap.dedent("\n".join(lines[first - 1:last])) + "\n"
+
+
+def gen_main_models():
+    import numpy as np
+    import ref_shims
+
+    mm, gp = ref_shims.load_ref_main_models()
+    import torch
+    from types import SimpleNamespace
+    import gdr_oracle as orc
+
+    REF = ref_shims.REF_MODEL_DIR
+
+    # ---------------- tree + codecs + tree mask ----------------
+    rng = np.random.RandomState(5)
+    args = SimpleNamespace(kary=30, position=1, output_vocab_size=30)
+    paths = set()
+    while len(paths) < 200:
+        depth = rng.choice([2, 3, 3, 3])
+        paths.add("-".join(str(rng.randint(0, 30)) for _ in range(depth)))
+    paths = sorted(paths)
+    builder = mm.TreeBuilder()
+    tok_paths = []
+    for di, p in enumerate(paths):
+        toks = mm.encode_single_newid(args, p)                       # main_models.py:297-319
+        tok_paths.append(toks)
+        builder.add(toks, di)                                         # main_models.py:137-151
+        if di % 3 == 0:
+            builder.add(toks + [0, 0], 1000 + di)                     # trailing pads are ignored
+    root = builder.build()
+    L = 6
+    arr = np.zeros((len(paths), L), dtype=np.int64)
+    for i, t in enumerate(tok_paths):
+        arr[i, 1:1 + len(t)] = t
+    decoded = mm.decode_token(args, arr)                              # main_models.py:322-346
+    assert decoded == paths, "reference codec round trip failed"
+    noeos = np.array([[0, 5, 40, 70, 0, 0], [0, 9, 33, 62, 95, 0]], dtype=np.int64)
+    decoded_noeos = mm.decode_token(args, noeos)
+
+    # flatten the reference trie for the fixture: (parent, token, child) edges in insertion order + leaf docs
+    edges, leaves, ids, stack = [], [], {id(root): 0}, [root]
+    while stack:
+        n = stack.pop()
+        for tok, ch in n.children.items():
+            ids[id(ch)] = len(ids)
+            edges.append((ids[id(n)], tok, ids[id(ch)]))
+            stack.append(ch)
+        for d in n.embedding_index:
+            leaves.append((ids[id(n)], d))
+
+    block = _ref_lines(os.path.join(REF, "transformers", "generation_utils_previous.py"), 714, 729)
+    assert block.startswith("if decode_tree:"), block[:40]
+    V = 128
+    out = {}
+    for cur_len in (1, 2, 3, 4, 5):
+        R = 48
+        ids_t = torch.zeros(R, cur_len, dtype=torch.int64)
+        for r in range(R):
+            t = tok_paths[rng.randint(len(tok_paths))]
+            n = min(cur_len - 1, len(t))
+            ids_t[r, 1:1 + n] = torch.tensor(t[:n])
+            if r % 7 == 3 and cur_len > 1:
+                ids_t[r, rng.randint(1, cur_len)] = 99 + rng.randint(20)   # off-tree prefix
+            if r % 11 == 5 and cur_len > 2:
+                ids_t[r, cur_len - 1] = 0                                   # finished (padded) row
+        g = torch.Generator().manual_seed(100 + cur_len)
+        scores = torch.log_softmax(torch.randn(R, V, generator=g), dim=-1)
+        scores[0, 3] = -0.0
+        scores[1, 7] = float("-inf")
+        ns = {"torch": torch, "decode_tree": root, "scores": scores.clone(), "input_ids": ids_t,
+              "num_beams": 4, "batch_size": R // 4}
+        exec(block, ns)                                                # generation_utils_previous.py:714-729
+        out[f"ids_{cur_len}"] = ids_t.numpy()
+        out[f"in_{cur_len}"] = scores.numpy()
+        out[f"out_{cur_len}"] = ns["scores"].numpy()
+    np.savez_compressed(os.path.join(GOLD, "tree.npz"), paths=np.array(paths), tok_arr=arr,
+                        decoded_noeos=np.array(decoded_noeos), noeos=noeos,
+                        edges=np.array(edges, dtype=np.int64), leaves=np.array(leaves, dtype=np.int64), **out)
+    print("wrote tree")
+
+    # ---------------- positional mask ----------------
+    sel_src = _ref_lines(os.path.join(REF, "transformers", "modeling_t5.py"), 1546, 1571)
+    assert sel_src.startswith("def select_valid_embedding(sequence):"), sel_src[:60]
+    pm = {}
+    for V_out, Lmax, sl in ((30, 10, 1), (30, 10, 4), (30, 10, 10), (10, 5, 5)):
+        Vdec = V_out * Lmax + 2
+        g = torch.Generator().manual_seed(V_out + sl)
+        x = torch.randn(3, sl, Vdec, generator=g) * 4
+        x[0, 0, 1] = -0.0
+        ns = {"torch": torch, "self": SimpleNamespace(output_vocab_size=V_out)}
+        exec(sel_src, ns)
+        y = ns["select_valid_embedding"](x.clone())                    # modeling_t5.py:1546-1571
+        key = f"{V_out}_{Lmax}_{sl}"
+        pm["in_" + key], pm["out_" + key] = x.numpy(), y.numpy()
+    # training-time buffer (modeling_t5.py:1279-1301): executed from source with a stub config/self
+    tr_src = _ref_lines(os.path.join(REF, "transformers", "modeling_t5.py"), 1279, 1301)
+    assert tr_src.startswith("if decode_embedding:"), tr_src[:40]
+    stub = SimpleNamespace()
+    ns = {"torch": torch, "decode_embedding": 2, "self": stub,
+          "config": SimpleNamespace(max_output_length=10, decode_vocab_size=302, output_vocab_size=30)}
+    exec(tr_src, ns)
+    pm["train_logit_mask_30_10"] = stub.logit_mask.numpy()
+    np.savez_compressed(os.path.join(GOLD, "position_mask.npz"), **pm)
+    print("wrote position_mask")
+
+    # ---------------- fine stage through the real validation_step_i ----------------
+    for case, (loss_func, D, C, per, B, K) in {"fine_stage_tanh": ("tanh", 64, 12, 20, 3, 5),
+                                               "fine_stage_sigmoid": ("sigmoid", 32, 9, 14, 2, 4)}.items():
+        g = torch.Generator().manual_seed(77 + D)
+        N = C * per
+        emb = torch.randn(N, D, generator=g) * D ** -0.5
+        doc_embed = [emb[i].clone() for i in range(N)]
+        cl_paths = paths[:C]
+        perm = torch.randperm(N, generator=g).tolist()
+        id_mapping = {cl_paths[c]: perm[c * per:(c + 1) * per][: per - (c % 3)] for c in range(C)}
+        beams = [torch.randperm(C, generator=g)[:K].tolist() for _ in range(B)]
+        dec_flat = [cl_paths[c] for row in beams for c in row]
+        outs = torch.zeros(B * K, L, dtype=torch.int64)
+        for i, p in enumerate(dec_flat):
+            t = mm.encode_single_newid(args, p)
+            outs[i, 1:1 + len(t)] = torch.tensor(t)
+        beam_scores = (-torch.cumsum(torch.rand(B, K, generator=g), dim=1)).flatten().tolist()
+        q = torch.randn(B, D, generator=g)
+        enc_hidden = torch.zeros(B * K, 4, D)
+        enc_hidden[::K, 0] = q                                          # encoder token-0 state of each query's first beam row
+        score_rate = [0, 0.5, 1, 3]
+        a = SimpleNamespace(decode_embedding=2, position=1, max_output_length=L, hierarchic_decode=0,
+                            output_vocab_size=30, softmax=0, gen_method="greedy", is_train_encoder=1,
+                            multiple_decoder=0, num_return_sequences=K, length_penalty=0.8, kary=30,
+                            label_length_cutoff=0, train_encoder_epoch=10 ** 9, use_query_embed_encoder=1,
+                            use_query_embed_decoder_avg=0, use_query_embed_decoder_special=0,
+                            loss_func=loss_func, score_rate=score_rate, eval_batch_size=B)
+        model = SimpleNamespace(
+            generate=lambda *x, **kw: ((outs, list(beam_scores)), SimpleNamespace(last_hidden_state=enc_hidden)),
+            config=SimpleNamespace(hidden_size=D))
+        stub_self = SimpleNamespace(args=a, epoch=0, model=model, root=None, cluster=set(cl_paths),
+                                    tokenizer=SimpleNamespace(decode=lambda ids: "q"),
+                                    id_mapping=id_mapping, doc_embed=doc_embed,
+                                    encoder=lambda query_enc=None, passage=None: query_enc[:, 0],   # main_models.py:102-109
+                                    softmax=torch.nn.Softmax(dim=-1))
+        batch = {"source_ids": torch.zeros(B, 3, dtype=torch.int64), "source_mask": torch.ones(B, 3, dtype=torch.int64),
+                 "target_mask": torch.ones(B, L, dtype=torch.int64), "rank": [], "oldid": [["gt"] * B]}
+        res = mm.T5FineTuner.validation_step_i(stub_self, batch, -1)      # main_models.py:1337-1642
+        docids = np.zeros((B, len(score_rate), K), dtype=np.int64)
+        for b in range(B):
+            for r in range(len(score_rate)):
+                docids[b, r] = [int(x) for x in res["inf_index_batch"][b][r][0][1].split(",")]
+        np.savez_compressed(os.path.join(GOLD, case + ".npz"), emb=emb.numpy(), q=q.numpy(),
+                            id_mapping_json=np.array(json.dumps(id_mapping)), dec=np.array(dec_flat).reshape(B, K),
+                            beam_scores=np.array(beam_scores, dtype=np.float64), score_rate=np.array(score_rate, dtype=np.float64),
+                            loss_func=np.array(loss_func), docids=docids)
+        # the restatement must agree with the reference right here, too
+        mine = orc.fine_stage(doc_embed, id_mapping, [dec_flat[b * K:(b + 1) * K] for b in range(B)], beam_scores, q,
+                              score_rate, loss_func, K)
+        for b in range(B):
+            for r in range(len(score_rate)):
+                assert mine[b][r][2] == docids[b, r].tolist(), (case, b, r)
+        print("wrote", case)
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLD, exist_ok=True)
+    if len(sys.argv) > 1:
+        {"dense": gen_dense, "main_models": gen_main_models}[sys.argv[1]]()
+    else:
+        for part in ("dense", "main_models"):      # separate processes: they need different `transformers`
+            subprocess.check_call([sys.executable, os.path.abspath(__file__), part])

@@ -1,0 +1,140 @@
+"""Host-side mirror of the reference API (gdr_b200.main_models / generation / store / sharded) on CPU."""
+import os
+import pickle
+import re
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+import gdr_oracle as orc
+from helpers import fine_stage_inputs, load_golden, rebuild_tree
+
+import gdr_b200
+from gdr_b200 import _cabi
+from gdr_b200.generation import flatten_trie
+from gdr_b200.main_models import Node, TreeBuilder, dec_2d, decode_token, encode_query, encode_single_newid
+from gdr_b200.sharded import global_to_local, pack_candidates, partition_clusters
+from gdr_b200.store import csr_from_reference
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ARGS = SimpleNamespace(kary=30, position=1, output_vocab_size=30)
+
+
+def test_codecs_match_reference_fixture():
+    g = load_golden("tree")
+    paths = [str(p) for p in g["paths"]]
+    assert encode_single_newid(ARGS, "3-17-22") == [5, 49, 84, 1]
+    assert decode_token(ARGS, g["tok_arr"]) == paths
+    assert decode_token(ARGS, g["noeos"]) == [str(x) for x in g["decoded_noeos"]]
+    for p in paths[:50]:
+        assert encode_single_newid(ARGS, p) == orc.encode_single_newid(p)
+    nk = SimpleNamespace(kary=0, position=1, output_vocab_size=10)
+    assert encode_single_newid(nk, "305") == orc.encode_single_newid("305", kary=0) == [5, 12, 27, 1]
+    assert dec_2d(list(range(6)), 2) == [[0, 1], [2, 3], [4, 5]]
+    h = torch.randn(3, 4, 8)
+    assert torch.equal(encode_query(h), h[:, 0]) and encode_query(None) is None
+
+
+def test_tree_builder_matches_reference_fixture_and_pickles():
+    g = load_golden("tree")
+    paths = [str(p) for p in g["paths"]]
+    b = TreeBuilder()
+    for di, p in enumerate(paths):
+        toks = encode_single_newid(ARGS, p)
+        b.add(toks, di)
+        if di % 3 == 0:
+            b.add(toks + [0, 0], 1000 + di)
+    ref_root = rebuild_tree(g["edges"], g["leaves"], Node)
+
+    def same(a, c):
+        assert list(a.children.keys()) == list(c.children.keys()) and a.embedding_index == c.embedding_index
+        for t in a.children:
+            same(a.children[t], c.children[t])
+    root = b.build()
+    same(root, ref_root)
+    same(pickle.loads(pickle.dumps(root)), ref_root)
+
+
+def test_flatten_trie_walk_equals_dict_walk():
+    g = load_golden("tree")
+    root = rebuild_tree(g["edges"], g["leaves"], Node)
+    fc, tok, child = flatten_trie(root)
+    assert fc[0] == 0 and fc[-1] == tok.size == child.size
+    for n in range(fc.size - 1):
+        seg = tok[fc[n]:fc[n + 1]]
+        assert np.all(np.diff(seg) > 0)
+    for cur_len in (1, 3, 5):
+        for row in g[f"ids_{cur_len}"]:
+            node = 0
+            for t in row[1:]:
+                seg = tok[fc[node]:fc[node + 1]]
+                hit = np.nonzero(seg == t)[0]
+                node = child[fc[node] + hit[0]] if hit.size else -1
+                if node < 0:
+                    break
+            allowed = [1] if node < 0 else tok[fc[node]:fc[node + 1]].tolist()
+            assert sorted(allowed) == sorted(orc.tree_mask_allowed(root, row.tolist()))
+
+
+def test_csr_from_reference_layout():
+    f = fine_stage_inputs("fine_stage_tanh")
+    emb, offsets, docid, keys = csr_from_reference(f["doc_embed"], f["id_mapping"])
+    assert keys == list(f["id_mapping"].keys())
+    for c, key in enumerate(keys):
+        lo, hi = int(offsets[c]), int(offsets[c + 1])
+        assert docid[lo:hi].tolist() == f["id_mapping"][key]
+        assert torch.equal(emb[lo:hi], f["emb"][docid[lo:hi]])
+    emb2, *_ = csr_from_reference(f["emb"], f["id_mapping"])
+    assert torch.equal(emb, emb2)
+
+
+def test_partition_is_balanced_and_complete():
+    rng = np.random.RandomState(1)
+    sizes = rng.randint(1, 400, 999)
+    for G in (1, 2, 4, 8):
+        owner = partition_clusters(sizes, G)
+        loads = [int(sizes[owner == r].sum()) for r in range(G)]
+        assert sum(loads) == int(sizes.sum()) and max(loads) - min(loads) <= 400
+        seen = np.zeros(sizes.size, dtype=int)
+        for r in range(G):
+            g2l, mine = global_to_local(owner, r)
+            seen[mine] += 1
+            assert np.array_equal(g2l[mine], np.arange(mine.size)) and np.all(g2l[owner != r] == -1)
+        assert np.all(seen == 1)
+
+
+def test_pack_candidates_roundtrip():
+    s = torch.randn(4, 7)
+    d = torch.randint(0, 1000, (4, 7), dtype=torch.int32)
+    p = pack_candidates(s, d)
+    assert torch.equal(p[0].view(torch.float32), s) and torch.equal(p[1], d)
+
+
+def test_cabi_library_loads_and_exports_every_declared_symbol():
+    """No compute calls here (no GPU): the .so must load and export what include/gdr_b200.h declares."""
+    header = open(os.path.join(ROOT, "include", "gdr_b200.h")).read()
+    declared = set(re.findall(r"\b(gdr_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_cabi.SYMBOLS), declared ^ set(_cabi.SYMBOLS)
+    lib = _cabi.lib()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.gdr_abi_version() == 1
+    assert lib.gdr_last_error() is not None
+
+
+def test_no_cpu_fallback_in_product_path():
+    """The product refuses CPU tensors instead of silently computing elsewhere."""
+    with pytest.raises(ValueError):
+        gdr_b200.compute_similarity(torch.randn(2, 8), torch.randn(3, 8))
+    with pytest.raises(ValueError):
+        gdr_b200.ClusterStore(torch.randn(4, 8), torch.tensor([0, 4]), torch.arange(4))
+    with pytest.raises(ValueError):
+        gdr_b200.position_mask_(torch.zeros(1, 2, 70), 30)
+    # and nothing under gdr_b200/ imports the oracle
+    pkg = os.path.join(ROOT, "gdr_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "gdr_oracle" not in src and "import oracle" not in src and "from oracle" not in src, fn

@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py — queries/sec of cluster-restricted scoring + top-100 (BASELINE.json `metric`).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg2|cfg3|cfg5s]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path (pair inversion -> gather-and-score -> per-query top-k) over one
+batch of synthetic queries.  N = 1 runs BASELINE.json configs[1] ("cfg2": 109,739 x 768 bf16 corpus,
+1,024 k-means-shaped clusters, batch 1,024 queries, beam 20, top-100).  N > 1 runs the cluster-sharded
+path of SURVEY.md §8e, weak scaling: every rank owns a cfg2-shaped shard (its own 1,024 clusters), the
+global batch is 1,024*N queries whose beams spread over all N*1,024 clusters, local top-k on each rank,
+one NCCL all-gather of packed (score, docid) candidates, merge top-k.
+Timing: W warm-up steps, then exactly K steps between barrier + synchronize, CUDA events on the
+launching stream, max over ranks.  L2 hygiene: each step reads a different replica of the store
+(`config.l2`: the replicas together are several times the 126 MB L2) and a different query batch.
+`--impl reference` (and the `cpu_baseline` object of the default arm) time the reference's own
+dense.py path — the oracle port, oracle/gdr_oracle.py — on the host cores.
+"""
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: N docs, C clusters, D, batch B, beam K, top-k      (BASELINE.json configs[1], [2]; cfg5s = per-GPU slice of [4])
+    "cfg2": dict(N=109739, C=1024, D=768, B=1024, K=20, k=100),
+    "cfg3": dict(N=73970, C=1024, D=768, B=1024, K=100, k=1000),
+    "cfg5s": dict(N=12500000, C=131072, D=768, B=1250, K=100, k=100),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for _, r in self.rows]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(rows[0][1]) if rows[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(rows)}
+
+
+def synth_shard(cfg, seed, device):
+    """SURVEY.md §8d recipe, generated on the device: emb = randn(N, D) * D^-0.5 (bf16), assign = randint(0, C),
+    CSR by stable sort.  Returns (emb [N, D] bf16 cluster-contiguous, offsets [C+1] cpu, docid [N])."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    N, C, D = cfg["N"], cfg["C"], cfg["D"]
+    assign = torch.randint(0, C, (N,), generator=g, device=device)
+    order = torch.argsort(assign, stable=True)
+    counts = torch.bincount(assign, minlength=C)
+    offsets = torch.zeros(C + 1, dtype=torch.int64, device=device)
+    offsets[1:] = torch.cumsum(counts, 0)
+    emb = torch.empty((N, D), dtype=torch.bfloat16, device=device)
+    step = 1 << 20
+    for i in range(0, N, step):   # chunked so the fp32 temporary stays small at 12.5 M rows
+        emb[i:i + step] = (torch.randn((min(step, N - i), D), generator=g, device=device) * D ** -0.5).to(torch.bfloat16)
+    return emb, offsets.cpu(), order
+
+
+def synth_batches(cfg, n_batches, C_total, B, seed, device):
+    """q = randn(B, D); beams = K distinct clusters per query (randperm-like), on the device."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    out = []
+    for _ in range(n_batches):
+        q = torch.randn((B, cfg["D"]), generator=g, device=device)
+        if C_total <= 8192:
+            beams = torch.argsort(torch.rand((B, C_total), generator=g, device=device), dim=1)[:, :cfg["K"]]
+        else:  # huge C: sample with replacement, duplicates are vanishingly rare and legal
+            beams = torch.randint(0, C_total, (B, cfg["K"]), generator=g, device=device)
+        out.append((q.contiguous(), beams.to(torch.int32).contiguous()))
+    return out
+
+
+def cpu_reference_qps(emb_cpu, offsets, docid, q_cpu, beams_cpu, k, min_seconds, max_queries):
+    """The reference's dense.py path (oracle port) on the host cores: per query gather + q @ p.T + topk."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import gdr_oracle as orc            # the one place bench.py may execute oracle/: the CPU baseline
+    torch.set_num_threads(os.cpu_count())
+    off = offsets.numpy()
+    done, t0 = 0, time.perf_counter()
+    chunk = 64
+    orc.dense_topk(q_cpu[:8], emb_cpu, off, docid, beams_cpu[:8].numpy(), k)     # warm-up
+    t0 = time.perf_counter()
+    while done < max_queries and (time.perf_counter() - t0 < min_seconds or done == 0):
+        sl = slice(done % q_cpu.shape[0], done % q_cpu.shape[0] + chunk)
+        orc.dense_topk(q_cpu[sl], emb_cpu, off, docid, beams_cpu[sl].numpy(), k)
+        done += min(chunk, q_cpu[sl].shape[0])
+    dt = time.perf_counter() - t0
+    return done / dt, done, dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="gdr_b200", choices=["gdr_b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--replicas", type=int, default=0, help="store replicas cycled to defeat L2 (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every step from the host instead of replaying a CUDA graph")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    cfg = dict(WORKLOADS[args.workload])
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    k, K, D = cfg["k"], cfg["K"], cfg["D"]
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        small = dict(cfg)
+        g = torch.Generator().manual_seed(1234)
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import gdr_oracle as orc
+        emb, offsets, docid = orc.synth_corpus(small["N"] if small["N"] <= 200000 else 200000,
+                                               small["C"] if small["N"] <= 200000 else 2048, D, seed=1234)
+        emb = emb.bfloat16().float()
+        C = offsets.size - 1
+        q, beams, _ = orc.synth_queries(256, C, K, D, seed=4321)
+        per_step = 64
+        torch.set_num_threads(os.cpu_count())
+        beams_t = torch.from_numpy(beams)
+        for i in range(args.warmup):
+            orc.dense_topk(q[:8], emb, offsets, docid, beams[:8], k)
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            lo = (i * per_step) % 256
+            orc.dense_topk(q[lo:lo + per_step], emb, offsets, docid, beams[lo:lo + per_step], k)
+        dt = time.perf_counter() - t0
+        qps = args.steps * per_step / dt
+        print(json.dumps({
+            "impl": "reference", "metric": "queries/sec, cluster-restricted scoring + top-k", "value": qps, "unit": "queries/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "docs": int(emb.shape[0]), "clusters": int(C), "dim": D, "beam": K, "top_k": k,
+                       "queries_per_step": per_step},
+            "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port",
+                             "sample": f"{args.steps} steps x {per_step} queries of the {args.workload} workload, oracle/gdr_oracle.dense_topk "
+                                       f"(reference dense.py:53-54 + Tensor.topk), torch {torch.__version__} CPU, {os.cpu_count()} threads"},
+            "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return
+
+    # ------------------------------------------------------------------ gdr_b200 arm (GPU)
+    import torch.distributed as dist
+    from gdr_b200 import ClusterStore
+    from gdr_b200.sharded import ShardedRetriever
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B_global = cfg["B"] * world
+    C_total = cfg["C"] * world
+    emb_bytes = cfg["N"] * D * 2
+    replicas = args.replicas or max(1, min(6, -(-640 * 2 ** 20 // emb_bytes)))     # >= 640 MB of distinct store bytes in rotation
+    stores = []
+    base_offsets = None
+    for r in range(replicas):
+        emb, offsets, docid = synth_shard(cfg, 1234 + 1000 * rank, dev) if r == 0 else (stores[0].emb.clone(), base_offsets, stores[0].docid.clone())
+        base_offsets = offsets
+        # docids are global: rank r's documents are numbered after those of ranks < r
+        stores.append(ClusterStore(emb, offsets, docid + rank * cfg["N"] if r == 0 else docid))
+    n_batches = 8
+    batches = synth_batches(cfg, n_batches, C_total, B_global, 4321, dev)     # same seed on every rank: replicated queries
+    if world > 1:
+        # rank r owns global clusters [r*C, (r+1)*C): contiguous blocks are already balanced for this synthetic corpus
+        g2l = torch.full((C_total,), -1, dtype=torch.int32, device=dev)
+        g2l[rank * cfg["C"]:(rank + 1) * cfg["C"]] = torch.arange(cfg["C"], dtype=torch.int32, device=dev)
+        retrievers = [ShardedRetriever(s, g2l) for s in stores]
+
+    out_s = torch.empty((1, B_global, k), dtype=torch.float32, device=dev)
+    out_d = torch.empty((1, B_global, k), dtype=torch.int32, device=dev)
+
+    def step(i):
+        q, beams = batches[i % n_batches]
+        if world == 1:
+            stores[i % replicas].score_topk(q, beams, k, out=(out_s, out_d))
+        else:
+            return retrievers[i % replicas].score_topk(q, beams, k)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, replicas)):
+        step(i)
+    barrier()
+    stats = stores[0].last_stats()
+
+    # CUDA graph of `period` consecutive steps (one per replica/batch combination), replayed: removes host launch latency
+    period = replicas * n_batches // math.gcd(replicas, n_batches)
+    use_graph = world == 1 and not args.no_graph and args.steps >= period
+    graph = None
+    if use_graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                for i in range(period):
+                    step(i)
+        torch.cuda.current_stream().wait_stream(side)
+        graph.replay()
+        barrier()
+    steps = (args.steps // period) * period if use_graph else args.steps
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.time()
+    e0.record()
+    if use_graph:
+        for _ in range(steps // period):
+            graph.replay()
+    else:
+        for i in range(steps):
+            step(i)
+    e1.record()
+    barrier()
+    t_wall1 = time.time()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    qps = steps * B_global / (ms * 1e-3)
+
+    # ---- per-phase device time of the dominant kernel (CUDA events recorded inside the library, same stream)
+    phase = {"invert": 0.0, "score_umma": 0.0, "score_simt": 0.0, "topk": 0.0}
+    n_prof = min(steps, 4 * period)
+    for s in stores:
+        s.set_profiling(True)
+    for i in range(n_prof):
+        torch.cuda._sleep(2_000_000)      # ~1 ms of GPU idle-spin so the host runs ahead: events then see back-to-back kernels
+        step(i)
+        for key, v in stores[i % replicas].last_phase_ms().items():
+            phase[key] += v / n_prof
+    for s in stores:
+        s.set_profiling(False)
+
+    # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region
+    q_host = [b[0].cpu().pin_memory() for b in batches]
+    beams_host = [b[1].cpu().pin_memory() for b in batches]
+    res_s = torch.empty((B_global, k), dtype=torch.float32).pin_memory()
+    res_d = torch.empty((B_global, k), dtype=torch.int32).pin_memory()
+    q_dev = [torch.empty_like(batches[0][0]) for _ in range(2)]
+    b_dev = [torch.empty_like(batches[0][1]) for _ in range(2)]
+
+    def e2e_step(i):
+        j = i & 1
+        q_dev[j].copy_(q_host[i % n_batches], non_blocking=True)
+        b_dev[j].copy_(beams_host[i % n_batches], non_blocking=True)
+        if world == 1:
+            stores[i % replicas].score_topk(q_dev[j], b_dev[j], k, out=(out_s, out_d))
+            res_s.copy_(out_s[0], non_blocking=True)
+            res_d.copy_(out_d[0], non_blocking=True)
+        else:
+            s, d = retrievers[i % replicas].score_topk(q_dev[j], b_dev[j], k)
+            res_s.copy_(s, non_blocking=True)
+            res_d.copy_(d, non_blocking=True)
+
+    e2e_steps = max(8, min(steps, 64))
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    e0.record()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_qps = e2e_steps * B_global / (e2e_ms * 1e-3)
+    h2d = B_global * D * 4 + B_global * K * 4
+    d2h = B_global * k * 8
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (every touched embedding read once + queries + results)
+    peak, peak_src = peaks()
+    beams0 = batches[0][1]
+    local = beams0[(beams0 >= rank * cfg["C"]) & (beams0 < (rank + 1) * cfg["C"])] - rank * cfg["C"]
+    emb_touched = int(stores[0].sizes_host[torch.unique(local).cpu().numpy()].sum()) * D * 2
+    alg_bytes = emb_touched + B_global * D * 4 + B_global * k * 8
+    dominant = max(("score_umma", "score_simt"), key=lambda n: phase[n])
+    dom_ms = phase[dominant]
+    achieved = alg_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    step_ms = ms / steps
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "kernel": {"score_umma": "k_score_umma (tcgen05 grouped GEMM)", "score_simt": "k_score_simt (GEMV)"}[dominant],
+                "kernel_ms": dom_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                "phase_ms": phase, "whole_step_frac": alg_bytes / (step_ms * 1e-3) / 1e9 / peak,
+                "frac_of_nominal_8TBs": achieved / 8000.0}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        nq = min(256, B_global)
+        emb_cpu = stores[0].emb.float().cpu()
+        lb = batches[0][1][:nq].cpu()
+        if world > 1:   # the CPU leg scores the rank-0 shard only
+            lb = torch.where((lb >= 0) & (lb < cfg["C"]), lb, torch.full_like(lb, -1))
+        v, done, dt = cpu_reference_qps(emb_cpu, torch.as_tensor(stores[0].offsets_host), stores[0].docid.cpu().numpy().astype("int64"),
+                                        batches[0][0][:nq].cpu(), lb, k, min_seconds=10.0, max_queries=20000)
+        cpu = {"value": v, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": f"{done} queries of the {args.workload} workload in {dt:.1f} s: oracle/gdr_oracle.dense_topk (reference dense.py:53-54 "
+                         f"+ Tensor.topk per query), torch {torch.__version__} CPU with {os.cpu_count()} threads"}
+
+    line = {
+        "metric": "queries/sec, cluster-restricted scoring + top-%d" % k, "value": qps, "unit": "queries/s", "n_gpus": world,
+        "steps": steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16 store x fp32 query, fp32 accumulate", "data": "synthetic",
+        "config": {"workload": args.workload + ("" if world == 1 else f" x{world} cluster-sharded"), "docs_per_gpu": cfg["N"],
+                   "clusters_per_gpu": cfg["C"], "dim": D, "global_batch": B_global, "beam": K, "top_k": k,
+                   "l2": f"{replicas} store replicas ({replicas * emb_bytes / 2**20:.0f} MB) and {n_batches} query batches cycled; inputs larger than L2",
+                   "cuda_graph": bool(use_graph), "parallelism": "single GPU" if world == 1 else f"clusters sharded over {world} GPUs + NCCL all-gather + merge"},
+        "clocks": clocks, "gpu_launches": int(stats["launches"]) * steps + (0 if world == 1 else steps),
+        "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+        "roofline": roofline, "cpu_baseline": cpu,
+        "path": {"simt_items": int(stats["simt_items"]), "umma_tiles": int(stats["umma_tiles"]), "clusters_touched": int(stats["clusters_touched"])},
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

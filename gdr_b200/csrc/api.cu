@@ -45,6 +45,8 @@ struct gdr_store {
     CUtensorMap tmap;
     int last_launches = 0;
     int umma_min_group = 8;
+    bool profiling = false;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 struct gdr_trie {
@@ -99,6 +101,8 @@ int gdr_store_destroy(gdr_store_t *s) {
     if (!s) return GDR_OK;
     cudaFree(s->cluster_ws);
     cudaFree(s->batch_ws);
+    for (auto &e : s->ev)
+        if (e) cudaEventDestroy(e);
     delete s;
     return GDR_OK;
 }
@@ -110,6 +114,7 @@ int gdr_score_topk(gdr_store_t *s, const float *q, const int32_t *beams, const f
     if (B < 0 || K <= 0 || k <= 0) return invalid("gdr_score_topk: need B >= 0, K > 0, k > 0");
     if (B == 0) return GDR_OK;
     if (!q || !beams || !out_scores || !out_docids) return invalid("gdr_score_topk: null pointer");
+    if (reinterpret_cast<uintptr_t>(q) & 15) return invalid("gdr_score_topk: q must be 16-byte aligned");
     if (act < GDR_ACT_NONE || act > GDR_ACT_SIGMOID) return invalid("gdr_score_topk: bad activation");
     if (n_alpha < 1 || (!alphas && n_alpha != 1)) return invalid("gdr_score_topk: n_alpha must be >= 1 (1 when alphas is null)");
     if (k > 4096) {
@@ -127,7 +132,6 @@ int gdr_score_topk(gdr_store_t *s, const float *q, const int32_t *beams, const f
     const int64_t simt_cap = pairs * ((s->max_cluster + SIMT_ROWS - 1) / SIMT_ROWS);
     const int64_t umma_cap = pairs * ((s->max_cluster + UMMA_ROWS - 1) / UMMA_ROWS);
     const bool umma_possible = s->has_tmap && !(flags & GDR_FORCE_SIMT);
-    const int64_t q_rows = (flags & GDR_Q_PER_BEAM) ? pairs : B;
     const bool global_keys = (size_t)stride * 4 + 8 * 4096 + 4 * 4096 + (size_t)(K + 1) * 4 > 96 * 1024;
 
     // carve the per-batch scratch
@@ -138,7 +142,6 @@ int gdr_score_topk(gdr_store_t *s, const float *q, const int32_t *beams, const f
     const size_t o_simt = take((size_t)simt_cap * sizeof(Item));
     const size_t o_umma = take(umma_possible ? (size_t)umma_cap * sizeof(Item) : 0);
     const size_t o_score = take((size_t)B * stride * 4);
-    const size_t o_qsplit = take(umma_possible ? (size_t)q_rows * 3 * s->dim * 2 : 0);
     const size_t o_keys = take(global_keys ? (size_t)B * stride * 4 : 0);
     if (off > s->batch_ws_bytes) {
         // growing the scratch synchronises; run one call per shape before capturing a CUDA graph
@@ -168,27 +171,47 @@ int gdr_score_topk(gdr_store_t *s, const float *q, const int32_t *beams, const f
     a.umma_items = reinterpret_cast<Item *>(ws + o_umma);
     a.scorebuf = reinterpret_cast<float *>(ws + o_score);
     a.stride = stride;
-    a.qsplit = reinterpret_cast<__nv_bfloat16 *>(ws + o_qsplit);
     a.gkeys = reinterpret_cast<uint32_t *>(ws + o_keys);
     a.umma_min_group = !umma_possible ? INT_MAX : ((flags & GDR_FORCE_UMMA) ? 1 : s->umma_min_group);
 
     int launches = 0;
+    const bool prof = s->profiling;
+    if (prof) GDR_CUDA(cudaEventRecord(s->ev[0], st));
     GDR_CUDA(launch_invert(a, st, &launches));
+    if (prof) GDR_CUDA(cudaEventRecord(s->ev[1], st));
     if (umma_possible) {
-        GDR_CUDA(launch_qsplit(a, st));
         GDR_CUDA(launch_score_umma(a, &s->tmap, st, s->sm_count));
-        launches += 2;
+        launches += 1;
     }
+    if (prof) GDR_CUDA(cudaEventRecord(s->ev[2], st));
     if (!(flags & GDR_FORCE_UMMA)) {
         GDR_CUDA(launch_score_simt(a, st, s->sm_count));
         launches += 1;
     }
+    if (prof) GDR_CUDA(cudaEventRecord(s->ev[3], st));
     for (int r = 0; r < n_alpha; ++r) {
         const float alpha = alphas ? alphas[r] : 1.0f;
         GDR_CUDA(launch_topk_store(a, alpha, out_scores + (int64_t)r * B * k, out_docids + (int64_t)r * B * k, st));
         launches += 1;
     }
+    if (prof) GDR_CUDA(cudaEventRecord(s->ev[4], st));
     s->last_launches = launches;
+    return GDR_OK;
+}
+
+int gdr_store_set_profiling(gdr_store_t *s, int32_t enable) {
+    if (!s) return invalid("gdr_store_set_profiling: store is null");
+    if (enable && !s->ev[0])
+        for (auto &e : s->ev) GDR_CUDA(cudaEventCreate(&e));
+    s->profiling = enable != 0;
+    return GDR_OK;
+}
+
+int gdr_store_last_phase_ms(gdr_store_t *s, float out[4]) {
+    if (!s || !out) return invalid("gdr_store_last_phase_ms: null argument");
+    if (!s->ev[0]) return invalid("gdr_store_last_phase_ms: profiling was never enabled");
+    GDR_CUDA(cudaEventSynchronize(s->ev[4]));
+    for (int i = 0; i < 4; ++i) GDR_CUDA(cudaEventElapsedTime(&out[i], s->ev[i], s->ev[i + 1]));
     return GDR_OK;
 }
 

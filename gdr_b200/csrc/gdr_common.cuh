@@ -34,7 +34,7 @@ struct __align__(16) Item {
 constexpr int SIMT_ROWS = 128;   // rows per SIMT item (one warp walks them 4 at a time)
 constexpr int SIMT_QT = 4;       // (query, beam) pairs per SIMT item
 constexpr int UMMA_ROWS = 128;   // rows per tcgen05 tile (UMMA_M)
-constexpr int UMMA_NQ = 64;      // max pairs per tcgen05 tile (UMMA_N)
+constexpr int UMMA_NQ = 32;      // max pairs per tcgen05 tile (UMMA_N)
 constexpr int MAX_DIM = 1024;
 
 // counters[] layout (device int32)
@@ -66,7 +66,6 @@ struct ScoreArgs {
     int32_t *counters;   // [CTR_COUNT]
     float *scorebuf;     // [B, stride]
     int64_t stride;
-    __nv_bfloat16 *qsplit;  // [rows(q), 3, dim] bf16 hi/mid/lo split of q (tcgen05 path)
     uint32_t *gkeys;     // [B, stride] keys scratch for the global-memory top-k variant
     int32_t umma_min_group;  // groups with at least this many pairs go to the tcgen05 path (INT_MAX = never)
 };
@@ -75,7 +74,6 @@ struct ScoreArgs {
 cudaError_t launch_invert(const ScoreArgs &a, cudaStream_t s, int *n_launches);
 cudaError_t launch_score_simt(const ScoreArgs &a, cudaStream_t s, int sm_count);
 cudaError_t launch_score_umma(const ScoreArgs &a, const CUtensorMap *tmap, cudaStream_t s, int sm_count);
-cudaError_t launch_qsplit(const ScoreArgs &a, cudaStream_t s);
 cudaError_t launch_topk_store(const ScoreArgs &a, float alpha, float *out_scores, int32_t *out_docids,
                               cudaStream_t s);
 cudaError_t launch_merge_topk(const float *scores, const int32_t *docids, int G, int B, int k_in, int64_t g_stride, int k,

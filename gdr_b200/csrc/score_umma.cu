@@ -1,7 +1,357 @@
-// tcgen05 grouped-GEMM scoring path — placeholder until the TMA/UMMA kernel lands.
+// Gather-and-score, tensor-core path: TMA-fed tcgen05 grouped GEMM with TMEM accumulators.
+//
+// Replaces main_models.py:1456-1462 + 1577-1582 for clusters that many queries of the batch
+// selected (a "group" = the (query, beam) pairs that name one cluster).  A GEMV would re-read the
+// cluster slab once per pair; here a slab tile is read from HBM ONCE (TMA, 128-byte swizzle) and
+// multiplied against all the group's queries on the 5th-gen tensor cores:
+//
+//     D[128 docs, N pairs] (fp32, TMEM)  +=  A[128 docs, 64 k] (bf16 smem, TMA)  x  B[N pairs, 64 k]^T (bf16 smem)
+//
+// Parity with the fp32 reference needs more than bf16(q): the fp32 query is split exactly into three
+// bf16 terms q = hi + mid + lo (by the filler warps, in registers), and each K step issues three MMAs (A x hi, A x mid, A x lo)
+// into the same accumulator; every product bf16 x bf16 is exact in fp32, so the result matches an
+// fp32 dot product to accumulation-order noise.  The kernel is still HBM-bound: per tile it moves
+// 128 x 768 x 2 B = 196 KB of embeddings and issues 12 x 4 x 3 MMAs of 128 x N x 16.
+//
+// Warp roles (448 threads, one persistent CTA per SM, tiles strided over CTAs):
+//   warp 0       TMA producer: A tiles of the store, 6-stage ring (96 KB in flight per SM), mbarrier complete_tx
+//   warp 1       MMA issuer (one lane): tcgen05.mma cta_group::1 kind::f16; commits free the A and B stages
+//   warps 2-9    B fillers, one K block per warp in flight (8 blocks' L2 latency overlapped): gather the
+//                group's fp32 query rows (L2-resident), split them into hi/mid/lo bf16 in registers, store
+//                into the 128B-swizzled K-major layout the UMMA descriptor expects, fence.proxy.async, arrive
+//   warps 10-13  epilogue: tcgen05.ld the accumulator (double-buffered in TMEM so it overlaps the next
+//                tile's MMAs), activation, coalesced stores into each query's candidate segment
 #include "gdr_common.cuh"
+
 namespace gdr {
-bool umma_make_tensor_map(CUtensorMap *, const void *, int64_t, int) { return false; }
-cudaError_t launch_qsplit(const ScoreArgs &, cudaStream_t) { return cudaErrorNotSupported; }
-cudaError_t launch_score_umma(const ScoreArgs &, const CUtensorMap *, cudaStream_t, int) { return cudaErrorNotSupported; }
+
+constexpr int UM_BLOCK_K = 64;                 // bf16 elements per K block = one 128-byte swizzle atom
+constexpr int UM_SA = 6;                       // A (store tiles, TMA) ring depth
+constexpr int UM_SB = 8;                       // B (query tiles) ring depth: one stage per filler warp, so a warp is never
+                                               // more than one mbarrier phase ahead of the MMA warp (parity waits stay unambiguous)
+constexpr int UM_FILL_WARPS = 8;
+constexpr int UM_A_BYTES = UMMA_ROWS * 128;    // 16 KB
+constexpr int UM_BT_BYTES = UMMA_NQ * 128;     // 4 KB per query term
+constexpr int UM_B_BYTES = 3 * UM_BT_BYTES;    // 12 KB
+constexpr int UM_THREADS = 64 + 32 * UM_FILL_WARPS + 128;   // 448
+constexpr int UM_TMEM_COLS = 2 * UMMA_NQ;      // 2 accumulators x 32 fp32 columns
+constexpr int UM_RING_BYTES = UM_SA * UM_A_BYTES + UM_SB * UM_B_BYTES;   // 192 KB
+constexpr int UM_SMEM_BYTES = UM_RING_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int UM_TASKS = 8;                    // 32-byte query pieces a filler lane keeps in flight (8 x 32 lanes = all of a 32-pair block)
+static_assert(UM_SB == UM_FILL_WARPS, "one B stage per filler warp");
+static_assert(UMMA_NQ == 32, "epilogue and filler lane maps assume 32 pairs per tile");
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tmap, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, 128-byte-swizzled shared-memory matrix descriptor (sm_100 format): rows are 128 B apart,
+// 8-row swizzle atoms 1024 B apart (SBO), LBO unused for swizzled K-major (encoded 1), version 1.
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3fffu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N runtime
+__device__ __forceinline__ uint32_t umma_idesc(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(UMMA_ROWS >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------
+// the grouped GEMM
+// ---------------------------------------------------------------------------------------------
+// fp32 -> (hi, mid, lo) bf16 with q == hi + mid + lo exactly (8 + 8 + 8 mantissa bits); two elements per call
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t &hi, uint32_t &mid, uint32_t &lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+    const float r0 = x0 - __low2float(h), r1 = x1 - __high2float(h);
+    const __nv_bfloat162 m = __floats2bfloat162_rn(r0, r1);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(r0 - __low2float(m), r1 - __high2float(m));
+    hi = *reinterpret_cast<const uint32_t *>(&h);
+    mid = *reinterpret_cast<const uint32_t *>(&m);
+    lo = *reinterpret_cast<const uint32_t *>(&l);
+}
+
+__global__ void __launch_bounds__(UM_THREADS, 1) k_score_umma(const __grid_constant__ CUtensorMap tmap, ScoreArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // 1024-byte alignment for SWIZZLE_128B
+    unsigned char *smem = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t bar_base = smem_base + UM_RING_BYTES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + UM_RING_BYTES + 192);
+
+    auto fullA = [&](int s) { return bar_base + 8u * s; };
+    auto emptyA = [&](int s) { return bar_base + 8u * (UM_SA + s); };
+    auto fullB = [&](int s) { return bar_base + 8u * (2 * UM_SA + s); };
+    auto emptyB = [&](int s) { return bar_base + 8u * (2 * UM_SA + UM_SB + s); };
+    auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * UM_SA + 2 * UM_SB + i); };
+    auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * UM_SA + 2 * UM_SB + 2 + i); };
+    auto a_smem = [&](int s) { return smem_base + (uint32_t)s * UM_A_BYTES; };
+    auto b_smem = [&](int s, int t) { return smem_base + UM_SA * UM_A_BYTES + (uint32_t)s * UM_B_BYTES + (uint32_t)t * UM_BT_BYTES; };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles = a.counters[CTR_N_UMMA];
+    const int nkb = a.dim / UM_BLOCK_K;
+    const int my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+        for (int s = 0; s < UM_SA; ++s) {
+            mbar_init(fullA(s), 1);            // TMA expect_tx arrive
+            mbar_init(emptyA(s), 1);           // tcgen05.commit
+        }
+        for (int s = 0; s < UM_SB; ++s) {
+            mbar_init(fullB(s), 1);            // the filler warp that owns the K block
+            mbar_init(emptyB(s), 1);           // tcgen05.commit
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(tfull_bar(i), 1);        // tcgen05.commit
+            mbar_init(tempty_bar(i), 4);       // 4 epilogue warps
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(UM_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int row0 = a.umma_items[tile].row0;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(emptyA(s), ph ^ 1u);
+                    mbar_arrive_expect_tx(fullA(s), UM_A_BYTES);
+                    tma_load_2d(a_smem(s), &tmap, kb * UM_BLOCK_K, row0, fullA(s));
+                    if (++s == UM_SA) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            int sa = 0, sb = 0;
+            uint32_t pha = 0, phb = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                const int nq = a.umma_items[tile].nrows_nq >> 16;
+                const uint32_t idesc = umma_idesc(((nq + 15) >> 4) << 4);
+                const int acc = it & 1;
+                const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
+                mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)acc * UMMA_NQ;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(fullB(sb), phb);
+                    mbar_wait(fullA(sa), pha);
+                    tc_fence_after();
+                    const uint64_t adesc = umma_smem_desc(a_smem(sa));
+#pragma unroll
+                    for (int k = 0; k < UM_BLOCK_K / 16; ++k) {
+#pragma unroll
+                        for (int t = 0; t < 3; ++t) {
+                            const uint64_t bdesc = umma_smem_desc(b_smem(sb, t));
+                            // +32 bytes per UMMA_K = 16 bf16 inside the swizzle atom: +2 in the (addr >> 4) field
+                            umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k | t) != 0 ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(emptyA(sa));
+                    umma_commit(emptyB(sb));
+                    if (++sa == UM_SA) { sa = 0; pha ^= 1u; }
+                    if (++sb == UM_SB) { sb = 0; phb ^= 1u; }
+                }
+                umma_commit(tfull_bar(acc));
+            }
+        }
+    } else if (warp < 2 + UM_FILL_WARPS) {
+        // ===================== B fillers: warp fw owns K blocks g = fw, fw + 8, ... of this CTA's stream =====================
+        const int fw = warp - 2;
+        const bool per_beam = (a.flags & GDR_Q_PER_BEAM) != 0;
+        const int total_kb = my_tiles * nkb;
+        int cur_it = -1, nq = 0, qrow = 0;
+        for (int g = fw; g < total_kb; g += UM_FILL_WARPS) {
+            const int it = g / nkb, kb = g - it * nkb;
+            if (it != cur_it) {                    // new tile: lane l caches the query row of pair l
+                cur_it = it;
+                const Item item = a.umma_items[blockIdx.x + it * gridDim.x];
+                nq = item.nrows_nq >> 16;
+                qrow = 0;
+                if (lane < nq) { const int p = a.grp_pair[item.slot0 + lane]; qrow = per_beam ? p : p / a.K; }
+            }
+            const int sb = g % UM_SB;
+            const uint32_t phb = (uint32_t)(g / UM_SB) & 1u;
+            unsigned char *bst = smem + UM_SA * UM_A_BYTES + (size_t)sb * UM_B_BYTES;
+            const int n_tasks = nq * 8;            // one task = 8 fp32 of one pair = one 16-byte chunk per term
+            bool waited = false;
+            for (int base = 0; base < n_tasks; base += 32 * UM_TASKS) {
+                float4 v[UM_TASKS][2];
+#pragma unroll
+                for (int u = 0; u < UM_TASKS; ++u) {          // all loads first: up to 16 LDG.128 in flight per lane
+                    const int idx = base + u * 32 + lane;
+                    const int j = idx >> 3, c = idx & 7;
+                    const int qr = __shfl_sync(0xffffffffu, qrow, j & 31);
+                    if (idx < n_tasks) {
+                        const float4 *src = reinterpret_cast<const float4 *>(a.q + (int64_t)qr * a.dim + kb * UM_BLOCK_K + c * 8);
+                        v[u][0] = __ldg(src);
+                        v[u][1] = __ldg(src + 1);
+                    }
+                }
+                if (!waited) { mbar_wait(emptyB(sb), phb ^ 1u); waited = true; }
+#pragma unroll
+                for (int u = 0; u < UM_TASKS; ++u) {
+                    const int idx = base + u * 32 + lane;
+                    if (idx < n_tasks) {
+                        const int j = idx >> 3, c = idx & 7;
+                        uint4 hi, mid, lo;
+                        split2(v[u][0].x, v[u][0].y, hi.x, mid.x, lo.x);
+                        split2(v[u][0].z, v[u][0].w, hi.y, mid.y, lo.y);
+                        split2(v[u][1].x, v[u][1].y, hi.z, mid.z, lo.z);
+                        split2(v[u][1].z, v[u][1].w, hi.w, mid.w, lo.w);
+                        unsigned char *dst = bst + j * 128 + ((c ^ (j & 7)) << 4);
+                        *reinterpret_cast<uint4 *>(dst) = hi;
+                        *reinterpret_cast<uint4 *>(dst + UM_BT_BYTES) = mid;
+                        *reinterpret_cast<uint4 *>(dst + 2 * UM_BT_BYTES) = lo;
+                    }
+                }
+            }
+            if (!waited) mbar_wait(emptyB(sb), phb ^ 1u);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(fullB(sb));
+        }
+    } else {
+        // ===================== epilogue (128 threads) =====================
+        const int wq = warp & 3;                    // TMEM lane quarter this warp may read
+        const int row = wq * 32 + lane;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const Item item = a.umma_items[tile];
+            const int nrows = item.nrows_nq & 0xffff, nq = item.nrows_nq >> 16;
+            int64_t off = 0;                       // destination (row 0) of column `lane`
+            if (lane < nq) {
+                const int p = a.grp_pair[item.slot0 + lane];
+                const int b = p / a.K;
+                off = (int64_t)b * a.stride + a.candoff[p + b] + item.rel0;
+            }
+            const int acc = it & 1;
+            const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
+            mbar_wait(tfull_bar(acc), acc_ph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)acc * UMMA_NQ;
+            uint32_t r[UMMA_NQ / 16][16];
+            const int nch = (nq + 15) >> 4;
+#pragma unroll
+            for (int ch = 0; ch < UMMA_NQ / 16; ++ch)
+                if (ch < nch) tmem_ld16(taddr + ch * 16, r[ch]);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));     // accumulator is in registers: release it to the MMA warp
+#pragma unroll
+            for (int ch = 0; ch < UMMA_NQ / 16; ++ch) {
+                if (ch < nch) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int c = ch * 16 + j;
+                        const int64_t o = __shfl_sync(0xffffffffu, off, c);
+                        if (c < nq && row < nrows) a.scorebuf[o + row] = apply_act(__uint_as_float(r[ch][j]), a.act);
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(UM_TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_tensorMapEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                             const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                             CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+bool umma_make_tensor_map(CUtensorMap *out, const void *emb, int64_t n_docs, int dim) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+        qres != cudaDriverEntryPointSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)n_docs};
+    const cuuint64_t gstride[1] = {(cuuint64_t)dim * 2};
+    const cuuint32_t box[2] = {UM_BLOCK_K, UMMA_ROWS};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = reinterpret_cast<PFN_tensorMapEncodeTiled>(fn)(
+        out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(emb), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+cudaError_t launch_score_umma(const ScoreArgs &a, const CUtensorMap *tmap, cudaStream_t s, int sm_count) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_score_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    k_score_umma<<<sm_count, UM_THREADS, UM_SMEM_BYTES, s>>>(*tmap, a);
+    return cudaGetLastError();
+}
+
 }  // namespace gdr

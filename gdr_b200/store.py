@@ -142,6 +142,15 @@ class ClusterStore:
             _cabi.check(_cabi.lib().gdr_store_last_stats(self._handle, arr, _cabi.stream_ptr()))
         return {"simt_items": arr[0], "umma_tiles": arr[1], "launches": arr[2], "clusters_touched": arr[3]}
 
+    def set_profiling(self, enable: bool) -> None:
+        _cabi.check(_cabi.lib().gdr_store_set_profiling(self._handle, int(enable)))
+
+    def last_phase_ms(self) -> Dict[str, float]:
+        arr = (ctypes.c_float * 4)()
+        with torch.cuda.device(self.emb.device):
+            _cabi.check(_cabi.lib().gdr_store_last_phase_ms(self._handle, arr))
+        return {"invert": arr[0], "score_umma": arr[1], "score_simt": arr[2], "topk": arr[3]}
+
     def bytes_touched(self, beams_host: torch.Tensor) -> int:
         """Algorithmic HBM bytes of the embeddings one batch touches: every touched cluster once
         (SURVEY.md §8d)."""

@@ -82,6 +82,13 @@ int gdr_score_topk(gdr_store_t *store, const float *q, const int32_t *beams, con
  * Synchronises `stream`. */
 int gdr_store_last_stats(gdr_store_t *store, int64_t out[4], void *stream);
 
+/* Measurement aid (bench.py): with profiling enabled, gdr_score_topk records CUDA events on the
+ * caller's stream between its phases; gdr_store_last_phase_ms synchronises and returns the device
+ * time of the most recent profiled call: out[0] = pair inversion, out[1] = tcgen05 scoring (incl. the
+ * query split), out[2] = SIMT scoring, out[3] = top-k (all alphas). */
+int gdr_store_set_profiling(gdr_store_t *store, int32_t enable);
+int gdr_store_last_phase_ms(gdr_store_t *store, float out[4]);
+
 /* ---- dense similarity (dense.py:53-54 / encoder.py:128-129): out[Q, P] = q @ p^T, fp32 out ----
  *   q DEV fp32 [Q, dim]; p DEV [P, dim] of p_dtype; out DEV fp32 [Q, P]. */
 int gdr_similarity(const float *q, int64_t Q, const void *p, int64_t P, int32_t dim, int32_t p_dtype,

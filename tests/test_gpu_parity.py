@@ -1,0 +1,230 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle: cluster-restricted scoring + top-k.
+Bar (north star / SURVEY.md §8d): docid lists equal position by position, a mismatch excused only
+for oracle near-ties (<= 1e-5*max(1,|s|)); scores within 1e-3 relative."""
+import numpy as np
+import pytest
+import torch
+
+import gdr_oracle as orc
+from helpers import assert_topk_parity, bf16_bits_to_float, fine_stage_inputs, load_golden
+
+pytestmark = pytest.mark.gpu
+
+FLAG_SIMT, FLAG_UMMA = 2, 4
+
+
+def _store(emb, offsets, docid, dtype):
+    from gdr_b200 import ClusterStore
+    return ClusterStore.from_csr(emb, offsets, docid, dtype=dtype)
+
+
+@pytest.mark.parametrize("name", ["dense_topk_d768", "dense_topk_d128", "dense_topk_zipf"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_golden_dense_topk(name, dtype):
+    g = load_golden(name)
+    emb = bf16_bits_to_float(g["emb_bf16_bits"])       # bf16-representable: both store dtypes hold the same values
+    st = _store(emb, g["offsets"], g["docid"], dtype)
+    q = torch.from_numpy(g["q"]).cuda()
+    beams = torch.from_numpy(g["beams"]).cuda()
+    k = int(g["k"])
+    s, d = st.score_topk(q, beams, k)
+    assert_topk_parity(s, d, g["scores_plain"], g["docids_plain"], name)
+    bias = torch.from_numpy(g["bias"]).cuda()
+    s, d = st.score_topk(q, beams, k, prob=bias, alphas=[1.0], act="tanh")
+    assert_topk_parity(s[0], d[0], g["scores_tanh_bias"], g["docids_tanh_bias"], name + "/tanh+bias")
+
+
+@pytest.mark.parametrize("name", ["fine_stage_tanh", "fine_stage_sigmoid"])
+@pytest.mark.parametrize("dtype", [torch.float32])
+def test_golden_fine_stage_drop_in(name, dtype):
+    """FineStage (mirror of main_models.py:1434-1637) reproduces the docid strings the real
+    validation_step_i returned."""
+    from types import SimpleNamespace
+    from gdr_b200 import FineStage
+    f = fine_stage_inputs(name)
+    K = len(f["dec"][0])
+    args = SimpleNamespace(num_return_sequences=K, score_rate=f["score_rate"], loss_func=f["loss_func"])
+    fs = FineStage(args, f["doc_embed"], f["id_mapping"], dtype=dtype)
+    out = fs(f["dec"], f["beam_scores"], f["q"], texts=["q"] * len(f["dec"]), gt_answers=["gt"] * len(f["dec"]))
+    ref = orc.fine_stage(f["doc_embed"], f["id_mapping"], f["dec"], f["beam_scores"], f["q"], f["score_rate"], f["loss_func"], K)
+    vals, ids = fs.retrieve(f["dec"], f["beam_scores"], f["q"])
+    for b in range(len(f["dec"])):
+        for r in range(len(f["score_rate"])):
+            assert out[b][r][0][0] == "q" and out[b][r][0][2] == "gt"
+            got = [int(x) for x in out[b][r][0][1].split(",")]
+            assert_topk_parity(vals[b, r][None], torch.tensor(got)[None], ref[b][r][0][None],
+                               torch.tensor(f["docids"][b, r])[None], f"{name} b{b} r{r}")
+    with pytest.raises(KeyError):
+        fs([["not-a-cluster"] * K] * len(f["dec"]), f["beam_scores"], f["q"])
+    big = FineStage(args, store=fs.store, k=10 ** 3)
+    with pytest.raises(RuntimeError):
+        big(f["dec"], f["beam_scores"], f["q"])
+
+
+CASES = [
+    # N, C, D, Q, K, k, zipf, dtype, flags
+    (20000, 256, 768, 64, 10, 100, 0.0, torch.float32, 0),
+    (20000, 256, 768, 64, 10, 100, 0.0, torch.bfloat16, FLAG_SIMT),
+    (20000, 128, 768, 256, 20, 100, 0.0, torch.bfloat16, 0),          # dense groups (~40 pairs per cluster)
+    (20000, 128, 768, 256, 20, 100, 0.0, torch.bfloat16, FLAG_UMMA),
+    (30000, 200, 256, 100, 16, 1000, 0.0, torch.bfloat16, 0),        # k = 1000
+    (30000, 300, 128, 50, 8, 64, 1.2, torch.bfloat16, 0),            # Zipf-skewed clusters (global-keys top-k)
+    (30000, 300, 128, 50, 8, 64, 1.2, torch.float32, 0),
+    (5000, 64, 1024, 33, 7, 50, 0.0, torch.bfloat16, 0),             # max dim
+    (5000, 64, 8, 33, 7, 50, 0.0, torch.float32, 0),                 # min dim
+    (5000, 64, 200, 33, 7, 50, 0.0, torch.bfloat16, 0),              # dim not a multiple of 64 (no TMA path)
+]
+
+
+@pytest.mark.parametrize("N,C,D,Q,K,k,zipf,dtype,flags", CASES)
+def test_seeded_synthetic(N, C, D, Q, K, k, zipf, dtype, flags):
+    emb, offsets, docid = orc.synth_corpus(N, C, D, seed=N + C, zipf=zipf)
+    if dtype == torch.bfloat16:
+        emb = emb.bfloat16().float()                 # the oracle consumes the rounded values
+    q, beams, beam_scores = orc.synth_queries(Q, C, K, D, seed=Q + K)
+    prob = torch.softmax(beam_scores, -1)
+    st = _store(emb, offsets, docid, dtype)
+    if flags == FLAG_UMMA and D % 64 != 0:
+        pytest.skip("tcgen05 path needs dim % 64 == 0")
+    s, d = st.score_topk(q.cuda(), torch.from_numpy(beams).cuda(), k, flags=flags)
+    ref_s, ref_d = orc.dense_topk(q, emb, offsets, docid, beams, k)
+    n_exc = assert_topk_parity(s, d, ref_s, ref_d, "plain")
+    s, d = st.score_topk(q.cuda(), torch.from_numpy(beams).cuda(), k, prob=prob.cuda(), alphas=[0.0, 1.0, 3.0], act="tanh", flags=flags)
+    for r, alpha in enumerate([0.0, 1.0, 3.0]):
+        ref_s, ref_d = orc.dense_topk(q, emb, offsets, docid, beams, k, bias=prob * alpha, act="tanh")
+        n_exc += assert_topk_parity(s[r], d[r], ref_s, ref_d, f"tanh alpha={alpha}")
+    assert n_exc <= 0.002 * 4 * Q * k + 2, f"too many near-tie excuses: {n_exc}"
+    stats = st.last_stats()
+    if flags == FLAG_SIMT:
+        assert stats["umma_tiles"] == 0
+    if flags == FLAG_UMMA:
+        assert stats["simt_items"] == 0 and stats["umma_tiles"] > 0
+
+
+def test_edge_cases_ragged_empty_absent_and_padding():
+    D = 64
+    sizes = [0, 1, 3, 0, 130, 257, 2, 0]                 # empty clusters, multi-tile clusters
+    offsets = np.concatenate([[0], np.cumsum(sizes)])
+    N = int(offsets[-1])
+    g = torch.Generator().manual_seed(8)
+    emb = (torch.randn(N, D, generator=g) * D ** -0.5).bfloat16().float()
+    docid = torch.randperm(N, generator=g).numpy()
+    q = torch.randn(5, D, generator=g)
+    beams = np.array([[0, 3, 7], [1, -1, 2], [4, 5, 6], [-1, -1, -1], [5, 5, 1]], dtype=np.int32)   # dup cluster, all absent
+    for dtype in (torch.float32, torch.bfloat16):
+        st = _store(emb, offsets, docid, dtype)
+        for k in (1, 4, 300, 1000):
+            s, d = st.score_topk(q.cuda(), torch.from_numpy(beams).cuda(), k)
+            ref_s, ref_d = orc.dense_topk(q, emb, offsets, docid, beams, k)
+            assert_topk_parity(s, d, ref_s, ref_d, f"edge k={k}")
+            assert torch.all(s[0] == float("-inf")) and torch.all(d[3] == -1)
+    # B = 0 is a no-op
+    s, d = st.score_topk(q[:0].cuda(), torch.zeros(0, 3, dtype=torch.int32).cuda(), 4)
+    assert s.shape == (0, 4)
+
+
+def test_mass_ties_are_deterministic_and_docid_ordered():
+    """tanh saturates to exactly 1.0 for large |q.d|: thousands of exact ties.  Ours
+    orders ties by ascending docid, so the result is the k smallest docids among the tied maximum."""
+    D, N, C = 64, 4000, 8
+    emb, offsets, docid = orc.synth_corpus(N, C, D, seed=1)
+    emb = (emb * 40).bfloat16().float()
+    q = torch.randn(6, D, generator=torch.Generator().manual_seed(2)) * 10
+    beams = np.stack([np.arange(C, dtype=np.int32)] * 6)
+    st = _store(emb, offsets, docid, torch.bfloat16)
+    k = 100
+    s1, d1 = st.score_topk(q.cuda(), torch.from_numpy(beams).cuda(), k, act="tanh")
+    s2, d2 = st.score_topk(q.cuda(), torch.from_numpy(beams[:, ::-1].copy()).cuda(), k, act="tanh")
+    assert torch.equal(d1, d2) and torch.equal(s1, s2), "result must not depend on candidate order"
+    full = torch.tanh(q @ emb.T)
+    for b in range(6):
+        ones = np.sort(docid[(full[b] == 1.0).numpy()])
+        if ones.size >= k:
+            assert d1[b].cpu().tolist() == ones[:k].tolist()
+            assert torch.all(s1[b] == 1.0)
+
+
+def test_per_beam_queries():
+    """One query vector per (query, beam): main_models.py:1467-1571,1583-1594."""
+    N, C, D, Q, K, k = 8000, 64, 128, 20, 5, 30
+    emb, offsets, docid = orc.synth_corpus(N, C, D, seed=3)
+    emb = emb.bfloat16().float()
+    q, beams, _ = orc.synth_queries(Q * K, C, K, D, seed=4)
+    beams = beams[:Q]
+    st = _store(emb, offsets, docid, torch.bfloat16)
+    s, d = st.score_topk(q.cuda(), torch.from_numpy(beams).cuda(), k, per_beam=True)
+    # oracle: each beam segment scored with its own query vector
+    ref_s = torch.full((Q, k), float("-inf"))
+    ref_d = torch.full((Q, k), -1, dtype=torch.int64)
+    for b in range(Q):
+        sc, ids = [], []
+        for i, c in enumerate(beams[b]):
+            rows = torch.arange(int(offsets[c]), int(offsets[c + 1]))
+            sc.append(orc.compute_similarity(q[b * K + i:b * K + i + 1], emb[rows])[0])
+            ids.append(torch.from_numpy(docid)[rows])
+        sc, ids = torch.cat(sc), torch.cat(ids)
+        v, i = sc.topk(k)
+        ref_s[b], ref_d[b] = v, ids[i]
+    assert_topk_parity(s, d, ref_s, ref_d, "per-beam")
+
+
+def test_full_size_cfg2_properties_and_oracle():
+    """BASELINE.json configs[1] at full size: 109,739 x 768 bf16, C = 1,024, 1,024 queries, beam 20, top-100."""
+    N, C, D, Q, K, k = 109739, 1024, 768, 1024, 20, 100
+    emb, offsets, docid = orc.synth_corpus(N, C, D, seed=1234)
+    emb = emb.bfloat16().float()
+    q, beams, _ = orc.synth_queries(Q, C, K, D, seed=4321)
+    st = _store(emb, offsets, docid, torch.bfloat16)
+    s, d = st.score_topk(q.cuda(), torch.from_numpy(beams).cuda(), k)
+    torch.cuda.synchronize()
+    # size-independent properties
+    assert torch.all(s[:, :-1] >= s[:, 1:]), "sorted descending"
+    row_of = torch.empty(N, dtype=torch.int64); row_of[torch.from_numpy(docid)] = torch.arange(N)
+    rows = row_of[d.cpu().long()]
+    owner = torch.from_numpy(np.searchsorted(offsets, rows.numpy(), side="right") - 1)
+    assert all(set(owner[b].tolist()) <= set(beams[b].tolist()) for b in range(Q)), "docids come from the beam clusters"
+    recomputed = torch.einsum("bkd,bd->bk", emb[rows].double(), q.double())
+    np.testing.assert_allclose(s.cpu().double().numpy(), recomputed.numpy(), rtol=1e-3, atol=1e-3)
+    # and the oracle itself on a 128-query slice
+    ref_s, ref_d = orc.dense_topk(q[:128], emb, offsets, docid, beams[:128], k)
+    assert_topk_parity(s[:128], d[:128], ref_s, ref_d, "cfg2")
+    # idempotence: same call, same bits
+    s2, d2 = st.score_topk(q.cuda(), torch.from_numpy(beams).cuda(), k)
+    assert torch.equal(s, s2) and torch.equal(d, d2)
+
+
+def test_cfg3_shape_top1000():
+    """BASELINE.json configs[2] shape: 73,970 x 768, beam 100, top-1000 (C = 1,024 assumed)."""
+    N, C, D, Q, K, k = 73970, 1024, 768, 64, 100, 1000
+    emb, offsets, docid = orc.synth_corpus(N, C, D, seed=77)
+    emb = emb.bfloat16().float()
+    q, beams, _ = orc.synth_queries(Q, C, K, D, seed=78)
+    st = _store(emb, offsets, docid, torch.bfloat16)
+    s, d = st.score_topk(q.cuda(), torch.from_numpy(beams).cuda(), k)
+    ref_s, ref_d = orc.dense_topk(q, emb, offsets, docid, beams, k)
+    assert_topk_parity(s, d, ref_s, ref_d, "cfg3")
+
+
+def test_compute_similarity_drop_in():
+    from gdr_b200 import DenseModel
+    g = torch.Generator().manual_seed(5)
+    for Q, P, D, dt in ((7, 33, 96, torch.float32), (130, 1000, 768, torch.float32), (64, 513, 768, torch.bfloat16)):
+        q = torch.randn(Q, D, generator=g)
+        p = (torch.randn(P, D, generator=g) * D ** -0.5).to(dt)
+        out = DenseModel().compute_similarity(q.cuda(), p.cuda())
+        ref = orc.compute_similarity(q, p.float())
+        np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=1e-3, atol=1e-4)
+
+
+def test_merge_topk_kernel():
+    from gdr_b200.sharded import ShardedRetriever, pack_candidates
+    g = torch.Generator().manual_seed(6)
+    G, B, k = 8, 50, 100
+    s = torch.randn(G, B, k, generator=g).sort(dim=-1, descending=True).values
+    d = torch.randint(0, 10 ** 8, (G, B, k), generator=g, dtype=torch.int64)
+    s[3, :, 40:] = float("-inf"); d[3, :, 40:] = -1
+    s[5] = float("-inf"); d[5] = -1
+    packed = torch.stack([pack_candidates(s[r], d[r].int()) for r in range(G)]).cuda()
+    ms, md = ShardedRetriever._cuda_merge(packed, k)
+    ref_s, ref_d = orc.merge_topk(s, d, k)
+    assert_topk_parity(ms, md, ref_s, ref_d, "merge")

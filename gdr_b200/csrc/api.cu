@@ -44,7 +44,7 @@ struct gdr_store {
     bool has_tmap = false;
     CUtensorMap tmap;
     int last_launches = 0;
-    int umma_min_group = 8;
+    int umma_min_group = 1;   // > 1 (env GDR_UMMA_MIN_GROUP) = mixed mode
     bool profiling = false;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 };
@@ -132,7 +132,7 @@ int gdr_score_topk(gdr_store_t *s, const float *q, const int32_t *beams, const f
     const int64_t simt_cap = pairs * ((s->max_cluster + SIMT_ROWS - 1) / SIMT_ROWS);
     const int64_t umma_cap = pairs * ((s->max_cluster + UMMA_ROWS - 1) / UMMA_ROWS);
     const bool umma_possible = s->has_tmap && !(flags & GDR_FORCE_SIMT);
-    const bool global_keys = (size_t)stride * 4 + 8 * 4096 + 4 * 4096 + (size_t)(K + 1) * 4 > 96 * 1024;
+    const bool global_keys = (size_t)stride * 4 + 8 * 4096 + 4 * 4096 + (size_t)(2 * K + 1) * 4 > 96 * 1024;
 
     // carve the per-batch scratch
     size_t off = 0;
@@ -172,19 +172,25 @@ int gdr_score_topk(gdr_store_t *s, const float *q, const int32_t *beams, const f
     a.scorebuf = reinterpret_cast<float *>(ws + o_score);
     a.stride = stride;
     a.gkeys = reinterpret_cast<uint32_t *>(ws + o_keys);
-    a.umma_min_group = !umma_possible ? INT_MAX : ((flags & GDR_FORCE_UMMA) ? 1 : s->umma_min_group);
+    // One scoring path per call: a batch that names each touched cluster about twice or more goes to the tcgen05
+    // grouped GEMM (slab read once for the whole group), a sparse batch to the SIMT GEMV.  GDR_UMMA_MIN_GROUP > 1
+    // (env) asks for the mixed mode instead: groups of at least that many pairs on tensor cores, the rest SIMT.
+    const bool mixed = umma_possible && !(flags & GDR_FORCE_UMMA) && s->umma_min_group > 1;
+    bool use_umma = umma_possible && ((flags & GDR_FORCE_UMMA) || mixed || 2 * (int64_t)s->n_clusters <= 3 * pairs);
+    const bool use_simt = !use_umma || mixed;
+    a.umma_min_group = !use_umma ? INT_MAX : (mixed ? s->umma_min_group : 1);
 
     int launches = 0;
     const bool prof = s->profiling;
     if (prof) GDR_CUDA(cudaEventRecord(s->ev[0], st));
     GDR_CUDA(launch_invert(a, st, &launches));
     if (prof) GDR_CUDA(cudaEventRecord(s->ev[1], st));
-    if (umma_possible) {
+    if (use_umma) {
         GDR_CUDA(launch_score_umma(a, &s->tmap, st, s->sm_count));
         launches += 1;
     }
     if (prof) GDR_CUDA(cudaEventRecord(s->ev[2], st));
-    if (!(flags & GDR_FORCE_UMMA)) {
+    if (use_simt) {
         GDR_CUDA(launch_score_simt(a, st, s->sm_count));
         launches += 1;
     }

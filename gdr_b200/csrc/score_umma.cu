@@ -8,10 +8,13 @@
 //     D[128 docs, N pairs] (fp32, TMEM)  +=  A[128 docs, 64 k] (bf16 smem, TMA)  x  B[N pairs, 64 k]^T (bf16 smem)
 //
 // Parity with the fp32 reference needs more than bf16(q): the fp32 query is split exactly into three
-// bf16 terms q = hi + mid + lo (by the filler warps, in registers), and each K step issues three MMAs (A x hi, A x mid, A x lo)
-// into the same accumulator; every product bf16 x bf16 is exact in fp32, so the result matches an
-// fp32 dot product to accumulation-order noise.  The kernel is still HBM-bound: per tile it moves
-// 128 x 768 x 2 B = 196 KB of embeddings and issues 12 x 4 x 3 MMAs of 128 x N x 16.
+// bf16 terms q = hi + mid + lo (by the filler warps, in registers).  The three terms are stacked along N
+// (B rows [0,TS) = hi, [TS,2TS) = mid, [2TS,3TS) = lo, TS = 16 or 32), so ONE MMA of N = 3*TS per K step
+// reads the A tile from shared memory once for all three (SS-mode MMAs are bound by the 128 B/clk smem
+// read of A, measured: three N=32 MMAs per K step were MIO-throttled); the epilogue adds the three TMEM
+// column groups.  Every product bf16 x bf16 is exact in fp32, so the result matches an fp32 dot product to
+// accumulation-order noise.  The kernel is still HBM-bound: per tile it moves 128 x 768 x 2 B = 196 KB of
+// embeddings and issues 12 x 4 MMAs of 128 x 96 x 16.
 //
 // Warp roles (448 threads, one persistent CTA per SM, tiles strided over CTAs):
 //   warp 0       TMA producer: A tiles of the store, 6-stage ring (96 KB in flight per SM), mbarrier complete_tx
@@ -34,7 +37,8 @@ constexpr int UM_A_BYTES = UMMA_ROWS * 128;    // 16 KB
 constexpr int UM_BT_BYTES = UMMA_NQ * 128;     // 4 KB per query term
 constexpr int UM_B_BYTES = 3 * UM_BT_BYTES;    // 12 KB
 constexpr int UM_THREADS = 64 + 32 * UM_FILL_WARPS + 128;   // 448
-constexpr int UM_TMEM_COLS = 2 * UMMA_NQ;      // 2 accumulators x 32 fp32 columns
+constexpr int UM_ACC_COLS = 128;               // TMEM columns reserved per accumulator (3 * 32 used)
+constexpr int UM_TMEM_COLS = 2 * UM_ACC_COLS;  // double-buffered accumulator
 constexpr int UM_RING_BYTES = UM_SA * UM_A_BYTES + UM_SB * UM_B_BYTES;   // 192 KB
 constexpr int UM_SMEM_BYTES = UM_RING_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int UM_TASKS = 8;                    // 32-byte query pieces a filler lane keeps in flight (8 x 32 lanes = all of a 32-pair block)
@@ -87,6 +91,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
+}
+// One lane of a converged warp; the guarded code stays warp-uniform for ptxas, so descriptors and barrier
+// addresses are computed on the uniform datapath instead of per-lane registers + R2UR moves.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "elect.sync _|P1, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -163,54 +179,53 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_score_umma(const __grid_const
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            int s = 0;
-            uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int row0 = a.umma_items[tile].row0;
-                for (int kb = 0; kb < nkb; ++kb) {
-                    mbar_wait(emptyA(s), ph ^ 1u);
+        // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
+        int s = 0;
+        uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int row0 = a.umma_items[tile].row0;
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(emptyA(s), ph ^ 1u);
+                if (elect_one()) {
                     mbar_arrive_expect_tx(fullA(s), UM_A_BYTES);
                     tma_load_2d(a_smem(s), &tmap, kb * UM_BLOCK_K, row0, fullA(s));
-                    if (++s == UM_SA) { s = 0; ph ^= 1u; }
                 }
+                __syncwarp();
+                if (++s == UM_SA) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            int sa = 0, sb = 0;
-            uint32_t pha = 0, phb = 0;
-            int it = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-                const int nq = a.umma_items[tile].nrows_nq >> 16;
-                const uint32_t idesc = umma_idesc(((nq + 15) >> 4) << 4);
-                const int acc = it & 1;
-                const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
-                mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
+        // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+        int sa = 0, sb = 0;
+        uint32_t pha = 0, phb = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int nq = a.umma_items[tile].nrows_nq >> 16;
+            const uint32_t idesc = umma_idesc(nq <= 16 ? 48 : 96);     // N = 3 terms x TS rows
+            const int acc = it & 1;
+            const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
+            mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)acc * UM_ACC_COLS;
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(fullB(sb), phb);
+                mbar_wait(fullA(sa), pha);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)acc * UMMA_NQ;
-                for (int kb = 0; kb < nkb; ++kb) {
-                    mbar_wait(fullB(sb), phb);
-                    mbar_wait(fullA(sa), pha);
-                    tc_fence_after();
+                if (elect_one()) {
                     const uint64_t adesc = umma_smem_desc(a_smem(sa));
+                    const uint64_t bdesc = umma_smem_desc(b_smem(sb, 0));
 #pragma unroll
                     for (int k = 0; k < UM_BLOCK_K / 16; ++k) {
-#pragma unroll
-                        for (int t = 0; t < 3; ++t) {
-                            const uint64_t bdesc = umma_smem_desc(b_smem(sb, t));
-                            // +32 bytes per UMMA_K = 16 bf16 inside the swizzle atom: +2 in the (addr >> 4) field
-                            umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k | t) != 0 ? 1u : 0u);
-                        }
+                        // +32 bytes per UMMA_K = 16 bf16 inside the swizzle atom: +2 in the (addr >> 4) field
+                        umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, k != 0 ? 1u : (kb != 0 ? 1u : 0u));
                     }
                     umma_commit(emptyA(sa));
                     umma_commit(emptyB(sb));
-                    if (++sa == UM_SA) { sa = 0; pha ^= 1u; }
-                    if (++sb == UM_SB) { sb = 0; phb ^= 1u; }
+                    if (kb == nkb - 1) umma_commit(tfull_bar(acc));
                 }
-                umma_commit(tfull_bar(acc));
+                __syncwarp();
+                if (++sa == UM_SA) { sa = 0; pha ^= 1u; }
+                if (++sb == UM_SB) { sb = 0; phb ^= 1u; }
             }
         }
     } else if (warp < 2 + UM_FILL_WARPS) {
@@ -232,6 +247,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_score_umma(const __grid_const
             const uint32_t phb = (uint32_t)(g / UM_SB) & 1u;
             unsigned char *bst = smem + UM_SA * UM_A_BYTES + (size_t)sb * UM_B_BYTES;
             const int n_tasks = nq * 8;            // one task = 8 fp32 of one pair = one 16-byte chunk per term
+            const int term_bytes = (nq <= 16 ? 16 : 32) * 128;     // rows of term t start t * TS rows into the B tile
             bool waited = false;
             for (int base = 0; base < n_tasks; base += 32 * UM_TASKS) {
                 float4 v[UM_TASKS][2];
@@ -259,8 +275,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_score_umma(const __grid_const
                         split2(v[u][1].z, v[u][1].w, hi.w, mid.w, lo.w);
                         unsigned char *dst = bst + j * 128 + ((c ^ (j & 7)) << 4);
                         *reinterpret_cast<uint4 *>(dst) = hi;
-                        *reinterpret_cast<uint4 *>(dst + UM_BT_BYTES) = mid;
-                        *reinterpret_cast<uint4 *>(dst + 2 * UM_BT_BYTES) = lo;
+                        *reinterpret_cast<uint4 *>(dst + term_bytes) = mid;
+                        *reinterpret_cast<uint4 *>(dst + 2 * term_bytes) = lo;
                     }
                 }
             }
@@ -287,25 +303,39 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_score_umma(const __grid_const
             const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
             mbar_wait(tfull_bar(acc), acc_ph);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)acc * UMMA_NQ;
-            uint32_t r[UMMA_NQ / 16][16];
-            const int nch = (nq + 15) >> 4;
+            const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)acc * UM_ACC_COLS;
+            // score[c] = D[c] + D[TS + c] + D[2*TS + c]  (hi + mid + lo terms)
+            float sum[UMMA_NQ];
+            if (nq <= 16) {
+                uint32_t r[3][16];
 #pragma unroll
-            for (int ch = 0; ch < UMMA_NQ / 16; ++ch)
-                if (ch < nch) tmem_ld16(taddr + ch * 16, r[ch]);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                for (int t = 0; t < 3; ++t) tmem_ld16(taddr + t * 16, r[t]);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    sum[j] = (__uint_as_float(r[0][j]) + __uint_as_float(r[1][j])) + __uint_as_float(r[2][j]);
+            } else {
+                uint32_t r[2][16];
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    tmem_ld16(taddr + t * 32, r[0]);
+                    tmem_ld16(taddr + t * 32 + 16, r[1]);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float v = __uint_as_float(r[j >> 4][j & 15]);
+                        sum[j] = t == 0 ? v : sum[j] + v;
+                    }
+                }
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));     // accumulator is in registers: release it to the MMA warp
 #pragma unroll
-            for (int ch = 0; ch < UMMA_NQ / 16; ++ch) {
-                if (ch < nch) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int c = ch * 16 + j;
-                        const int64_t o = __shfl_sync(0xffffffffu, off, c);
-                        if (c < nq && row < nrows) a.scorebuf[o + row] = apply_act(__uint_as_float(r[ch][j]), a.act);
-                    }
+            for (int c = 0; c < UMMA_NQ; ++c) {
+                if (c < nq) {                                 // warp-uniform
+                    const int64_t o = __shfl_sync(0xffffffffu, off, c);
+                    if (row < nrows) a.scorebuf[o + row] = apply_act(sum[c], a.act);
                 }
             }
         }

@@ -112,9 +112,8 @@ __device__ __forceinline__ void bitonic_sort_desc(uint64_t *v, int cap) {
 struct StoreSrc {   // a query's candidates = its K beam segments of the score buffer
     const float *sb;        // score buffer row of this query
     const int32_t *co;      // [K+1] segment starts (shared memory)
+    const int32_t *cbase;   // [K] first store row of each beam's cluster (shared memory)
     const float *prob;      // [K] or null
-    const int32_t *beams;   // [K]
-    const int32_t *offsets;
     const int32_t *docid;
     int K;
     float alpha;
@@ -134,7 +133,7 @@ struct StoreSrc {   // a query's candidates = its K beam segments of the score b
     }
     __device__ int32_t doc(int j) const {
         const int i = seg(j);
-        return docid[offsets[beams[i]] + (j - co[i])];
+        return docid[cbase[i] + (j - co[i])];
     }
 };
 
@@ -149,7 +148,7 @@ struct ListSrc {    // explicit candidate lists from G ranks: [G, B, k_in]
 };
 
 template <typename Src>
-__device__ void topk_body(const Src &src, int n, int k, int cap, uint32_t *keys, uint64_t *sel, uint32_t *hist,
+__device__ void topk_general(const Src &src, int n, int k, int cap, uint32_t *keys, uint64_t *sel, uint32_t *hist,
                           TkShared *sh, float *out_s, int32_t *out_d) {
     const int tid = threadIdx.x;
     if (tid == 0) { sh->sel_count = 0; sh->eq2_count = 0; }
@@ -208,7 +207,135 @@ __device__ void topk_body(const Src &src, int n, int k, int cap, uint32_t *keys,
     }
 }
 
-// dynamic shared memory layout: sel[cap] u64 | hist[TK_BINS] u32 | co[K+1] i32 | keys[...] u32 (smem variant)
+
+// ---- fast path ---------------------------------------------------------------------------------
+// Two passes over the n keys instead of five: (1) build keys + 4096-bin histogram of the top 12 key bits,
+// (2) classify against the boundary bin: keys above it are selected outright, keys inside it (n/64 on
+// spread-out scores) go to a small boundary list that is resolved by rank counting on (key, ~docid).
+// The k survivors are ordered by rank counting as well (k <= 256) — no bitonic network, ~7 barriers in all.
+// Falls back to the general radix select when the boundary bin holds more than TK_BND keys (mass ties).
+constexpr int TK_BND = 256;
+
+template <typename Src>
+__device__ void topk_body(const Src &src, int n, int k, int cap, uint32_t *keys, uint64_t *sel, uint32_t *hist,
+                          TkShared *sh, float *out_s, int32_t *out_d) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (n <= k || cap > 256) {     // few candidates (take all) or large k: general path
+        topk_general(src, n, k, cap, keys, sel, hist, sh, out_s, out_d);
+        return;
+    }
+    for (int i = tid; i < TK_BINS; i += TK_THREADS) hist[i] = 0;
+    if (tid == 0) { sh->sel_count = 0; sh->eq2_count = 0; }
+    __syncthreads();
+    for (int j = tid; j < n; j += TK_THREADS) {
+        const uint32_t key = float_to_ordered(src.score(j));
+        keys[j] = key;
+        atomicAdd(&hist[key >> 20], 1u);
+    }
+    __syncthreads();
+    // boundary bin: warp w sums bins [512w, 512w + 512) with conflict-free strided reads ...
+    {
+        int part = 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) part += hist[warp * 512 + i * 32 + lane];
+#pragma unroll
+        for (int d = 16; d; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+        if (lane == 0) sh->warp_tot[warp] = part;
+    }
+    __syncthreads();
+    // ... then every warp redundantly walks down from the top to the 512-bin range and the bin where the
+    // cumulative count reaches k (no further barrier needed: all threads end up with the same d / gt / eq)
+    int above = 0, range = TK_THREADS / 32 - 1;
+    for (; range > 0; --range) {
+        const int t = sh->warp_tot[range];
+        if (above + t >= k) break;
+        above += t;
+    }
+    int d_bin, gt, eq;
+    {
+        const int top = range * 512 + 512 - lane * 16;       // lane owns bins [top-16, top), lane 0 the highest
+        int local = 0;
+#pragma unroll
+        for (int i = 1; i <= 16; ++i) local += hist[top - i];
+        int incl = local;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const int need_here = k - above;
+        const bool mine = (incl - local) < need_here && need_here <= incl;
+        int fb = 0, fg = 0, fe = 0;
+        if (mine) {
+            int running = above + incl - local;
+            for (int i = 1; i <= 16; ++i) {
+                const int h = hist[top - i];
+                if (running + h >= k) { fb = top - i; fg = running; fe = h; break; }
+                running += h;
+            }
+        }
+        const unsigned who = __ballot_sync(0xffffffffu, mine);
+        const int srcl = __ffs(who) - 1;
+        d_bin = __shfl_sync(0xffffffffu, fb, srcl);
+        gt = __shfl_sync(0xffffffffu, fg, srcl);
+        eq = __shfl_sync(0xffffffffu, fe, srcl);
+    }
+    if (eq > TK_BND) {             // mass ties in the boundary bin: general path (uniform decision)
+        __syncthreads();
+        topk_general(src, n, k, cap, keys, sel, hist, sh, out_s, out_d);
+        return;
+    }
+    // classify: sel[0, gt) <- keys above the boundary bin; bnd[0, eq) <- keys inside it   (bnd aliases hist)
+    uint64_t *bnd = reinterpret_cast<uint64_t *>(hist);           // 2 x TK_BND x 8 B << 16 KB
+    uint64_t *bnd2 = bnd + TK_BND;
+    __syncthreads();                                              // everyone is done reading hist
+    for (int j = tid; j < n; j += TK_THREADS) {
+        const uint32_t key = keys[j];
+        const int bin = (int)(key >> 20);
+        if (bin > d_bin) sel[atomicAdd(&sh->sel_count, 1)] = ((uint64_t)key << 32) | (uint32_t)j;
+        else if (bin == d_bin) bnd[atomicAdd(&sh->eq2_count, 1)] = ((uint64_t)key << 32) | (uint32_t)j;
+    }
+    __syncthreads();
+    const int need = k - gt;                                      // 1 <= need <= eq
+    if (need == eq) {
+        if (tid < eq) sel[gt + tid] = bnd[tid];
+    } else {
+        // order the boundary keys by (key desc, docid asc); duplicates of the same (key, docid) by list position
+        if (tid < eq) {
+            const uint64_t e = bnd[tid];
+            bnd2[tid] = (e & 0xffffffff00000000ull) | (uint32_t)~(uint32_t)src.doc((int)(uint32_t)e);
+        }
+        __syncthreads();
+        if (tid < eq) {
+            const uint64_t mine = bnd2[tid];
+            int rank = 0;
+            for (int u = 0; u < eq; ++u) {
+                const uint64_t o = bnd2[u];
+                rank += (o > mine) || (o == mine && u < tid);
+            }
+            if (rank < need) sel[gt + rank] = bnd[tid];
+        }
+    }
+    __syncthreads();
+    // (key, candidate index) -> (key, ~docid), then order the k survivors by rank counting and write them out
+    if (tid < k) {
+        const uint64_t e = sel[tid];
+        sel[tid] = (e & 0xffffffff00000000ull) | (uint32_t)~(uint32_t)src.doc((int)(uint32_t)e);
+    }
+    __syncthreads();
+    if (tid < k) {
+        const uint64_t mine = sel[tid];
+        int rank = 0;
+        for (int u = 0; u < k; ++u) {
+            const uint64_t o = sel[u];
+            rank += (o > mine) || (o == mine && u < tid);
+        }
+        out_s[rank] = ordered_to_float((uint32_t)(mine >> 32));
+        out_d[rank] = (int32_t)(~(uint32_t)mine);
+    }
+}
+
+// dynamic shared memory layout: sel[cap] u64 | hist[TK_BINS] u32 | co[K+1] i32 | cbase[K] i32 | keys[...] u32 (smem variant)
 template <bool KEYS_IN_SMEM>
 __global__ void __launch_bounds__(TK_THREADS) k_topk_store(ScoreArgs a, float alpha, int cap, float *out_scores,
                                                            int32_t *out_docids) {
@@ -218,11 +345,18 @@ __global__ void __launch_bounds__(TK_THREADS) k_topk_store(ScoreArgs a, float al
     uint32_t *hist = reinterpret_cast<uint32_t *>(sel + cap);
     int32_t *co = reinterpret_cast<int32_t *>(hist + TK_BINS);
     const int b = blockIdx.x;
-    for (int i = threadIdx.x; i <= a.K; i += TK_THREADS) co[i] = a.candoff[(int64_t)b * (a.K + 1) + i];
+    int32_t *cbase = co + a.K + 1;
+    for (int i = threadIdx.x; i <= a.K; i += TK_THREADS) {
+        co[i] = a.candoff[(int64_t)b * (a.K + 1) + i];
+        if (i < a.K) {
+            const int c = a.beams[(int64_t)b * a.K + i];
+            cbase[i] = (c >= 0 && c < a.n_clusters) ? a.offsets[c] : 0;
+        }
+    }
     __syncthreads();
-    uint32_t *keys = KEYS_IN_SMEM ? reinterpret_cast<uint32_t *>(co + a.K + 1) : a.gkeys + (int64_t)b * a.stride;
-    StoreSrc src{a.scorebuf + (int64_t)b * a.stride, co, a.prob ? a.prob + (int64_t)b * a.K : nullptr,
-                 a.beams + (int64_t)b * a.K, a.offsets, a.docid, a.K, alpha};
+    uint32_t *keys = KEYS_IN_SMEM ? reinterpret_cast<uint32_t *>(cbase + a.K) : a.gkeys + (int64_t)b * a.stride;
+    StoreSrc src{a.scorebuf + (int64_t)b * a.stride, co, cbase, a.prob ? a.prob + (int64_t)b * a.K : nullptr,
+                 a.docid, a.K, alpha};
     topk_body(src, co[a.K], a.k, cap, keys, sel, hist, &sh, out_scores + (int64_t)b * a.k,
               out_docids + (int64_t)b * a.k);
 }
@@ -246,7 +380,7 @@ static int pow2_at_least(int x) { int p = 2; while (p < x) p <<= 1; return p; }
 cudaError_t launch_topk_store(const ScoreArgs &a, float alpha, float *out_scores, int32_t *out_docids, cudaStream_t s) {
     if (a.B == 0) return cudaSuccess;
     const int cap = pow2_at_least(a.k);
-    const size_t fixed = (size_t)cap * 8 + TK_BINS * 4 + (size_t)(a.K + 1) * 4;
+    const size_t fixed = (size_t)cap * 8 + TK_BINS * 4 + (size_t)(2 * a.K + 1) * 4;
     const size_t with_keys = fixed + (size_t)a.stride * 4;
     if (with_keys <= 96 * 1024) {
         static bool attr_set = false;

@@ -46,6 +46,7 @@ struct gdr_store {
     int last_launches = 0;
     int umma_min_group = 1;   // > 1 (env GDR_UMMA_MIN_GROUP) = mixed mode
     bool profiling = false;
+    long long *dbg = nullptr;   // device timeline scratch for GDR_UMMA_TRACE
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -93,6 +94,7 @@ int gdr_store_create(gdr_store_t **out, const void *emb, int64_t n_docs, int32_t
     }
     if (dtype == GDR_DTYPE_BF16 && dim % 64 == 0) s->has_tmap = umma_make_tensor_map(&s->tmap, emb, n_docs, dim);
     if (const char *env = getenv("GDR_UMMA_MIN_GROUP")) s->umma_min_group = atoi(env);
+    if (getenv("GDR_UMMA_TRACE")) { cudaMalloc(&s->dbg, 512 * sizeof(long long)); cudaMemset(s->dbg, 0, 512 * sizeof(long long)); }
     *out = s;
     return GDR_OK;
 }
@@ -132,7 +134,7 @@ int gdr_score_topk(gdr_store_t *s, const float *q, const int32_t *beams, const f
     const int64_t simt_cap = pairs * ((s->max_cluster + SIMT_ROWS - 1) / SIMT_ROWS);
     const int64_t umma_cap = pairs * ((s->max_cluster + UMMA_ROWS - 1) / UMMA_ROWS);
     const bool umma_possible = s->has_tmap && !(flags & GDR_FORCE_SIMT);
-    const bool global_keys = (size_t)stride * 4 + 8 * 4096 + 4 * 4096 + (size_t)(2 * K + 1) * 4 > 96 * 1024;
+    const bool global_keys = (size_t)stride * 4 + 8 * 4096 + 4 * 2048 + (size_t)(2 * K + 1) * 4 > 96 * 1024;
 
     // carve the per-batch scratch
     size_t off = 0;
@@ -160,6 +162,7 @@ int gdr_score_topk(gdr_store_t *s, const float *q, const int32_t *beams, const f
     a.emb = s->emb; a.offsets = s->offsets; a.docid = s->docid;
     a.dim = s->dim; a.dtype = s->dtype; a.n_clusters = s->n_clusters; a.max_cluster = s->max_cluster; a.n_docs = s->n_docs;
     a.q = q; a.beams = beams; a.prob = prob; a.B = B; a.K = K; a.act = act; a.k = k; a.flags = flags;
+    if (const char *dbg = getenv("GDR_UMMA_DEBUG")) a.flags |= (uint32_t)atoi(dbg) << 27;   // timing experiments only
     a.cnt = s->cluster_ws;
     a.grp_off = s->cluster_ws + n;
     a.simt_off = a.grp_off + (n + 1);
@@ -178,6 +181,7 @@ int gdr_score_topk(gdr_store_t *s, const float *q, const int32_t *beams, const f
     const bool mixed = umma_possible && !(flags & GDR_FORCE_UMMA) && s->umma_min_group > 1;
     bool use_umma = umma_possible && ((flags & GDR_FORCE_UMMA) || mixed || 2 * (int64_t)s->n_clusters <= 3 * pairs);
     const bool use_simt = !use_umma || mixed;
+    a.dbg = s->dbg;
     a.umma_min_group = !use_umma ? INT_MAX : (mixed ? s->umma_min_group : 1);
 
     int launches = 0;
@@ -225,6 +229,13 @@ int gdr_store_last_stats(gdr_store_t *s, int64_t out[4], void *stream) {
     if (!s || !out) return invalid("gdr_store_last_stats: null argument");
     int32_t c[CTR_COUNT];
     GDR_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    if (s->dbg) {   // GDR_UMMA_TRACE: dump the device timeline of CTA 0 (ns, relative to kernel start)
+        long long h[512];
+        GDR_CUDA(cudaMemcpy(h, s->dbg, sizeof(h), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[umma trace] ");
+        for (int i = 1; i < 512 && h[i]; ++i) fprintf(stderr, "%lld ", h[i] - h[0]);
+        fprintf(stderr, "\n");
+    }
     const size_t n = (size_t)s->n_clusters;
     GDR_CUDA(cudaMemcpy(c, s->cluster_ws + n + 3 * (n + 1), sizeof(c), cudaMemcpyDeviceToHost));
     out[0] = c[CTR_N_SIMT];

@@ -67,6 +67,7 @@ struct ScoreArgs {
     float *scorebuf;     // [B, stride]
     int64_t stride;
     uint32_t *gkeys;     // [B, stride] keys scratch for the global-memory top-k variant
+    long long *dbg;      // [512] optional timeline scratch (GDR_UMMA_TRACE=1), else null
     int32_t umma_min_group;  // groups with at least this many pairs go to the tcgen05 path (INT_MAX = never)
 };
 

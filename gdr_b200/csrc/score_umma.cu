@@ -16,7 +16,7 @@
 // accumulation-order noise.  The kernel is still HBM-bound: per tile it moves 128 x 768 x 2 B = 196 KB of
 // embeddings and issues 12 x 4 MMAs of 128 x 96 x 16.
 //
-// Warp roles (448 threads, one persistent CTA per SM, tiles strided over CTAs):
+// Warp roles (480 threads, one persistent CTA per SM, tiles strided over CTAs):
 //   warp 0       TMA producer: A tiles of the store, 6-stage ring (96 KB in flight per SM), mbarrier complete_tx
 //   warp 1       MMA issuer (one lane): tcgen05.mma cta_group::1 kind::f16; commits free the A and B stages
 //   warps 2-9    B fillers, one K block per warp in flight (8 blocks' L2 latency overlapped): gather the
@@ -24,23 +24,38 @@
 //                into the 128B-swizzled K-major layout the UMMA descriptor expects, fence.proxy.async, arrive
 //   warps 10-13  epilogue: tcgen05.ld the accumulator (double-buffered in TMEM so it overlaps the next
 //                tile's MMAs), activation, coalesced stores into each query's candidate segment
+//   warp 14      tile metadata: walks item -> pair -> candidate offset (three dependent L2 round trips) for four
+//                tiles at a time, up to four tiles ahead, into a shared-memory ring, so no other role ever has a
+//                global-memory latency on its per-tile critical path (measured: with each role fetching its own
+//                metadata the empty barrier skeleton alone cost 4 us per tile, as much as the tile's HBM time)
 #include "gdr_common.cuh"
 
 namespace gdr {
 
 constexpr int UM_BLOCK_K = 64;                 // bf16 elements per K block = one 128-byte swizzle atom
-constexpr int UM_SA = 6;                       // A (store tiles, TMA) ring depth
-constexpr int UM_SB = 8;                       // B (query tiles) ring depth: one stage per filler warp, so a warp is never
-                                               // more than one mbarrier phase ahead of the MMA warp (parity waits stay unambiguous)
+constexpr int UM_SA = 8;                       // ONE ring of 8 stages, each = A tile (TMA) + B tile (filler warp s): one full and one
+constexpr int UM_SB = 8;                       // empty barrier per stage, so the MMA warp pays one wait + one commit per K block (it is
+                                               // issue-latency-bound: ~90 cycles per mbarrier try_wait, measured).  One stage per filler
+                                               // warp keeps every waiter at most one mbarrier phase ahead (parity waits stay unambiguous).
 constexpr int UM_FILL_WARPS = 8;
 constexpr int UM_A_BYTES = UMMA_ROWS * 128;    // 16 KB
 constexpr int UM_BT_BYTES = UMMA_NQ * 128;     // 4 KB per query term
 constexpr int UM_B_BYTES = 3 * UM_BT_BYTES;    // 12 KB
-constexpr int UM_THREADS = 64 + 32 * UM_FILL_WARPS + 128;   // 448
+constexpr int UM_THREADS = 64 + 32 * UM_FILL_WARPS + 128 + 32;   // 480
 constexpr int UM_ACC_COLS = 128;               // TMEM columns reserved per accumulator (3 * 32 used)
 constexpr int UM_TMEM_COLS = 2 * UM_ACC_COLS;  // double-buffered accumulator
-constexpr int UM_RING_BYTES = UM_SA * UM_A_BYTES + UM_SB * UM_B_BYTES;   // 192 KB
-constexpr int UM_SMEM_BYTES = UM_RING_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int UM_RING_BYTES = UM_SA * UM_A_BYTES + UM_SB * UM_B_BYTES;   // 224 KB
+static_assert(UM_SA == UM_SB, "A and B share one ring");
+constexpr int UM_MD = 4;                       // tile-metadata ring depth
+struct __align__(16) TileMeta {                // one tile's metadata, written by the metadata warp
+    int32_t row0, nrows, nq, rel0;
+    int32_t qrow[UMMA_NQ];                     // query row of each pair (B fillers)
+    int64_t off[UMMA_NQ];                      // score-buffer offset of each pair's first row (epilogue)
+};
+constexpr int UM_META_CONSUMERS = 2 + UM_FILL_WARPS + 4;    // TMA, MMA, fillers, epilogue warps
+constexpr int UM_BAR_BYTES = 512;
+constexpr int UM_SMEM_BYTES = UM_RING_BYTES + UM_BAR_BYTES + UM_MD * (int)sizeof(TileMeta);
+static_assert(UM_SMEM_BYTES <= 227 * 1024, "shared memory budget");
 constexpr int UM_TASKS = 8;                    // 32-byte query pieces a filler lane keeps in flight (8 x 32 lanes = all of a 32-pair block)
 static_assert(UM_SB == UM_FILL_WARPS, "one B stage per filler warp");
 static_assert(UMMA_NQ == 32, "epilogue and filler lane maps assume 32 pairs per tile");
@@ -131,41 +146,60 @@ __device__ __forceinline__ void split2(float x0, float x1, uint32_t &hi, uint32_
     lo = *reinterpret_cast<const uint32_t *>(&l);
 }
 
-__global__ void __launch_bounds__(UM_THREADS, 1) k_score_umma(const __grid_constant__ CUtensorMap tmap, ScoreArgs a) {
-    extern __shared__ unsigned char smem_raw[];
-    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // 1024-byte alignment for SWIZZLE_128B
-    unsigned char *smem = smem_raw + (smem_base - smem_u32(smem_raw));
-    const uint32_t bar_base = smem_base + UM_RING_BYTES;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + UM_RING_BYTES + 192);
+__device__ __forceinline__ long long gtime() {
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// timeline trace (GDR_UMMA_TRACE=1): CTA 0's MMA warp stamps slot i with the global timer
+#define UM_TRACE(i) do { if (a.dbg && blockIdx.x == 0 && lane == 0 && (i) < 512) a.dbg[(i)] = gtime(); } while (0)
 
-    auto fullA = [&](int s) { return bar_base + 8u * s; };
-    auto emptyA = [&](int s) { return bar_base + 8u * (UM_SA + s); };
-    auto fullB = [&](int s) { return bar_base + 8u * (2 * UM_SA + s); };
-    auto emptyB = [&](int s) { return bar_base + 8u * (2 * UM_SA + UM_SB + s); };
-    auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * UM_SA + 2 * UM_SB + i); };
-    auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * UM_SA + 2 * UM_SB + 2 + i); };
+__global__ void __launch_bounds__(UM_THREADS, 1) k_score_umma(const __grid_constant__ CUtensorMap tmap, ScoreArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem[];             // SWIZZLE_128B tiles need 1024-byte alignment
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_base = smem_base + UM_RING_BYTES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + UM_RING_BYTES + 256);   // after the 28 barriers
+    TileMeta *meta = reinterpret_cast<TileMeta *>(smem + UM_RING_BYTES + UM_BAR_BYTES);
+
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (UM_SA + s); };
+    auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * UM_SA + i); };
+    auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * UM_SA + 2 + i); };
+    auto mfull_bar = [&](int i) { return bar_base + 8u * (2 * UM_SA + 4 + i); };
+    auto mempty_bar = [&](int i) { return bar_base + 8u * (2 * UM_SA + 4 + UM_MD + i); };
+    // consumer side of the metadata ring: wait for tile `it`'s slot, copy what the role needs, release the slot
+    auto meta_acquire = [&](int it) -> const TileMeta * {
+        mbar_wait(mfull_bar(it % UM_MD), (uint32_t)(it / UM_MD) & 1u);
+        return meta + it % UM_MD;
+    };
+    auto meta_release = [&](int it) {
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(mempty_bar(it % UM_MD));
+    };
     auto a_smem = [&](int s) { return smem_base + (uint32_t)s * UM_A_BYTES; };
     auto b_smem = [&](int s, int t) { return smem_base + UM_SA * UM_A_BYTES + (uint32_t)s * UM_B_BYTES + (uint32_t)t * UM_BT_BYTES; };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_tiles = a.counters[CTR_N_UMMA];
+    if (warp == 1) UM_TRACE(0);
+    const int n_tiles = (a.flags & (1u << 31)) ? 0 : a.counters[CTR_N_UMMA];
     const int nkb = a.dim / UM_BLOCK_K;
     const int my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
         for (int s = 0; s < UM_SA; ++s) {
-            mbar_init(fullA(s), 1);            // TMA expect_tx arrive
-            mbar_init(emptyA(s), 1);           // tcgen05.commit
-        }
-        for (int s = 0; s < UM_SB; ++s) {
-            mbar_init(fullB(s), 1);            // the filler warp that owns the K block
-            mbar_init(emptyB(s), 1);           // tcgen05.commit
+            mbar_init(full_bar(s), 2);         // TMA expect_tx arrive + the filler warp that owns the stage
+            mbar_init(empty_bar(s), 1);        // tcgen05.commit
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(tfull_bar(i), 1);        // tcgen05.commit
             mbar_init(tempty_bar(i), 4);       // 4 epilogue warps
         }
+        for (int i = 0; i < UM_MD; ++i) {
+            mbar_init(mfull_bar(i), 1);        // metadata warp
+            mbar_init(mempty_bar(i), UM_META_CONSUMERS);
+        }
+        if (smem_base & 1023u) __trap();       // the dynamic shared window must start 1024-byte aligned
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -182,13 +216,17 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_score_umma(const __grid_const
         // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
         int s = 0;
         uint32_t ph = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int row0 = a.umma_items[tile].row0;
+        for (int it = 0; it < my_tiles; ++it) {
+            const int row0 = meta_acquire(it)->row0;
+            meta_release(it);
             for (int kb = 0; kb < nkb; ++kb) {
-                mbar_wait(emptyA(s), ph ^ 1u);
+                mbar_wait(empty_bar(s), ph ^ 1u);
                 if (elect_one()) {
-                    mbar_arrive_expect_tx(fullA(s), UM_A_BYTES);
-                    tma_load_2d(a_smem(s), &tmap, kb * UM_BLOCK_K, row0, fullA(s));
+                    if (a.flags & (1u << 28)) mbar_arrive(full_bar(s));
+                    else {
+                    mbar_arrive_expect_tx(full_bar(s), UM_A_BYTES);
+                    tma_load_2d(a_smem(s), &tmap, kb * UM_BLOCK_K, row0, full_bar(s));
+                    }
                 }
                 __syncwarp();
                 if (++s == UM_SA) { s = 0; ph ^= 1u; }
@@ -196,36 +234,40 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_score_umma(const __grid_const
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
-        int sa = 0, sb = 0;
-        uint32_t pha = 0, phb = 0;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            const int nq = a.umma_items[tile].nrows_nq >> 16;
+        int sa = 0;
+        uint32_t pha = 0;
+        UM_TRACE(1);
+        int tr = 2;
+        for (int it = 0; it < my_tiles; ++it) {
+            const int nq = meta_acquire(it)->nq;
+            meta_release(it);
+            UM_TRACE(tr); ++tr;           // metadata of tile `it` in hand
             const uint32_t idesc = umma_idesc(nq <= 16 ? 48 : 96);     // N = 3 terms x TS rows
             const int acc = it & 1;
             const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
             mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
             tc_fence_after();
+            UM_TRACE(tr); ++tr;           // accumulator free
             const uint32_t d_tmem = tmem_base + (uint32_t)acc * UM_ACC_COLS;
             for (int kb = 0; kb < nkb; ++kb) {
-                mbar_wait(fullB(sb), phb);
-                mbar_wait(fullA(sa), pha);
+                mbar_wait(full_bar(sa), pha);
                 tc_fence_after();
+                if (it < 3) { UM_TRACE(tr); ++tr; }   // K block data in hand (first three tiles only)
                 if (elect_one()) {
+                    if (!(a.flags & (1u << 29))) {
                     const uint64_t adesc = umma_smem_desc(a_smem(sa));
-                    const uint64_t bdesc = umma_smem_desc(b_smem(sb, 0));
+                    const uint64_t bdesc = umma_smem_desc(b_smem(sa, 0));
 #pragma unroll
                     for (int k = 0; k < UM_BLOCK_K / 16; ++k) {
                         // +32 bytes per UMMA_K = 16 bf16 inside the swizzle atom: +2 in the (addr >> 4) field
                         umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, k != 0 ? 1u : (kb != 0 ? 1u : 0u));
                     }
-                    umma_commit(emptyA(sa));
-                    umma_commit(emptyB(sb));
+                    }
+                    umma_commit(empty_bar(sa));
                     if (kb == nkb - 1) umma_commit(tfull_bar(acc));
                 }
                 __syncwarp();
                 if (++sa == UM_SA) { sa = 0; pha ^= 1u; }
-                if (++sb == UM_SB) { sb = 0; phb ^= 1u; }
             }
         }
     } else if (warp < 2 + UM_FILL_WARPS) {
@@ -233,20 +275,25 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_score_umma(const __grid_const
         const int fw = warp - 2;
         const bool per_beam = (a.flags & GDR_Q_PER_BEAM) != 0;
         const int total_kb = my_tiles * nkb;
+        // every filler warp consumes every tile's metadata slot (lane l caches the query row of pair l), including
+        // tiles in which it owns no K block, so the slot's consumer count is the same for all tiles
         int cur_it = -1, nq = 0, qrow = 0;
+        auto advance_to = [&](int it_target) {
+            while (cur_it < it_target) {
+                ++cur_it;
+                const TileMeta *m = meta_acquire(cur_it);
+                nq = m->nq;
+                qrow = m->qrow[lane];
+                meta_release(cur_it);
+            }
+        };
         for (int g = fw; g < total_kb; g += UM_FILL_WARPS) {
             const int it = g / nkb, kb = g - it * nkb;
-            if (it != cur_it) {                    // new tile: lane l caches the query row of pair l
-                cur_it = it;
-                const Item item = a.umma_items[blockIdx.x + it * gridDim.x];
-                nq = item.nrows_nq >> 16;
-                qrow = 0;
-                if (lane < nq) { const int p = a.grp_pair[item.slot0 + lane]; qrow = per_beam ? p : p / a.K; }
-            }
+            advance_to(it);
             const int sb = g % UM_SB;
             const uint32_t phb = (uint32_t)(g / UM_SB) & 1u;
             unsigned char *bst = smem + UM_SA * UM_A_BYTES + (size_t)sb * UM_B_BYTES;
-            const int n_tasks = nq * 8;            // one task = 8 fp32 of one pair = one 16-byte chunk per term
+            const int n_tasks = (a.flags & (1u << 30)) ? 0 : nq * 8;   // one task = 8 fp32 of one pair = one 16-byte chunk per term
             const int term_bytes = (nq <= 16 ? 16 : 32) * 128;     // rows of term t start t * TS rows into the B tile
             bool waited = false;
             for (int base = 0; base < n_tasks; base += 32 * UM_TASKS) {
@@ -262,7 +309,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_score_umma(const __grid_const
                         v[u][1] = __ldg(src + 1);
                     }
                 }
-                if (!waited) { mbar_wait(emptyB(sb), phb ^ 1u); waited = true; }
+                if (!waited) { mbar_wait(empty_bar(sb), phb ^ 1u); waited = true; }
 #pragma unroll
                 for (int u = 0; u < UM_TASKS; ++u) {
                     const int idx = base + u * 32 + lane;
@@ -280,25 +327,21 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_score_umma(const __grid_const
                     }
                 }
             }
-            if (!waited) mbar_wait(emptyB(sb), phb ^ 1u);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (!waited) mbar_wait(empty_bar(sb), phb ^ 1u);
+            if (!(a.flags & (1u << 27))) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(fullB(sb));
+            if (lane == 0) mbar_arrive(full_bar(sb));
         }
-    } else {
+        advance_to(my_tiles - 1);
+    } else if (warp < 2 + UM_FILL_WARPS + 4) {
         // ===================== epilogue (128 threads) =====================
         const int wq = warp & 3;                    // TMEM lane quarter this warp may read
         const int row = wq * 32 + lane;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            const Item item = a.umma_items[tile];
-            const int nrows = item.nrows_nq & 0xffff, nq = item.nrows_nq >> 16;
-            int64_t off = 0;                       // destination (row 0) of column `lane`
-            if (lane < nq) {
-                const int p = a.grp_pair[item.slot0 + lane];
-                const int b = p / a.K;
-                off = (int64_t)b * a.stride + a.candoff[p + b] + item.rel0;
-            }
+        for (int it = 0; it < my_tiles; ++it) {
+            const TileMeta *m = meta_acquire(it);
+            const int nrows = m->nrows, nq = m->nq;
+            const int64_t off = m->off[lane];      // lane l owns column l: where pair l's scores of this tile start
+            meta_release(it);
             const int acc = it & 1;
             const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
             mbar_wait(tfull_bar(acc), acc_ph);
@@ -336,6 +379,49 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_score_umma(const __grid_const
                 if (c < nq) {                                 // warp-uniform
                     const int64_t o = __shfl_sync(0xffffffffu, off, c);
                     if (row < nrows) a.scorebuf[o + row] = apply_act(sum[c], a.act);
+                }
+            }
+        }
+    }
+
+    else {
+        // ===================== tile metadata (one warp, four tiles per round so the three dependent loads overlap) =====================
+        for (int it0 = 0; it0 < my_tiles; it0 += UM_MD) {
+            Item item[UM_MD];
+            int pr[UM_MD];
+            int64_t off[UM_MD];
+#pragma unroll
+            for (int u = 0; u < UM_MD; ++u)
+                if (it0 + u < my_tiles) item[u] = a.umma_items[blockIdx.x + (it0 + u) * gridDim.x];
+#pragma unroll
+            for (int u = 0; u < UM_MD; ++u) {
+                pr[u] = 0;
+                if (it0 + u < my_tiles && lane < (item[u].nrows_nq >> 16)) pr[u] = a.grp_pair[item[u].slot0 + lane];
+            }
+#pragma unroll
+            for (int u = 0; u < UM_MD; ++u) {
+                off[u] = 0;
+                if (it0 + u < my_tiles && lane < (item[u].nrows_nq >> 16)) {
+                    const int b = pr[u] / a.K;
+                    off[u] = (int64_t)b * a.stride + a.candoff[pr[u] + b] + item[u].rel0;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UM_MD; ++u) {
+                const int it = it0 + u;
+                if (it < my_tiles) {
+                    mbar_wait(mempty_bar(u), ((uint32_t)(it / UM_MD) & 1u) ^ 1u);
+                    TileMeta *m = meta + u;
+                    if (lane == 0) {
+                        m->row0 = item[u].row0;
+                        m->nrows = item[u].nrows_nq & 0xffff;
+                        m->nq = item[u].nrows_nq >> 16;
+                        m->rel0 = item[u].rel0;
+                    }
+                    m->qrow[lane] = (a.flags & GDR_Q_PER_BEAM) ? pr[u] : pr[u] / a.K;
+                    m->off[lane] = off[u];
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(mfull_bar(u));
                 }
             }
         }

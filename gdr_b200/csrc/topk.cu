@@ -5,7 +5,7 @@
 // One CTA per query.  Candidate scores are read once from the score buffer (written by the scoring
 // kernels, normally still L2-resident), biased, mapped to order-preserving uint32 keys and kept in
 // shared memory (global scratch when a query has too many candidates).  The k-th largest key is
-// found with three histogram passes (12 + 10 + 10 bits, early exit when a bucket is taken whole);
+// found with three histogram passes (11 + 11 + 10 bits, early exit when a bucket is taken whole);
 // exact score ties at the threshold are broken by ascending docid with a second select over the
 // tied candidates, so the result does not depend on candidate order (and therefore not on how the
 // corpus is sharded across GPUs).  The same kernel, with an explicit candidate list as source,
@@ -15,7 +15,7 @@
 namespace gdr {
 
 constexpr int TK_THREADS = 256;
-constexpr int TK_BINS = 4096;
+constexpr int TK_BINS = 2048;      // 11-bit digits (sign + exponent + 2 mantissa bits in the first pass): 8 KB of shared memory
 
 struct TkShared {
     int sel_count;
@@ -39,8 +39,8 @@ __device__ Threshold radix_select(int n, int kk, uint32_t *hist, TkShared *sh, K
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #pragma unroll 1
     for (int pass = 0; pass < 3; ++pass) {
-        const int shift = pass == 0 ? 20 : (pass == 1 ? 10 : 0);
-        const int nb = pass == 0 ? 4096 : 1024;
+        const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);      // 11 + 11 + 10 bits
+        const int nb = pass == 2 ? 1024 : 2048;
         for (int i = tid; i < nb; i += TK_THREADS) hist[i] = 0;
         __syncthreads();
         for (int j = tid; j < n; j += TK_THREADS) {
@@ -209,8 +209,8 @@ __device__ void topk_general(const Src &src, int n, int k, int cap, uint32_t *ke
 
 
 // ---- fast path ---------------------------------------------------------------------------------
-// Two passes over the n keys instead of five: (1) build keys + 4096-bin histogram of the top 12 key bits,
-// (2) classify against the boundary bin: keys above it are selected outright, keys inside it (n/64 on
+// Two passes over the n keys instead of five: (1) build keys + 2048-bin histogram of the top 11 key bits,
+// (2) classify against the boundary bin: keys above it are selected outright, keys inside it (~n/32 on
 // spread-out scores) go to a small boundary list that is resolved by rank counting on (key, ~docid).
 // The k survivors are ordered by rank counting as well (k <= 256) — no bitonic network, ~7 barriers in all.
 // Falls back to the general radix select when the boundary bin holds more than TK_BND keys (mass ties).
@@ -230,20 +230,20 @@ __device__ void topk_body(const Src &src, int n, int k, int cap, uint32_t *keys,
     for (int j = tid; j < n; j += TK_THREADS) {
         const uint32_t key = float_to_ordered(src.score(j));
         keys[j] = key;
-        atomicAdd(&hist[key >> 20], 1u);
+        atomicAdd(&hist[key >> 21], 1u);
     }
     __syncthreads();
-    // boundary bin: warp w sums bins [512w, 512w + 512) with conflict-free strided reads ...
+    // boundary bin: warp w sums bins [256w, 256w + 256) with conflict-free strided reads ...
     {
         int part = 0;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) part += hist[warp * 512 + i * 32 + lane];
+        for (int i = 0; i < 8; ++i) part += hist[warp * 256 + i * 32 + lane];
 #pragma unroll
         for (int d = 16; d; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
         if (lane == 0) sh->warp_tot[warp] = part;
     }
     __syncthreads();
-    // ... then every warp redundantly walks down from the top to the 512-bin range and the bin where the
+    // ... then every warp redundantly walks down from the top to the 256-bin range and the bin where the
     // cumulative count reaches k (no further barrier needed: all threads end up with the same d / gt / eq)
     int above = 0, range = TK_THREADS / 32 - 1;
     for (; range > 0; --range) {
@@ -253,10 +253,10 @@ __device__ void topk_body(const Src &src, int n, int k, int cap, uint32_t *keys,
     }
     int d_bin, gt, eq;
     {
-        const int top = range * 512 + 512 - lane * 16;       // lane owns bins [top-16, top), lane 0 the highest
+        const int top = range * 256 + 256 - lane * 8;        // lane owns bins [top-8, top), lane 0 the highest
         int local = 0;
 #pragma unroll
-        for (int i = 1; i <= 16; ++i) local += hist[top - i];
+        for (int i = 1; i <= 8; ++i) local += hist[top - i];
         int incl = local;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -268,7 +268,7 @@ __device__ void topk_body(const Src &src, int n, int k, int cap, uint32_t *keys,
         int fb = 0, fg = 0, fe = 0;
         if (mine) {
             int running = above + incl - local;
-            for (int i = 1; i <= 16; ++i) {
+            for (int i = 1; i <= 8; ++i) {
                 const int h = hist[top - i];
                 if (running + h >= k) { fb = top - i; fg = running; fe = h; break; }
                 running += h;
@@ -286,12 +286,12 @@ __device__ void topk_body(const Src &src, int n, int k, int cap, uint32_t *keys,
         return;
     }
     // classify: sel[0, gt) <- keys above the boundary bin; bnd[0, eq) <- keys inside it   (bnd aliases hist)
-    uint64_t *bnd = reinterpret_cast<uint64_t *>(hist);           // 2 x TK_BND x 8 B << 16 KB
+    uint64_t *bnd = reinterpret_cast<uint64_t *>(hist);           // 2 x TK_BND x 8 B = 4 KB <= the 8 KB histogram
     uint64_t *bnd2 = bnd + TK_BND;
     __syncthreads();                                              // everyone is done reading hist
     for (int j = tid; j < n; j += TK_THREADS) {
         const uint32_t key = keys[j];
-        const int bin = (int)(key >> 20);
+        const int bin = (int)(key >> 21);
         if (bin > d_bin) sel[atomicAdd(&sh->sel_count, 1)] = ((uint64_t)key << 32) | (uint32_t)j;
         else if (bin == d_bin) bnd[atomicAdd(&sh->eq2_count, 1)] = ((uint64_t)key << 32) | (uint32_t)j;
     }
@@ -337,8 +337,8 @@ __device__ void topk_body(const Src &src, int n, int k, int cap, uint32_t *keys,
 
 // dynamic shared memory layout: sel[cap] u64 | hist[TK_BINS] u32 | co[K+1] i32 | cbase[K] i32 | keys[...] u32 (smem variant)
 template <bool KEYS_IN_SMEM>
-__global__ void __launch_bounds__(TK_THREADS) k_topk_store(ScoreArgs a, float alpha, int cap, float *out_scores,
-                                                           int32_t *out_docids) {
+__global__ void __launch_bounds__(TK_THREADS, 8) k_topk_store(ScoreArgs a, float alpha, int cap, float *out_scores,
+                                                              int32_t *out_docids) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ TkShared sh;
     uint64_t *sel = reinterpret_cast<uint64_t *>(smem);
@@ -380,7 +380,7 @@ static int pow2_at_least(int x) { int p = 2; while (p < x) p <<= 1; return p; }
 cudaError_t launch_topk_store(const ScoreArgs &a, float alpha, float *out_scores, int32_t *out_docids, cudaStream_t s) {
     if (a.B == 0) return cudaSuccess;
     const int cap = pow2_at_least(a.k);
-    const size_t fixed = (size_t)cap * 8 + TK_BINS * 4 + (size_t)(2 * a.K + 1) * 4;
+    const size_t fixed = (size_t)cap * 8 + (size_t)TK_BINS * 4 + (size_t)(2 * a.K + 1) * 4;
     const size_t with_keys = fixed + (size_t)a.stride * 4;
     if (with_keys <= 96 * 1024) {
         static bool attr_set = false;

@@ -137,6 +137,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--replicas", type=int, default=0, help="store replicas cycled to defeat L2 (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pipeline", type=int, default=3, help="independent batches kept in flight on separate CUDA streams (1 = strictly serial)")
     ap.add_argument("--no-graph", action="store_true", help="launch every step from the host instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -210,30 +211,67 @@ def main():
         # rank r owns global clusters [r*C, (r+1)*C): contiguous blocks are already balanced for this synthetic corpus
         g2l = torch.full((C_total,), -1, dtype=torch.int32, device=dev)
         g2l[rank * cfg["C"]:(rank + 1) * cfg["C"]] = torch.arange(cfg["C"], dtype=torch.int32, device=dev)
-        retrievers = [ShardedRetriever(s, g2l) for s in stores]
 
-    out_s = torch.empty((1, B_global, k), dtype=torch.float32, device=dev)
-    out_d = torch.empty((1, B_global, k), dtype=torch.int32, device=dev)
+    # Batches are independent, so `n_pipe` of them are kept in flight on `n_pipe` CUDA streams, each with its own
+    # store handles (= its own scratch) and result buffers: the latency-bound inversion and top-k kernels of one batch
+    # co-reside with, and hide under, the HBM-bound scoring kernel of its neighbours.
+    n_pipe = 1 if world > 1 else max(1, args.pipeline)
+    pipes = []
+    for p in range(n_pipe):
+        st_p = stores if p == 0 else [ClusterStore(s0.emb, torch.as_tensor(s0.offsets_host), s0.docid) for s0 in stores]
+        pipes.append(dict(
+            stream=torch.cuda.Stream(), stores=st_p,
+            retr=[ShardedRetriever(x, g2l) for x in st_p] if world > 1 else None,
+            q=torch.empty_like(batches[0][0]), b=torch.empty_like(batches[0][1]),
+            out_s=torch.empty((1, B_global, k), dtype=torch.float32, device=dev),
+            out_d=torch.empty((1, B_global, k), dtype=torch.int32, device=dev),
+            res_s=torch.empty((B_global, k), dtype=torch.float32).pin_memory(),
+            res_d=torch.empty((B_global, k), dtype=torch.int32).pin_memory()))
 
-    def step(i):
+    def step(i, P=None):
+        """One pass of the hot path over one device-resident batch."""
+        P = P or pipes[0]
         q, beams = batches[i % n_batches]
         if world == 1:
-            stores[i % replicas].score_topk(q, beams, k, out=(out_s, out_d))
+            P["stores"][i % replicas].score_topk(q, beams, k, out=(P["out_s"], P["out_d"]))
         else:
-            return retrievers[i % replicas].score_topk(q, beams, k)
+            return P["retr"][i % replicas].score_topk(q, beams, k)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(args.warmup, replicas)):
-        step(i)
+    def fork(cur):
+        for P in pipes:
+            P["stream"].wait_stream(cur)
+
+    def join(cur):
+        for P in pipes:
+            cur.wait_stream(P["stream"])
+
+    def run_steps(n, cur):
+        """n steps round-robin over the pipes' streams (fork/join on `cur`, so it is capturable into one graph)."""
+        if n_pipe == 1:
+            for i in range(n):
+                step(i)
+            return
+        fork(cur)
+        for i in range(n):
+            P = pipes[i % n_pipe]
+            with torch.cuda.stream(P["stream"]):
+                step(i, P)
+        join(cur)
+
+    for P in pipes:                                   # every (pipe, replica) handle allocates its scratch once
+        with torch.cuda.stream(P["stream"]):
+            for i in range(max(args.warmup, replicas)):
+                step(i, P)
     barrier()
     stats = stores[0].last_stats()
 
-    # CUDA graph of `period` consecutive steps (one per replica/batch combination), replayed: removes host launch latency
-    period = replicas * n_batches // math.gcd(replicas, n_batches)
+    # CUDA graph of `period` consecutive steps (every replica / batch / pipe combination once), replayed: no host launch latency
+    period = math.lcm(replicas, n_batches, n_pipe)
     use_graph = world == 1 and not args.no_graph and args.steps >= period
     graph = None
     if use_graph:
@@ -242,8 +280,7 @@ def main():
         with torch.cuda.stream(side):
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, stream=side):
-                for i in range(period):
-                    step(i)
+                run_steps(period, side)
         torch.cuda.current_stream().wait_stream(side)
         graph.replay()
         barrier()
@@ -258,8 +295,7 @@ def main():
         for _ in range(steps // period):
             graph.replay()
     else:
-        for i in range(steps):
-            step(i)
+        run_steps(steps, torch.cuda.current_stream())
     e1.record()
     barrier()
     t_wall1 = time.time()
@@ -284,34 +320,39 @@ def main():
     for s in stores:
         s.set_profiling(False)
 
-    # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region
+    # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region.
+    # Every step copies ITS inputs host->device and ITS results device->host; steps are issued round-robin on
+    # `n_pipe` CUDA streams (each with its own device/host buffers and its own store handle = its own scratch),
+    # so step i+1's H2D overlaps step i's kernels and step i-1's D2H — the way a serving loop would run it.
     q_host = [b[0].cpu().pin_memory() for b in batches]
     beams_host = [b[1].cpu().pin_memory() for b in batches]
-    res_s = torch.empty((B_global, k), dtype=torch.float32).pin_memory()
-    res_d = torch.empty((B_global, k), dtype=torch.int32).pin_memory()
-    q_dev = [torch.empty_like(batches[0][0]) for _ in range(2)]
-    b_dev = [torch.empty_like(batches[0][1]) for _ in range(2)]
 
     def e2e_step(i):
-        j = i & 1
-        q_dev[j].copy_(q_host[i % n_batches], non_blocking=True)
-        b_dev[j].copy_(beams_host[i % n_batches], non_blocking=True)
-        if world == 1:
-            stores[i % replicas].score_topk(q_dev[j], b_dev[j], k, out=(out_s, out_d))
-            res_s.copy_(out_s[0], non_blocking=True)
-            res_d.copy_(out_d[0], non_blocking=True)
-        else:
-            s, d = retrievers[i % replicas].score_topk(q_dev[j], b_dev[j], k)
-            res_s.copy_(s, non_blocking=True)
-            res_d.copy_(d, non_blocking=True)
+        P = pipes[i % n_pipe]
+        with torch.cuda.stream(P["stream"]):
+            P["q"].copy_(q_host[i % n_batches], non_blocking=True)
+            P["b"].copy_(beams_host[i % n_batches], non_blocking=True)
+            if world == 1:
+                P["stores"][i % replicas].score_topk(P["q"], P["b"], k, out=(P["out_s"], P["out_d"]))
+                P["res_s"].copy_(P["out_s"][0], non_blocking=True)
+                P["res_d"].copy_(P["out_d"][0], non_blocking=True)
+            else:
+                s_, d_ = P["retr"][i % replicas].score_topk(P["q"], P["b"], k)
+                P["res_s"].copy_(s_, non_blocking=True)
+                P["res_d"].copy_(d_, non_blocking=True)
 
-    e2e_steps = max(8, min(steps, 64))
-    for i in range(3):
+    e2e_steps = max(12, min(steps, 96))
+    for i in range(2 * n_pipe * replicas):      # warm-up: every (pipe, replica) handle allocates its scratch
         e2e_step(i)
     barrier()
+    cur = torch.cuda.current_stream()
     e0.record()
+    for P in pipes:
+        P["stream"].wait_event(e0)
     for i in range(e2e_steps):
         e2e_step(i)
+    for P in pipes:
+        cur.wait_stream(P["stream"])
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
@@ -364,9 +405,10 @@ def main():
         "config": {"workload": args.workload + ("" if world == 1 else f" x{world} cluster-sharded"), "docs_per_gpu": cfg["N"],
                    "clusters_per_gpu": cfg["C"], "dim": D, "global_batch": B_global, "beam": K, "top_k": k,
                    "l2": f"{replicas} store replicas ({replicas * emb_bytes / 2**20:.0f} MB) and {n_batches} query batches cycled; inputs larger than L2",
-                   "cuda_graph": bool(use_graph), "parallelism": "single GPU" if world == 1 else f"clusters sharded over {world} GPUs + NCCL all-gather + merge"},
+                   "cuda_graph": bool(use_graph), "batches_in_flight": n_pipe, "parallelism": "single GPU" if world == 1 else f"clusters sharded over {world} GPUs + NCCL all-gather + merge"},
         "clocks": clocks, "gpu_launches": int(stats["launches"]) * steps + (0 if world == 1 else steps),
-        "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+        "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "pipeline": f"{n_pipe} batches in flight on {n_pipe} CUDA streams, pinned host buffers, per-step H2D of q+beams and D2H of (score, docid)"},
         "roofline": roofline, "cpu_baseline": cpu,
         "path": {"simt_items": int(stats["simt_items"]), "umma_tiles": int(stats["umma_tiles"]), "clusters_touched": int(stats["clusters_touched"])},
     }

@@ -233,8 +233,14 @@ int gdr_store_last_stats(gdr_store_t *s, int64_t out[4], void *stream) {
         long long h[512];
         GDR_CUDA(cudaMemcpy(h, s->dbg, sizeof(h), cudaMemcpyDeviceToHost));
         fprintf(stderr, "[umma trace] ");
-        for (int i = 1; i < 512 && h[i]; ++i) fprintf(stderr, "%lld ", h[i] - h[0]);
-        fprintf(stderr, "\n");
+        for (int i = 1; i < 200 && h[i]; ++i) fprintf(stderr, "%lld ", h[i] - h[0]);
+        long long smin = 1LL << 62, smax = 0, emin = 1LL << 62, emax = 0;
+        for (int c = 0; c < 148; ++c) {
+            const long long st = h[200 + 2 * c] - h[0], en = h[201 + 2 * c] - h[0];
+            if (!h[200 + 2 * c]) continue;
+            smin = st < smin ? st : smin; smax = st > smax ? st : smax; emin = en < emin ? en : emin; emax = en > emax ? en : emax;
+        }
+        fprintf(stderr, "| CTA loop start min %lld max %lld, end min %lld max %lld\n", smin, smax, emin, emax);
     }
     const size_t n = (size_t)s->n_clusters;
     GDR_CUDA(cudaMemcpy(c, s->cluster_ws + n + 3 * (n + 1), sizeof(c), cudaMemcpyDeviceToHost));

@@ -87,6 +87,29 @@ cudaError_t launch_tree_mask(const int32_t *first_child, const int32_t *child_to
 cudaError_t launch_position_mask(float *logits, int64_t bz, int sl, int V, int v_out, int last_eos_only,
                                  cudaStream_t s);
 
+// ----- programmatic dependent launch ---------------------------------------------------------
+// Every kernel of the chain (count -> scan -> fill -> score -> top-k) is launched with the PDL attribute: its
+// CTAs may be scheduled, and run their prologue (shared-memory carve-up, barrier init, TMEM allocation), while
+// the previous kernel is still draining.  pdl_wait() blocks until the previous kernel has completed and its
+// writes are visible; it must precede the first access to anything an earlier kernel produced or still reads.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ----- small device helpers -----------------------------------------------------------------
 __device__ __forceinline__ uint32_t float_to_ordered(float f) {
     uint32_t u = __float_as_uint(f);

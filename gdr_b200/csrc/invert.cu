@@ -40,6 +40,8 @@ __device__ __forceinline__ void count_query(const ScoreArgs &a, int b, int lane,
 }
 
 __global__ void __launch_bounds__(128) k_count(ScoreArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();                 // candoff is still read by the previous call's top-k
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (warp < a.B) count_query(a, warp, threadIdx.x & 31, a.cnt);
 }
@@ -106,6 +108,8 @@ __device__ __forceinline__ void block_scan3(int &x, int &y, int &z, int tot[3], 
 
 __global__ void __launch_bounds__(1024) k_scan(ScoreArgs a) {
     __shared__ int wsum[32][3];
+    pdl_launch_dependents();
+    pdl_wait();
     int carry[3] = {0, 0, 0};
     int touched = 0;
     const int C = a.n_clusters;
@@ -147,6 +151,8 @@ __global__ void __launch_bounds__(1024) k_scan(ScoreArgs a) {
 }
 
 __global__ void __launch_bounds__(256) k_fill(ScoreArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t n_pairs = (int64_t)a.B * a.K;
     if (t < n_pairs) {
@@ -174,8 +180,10 @@ __global__ void __launch_bounds__(1024) k_invert_small(ScoreArgs a) {
     __shared__ int wsum[32][3];
     const int C = a.n_clusters;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_launch_dependents();
     for (int c = tid; c < C; c += 1024) s_cnt[c] = 0;
     __syncthreads();
+    pdl_wait();
     for (int b = warp; b < a.B; b += 32) count_query(a, b, lane, s_cnt);
     __syncthreads();
     int carry[3] = {0, 0, 0};
@@ -221,16 +229,15 @@ __global__ void __launch_bounds__(1024) k_invert_small(ScoreArgs a) {
 
 cudaError_t launch_invert(const ScoreArgs &a, cudaStream_t s, int *n_launches) {
     if (a.n_clusters <= INV_SMALL_C && a.B <= 64 && (int64_t)a.B * a.K <= 65536) {   // small batches (the reference's eval_batch_size 1-64)
-        k_invert_small<<<1, 1024, 0, s>>>(a);
         *n_launches += 1;
-        return cudaGetLastError();
+        return launch_pdl(k_invert_small, dim3(1), dim3(1024), 0, s, a);
     }
-    k_count<<<(a.B + 3) / 4, 128, 0, s>>>(a);
-    k_scan<<<1, 1024, 0, s>>>(a);
+    cudaError_t e = launch_pdl(k_count, dim3((a.B + 3) / 4), dim3(128), 0, s, a);
+    if (e == cudaSuccess) e = launch_pdl(k_scan, dim3(1), dim3(1024), 0, s, a);
     const int64_t n = max((int64_t)a.B * a.K, (int64_t)a.n_clusters);
-    k_fill<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a);
+    if (e == cudaSuccess) e = launch_pdl(k_fill, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, a);
     *n_launches += 3;
-    return cudaGetLastError();
+    return e;
 }
 
 }  // namespace gdr

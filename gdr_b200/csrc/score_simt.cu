@@ -141,6 +141,8 @@ __global__ void __launch_bounds__(128) k_score_simt(ScoreArgs a) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    pdl_launch_dependents();
+    pdl_wait();
     const int n_items = a.counters[CTR_N_SIMT];
     const bool per_beam = (a.flags & GDR_Q_PER_BEAM) != 0;
     const T *emb = reinterpret_cast<const T *>(a.emb);
@@ -226,9 +228,9 @@ template <typename T> static int cpl_for(int dim) {
 cudaError_t launch_score_simt(const ScoreArgs &a, cudaStream_t s, int sm_count) {
     const int grid = sm_count * 8;   // persistent warps: 8 CTAs x 4 warps per SM, items strided
     if (a.dtype == GDR_DTYPE_BF16) {
-        GDR_DISPATCH_CPL(__nv_bfloat16, cpl_for<__nv_bfloat16>(a.dim), (k_score_simt<__nv_bfloat16, CPL><<<grid, 128, 0, s>>>(a)));
+        GDR_DISPATCH_CPL(__nv_bfloat16, cpl_for<__nv_bfloat16>(a.dim), return launch_pdl(k_score_simt<__nv_bfloat16, CPL>, dim3(grid), dim3(128), 0, s, a));
     } else {
-        GDR_DISPATCH_CPL(float, cpl_for<float>(a.dim), (k_score_simt<float, CPL><<<grid, 128, 0, s>>>(a)));
+        GDR_DISPATCH_CPL(float, cpl_for<float>(a.dim), return launch_pdl(k_score_simt<float, CPL>, dim3(grid), dim3(128), 0, s, a));
     }
     return cudaGetLastError();
 }

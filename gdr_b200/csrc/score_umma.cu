@@ -17,7 +17,7 @@
 // embeddings and issues 12 x 4 MMAs of 128 x 96 x 16.
 //
 // Warp roles (480 threads, one persistent CTA per SM, tiles strided over CTAs):
-//   warp 0       TMA producer: A tiles of the store, 6-stage ring (96 KB in flight per SM), mbarrier complete_tx
+//   warp 0       TMA producer: A tiles of the store, 8-stage ring shared with B (128 KB of A in flight per SM)
 //   warp 1       MMA issuer (one lane): tcgen05.mma cta_group::1 kind::f16; commits free the A and B stages
 //   warps 2-9    B fillers, one K block per warp in flight (8 blocks' L2 latency overlapped): gather the
 //                group's fp32 query rows (L2-resident), split them into hi/mid/lo bf16 in registers, store
@@ -52,7 +52,7 @@ struct __align__(16) TileMeta {                // one tile's metadata, written b
     int32_t qrow[UMMA_NQ];                     // query row of each pair (B fillers)
     int64_t off[UMMA_NQ];                      // score-buffer offset of each pair's first row (epilogue)
 };
-constexpr int UM_META_CONSUMERS = 2 + UM_FILL_WARPS + 4;    // TMA, MMA, fillers, epilogue warps
+constexpr int UM_META_CONSUMERS = 1 + UM_FILL_WARPS + 4;    // MMA, fillers, epilogue warps
 constexpr int UM_BAR_BYTES = 512;
 constexpr int UM_SMEM_BYTES = UM_RING_BYTES + UM_BAR_BYTES + UM_MD * (int)sizeof(TileMeta);
 static_assert(UM_SMEM_BYTES <= 227 * 1024, "shared memory budget");
@@ -152,7 +152,7 @@ __device__ __forceinline__ long long gtime() {
     return t;
 }
 // timeline trace (GDR_UMMA_TRACE=1): CTA 0's MMA warp stamps slot i with the global timer
-#define UM_TRACE(i) do { if (a.dbg && blockIdx.x == 0 && lane == 0 && (i) < 512) a.dbg[(i)] = gtime(); } while (0)
+#define UM_TRACE(i) do { if (a.dbg && blockIdx.x == 0 && lane == 0 && (i) < 200) a.dbg[(i)] = gtime(); } while (0)
 
 __global__ void __launch_bounds__(UM_THREADS, 1) k_score_umma(const __grid_constant__ CUtensorMap tmap, ScoreArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];             // SWIZZLE_128B tiles need 1024-byte alignment
@@ -181,9 +181,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_score_umma(const __grid_const
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 1) UM_TRACE(0);
-    const int n_tiles = (a.flags & (1u << 31)) ? 0 : a.counters[CTR_N_UMMA];
+    pdl_launch_dependents();
     const int nkb = a.dim / UM_BLOCK_K;
-    const int my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
@@ -211,14 +210,21 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_score_umma(const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // everything above (barrier init, TMEM allocation) overlapped the inversion kernels; its outputs are read from here on
+    pdl_wait();
+    const int n_tiles = (a.flags & (1u << 31)) ? 0 : a.counters[CTR_N_UMMA];
+    const int my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
     if (warp == 0) {
         // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
         int s = 0;
         uint32_t ph = 0;
+        // the TMA warp needs only row0 (one load, fetched a tile ahead) and must not wait for the three-load
+        // metadata chain: the first TMA is what the whole CTA's start-up latency hangs on
+        int row0_next = my_tiles > 0 ? a.umma_items[blockIdx.x].row0 : 0;
         for (int it = 0; it < my_tiles; ++it) {
-            const int row0 = meta_acquire(it)->row0;
-            meta_release(it);
+            const int row0 = row0_next;
+            if (it + 1 < my_tiles) row0_next = a.umma_items[blockIdx.x + (it + 1) * gridDim.x].row0;
             for (int kb = 0; kb < nkb; ++kb) {
                 mbar_wait(empty_bar(s), ph ^ 1u);
                 if (elect_one()) {
@@ -237,6 +243,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_score_umma(const __grid_const
         int sa = 0;
         uint32_t pha = 0;
         UM_TRACE(1);
+        if (a.dbg && lane == 0) a.dbg[200 + 2 * blockIdx.x] = gtime();      // every CTA: loop start / end
         int tr = 2;
         for (int it = 0; it < my_tiles; ++it) {
             const int nq = meta_acquire(it)->nq;
@@ -270,6 +277,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_score_umma(const __grid_const
                 if (++sa == UM_SA) { sa = 0; pha ^= 1u; }
             }
         }
+        if (a.dbg && lane == 0) a.dbg[201 + 2 * blockIdx.x] = gtime();
     } else if (warp < 2 + UM_FILL_WARPS) {
         // ===================== B fillers: warp fw owns K blocks g = fw, fw + 8, ... of this CTA's stream =====================
         const int fw = warp - 2;
@@ -466,8 +474,7 @@ cudaError_t launch_score_umma(const ScoreArgs &a, const CUtensorMap *tmap, cudaS
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    k_score_umma<<<sm_count, UM_THREADS, UM_SMEM_BYTES, s>>>(*tmap, a);
-    return cudaGetLastError();
+    return launch_pdl(k_score_umma, dim3(sm_count), dim3(UM_THREADS), UM_SMEM_BYTES, s, *tmap, a);
 }
 
 }  // namespace gdr

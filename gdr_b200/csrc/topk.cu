@@ -20,6 +20,8 @@ constexpr int TK_BINS = 2048;      // 11-bit digits (sign + exponent + 2 mantiss
 struct TkShared {
     int sel_count;
     int eq2_count;
+    int bnd_count;
+    uint32_t hist2[256];
     int found_bin, found_gt, found_eq;
     int warp_tot[TK_THREADS / 32];
 };
@@ -135,6 +137,16 @@ struct StoreSrc {   // a query's candidates = its K beam segments of the score b
         const int i = seg(j);
         return docid[cbase[i] + (j - co[i])];
     }
+    // four consecutive candidates starting at j4 (multiple of 4; the score row is 16-byte aligned and padded)
+    __device__ void score4(int j4, int n, float (&s)[4]) const {
+        const float4 v = *reinterpret_cast<const float4 *>(sb + j4);
+        s[0] = v.x; s[1] = v.y; s[2] = v.z; s[3] = v.w;
+        if (prob) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (j4 + e < n) s[e] = __fadd_rn(s[e], __fmul_rn(alpha, prob[seg(j4 + e)]));
+        }
+    }
 };
 
 struct ListSrc {    // explicit candidate lists from G ranks: [G, B, k_in]
@@ -145,6 +157,10 @@ struct ListSrc {    // explicit candidate lists from G ranks: [G, B, k_in]
     __device__ int64_t at(int j) const { return (int64_t)(j / k_in) * g_stride + (j % k_in); }
     __device__ float score(int j) const { return scores[at(j)]; }
     __device__ int32_t doc(int j) const { return docids[at(j)]; }
+    __device__ void score4(int j4, int n, float (&s)[4]) const {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) s[e] = j4 + e < n ? scores[at(j4 + e)] : 0.f;
+    }
 };
 
 template <typename Src>
@@ -208,29 +224,103 @@ __device__ void topk_general(const Src &src, int n, int k, int cap, uint32_t *ke
 }
 
 
+// One warp, 256 bins, lane owns bins [256 - 8*lane - 8, 256 - 8*lane) (lane 0 the highest): find the bin d where
+// the count accumulated from the top reaches `need`; gt = count strictly above d, eq = count in d.
+__device__ __forceinline__ void scan_down8(const uint32_t *bins, int lane, int need, int &d, int &gt, int &eq) {
+    const int top = 256 - lane * 8;
+    int local = 0;
+#pragma unroll
+    for (int i = 1; i <= 8; ++i) local += (int)bins[top - i];
+    int incl = local;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, s);
+        if (lane >= s) incl += t;
+    }
+    const bool mine = (incl - local) < need && need <= incl;
+    int fb = 0, fg = 0, fe = 0;
+    if (mine) {
+        int running = incl - local;
+        for (int i = 1; i <= 8; ++i) {
+            const int h = (int)bins[top - i];
+            if (running + h >= need) { fb = top - i; fg = running; fe = h; break; }
+            running += h;
+        }
+    }
+    const unsigned who = __ballot_sync(0xffffffffu, mine);
+    const int srcl = __ffs(who) - 1;
+    d = __shfl_sync(0xffffffffu, fb, srcl);
+    gt = __shfl_sync(0xffffffffu, fg, srcl);
+    eq = __shfl_sync(0xffffffffu, fe, srcl);
+}
+
 // ---- fast path ---------------------------------------------------------------------------------
-// Two passes over the n keys instead of five: (1) build keys + 2048-bin histogram of the top 11 key bits,
-// (2) classify against the boundary bin: keys above it are selected outright, keys inside it (~n/32 on
-// spread-out scores) go to a small boundary list that is resolved by rank counting on (key, ~docid).
-// The k survivors are ordered by rank counting as well (k <= 256) — no bitonic network, ~7 barriers in all.
-// Falls back to the general radix select when the boundary bin holds more than TK_BND keys (mass ties).
+// For k <= 128 (the reference's top-100) and more candidates than k.  Two passes over the n keys:
+//   (1) build keys (128-bit loads) + 2048-bin histogram of the top 11 key bits;
+//   (2) classify against the boundary bin: keys above it are selected outright, keys inside it (~n/32 on
+//       spread-out scores) go to a short boundary list and into a 256-bin histogram of the next 8 bits;
+// the boundary list is then cut by that second histogram, what is left tied after 19 bits (normally 1-2
+// keys) is ordered by rank counting on (key, ~docid), and the k survivors are sorted by ONE warp with a
+// register bitonic network (4 keys per lane, shuffles only).  ~8 block barriers in all.  Falls back to the
+// general radix select when the boundary bin holds more than TK_BND keys (mass ties).
 constexpr int TK_BND = 256;
+
+// descending bitonic sort of 128 u64 keys held 4 per lane (element index = lane * 4 + r)
+__device__ __forceinline__ void warp_bitonic128_desc(uint64_t (&v)[4], int lane) {
+#pragma unroll
+    for (int size = 2; size <= 128; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride >= 4) {
+                const int lm = stride >> 2;
+                const bool lower = (lane & lm) == 0;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const uint64_t other = __shfl_xor_sync(0xffffffffu, v[r], lm);
+                    const bool desc = (((lane * 4 + r) & size) == 0);
+                    const bool want_max = (lower == desc);
+                    const uint64_t mx = v[r] > other ? v[r] : other, mn = v[r] > other ? other : v[r];
+                    v[r] = want_max ? mx : mn;
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    if ((r & stride) == 0) {
+                        const int p = r | stride;
+                        const bool desc = (((lane * 4 + r) & size) == 0);
+                        const uint64_t mx = v[r] > v[p] ? v[r] : v[p], mn = v[r] > v[p] ? v[p] : v[r];
+                        v[r] = desc ? mx : mn;
+                        v[p] = desc ? mn : mx;
+                    }
+                }
+            }
+        }
+    }
+}
 
 template <typename Src>
 __device__ void topk_body(const Src &src, int n, int k, int cap, uint32_t *keys, uint64_t *sel, uint32_t *hist,
                           TkShared *sh, float *out_s, int32_t *out_d) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (n <= k || cap > 256) {     // few candidates (take all) or large k: general path
+    if (n <= k || cap > 128) {     // few candidates (take all) or large k: general path
         topk_general(src, n, k, cap, keys, sel, hist, sh, out_s, out_d);
         return;
     }
     for (int i = tid; i < TK_BINS; i += TK_THREADS) hist[i] = 0;
-    if (tid == 0) { sh->sel_count = 0; sh->eq2_count = 0; }
+    sh->hist2[tid] = 0;                                           // TK_THREADS == 256 bins
+    if (tid == 0) { sh->sel_count = 0; sh->eq2_count = 0; sh->bnd_count = 0; }
     __syncthreads();
-    for (int j = tid; j < n; j += TK_THREADS) {
-        const uint32_t key = float_to_ordered(src.score(j));
-        keys[j] = key;
-        atomicAdd(&hist[key >> 21], 1u);
+    // pass 1: keys + histogram, four candidates per thread and iteration
+    for (int j4 = tid * 4; j4 < n; j4 += TK_THREADS * 4) {
+        float s4[4];
+        src.score4(j4, n, s4);
+        uint32_t k4[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            k4[e] = float_to_ordered(s4[e]);
+            if (j4 + e < n) atomicAdd(&hist[k4[e] >> 21], 1u);
+        }
+        *reinterpret_cast<uint4 *>(keys + j4) = make_uint4(k4[0], k4[1], k4[2], k4[3]);
     }
     __syncthreads();
     // boundary bin: warp w sums bins [256w, 256w + 256) with conflict-free strided reads ...
@@ -252,90 +342,92 @@ __device__ void topk_body(const Src &src, int n, int k, int cap, uint32_t *keys,
         above += t;
     }
     int d_bin, gt, eq;
-    {
-        const int top = range * 256 + 256 - lane * 8;        // lane owns bins [top-8, top), lane 0 the highest
-        int local = 0;
-#pragma unroll
-        for (int i = 1; i <= 8; ++i) local += hist[top - i];
-        int incl = local;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += t;
-        }
-        const int need_here = k - above;
-        const bool mine = (incl - local) < need_here && need_here <= incl;
-        int fb = 0, fg = 0, fe = 0;
-        if (mine) {
-            int running = above + incl - local;
-            for (int i = 1; i <= 8; ++i) {
-                const int h = hist[top - i];
-                if (running + h >= k) { fb = top - i; fg = running; fe = h; break; }
-                running += h;
-            }
-        }
-        const unsigned who = __ballot_sync(0xffffffffu, mine);
-        const int srcl = __ffs(who) - 1;
-        d_bin = __shfl_sync(0xffffffffu, fb, srcl);
-        gt = __shfl_sync(0xffffffffu, fg, srcl);
-        eq = __shfl_sync(0xffffffffu, fe, srcl);
-    }
+    scan_down8(hist + range * 256, lane, k - above, d_bin, gt, eq);
+    d_bin += range * 256;
+    gt += above;
     if (eq > TK_BND) {             // mass ties in the boundary bin: general path (uniform decision)
         __syncthreads();
         topk_general(src, n, k, cap, keys, sel, hist, sh, out_s, out_d);
         return;
     }
-    // classify: sel[0, gt) <- keys above the boundary bin; bnd[0, eq) <- keys inside it   (bnd aliases hist)
+    // pass 2: classify.  sel[0, gt) <- keys above the boundary bin; bnd[0, eq) <- keys inside it (bnd aliases hist)
     uint64_t *bnd = reinterpret_cast<uint64_t *>(hist);           // 2 x TK_BND x 8 B = 4 KB <= the 8 KB histogram
     uint64_t *bnd2 = bnd + TK_BND;
     __syncthreads();                                              // everyone is done reading hist
-    for (int j = tid; j < n; j += TK_THREADS) {
-        const uint32_t key = keys[j];
-        const int bin = (int)(key >> 21);
-        if (bin > d_bin) sel[atomicAdd(&sh->sel_count, 1)] = ((uint64_t)key << 32) | (uint32_t)j;
-        else if (bin == d_bin) bnd[atomicAdd(&sh->eq2_count, 1)] = ((uint64_t)key << 32) | (uint32_t)j;
+    for (int j4 = tid * 4; j4 < n; j4 += TK_THREADS * 4) {
+        const uint4 kv = *reinterpret_cast<const uint4 *>(keys + j4);
+        const uint32_t k4[4] = {kv.x, kv.y, kv.z, kv.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (j4 + e < n) {
+                const uint32_t key = k4[e];
+                const int bin = (int)(key >> 21);
+                if (bin > d_bin) sel[atomicAdd(&sh->sel_count, 1)] = ((uint64_t)key << 32) | (uint32_t)(j4 + e);
+                else if (bin == d_bin) {
+                    bnd[atomicAdd(&sh->bnd_count, 1)] = ((uint64_t)key << 32) | (uint32_t)(j4 + e);
+                    atomicAdd(&sh->hist2[(key >> 13) & 255u], 1u);
+                }
+            }
+        }
     }
     __syncthreads();
-    const int need = k - gt;                                      // 1 <= need <= eq
-    if (need == eq) {
-        if (tid < eq) sel[gt + tid] = bnd[tid];
+    // cut the boundary list with the next 8 key bits
+    int d2, gt2, eq2;
+    scan_down8(sh->hist2, lane, k - gt, d2, gt2, eq2);
+    const int need2 = k - gt - gt2;                               // 1 <= need2 <= eq2
+    if (tid < eq) {
+        const uint64_t e = bnd[tid];
+        const int sub = (int)((e >> 45) & 255u);
+        if (sub > d2) sel[atomicAdd(&sh->sel_count, 1)] = e;
+        else if (sub == d2) bnd2[atomicAdd(&sh->eq2_count, 1)] = e;
+    }
+    __syncthreads();
+    if (need2 == eq2) {
+        if (tid < eq2) sel[gt + gt2 + tid] = bnd2[tid];
     } else {
-        // order the boundary keys by (key desc, docid asc); duplicates of the same (key, docid) by list position
-        if (tid < eq) {
-            const uint64_t e = bnd[tid];
-            bnd2[tid] = (e & 0xffffffff00000000ull) | (uint32_t)~(uint32_t)src.doc((int)(uint32_t)e);
+        // still tied after 19 key bits: order by (key desc, docid asc); identical (key, docid) pairs by list position
+        uint64_t mine = 0, orig = 0;
+        if (tid < eq2) {
+            orig = bnd2[tid];
+            mine = (orig & 0xffffffff00000000ull) | (uint32_t)~(uint32_t)src.doc((int)(uint32_t)orig);
+            bnd2[tid] = mine;                                     // own slot only; others read it after the barrier
         }
         __syncthreads();
-        if (tid < eq) {
-            const uint64_t mine = bnd2[tid];
+        if (tid < eq2) {
             int rank = 0;
-            for (int u = 0; u < eq; ++u) {
+            for (int u = 0; u < eq2; ++u) {
                 const uint64_t o = bnd2[u];
                 rank += (o > mine) || (o == mine && u < tid);
             }
-            if (rank < need) sel[gt + rank] = bnd[tid];
+            if (rank < need2) sel[gt + gt2 + rank] = orig;
         }
     }
     __syncthreads();
-    // (key, candidate index) -> (key, ~docid), then order the k survivors by rank counting and write them out
-    if (tid < k) {
-        const uint64_t e = sel[tid];
-        sel[tid] = (e & 0xffffffff00000000ull) | (uint32_t)~(uint32_t)src.doc((int)(uint32_t)e);
-    }
-    __syncthreads();
-    if (tid < k) {
-        const uint64_t mine = sel[tid];
-        int rank = 0;
-        for (int u = 0; u < k; ++u) {
-            const uint64_t o = sel[u];
-            rank += (o > mine) || (o == mine && u < tid);
+    // one warp: (key, candidate index) -> (key, ~docid), sort the k survivors, write them out
+    if (warp == 0) {
+        uint64_t v[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int i = lane * 4 + r;
+            v[r] = 0;
+            if (i < k) {
+                const uint64_t e = sel[i];
+                v[r] = (e & 0xffffffff00000000ull) | (uint32_t)~(uint32_t)src.doc((int)(uint32_t)e);
+            }
         }
-        out_s[rank] = ordered_to_float((uint32_t)(mine >> 32));
-        out_d[rank] = (int32_t)(~(uint32_t)mine);
+        warp_bitonic128_desc(v, lane);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int i = lane * 4 + r;
+            if (i < k) {
+                out_s[i] = ordered_to_float((uint32_t)(v[r] >> 32));
+                out_d[i] = (int32_t)(~(uint32_t)v[r]);
+            }
+        }
     }
 }
 
-// dynamic shared memory layout: sel[cap] u64 | hist[TK_BINS] u32 | co[K+1] i32 | cbase[K] i32 | keys[...] u32 (smem variant)
+// dynamic shared memory layout: sel[cap] u64 | hist[TK_BINS] u32 | keys[stride] u32 (smem variant) | co[K+1] i32 | cbase[K] i32
 template <bool KEYS_IN_SMEM>
 __global__ void __launch_bounds__(TK_THREADS, 8) k_topk_store(ScoreArgs a, float alpha, int cap, float *out_scores,
                                                               int32_t *out_docids) {
@@ -343,9 +435,12 @@ __global__ void __launch_bounds__(TK_THREADS, 8) k_topk_store(ScoreArgs a, float
     __shared__ TkShared sh;
     uint64_t *sel = reinterpret_cast<uint64_t *>(smem);
     uint32_t *hist = reinterpret_cast<uint32_t *>(sel + cap);
-    int32_t *co = reinterpret_cast<int32_t *>(hist + TK_BINS);
+    uint32_t *skeys = hist + TK_BINS;                              // 16-byte aligned: cap * 8 + 8 KB
+    int32_t *co = reinterpret_cast<int32_t *>(skeys + (KEYS_IN_SMEM ? a.stride : 0));
     const int b = blockIdx.x;
     int32_t *cbase = co + a.K + 1;
+    pdl_launch_dependents();
+    pdl_wait();
     for (int i = threadIdx.x; i <= a.K; i += TK_THREADS) {
         co[i] = a.candoff[(int64_t)b * (a.K + 1) + i];
         if (i < a.K) {
@@ -354,7 +449,7 @@ __global__ void __launch_bounds__(TK_THREADS, 8) k_topk_store(ScoreArgs a, float
         }
     }
     __syncthreads();
-    uint32_t *keys = KEYS_IN_SMEM ? reinterpret_cast<uint32_t *>(cbase + a.K) : a.gkeys + (int64_t)b * a.stride;
+    uint32_t *keys = KEYS_IN_SMEM ? skeys : a.gkeys + (int64_t)b * a.stride;
     StoreSrc src{a.scorebuf + (int64_t)b * a.stride, co, cbase, a.prob ? a.prob + (int64_t)b * a.K : nullptr,
                  a.docid, a.K, alpha};
     topk_body(src, co[a.K], a.k, cap, keys, sel, hist, &sh, out_scores + (int64_t)b * a.k,
@@ -388,14 +483,14 @@ cudaError_t launch_topk_store(const ScoreArgs &a, float alpha, float *out_scores
             cudaFuncSetAttribute(k_topk_store<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
             attr_set = true;
         }
-        k_topk_store<true><<<a.B, TK_THREADS, with_keys, s>>>(a, alpha, cap, out_scores, out_docids);
+        return launch_pdl(k_topk_store<true>, dim3(a.B), dim3(TK_THREADS), with_keys, s, a, alpha, cap, out_scores, out_docids);
     } else {
         static bool attr_set = false;
         if (!attr_set) {
             cudaFuncSetAttribute(k_topk_store<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
             attr_set = true;
         }
-        k_topk_store<false><<<a.B, TK_THREADS, fixed, s>>>(a, alpha, cap, out_scores, out_docids);
+        return launch_pdl(k_topk_store<false>, dim3(a.B), dim3(TK_THREADS), fixed, s, a, alpha, cap, out_scores, out_docids);
     }
     return cudaGetLastError();
 }
@@ -405,7 +500,7 @@ cudaError_t launch_merge_topk(const float *scores, const int32_t *docids, int G,
     if (B == 0) return cudaSuccess;
     const int cap = pow2_at_least(k);
     const int n = G * k_in;
-    const size_t smem = (size_t)cap * 8 + TK_BINS * 4 + (size_t)n * 4;
+    const size_t smem = (size_t)cap * 8 + TK_BINS * 4 + (size_t)((n + 3) / 4 * 4) * 4;
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
     static bool attr_set = false;
     if (!attr_set) {

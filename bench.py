@@ -26,6 +26,7 @@ import sys
 import threading
 import time
 
+import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -131,12 +132,16 @@ def cpu_reference_qps(emb_cpu, offsets, docid, q_cpu, beams_cpu, k, min_seconds,
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=1536)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="gdr_b200", choices=["gdr_b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--replicas", type=int, default=0, help="store replicas cycled to defeat L2 (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="auto", choices=["auto", "replica", "sharded"],
+                    help="N > 1: replica = every rank holds the corpus and its own query batches (no collective); sharded = clusters "
+                         "sharded over ranks, queries replicated, NCCL all-gather of candidates + merge (auto: sharded for cfg5s)")
+    ap.add_argument("--path", default="auto", choices=["auto", "simt", "umma"], help="force a scoring path")
     ap.add_argument("--pipeline", type=int, default=3, help="independent batches kept in flight on separate CUDA streams (1 = strictly serial)")
     ap.add_argument("--no-graph", action="store_true", help="launch every step from the host instead of replaying a CUDA graph")
     args = ap.parse_args()
@@ -194,20 +199,24 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    B_global = cfg["B"] * world
-    C_total = cfg["C"] * world
+    sharded = world > 1 and (args.mode == "sharded" or (args.mode == "auto" and args.workload == "cfg5s"))
+    B_global = cfg["B"] * world          # queries per step over all ranks
+    B_rank = B_global if sharded else cfg["B"]      # queries each rank handles per step (sharded: all of them, replicated)
+    C_total = cfg["C"] * world if sharded else cfg["C"]
+    path_flags = {"auto": 0, "simt": 2, "umma": 4}[args.path]
     emb_bytes = cfg["N"] * D * 2
     replicas = args.replicas or max(1, min(6, -(-640 * 2 ** 20 // emb_bytes)))     # >= 640 MB of distinct store bytes in rotation
     stores = []
     base_offsets = None
     for r in range(replicas):
-        emb, offsets, docid = synth_shard(cfg, 1234 + 1000 * rank, dev) if r == 0 else (stores[0].emb.clone(), base_offsets, stores[0].docid.clone())
+        emb, offsets, docid = synth_shard(cfg, 1234 + (1000 * rank if sharded else 0), dev) if r == 0 else (stores[0].emb.clone(), base_offsets, stores[0].docid.clone())
         base_offsets = offsets
         # docids are global: rank r's documents are numbered after those of ranks < r
-        stores.append(ClusterStore(emb, offsets, docid + rank * cfg["N"] if r == 0 else docid))
+        stores.append(ClusterStore(emb, offsets, docid + (rank * cfg["N"] if sharded else 0) if r == 0 else docid))
     n_batches = 8
-    batches = synth_batches(cfg, n_batches, C_total, B_global, 4321, dev)     # same seed on every rank: replicated queries
-    if world > 1:
+    # sharded: same seed on every rank = replicated queries; replica: every rank draws its own batches
+    batches = synth_batches(cfg, n_batches, C_total, B_rank, 4321 + (0 if sharded or world == 1 else rank), dev)
+    if sharded:
         # rank r owns global clusters [r*C, (r+1)*C): contiguous blocks are already balanced for this synthetic corpus
         g2l = torch.full((C_total,), -1, dtype=torch.int32, device=dev)
         g2l[rank * cfg["C"]:(rank + 1) * cfg["C"]] = torch.arange(cfg["C"], dtype=torch.int32, device=dev)
@@ -215,25 +224,25 @@ def main():
     # Batches are independent, so `n_pipe` of them are kept in flight on `n_pipe` CUDA streams, each with its own
     # store handles (= its own scratch) and result buffers: the latency-bound inversion and top-k kernels of one batch
     # co-reside with, and hide under, the HBM-bound scoring kernel of its neighbours.
-    n_pipe = 1 if world > 1 else max(1, args.pipeline)
+    n_pipe = 1 if sharded else max(1, args.pipeline)
     pipes = []
     for p in range(n_pipe):
         st_p = stores if p == 0 else [ClusterStore(s0.emb, torch.as_tensor(s0.offsets_host), s0.docid) for s0 in stores]
         pipes.append(dict(
             stream=torch.cuda.Stream(), stores=st_p,
-            retr=[ShardedRetriever(x, g2l) for x in st_p] if world > 1 else None,
+            retr=[ShardedRetriever(x, g2l) for x in st_p] if sharded else None,
             q=torch.empty_like(batches[0][0]), b=torch.empty_like(batches[0][1]),
-            out_s=torch.empty((1, B_global, k), dtype=torch.float32, device=dev),
-            out_d=torch.empty((1, B_global, k), dtype=torch.int32, device=dev),
-            res_s=torch.empty((B_global, k), dtype=torch.float32).pin_memory(),
-            res_d=torch.empty((B_global, k), dtype=torch.int32).pin_memory()))
+            out_s=torch.empty((1, B_rank, k), dtype=torch.float32, device=dev),
+            out_d=torch.empty((1, B_rank, k), dtype=torch.int32, device=dev),
+            res_s=torch.empty((B_rank, k), dtype=torch.float32).pin_memory(),
+            res_d=torch.empty((B_rank, k), dtype=torch.int32).pin_memory()))
 
     def step(i, P=None):
         """One pass of the hot path over one device-resident batch."""
         P = P or pipes[0]
         q, beams = batches[i % n_batches]
-        if world == 1:
-            P["stores"][i % replicas].score_topk(q, beams, k, out=(P["out_s"], P["out_d"]))
+        if not sharded:
+            P["stores"][i % replicas].score_topk(q, beams, k, out=(P["out_s"], P["out_d"]), flags=path_flags)
         else:
             return P["retr"][i % replicas].score_topk(q, beams, k)
 
@@ -272,7 +281,7 @@ def main():
 
     # CUDA graph of `period` consecutive steps (every replica / batch / pipe combination once), replayed: no host launch latency
     period = math.lcm(replicas, n_batches, n_pipe)
-    use_graph = world == 1 and not args.no_graph and args.steps >= period
+    use_graph = not sharded and not args.no_graph and args.steps >= period
     graph = None
     if use_graph:
         side = torch.cuda.Stream()
@@ -332,8 +341,8 @@ def main():
         with torch.cuda.stream(P["stream"]):
             P["q"].copy_(q_host[i % n_batches], non_blocking=True)
             P["b"].copy_(beams_host[i % n_batches], non_blocking=True)
-            if world == 1:
-                P["stores"][i % replicas].score_topk(P["q"], P["b"], k, out=(P["out_s"], P["out_d"]))
+            if not sharded:
+                P["stores"][i % replicas].score_topk(P["q"], P["b"], k, out=(P["out_s"], P["out_d"]), flags=path_flags)
                 P["res_s"].copy_(P["out_s"][0], non_blocking=True)
                 P["res_d"].copy_(P["out_d"][0], non_blocking=True)
             else:
@@ -361,8 +370,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
     e2e_qps = e2e_steps * B_global / (e2e_ms * 1e-3)
-    h2d = B_global * D * 4 + B_global * K * 4
-    d2h = B_global * k * 8
+    h2d = B_rank * D * 4 + B_rank * K * 4          # per rank and step
+    d2h = B_rank * k * 8
 
     if rank != 0:
         if world > 1:
@@ -372,9 +381,10 @@ def main():
     # ---- roofline of the dominant kernel (every touched embedding read once + queries + results)
     peak, peak_src = peaks()
     beams0 = batches[0][1]
-    local = beams0[(beams0 >= rank * cfg["C"]) & (beams0 < (rank + 1) * cfg["C"])] - rank * cfg["C"]
+    lo_c = rank * cfg["C"] if sharded else 0
+    local = beams0[(beams0 >= lo_c) & (beams0 < lo_c + cfg["C"])] - lo_c
     emb_touched = int(stores[0].sizes_host[torch.unique(local).cpu().numpy()].sum()) * D * 2
-    alg_bytes = emb_touched + B_global * D * 4 + B_global * k * 8
+    alg_bytes = emb_touched + B_rank * D * 4 + B_rank * k * 8      # rank 0's launch
     dominant = max(("score_umma", "score_simt"), key=lambda n: phase[n])
     dom_ms = phase[dominant]
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
@@ -387,12 +397,15 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline:
-        nq = min(256, B_global)
-        emb_cpu = stores[0].emb.float().cpu()
+        nq = min(256, B_rank)
+        n_cpu = min(cfg["N"], 400000)       # bounded sample of the corpus for huge shards
+        c_cpu = int(np.searchsorted(stores[0].offsets_host, n_cpu, side="right") - 1)
+        n_cpu = int(stores[0].offsets_host[c_cpu])
+        emb_cpu = stores[0].emb[:n_cpu].float().cpu()
         lb = batches[0][1][:nq].cpu()
-        if world > 1:   # the CPU leg scores the rank-0 shard only
-            lb = torch.where((lb >= 0) & (lb < cfg["C"]), lb, torch.full_like(lb, -1))
-        v, done, dt = cpu_reference_qps(emb_cpu, torch.as_tensor(stores[0].offsets_host), stores[0].docid.cpu().numpy().astype("int64"),
+        if sharded or c_cpu < cfg["C"]:   # the CPU leg scores (a prefix of) the rank-0 shard only
+            lb = torch.where((lb >= 0) & (lb < c_cpu), lb, torch.full_like(lb, -1))
+        v, done, dt = cpu_reference_qps(emb_cpu, torch.as_tensor(stores[0].offsets_host[:c_cpu + 1]), stores[0].docid[:n_cpu].cpu().numpy().astype("int64"),
                                         batches[0][0][:nq].cpu(), lb, k, min_seconds=10.0, max_queries=20000)
         cpu = {"value": v, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port",
                "sample": f"{done} queries of the {args.workload} workload in {dt:.1f} s: oracle/gdr_oracle.dense_topk (reference dense.py:53-54 "
@@ -402,11 +415,14 @@ def main():
         "metric": "queries/sec, cluster-restricted scoring + top-%d" % k, "value": qps, "unit": "queries/s", "n_gpus": world,
         "steps": steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16 store x fp32 query, fp32 accumulate", "data": "synthetic",
-        "config": {"workload": args.workload + ("" if world == 1 else f" x{world} cluster-sharded"), "docs_per_gpu": cfg["N"],
+        "config": {"workload": args.workload + ("" if world == 1 else (f" x{world} cluster-sharded" if sharded else f" x{world} replicas, queries sharded")),
+                   "docs_per_gpu": cfg["N"],
                    "clusters_per_gpu": cfg["C"], "dim": D, "global_batch": B_global, "beam": K, "top_k": k,
                    "l2": f"{replicas} store replicas ({replicas * emb_bytes / 2**20:.0f} MB) and {n_batches} query batches cycled; inputs larger than L2",
-                   "cuda_graph": bool(use_graph), "batches_in_flight": n_pipe, "parallelism": "single GPU" if world == 1 else f"clusters sharded over {world} GPUs + NCCL all-gather + merge"},
-        "clocks": clocks, "gpu_launches": int(stats["launches"]) * steps + (0 if world == 1 else steps),
+                   "cuda_graph": bool(use_graph), "batches_in_flight": n_pipe, "scoring_path": args.path,
+                   "parallelism": "single GPU" if world == 1 else (f"clusters sharded over {world} GPUs, queries replicated, NCCL all-gather of candidates + merge"
+                                                                   if sharded else f"corpus replicated on {world} GPUs, queries sharded, no data-path collective")},
+        "clocks": clocks, "gpu_launches": (int(stats["launches"]) * steps + (steps if sharded else 0)) * (1 if sharded else world),
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "pipeline": f"{n_pipe} batches in flight on {n_pipe} CUDA streams, pinned host buffers, per-step H2D of q+beams and D2H of (score, docid)"},
         "roofline": roofline, "cpu_baseline": cpu,

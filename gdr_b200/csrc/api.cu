@@ -175,11 +175,12 @@ int gdr_score_topk(gdr_store_t *s, const float *q, const int32_t *beams, const f
     a.scorebuf = reinterpret_cast<float *>(ws + o_score);
     a.stride = stride;
     a.gkeys = reinterpret_cast<uint32_t *>(ws + o_keys);
-    // One scoring path per call: a batch that names each touched cluster about twice or more goes to the tcgen05
-    // grouped GEMM (slab read once for the whole group), a sparse batch to the SIMT GEMV.  GDR_UMMA_MIN_GROUP > 1
+    // One scoring path per call: a batch that names each cluster three or more times on average goes to the tcgen05
+    // grouped GEMM (slab read once for the whole group); a sparse batch goes to the SIMT GEMV, which serves up to four
+    // pairs per slab read and measured 89% of HBM peak at ~1 pair per cluster (cfg5 slice) against 77% for tcgen05.  GDR_UMMA_MIN_GROUP > 1
     // (env) asks for the mixed mode instead: groups of at least that many pairs on tensor cores, the rest SIMT.
     const bool mixed = umma_possible && !(flags & GDR_FORCE_UMMA) && s->umma_min_group > 1;
-    bool use_umma = umma_possible && ((flags & GDR_FORCE_UMMA) || mixed || 2 * (int64_t)s->n_clusters <= 3 * pairs);
+    bool use_umma = umma_possible && ((flags & GDR_FORCE_UMMA) || mixed || pairs >= 3 * (int64_t)s->n_clusters);
     const bool use_simt = !use_umma || mixed;
     a.dbg = s->dbg;
     a.umma_min_group = !use_umma ? INT_MAX : (mixed ? s->umma_min_group : 1);

@@ -106,6 +106,8 @@ __device__ __forceinline__ void block_scan3(int &x, int &y, int &z, int tot[3], 
     __syncthreads();
 }
 
+constexpr int SCAN_PER_THREAD = 8;   // clusters per thread and round: 8,192 clusters per block-wide scan
+
 __global__ void __launch_bounds__(1024) k_scan(ScoreArgs a) {
     __shared__ int wsum[32][3];
     pdl_launch_dependents();
@@ -113,23 +115,36 @@ __global__ void __launch_bounds__(1024) k_scan(ScoreArgs a) {
     int carry[3] = {0, 0, 0};
     int touched = 0;
     const int C = a.n_clusters;
-    for (int c0 = 0; c0 < C; c0 += 1024) {
-        const int c = c0 + threadIdx.x;
-        int g = 0, ns = 0, nu = 0;
-        if (c < C) {
-            g = a.cnt[c];
-            const int size = a.offsets[c + 1] - a.offsets[c];
-            if (g > 0 && size > 0) {
-                touched++;
-                item_counts(a, g, size, ns, nu);
+    for (int c0 = 0; c0 < C; c0 += 1024 * SCAN_PER_THREAD) {
+        const int cb = c0 + threadIdx.x * SCAN_PER_THREAD;      // this thread's consecutive clusters
+        int g[SCAN_PER_THREAD], ns[SCAN_PER_THREAD], nu[SCAN_PER_THREAD];
+        int sg = 0, ss = 0, su = 0;
+#pragma unroll
+        for (int i = 0; i < SCAN_PER_THREAD; ++i) {
+            g[i] = ns[i] = nu[i] = 0;
+            const int c = cb + i;
+            if (c < C) {
+                g[i] = a.cnt[c];
+                const int size = a.offsets[c + 1] - a.offsets[c];
+                if (g[i] > 0 && size > 0) {
+                    touched++;
+                    item_counts(a, g[i], size, ns[i], nu[i]);
+                }
             }
+            sg += g[i]; ss += ns[i]; su += nu[i];
         }
         int tot[3];
-        block_scan3(g, ns, nu, tot, wsum);
-        if (c < C) {
-            a.grp_off[c] = carry[0] + g;
-            a.simt_off[c] = carry[1] + ns;
-            a.umma_off[c] = carry[2] + nu;
+        block_scan3(sg, ss, su, tot, wsum);                      // exclusive prefix of the per-thread sums
+        sg += carry[0]; ss += carry[1]; su += carry[2];
+#pragma unroll
+        for (int i = 0; i < SCAN_PER_THREAD; ++i) {
+            const int c = cb + i;
+            if (c < C) {
+                a.grp_off[c] = sg;
+                a.simt_off[c] = ss;
+                a.umma_off[c] = su;
+            }
+            sg += g[i]; ss += ns[i]; su += nu[i];
         }
         carry[0] += tot[0]; carry[1] += tot[1]; carry[2] += tot[2];
     }

@@ -144,6 +144,8 @@ int gdr_score_topk(gdr_store_t *s, const float *q, const int32_t *beams, const f
     const size_t o_simt = take((size_t)simt_cap * sizeof(Item));
     const size_t o_umma = take(umma_possible ? (size_t)umma_cap * sizeof(Item) : 0);
     const size_t o_score = take((size_t)B * stride * 4);
+    const int64_t q_rows = (flags & GDR_Q_PER_BEAM) ? pairs : B;
+    const size_t o_qsplit = take(umma_possible ? (size_t)q_rows * 3 * s->dim * 2 : 0);
     const size_t o_keys = take(global_keys ? (size_t)B * stride * 4 : 0);
     if (off > s->batch_ws_bytes) {
         // growing the scratch synchronises; run one call per shape before capturing a CUDA graph
@@ -175,6 +177,7 @@ int gdr_score_topk(gdr_store_t *s, const float *q, const int32_t *beams, const f
     a.scorebuf = reinterpret_cast<float *>(ws + o_score);
     a.stride = stride;
     a.gkeys = reinterpret_cast<uint32_t *>(ws + o_keys);
+    a.qsplit = nullptr;   // set below when the tcgen05 path is taken
     // One scoring path per call: a batch that names each cluster three or more times on average goes to the tcgen05
     // grouped GEMM (slab read once for the whole group); a sparse batch goes to the SIMT GEMV, which serves up to four
     // pairs per slab read and measured 89% of HBM peak at ~1 pair per cluster (cfg5 slice) against 77% for tcgen05.  GDR_UMMA_MIN_GROUP > 1
@@ -183,6 +186,7 @@ int gdr_score_topk(gdr_store_t *s, const float *q, const int32_t *beams, const f
     bool use_umma = umma_possible && ((flags & GDR_FORCE_UMMA) || mixed || pairs >= 3 * (int64_t)s->n_clusters);
     const bool use_simt = !use_umma || mixed;
     a.dbg = s->dbg;
+    if (use_umma) a.qsplit = reinterpret_cast<__nv_bfloat16 *>(ws + o_qsplit);
     a.umma_min_group = !use_umma ? INT_MAX : (mixed ? s->umma_min_group : 1);
 
     int launches = 0;

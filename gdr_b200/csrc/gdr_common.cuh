@@ -66,6 +66,7 @@ struct ScoreArgs {
     int32_t *counters;   // [CTR_COUNT]
     float *scorebuf;     // [B, stride]
     int64_t stride;
+    __nv_bfloat16 *qsplit;  // [rows(q), 3, dim] exact bf16 hi/mid/lo split of the fp32 queries (tcgen05 path), else null
     uint32_t *gkeys;     // [B, stride] keys scratch for the global-memory top-k variant
     long long *dbg;      // [512] optional timeline scratch (GDR_UMMA_TRACE=1), else null
     int32_t umma_min_group;  // groups with at least this many pairs go to the tcgen05 path (INT_MAX = never)

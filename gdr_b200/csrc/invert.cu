@@ -12,8 +12,38 @@
 
 namespace gdr {
 
+// fp32 -> (hi, mid, lo) bf16 with x == hi + mid + lo exactly (8 + 8 + 8 mantissa bits)
+__device__ __forceinline__ void split3(float x, __nv_bfloat16 &hi, __nv_bfloat16 &mid, __nv_bfloat16 &lo) {
+    hi = __float2bfloat16_rn(x);
+    const float r1 = x - __bfloat162float(hi);
+    mid = __float2bfloat16_rn(r1);
+    lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+}
+
+// One warp: rows [row0, row0 + nrows) of q -> a.qsplit[row][term][dim] (the B operand of the tcgen05 path)
+__device__ __forceinline__ void split_rows(const ScoreArgs &a, int64_t row0, int nrows, int lane) {
+    for (int r = 0; r < nrows; ++r) {
+        const float *src = a.q + (row0 + r) * a.dim;
+        __nv_bfloat16 *dst = a.qsplit + (row0 + r) * 3 * a.dim;
+        for (int e = lane * 4; e < a.dim; e += 128) {
+            const float4 v = *reinterpret_cast<const float4 *>(src + e);
+            const float x[4] = {v.x, v.y, v.z, v.w};
+            __nv_bfloat16 t[3][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) split3(x[i], t[0][i], t[1][i], t[2][i]);
+#pragma unroll
+            for (int term = 0; term < 3; ++term)
+                *reinterpret_cast<uint2 *>(dst + term * a.dim + e) = *reinterpret_cast<const uint2 *>(t[term]);
+        }
+    }
+}
+
 // One warp: count query b's beams into cnt[] and write its candidate-segment starts.
 __device__ __forceinline__ void count_query(const ScoreArgs &a, int b, int lane, int32_t *cnt) {
+    if (a.qsplit) {
+        if (a.flags & GDR_Q_PER_BEAM) split_rows(a, (int64_t)b * a.K, a.K, lane);
+        else split_rows(a, b, 1, lane);
+    }
     const int32_t *beams = a.beams + (int64_t)b * a.K;
     int32_t *co = a.candoff + (int64_t)b * (a.K + 1);
     int carry = 0;

@@ -8,7 +8,7 @@
 //     D[128 docs, N pairs] (fp32, TMEM)  +=  A[128 docs, 64 k] (bf16 smem, TMA)  x  B[N pairs, 64 k]^T (bf16 smem)
 //
 // Parity with the fp32 reference needs more than bf16(q): the fp32 query is split exactly into three
-// bf16 terms q = hi + mid + lo (by the filler warps, in registers).  The three terms are stacked along N
+// bf16 terms q = hi + mid + lo (k_count writes them once per batch).  The three terms are stacked along N
 // (B rows [0,TS) = hi, [TS,2TS) = mid, [2TS,3TS) = lo, TS = 16 or 32), so ONE MMA of N = 3*TS per K step
 // reads the A tile from shared memory once for all three (SS-mode MMAs are bound by the 128 B/clk smem
 // read of A, measured: three N=32 MMAs per K step were MIO-throttled); the epilogue adds the three TMEM
@@ -16,15 +16,15 @@
 // accumulation-order noise.  The kernel is still HBM-bound: per tile it moves 128 x 768 x 2 B = 196 KB of
 // embeddings and issues 12 x 4 MMAs of 128 x 96 x 16.
 //
-// Warp roles (480 threads, one persistent CTA per SM, tiles strided over CTAs):
-//   warp 0       TMA producer: A tiles of the store, 8-stage ring shared with B (128 KB of A in flight per SM)
+// Warp roles (320 threads, one persistent CTA per SM, tiles strided over CTAs):
+//   warp 0       TMA producer: A tiles of the store, 6-stage ring shared with B (96 KB of A in flight per SM)
 //   warp 1       MMA issuer (one lane): tcgen05.mma cta_group::1 kind::f16; commits free the A and B stages
-//   warps 2-9    B fillers, one K block per warp in flight (8 blocks' L2 latency overlapped): gather the
-//                group's fp32 query rows (L2-resident), split them into hi/mid/lo bf16 in registers, store
-//                into the 128B-swizzled K-major layout the UMMA descriptor expects, fence.proxy.async, arrive
-//   warps 10-13  epilogue: tcgen05.ld the accumulator (double-buffered in TMEM so it overlaps the next
+//   warps 2-4    B fillers: gather the group's query rows from the pre-split bf16 table (hi/mid/lo terms written once
+//                per batch by k_count, L2-resident) with 16-byte cp.async straight into the 128B-swizzled K-major layout
+//                the UMMA descriptor expects; wait_group -> fence.proxy.async -> arrive.  Two stages per warp.
+//   warps 5-8    epilogue: tcgen05.ld the accumulator (double-buffered in TMEM so it overlaps the next
 //                tile's MMAs), activation, coalesced stores into each query's candidate segment
-//   warp 14      tile metadata: walks item -> pair -> candidate offset (three dependent L2 round trips) for four
+//   warp 9       tile metadata: walks item -> pair -> candidate offset (three dependent L2 round trips) for four
 //                tiles at a time, up to four tiles ahead, into a shared-memory ring, so no other role ever has a
 //                global-memory latency on its per-tile critical path (measured: with each role fetching its own
 //                metadata the empty barrier skeleton alone cost 4 us per tile, as much as the tile's HBM time)
@@ -37,14 +37,14 @@ constexpr int UM_SA = 8;                       // ONE ring of 8 stages, each = A
 constexpr int UM_SB = 8;                       // empty barrier per stage, so the MMA warp pays one wait + one commit per K block (it is
                                                // issue-latency-bound: ~90 cycles per mbarrier try_wait, measured).  One stage per filler
                                                // warp keeps every waiter at most one mbarrier phase ahead (parity waits stay unambiguous).
-constexpr int UM_FILL_WARPS = 8;
+constexpr int UM_FILL_WARPS = UM_SB / 2;       // each filler warp owns two stages (one cp.async group in flight per stage)
 constexpr int UM_A_BYTES = UMMA_ROWS * 128;    // 16 KB
 constexpr int UM_BT_BYTES = UMMA_NQ * 128;     // 4 KB per query term
 constexpr int UM_B_BYTES = 3 * UM_BT_BYTES;    // 12 KB
-constexpr int UM_THREADS = 64 + 32 * UM_FILL_WARPS + 128 + 32;   // 480
+constexpr int UM_THREADS = 64 + 32 * UM_FILL_WARPS + 128 + 32;   // 320
 constexpr int UM_ACC_COLS = 128;               // TMEM columns reserved per accumulator (3 * 32 used)
 constexpr int UM_TMEM_COLS = 2 * UM_ACC_COLS;  // double-buffered accumulator
-constexpr int UM_RING_BYTES = UM_SA * UM_A_BYTES + UM_SB * UM_B_BYTES;   // 224 KB
+constexpr int UM_RING_BYTES = UM_SA * UM_A_BYTES + UM_SB * UM_B_BYTES;   // 168 KB: leaves room for co-resident top-k / inversion CTAs
 static_assert(UM_SA == UM_SB, "A and B share one ring");
 constexpr int UM_MD = 4;                       // tile-metadata ring depth
 struct __align__(16) TileMeta {                // one tile's metadata, written by the metadata warp
@@ -57,7 +57,7 @@ constexpr int UM_BAR_BYTES = 512;
 constexpr int UM_SMEM_BYTES = UM_RING_BYTES + UM_BAR_BYTES + UM_MD * (int)sizeof(TileMeta);
 static_assert(UM_SMEM_BYTES <= 227 * 1024, "shared memory budget");
 constexpr int UM_TASKS = 8;                    // 32-byte query pieces a filler lane keeps in flight (8 x 32 lanes = all of a 32-pair block)
-static_assert(UM_SB == UM_FILL_WARPS, "one B stage per filler warp");
+static_assert(UM_SB == 2 * UM_FILL_WARPS, "two B stages per filler warp");
 static_assert(UMMA_NQ == 32, "epilogue and filler lane maps assume 32 pairs per tile");
 
 // ---------------------------------------------------------------------------------------------
@@ -279,10 +279,14 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_score_umma(const __grid_const
         }
         if (a.dbg && lane == 0) a.dbg[201 + 2 * blockIdx.x] = gtime();
     } else if (warp < 2 + UM_FILL_WARPS) {
-        // ===================== B fillers: warp fw owns K blocks g = fw, fw + 8, ... of this CTA's stream =====================
+        // ===================== B fillers: warp fw owns stages fw and fw + S/2, i.e. K blocks g = fw, fw + S/2, fw + S, ... =====================
+        // Pure copies: the three bf16 terms of every query were written once per batch by k_count (a.qsplit, L2-resident);
+        // each lane issues 16-byte cp.async (LDGSTS) straight into the swizzled B tile, commits the group and moves on to
+        // its next K block; the PREVIOUS block's group is then complete (wait_group 1), gets its generic->async proxy
+        // fence and is published to the MMA warp.  No register staging, no L2 latency on the warp's critical path.
         const int fw = warp - 2;
-        const bool per_beam = (a.flags & GDR_Q_PER_BEAM) != 0;
         const int total_kb = my_tiles * nkb;
+        const uint32_t b_ring = smem_base + UM_SA * UM_A_BYTES;
         // every filler warp consumes every tile's metadata slot (lane l caches the query row of pair l), including
         // tiles in which it owns no K block, so the slot's consumer count is the same for all tiles
         int cur_it = -1, nq = 0, qrow = 0;
@@ -295,51 +299,42 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_score_umma(const __grid_const
                 meta_release(cur_it);
             }
         };
+        auto publish = [&](int g_done, int pending_groups) {
+            if (pending_groups) asm volatile("cp.async.wait_group 1;" ::: "memory");
+            else asm volatile("cp.async.wait_group 0;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_bar(g_done % UM_SB));
+        };
+        const int64_t row_stride = 3 * (int64_t)a.dim;                 // bf16 elements per query row of the split table
+        int prev_g = -1;
         for (int g = fw; g < total_kb; g += UM_FILL_WARPS) {
             const int it = g / nkb, kb = g - it * nkb;
             advance_to(it);
             const int sb = g % UM_SB;
             const uint32_t phb = (uint32_t)(g / UM_SB) & 1u;
-            unsigned char *bst = smem + UM_SA * UM_A_BYTES + (size_t)sb * UM_B_BYTES;
-            const int n_tasks = (a.flags & (1u << 30)) ? 0 : nq * 8;   // one task = 8 fp32 of one pair = one 16-byte chunk per term
-            const int term_bytes = (nq <= 16 ? 16 : 32) * 128;     // rows of term t start t * TS rows into the B tile
-            bool waited = false;
-            for (int base = 0; base < n_tasks; base += 32 * UM_TASKS) {
-                float4 v[UM_TASKS][2];
+            const uint32_t bst = b_ring + (uint32_t)sb * UM_B_BYTES;
+            const int nq_eff = (a.flags & (1u << 30)) ? 0 : nq;         // 3 terms x 8 16-byte chunks per pair and K block
+            const int ts = nq <= 16 ? 16 : 32;                            // rows of term t start t * TS rows into the B tile
+            mbar_wait(empty_bar(sb), phb ^ 1u);
+            // lane -> (pair jb + lane/8, chunk lane%8): four pairs x eight 16-byte chunks per instruction, one term at a time
+            const int jl = lane >> 3, c = lane & 7;
+            for (int jb = 0; jb < nq_eff; jb += 4) {
+                const int j = jb + jl;
+                const int qr = __shfl_sync(0xffffffffu, qrow, j & 31);
+                if (j < nq_eff) {
+                    const __nv_bfloat16 *src = a.qsplit + (int64_t)qr * row_stride + kb * UM_BLOCK_K + c * 8;
+                    const uint32_t dst = bst + (uint32_t)(j * 128 + ((c ^ (j & 7)) << 4));
 #pragma unroll
-                for (int u = 0; u < UM_TASKS; ++u) {          // all loads first: up to 16 LDG.128 in flight per lane
-                    const int idx = base + u * 32 + lane;
-                    const int j = idx >> 3, c = idx & 7;
-                    const int qr = __shfl_sync(0xffffffffu, qrow, j & 31);
-                    if (idx < n_tasks) {
-                        const float4 *src = reinterpret_cast<const float4 *>(a.q + (int64_t)qr * a.dim + kb * UM_BLOCK_K + c * 8);
-                        v[u][0] = __ldg(src);
-                        v[u][1] = __ldg(src + 1);
-                    }
-                }
-                if (!waited) { mbar_wait(empty_bar(sb), phb ^ 1u); waited = true; }
-#pragma unroll
-                for (int u = 0; u < UM_TASKS; ++u) {
-                    const int idx = base + u * 32 + lane;
-                    if (idx < n_tasks) {
-                        const int j = idx >> 3, c = idx & 7;
-                        uint4 hi, mid, lo;
-                        split2(v[u][0].x, v[u][0].y, hi.x, mid.x, lo.x);
-                        split2(v[u][0].z, v[u][0].w, hi.y, mid.y, lo.y);
-                        split2(v[u][1].x, v[u][1].y, hi.z, mid.z, lo.z);
-                        split2(v[u][1].z, v[u][1].w, hi.w, mid.w, lo.w);
-                        unsigned char *dst = bst + j * 128 + ((c ^ (j & 7)) << 4);
-                        *reinterpret_cast<uint4 *>(dst) = hi;
-                        *reinterpret_cast<uint4 *>(dst + term_bytes) = mid;
-                        *reinterpret_cast<uint4 *>(dst + 2 * term_bytes) = lo;
-                    }
+                    for (int t = 0; t < 3; ++t)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)(t * ts * 128)), "l"(src + t * a.dim) : "memory");
                 }
             }
-            if (!waited) mbar_wait(empty_bar(sb), phb ^ 1u);
-            if (!(a.flags & (1u << 27))) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(full_bar(sb));
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            if (prev_g >= 0) publish(prev_g, 1);
+            prev_g = g;
         }
+        if (prev_g >= 0) publish(prev_g, 0);
         advance_to(my_tiles - 1);
     } else if (warp < 2 + UM_FILL_WARPS + 4) {
         // ===================== epilogue (128 threads) =====================

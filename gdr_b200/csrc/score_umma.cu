@@ -33,8 +33,8 @@
 namespace gdr {
 
 constexpr int UM_BLOCK_K = 64;                 // bf16 elements per K block = one 128-byte swizzle atom
-constexpr int UM_SA = 8;                       // ONE ring of 8 stages, each = A tile (TMA) + B tile (filler warp s): one full and one
-constexpr int UM_SB = 8;                       // empty barrier per stage, so the MMA warp pays one wait + one commit per K block (it is
+constexpr int UM_SA = 6;                       // ONE ring of 6 stages, each = A tile (TMA) + B tile (filler warp s): one full and one
+constexpr int UM_SB = 6;                       // empty barrier per stage, so the MMA warp pays one wait + one commit per K block (it is
                                                // issue-latency-bound: ~90 cycles per mbarrier try_wait, measured).  One stage per filler
                                                // warp keeps every waiter at most one mbarrier phase ahead (parity waits stay unambiguous).
 constexpr int UM_FILL_WARPS = UM_SB / 2;       // each filler warp owns two stages (one cp.async group in flight per stage)

@@ -111,16 +111,32 @@ def test_edge_cases_ragged_empty_absent_and_padding():
     docid = torch.randperm(N, generator=g).numpy()
     q = torch.randn(5, D, generator=g)
     beams = np.array([[0, 3, 7], [1, -1, 2], [4, 5, 6], [-1, -1, -1], [5, 5, 1]], dtype=np.int32)   # dup cluster, all absent
-    for dtype in (torch.float32, torch.bfloat16):
+    for dtype, flags in ((torch.float32, 0), (torch.bfloat16, 0), (torch.bfloat16, FLAG_UMMA)):
         st = _store(emb, offsets, docid, dtype)
         for k in (1, 4, 300, 1000):
-            s, d = st.score_topk(q.cuda(), torch.from_numpy(beams).cuda(), k)
+            s, d = st.score_topk(q.cuda(), torch.from_numpy(beams).cuda(), k, flags=flags)
             ref_s, ref_d = orc.dense_topk(q, emb, offsets, docid, beams, k)
             assert_topk_parity(s, d, ref_s, ref_d, f"edge k={k}")
             assert torch.all(s[0] == float("-inf")) and torch.all(d[3] == -1)
     # B = 0 is a no-op
     s, d = st.score_topk(q[:0].cuda(), torch.zeros(0, 3, dtype=torch.int32).cuda(), 4)
     assert s.shape == (0, 4)
+
+
+def test_large_groups_are_chunked_on_the_tensor_path():
+    """More pairs per cluster than one tcgen05 tile holds (32): groups are split into chunks, clusters into 128-row tiles."""
+    N, C, D, Q, K, k = 6000, 12, 128, 200, 6, 100         # 100 pairs per cluster, clusters of ~500 rows
+    emb, offsets, docid = orc.synth_corpus(N, C, D, seed=21)
+    emb = emb.bfloat16().float()
+    q, beams, beam_scores = orc.synth_queries(Q, C, K, D, seed=22)
+    st = _store(emb, offsets, docid, torch.bfloat16)
+    ref_s, ref_d = orc.dense_topk(q, emb, offsets, docid, beams, k)
+    for flags in (0, FLAG_UMMA, FLAG_SIMT):
+        s, d = st.score_topk(q.cuda(), torch.from_numpy(beams).cuda(), k, flags=flags)
+        assert_topk_parity(s, d, ref_s, ref_d, f"large groups flags={flags}")
+    assert st.last_stats()["umma_tiles"] == 0
+    st.score_topk(q.cuda(), torch.from_numpy(beams).cuda(), k)
+    assert st.last_stats()["umma_tiles"] >= 150           # default policy: dense batch -> tensor path, ~4 row tiles x 4 chunks x 12 clusters
 
 
 def test_mass_ties_are_deterministic_and_docid_ordered():
@@ -144,7 +160,8 @@ def test_mass_ties_are_deterministic_and_docid_ordered():
             assert torch.all(s1[b] == 1.0)
 
 
-def test_per_beam_queries():
+@pytest.mark.parametrize("flags", [0, FLAG_SIMT, FLAG_UMMA])
+def test_per_beam_queries(flags):
     """One query vector per (query, beam): main_models.py:1467-1571,1583-1594."""
     N, C, D, Q, K, k = 8000, 64, 128, 20, 5, 30
     emb, offsets, docid = orc.synth_corpus(N, C, D, seed=3)
@@ -152,7 +169,7 @@ def test_per_beam_queries():
     q, beams, _ = orc.synth_queries(Q * K, C, K, D, seed=4)
     beams = beams[:Q]
     st = _store(emb, offsets, docid, torch.bfloat16)
-    s, d = st.score_topk(q.cuda(), torch.from_numpy(beams).cuda(), k, per_beam=True)
+    s, d = st.score_topk(q.cuda(), torch.from_numpy(beams).cuda(), k, per_beam=True, flags=flags)
     # oracle: each beam segment scored with its own query vector
     ref_s = torch.full((Q, k), float("-inf"))
     ref_d = torch.full((Q, k), -1, dtype=torch.int64)

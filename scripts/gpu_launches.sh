@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 48 --csv --log-file gpurun_out/launches.csv \
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -s 40 -c 48 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 16 --warmup 3 --no-cpu-baseline --no-graph "$@" > gpurun_out/ncu_bench.log 2>&1
 python - <<'PY'
 import csv, collections

@@ -191,20 +191,24 @@ int gdr_score_topk(gdr_store_t *s, const float *q, const int32_t *beams, const f
 
     int launches = 0;
     const bool prof = s->profiling;
+    if (s->dbg) {   // kernel timeline: min-start slots to +inf, max-end slots to 0
+        static const unsigned long long init[6] = {~0ull, 0ull, ~0ull, 0ull, ~0ull, 0ull};
+        GDR_CUDA(cudaMemcpyAsync(s->dbg + 500, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    }
     if (prof) GDR_CUDA(cudaEventRecord(s->ev[0], st));
-    GDR_CUDA(launch_invert(a, st, &launches));
+    if (!(flags & GDR_SKIP_INVERT)) GDR_CUDA(launch_invert(a, st, &launches));
     if (prof) GDR_CUDA(cudaEventRecord(s->ev[1], st));
-    if (use_umma) {
+    if (use_umma && !(flags & GDR_SKIP_SCORE)) {
         GDR_CUDA(launch_score_umma(a, &s->tmap, st, s->sm_count));
         launches += 1;
     }
     if (prof) GDR_CUDA(cudaEventRecord(s->ev[2], st));
-    if (use_simt) {
+    if (use_simt && !(flags & GDR_SKIP_SCORE)) {
         GDR_CUDA(launch_score_simt(a, st, s->sm_count));
         launches += 1;
     }
     if (prof) GDR_CUDA(cudaEventRecord(s->ev[3], st));
-    for (int r = 0; r < n_alpha; ++r) {
+    for (int r = 0; r < n_alpha && !(flags & GDR_SKIP_TOPK); ++r) {
         const float alpha = alphas ? alphas[r] : 1.0f;
         GDR_CUDA(launch_topk_store(a, alpha, out_scores + (int64_t)r * B * k, out_docids + (int64_t)r * B * k, st));
         launches += 1;
@@ -246,6 +250,7 @@ int gdr_store_last_stats(gdr_store_t *s, int64_t out[4], void *stream) {
             smin = st < smin ? st : smin; smax = st > smax ? st : smax; emin = en < emin ? en : emin; emax = en > emax ? en : emax;
         }
         fprintf(stderr, "| CTA loop start min %lld max %lld, end min %lld max %lld\n", smin, smax, emin, emax);
+        fprintf(stderr, "[timeline] %lld %lld %lld %lld %lld %lld\n", h[500], h[501], h[502], h[503], h[504], h[505]);
     }
     const size_t n = (size_t)s->n_clusters;
     GDR_CUDA(cudaMemcpy(c, s->cluster_ws + n + 3 * (n + 1), sizeof(c), cudaMemcpyDeviceToHost));

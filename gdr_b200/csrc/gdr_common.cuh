@@ -111,6 +111,19 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// ----- optional kernel timeline (GDR_UMMA_TRACE): slots 500..511 of a.dbg hold min start / max end per kernel class
+__device__ __forceinline__ unsigned long long gdr_gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void trace_start(long long *dbg, int slot) {
+    if (dbg && threadIdx.x == 0) atomicMin(reinterpret_cast<unsigned long long *>(dbg) + 500 + slot, gdr_gtime());
+}
+__device__ __forceinline__ void trace_end(long long *dbg, int slot) {
+    if (dbg && threadIdx.x == 0) atomicMax(reinterpret_cast<unsigned long long *>(dbg) + 500 + slot, gdr_gtime());
+}
+
 // ----- small device helpers -----------------------------------------------------------------
 __device__ __forceinline__ uint32_t float_to_ordered(float f) {
     uint32_t u = __float_as_uint(f);

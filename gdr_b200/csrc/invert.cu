@@ -72,6 +72,7 @@ __device__ __forceinline__ void count_query(const ScoreArgs &a, int b, int lane,
 __global__ void __launch_bounds__(128) k_count(ScoreArgs a) {
     pdl_launch_dependents();
     pdl_wait();                 // candoff is still read by the previous call's top-k
+    trace_start(a.dbg, 0);
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (warp < a.B) count_query(a, warp, threadIdx.x & 31, a.cnt);
 }
@@ -211,6 +212,7 @@ __global__ void __launch_bounds__(256) k_fill(ScoreArgs a) {
         const int c = (int)t;
         write_items(a, c, a.grp_off[c], a.grp_off[c + 1] - a.grp_off[c], a.simt_off[c], a.umma_off[c]);
     }
+    trace_end(a.dbg, 1);
 }
 
 // Small batches (B <= 64, C <= 2048): the whole inversion in ONE CTA with the per-cluster arrays in shared

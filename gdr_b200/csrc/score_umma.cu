@@ -33,10 +33,11 @@
 namespace gdr {
 
 constexpr int UM_BLOCK_K = 64;                 // bf16 elements per K block = one 128-byte swizzle atom
-constexpr int UM_SA = 6;                       // ONE ring of 6 stages, each = A tile (TMA) + B tile (filler warp s): one full and one
-constexpr int UM_SB = 6;                       // empty barrier per stage, so the MMA warp pays one wait + one commit per K block (it is
-                                               // issue-latency-bound: ~90 cycles per mbarrier try_wait, measured).  One stage per filler
-                                               // warp keeps every waiter at most one mbarrier phase ahead (parity waits stay unambiguous).
+constexpr int UM_SA = 6;                       // ONE ring of 6 stages, each = A tile (TMA) + B tile (cp.async): one full and one empty
+constexpr int UM_SB = 6;                       // barrier per stage, so the MMA warp pays one wait + one commit per K block.  Every stage
+                                               // is owned by exactly one filler warp, which keeps each waiter at most one mbarrier phase
+                                               // ahead (parity waits stay unambiguous).  6 x 28 KB = 168 KB leaves ~58 KB of the SM for
+                                               // co-resident top-k / inversion CTAs of neighbouring batches (8 stages: same speed alone).
 constexpr int UM_FILL_WARPS = UM_SB / 2;       // each filler warp owns two stages (one cp.async group in flight per stage)
 constexpr int UM_A_BYTES = UMMA_ROWS * 128;    // 16 KB
 constexpr int UM_BT_BYTES = UMMA_NQ * 128;     // 4 KB per query term
@@ -56,7 +57,6 @@ constexpr int UM_META_CONSUMERS = 1 + UM_FILL_WARPS + 4;    // MMA, fillers, epi
 constexpr int UM_BAR_BYTES = 512;
 constexpr int UM_SMEM_BYTES = UM_RING_BYTES + UM_BAR_BYTES + UM_MD * (int)sizeof(TileMeta);
 static_assert(UM_SMEM_BYTES <= 227 * 1024, "shared memory budget");
-constexpr int UM_TASKS = 8;                    // 32-byte query pieces a filler lane keeps in flight (8 x 32 lanes = all of a 32-pair block)
 static_assert(UM_SB == 2 * UM_FILL_WARPS, "two B stages per filler warp");
 static_assert(UMMA_NQ == 32, "epilogue and filler lane maps assume 32 pairs per tile");
 
@@ -135,17 +135,6 @@ __device__ __forceinline__ uint32_t umma_idesc(int n) {
 // ---------------------------------------------------------------------------------------------
 // the grouped GEMM
 // ---------------------------------------------------------------------------------------------
-// fp32 -> (hi, mid, lo) bf16 with q == hi + mid + lo exactly (8 + 8 + 8 mantissa bits); two elements per call
-__device__ __forceinline__ void split2(float x0, float x1, uint32_t &hi, uint32_t &mid, uint32_t &lo) {
-    const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
-    const float r0 = x0 - __low2float(h), r1 = x1 - __high2float(h);
-    const __nv_bfloat162 m = __floats2bfloat162_rn(r0, r1);
-    const __nv_bfloat162 l = __floats2bfloat162_rn(r0 - __low2float(m), r1 - __high2float(m));
-    hi = *reinterpret_cast<const uint32_t *>(&h);
-    mid = *reinterpret_cast<const uint32_t *>(&m);
-    lo = *reinterpret_cast<const uint32_t *>(&l);
-}
-
 __device__ __forceinline__ long long gtime() {
     long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -212,6 +201,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_score_umma(const __grid_const
     const uint32_t tmem_base = *tmem_slot;
     // everything above (barrier init, TMEM allocation) overlapped the inversion kernels; its outputs are read from here on
     pdl_wait();
+    trace_start(a.dbg, 2);
     const int n_tiles = (a.flags & (1u << 31)) ? 0 : a.counters[CTR_N_UMMA];
     const int my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
@@ -432,6 +422,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_score_umma(const __grid_const
 
     tc_fence_before();
     __syncthreads();
+    trace_end(a.dbg, 3);
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(UM_TMEM_COLS) : "memory");
     }

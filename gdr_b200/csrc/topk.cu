@@ -441,6 +441,7 @@ __global__ void __launch_bounds__(TK_THREADS, 8) k_topk_store(ScoreArgs a, float
     int32_t *cbase = co + a.K + 1;
     pdl_launch_dependents();
     pdl_wait();
+    trace_start(a.dbg, 4);
     for (int i = threadIdx.x; i <= a.K; i += TK_THREADS) {
         co[i] = a.candoff[(int64_t)b * (a.K + 1) + i];
         if (i < a.K) {
@@ -454,6 +455,7 @@ __global__ void __launch_bounds__(TK_THREADS, 8) k_topk_store(ScoreArgs a, float
                  a.docid, a.K, alpha};
     topk_body(src, co[a.K], a.k, cap, keys, sel, hist, &sh, out_scores + (int64_t)b * a.k,
               out_docids + (int64_t)b * a.k);
+    trace_end(a.dbg, 5);
 }
 
 __global__ void __launch_bounds__(TK_THREADS) k_topk_merge(ListSrc src0, int n, int k, int cap, float *out_scores,

@@ -37,6 +37,14 @@ extern "C" {
 #define GDR_Q_PER_BEAM 1u       /* q is [B*K, D]: one query vector per (query, beam), main_models.py:1467-1571,1583-1594 */
 #define GDR_FORCE_SIMT 2u       /* never use the tcgen05 grouped-GEMM path                */
 #define GDR_FORCE_UMMA 4u       /* use the tcgen05 path for every non-empty group         */
+/* Phase selection: a call normally runs inversion -> scoring -> top-k on `stream`.  A caller that pipelines batches
+ * may issue the three phases of one batch as three calls (same arguments) on three streams, ordered with events, so
+ * that the scoring kernels of consecutive batches run back to back while the inversion and top-k kernels of
+ * neighbouring batches fill in around them.  (Measured at cfg2: no better than simply running whole batches on
+ * three streams, DESIGN.md §7 — the flags are kept for callers that want to schedule the phases themselves.) */
+#define GDR_SKIP_INVERT 256u
+#define GDR_SKIP_SCORE 512u
+#define GDR_SKIP_TOPK 1024u
 
 typedef struct gdr_store gdr_store_t;
 typedef struct gdr_trie gdr_trie_t;

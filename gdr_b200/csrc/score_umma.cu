@@ -454,11 +454,14 @@ bool umma_make_tensor_map(CUtensorMap *out, const void *emb, int64_t n_docs, int
 }
 
 cudaError_t launch_score_umma(const ScoreArgs &a, const CUtensorMap *tmap, cudaStream_t s, int sm_count) {
-    static bool attr_set = false;
+    static unsigned long long attr_set_mask = 0;      // one bit per device: the attribute is per device and function
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const bool attr_set = (attr_set_mask >> (dev & 63)) & 1ull;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(k_score_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        attr_set_mask |= 1ull << (dev & 63);
     }
     return launch_pdl(k_score_umma, dim3(sm_count), dim3(UM_THREADS), UM_SMEM_BYTES, s, *tmap, a);
 }

@@ -483,14 +483,14 @@ cudaError_t launch_topk_store(const ScoreArgs &a, float alpha, float *out_scores
         static bool attr_set = false;
         if (!attr_set) {
             cudaFuncSetAttribute(k_topk_store<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-            attr_set = true;
+            attr_set_mask |= 1ull << (dev & 63);
         }
         return launch_pdl(k_topk_store<true>, dim3(a.B), dim3(TK_THREADS), with_keys, s, a, alpha, cap, out_scores, out_docids);
     } else {
         static bool attr_set = false;
         if (!attr_set) {
             cudaFuncSetAttribute(k_topk_store<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-            attr_set = true;
+            attr_set_mask |= 1ull << (dev & 63);
         }
         return launch_pdl(k_topk_store<false>, dim3(a.B), dim3(TK_THREADS), fixed, s, a, alpha, cap, out_scores, out_docids);
     }
@@ -504,10 +504,13 @@ cudaError_t launch_merge_topk(const float *scores, const int32_t *docids, int G,
     const int n = G * k_in;
     const size_t smem = (size_t)cap * 8 + TK_BINS * 4 + (size_t)((n + 3) / 4 * 4) * 4;
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
-    static bool attr_set = false;
+    static unsigned long long attr_set_mask = 0;      // one bit per device: the attribute is per device and function
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const bool attr_set = (attr_set_mask >> (dev & 63)) & 1ull;
     if (!attr_set) {
         cudaFuncSetAttribute(k_topk_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
+        attr_set_mask |= 1ull << (dev & 63);
     }
     ListSrc src{scores, docids, g_stride, k_in};
     k_topk_merge<<<B, TK_THREADS, smem, s>>>(src, n, k, cap, out_scores, out_docids);

@@ -7,7 +7,7 @@ Lightning harness, data loading and metrics.
     encode_single_newid          main_models.py:297-319
     decode_token                 main_models.py:322-346
     dec_2d                       main_utils.py:70-76
-    encode_query                 main_models.py:102-109   (EncoderModel.encode_query with self.output = None)
+    EncoderModel, encode_query   main_models.py:62-109    (query embedding = T5 encoder token-0 state)
     FineStage                    main_models.py:1434-1637 (the fine-grained stage of validation_step_i)
 """
 from __future__ import annotations
@@ -111,6 +111,28 @@ def encode_query(qry_hidden: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
     if qry_hidden is None:
         return None
     return qry_hidden[:, 0]
+
+
+class EncoderModel(torch.nn.Module):
+    """reference main_models.py:62-109.  The reference wraps a DPR context encoder (stock PyTorch, loaded from local
+    checkpoints); here the wrapped module is whatever the caller supplies.  `forward(query_enc=h)` is the part on the
+    hot path: the query embedding is `h[:, 0]` (or the optional pooler `self.output`)."""
+
+    def __init__(self, model: Optional[torch.nn.Module] = None, output: Optional[torch.nn.Module] = None, args=None):
+        super().__init__()
+        self.model, self.output, self.args = model, output, args
+
+    def forward(self, passage=None, query_enc=None):
+        if passage is not None:                                      # main_models.py:80-86 — stock PyTorch forward
+            passage = {k: v.view(-1, v.size(-1)) for k, v in passage.items()}
+            return self.model(**passage, return_dict=True).pooler_output
+        if query_enc is not None:
+            return self.encode_query(query_enc)
+
+    def encode_query(self, qry_hidden):                              # main_models.py:102-109
+        if qry_hidden is None:
+            return None
+        return self.output(q=qry_hidden) if self.output is not None else qry_hidden[:, 0]
 
 
 class FineStage:

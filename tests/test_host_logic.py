@@ -35,6 +35,7 @@ def test_codecs_match_reference_fixture():
     assert dec_2d(list(range(6)), 2) == [[0, 1], [2, 3], [4, 5]]
     h = torch.randn(3, 4, 8)
     assert torch.equal(encode_query(h), h[:, 0]) and encode_query(None) is None
+    assert torch.equal(gdr_b200.EncoderModel()(query_enc=h), h[:, 0])
 
 
 def test_tree_builder_matches_reference_fixture_and_pickles():

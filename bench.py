@@ -432,9 +432,9 @@ def main():
     line = {
         "metric": "queries/sec, cluster-restricted scoring + top-%d" % k, "value": qps, "unit": "queries/s", "n_gpus": world,
         "steps": steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16 store x fp32 query, fp32 accumulate", "data": "synthetic",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": args.workload + ("" if world == 1 else (f" x{world} cluster-sharded" if sharded else f" x{world} replicas, queries sharded")),
-                   "docs_per_gpu": cfg["N"],
+                   "precision": "bf16 embeddings x fp32 queries (exact 3-term bf16 split), fp32 accumulate", "docs_per_gpu": cfg["N"],
                    "clusters_per_gpu": cfg["C"], "dim": D, "global_batch": B_global, "beam": K, "top_k": k,
                    "l2": f"{replicas} store replicas ({replicas * emb_bytes / 2**20:.0f} MB) and {n_batches} query batches cycled; inputs larger than L2",
                    "cuda_graph": bool(use_graph), "batches_in_flight": n_pipe, "scoring_path": args.path,

@@ -29,6 +29,8 @@ SYMBOLS = {
     "gdr_trie_destroy": (c_int32, [c_void_p]),
     "gdr_tree_mask": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int64, c_int32, c_int32,
                                 c_int32, c_void_p]),
+    "gdr_beam_step": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                                c_int32, c_void_p, c_void_p, c_void_p]),
     "gdr_position_mask": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p]),
 }
 

@@ -53,6 +53,9 @@ struct gdr_store {
 struct gdr_trie {
     int32_t *first_child = nullptr, *child_tok = nullptr, *child_node = nullptr;
     int32_t n_nodes = 0, n_edges = 0;
+    int32_t fanout = 1;          // max children of any node (>= 1: the off-tree EOS candidate)
+    void *cand_ws = nullptr;     // beam-step candidates: [R, fanout] fp32 values | [R, fanout] int32 flat token ids
+    size_t cand_ws_bytes = 0;
 };
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -309,6 +312,7 @@ int gdr_trie_create(gdr_trie_t **out, const int32_t *first_child, const int32_t 
     gdr_trie *t = new (std::nothrow) gdr_trie();
     if (!t) return GDR_ERR_NOMEM;
     t->n_nodes = n_nodes; t->n_edges = n_edges;
+    for (int i = 0; i < n_nodes; ++i) t->fanout = first_child[i + 1] - first_child[i] > t->fanout ? first_child[i + 1] - first_child[i] : t->fanout;
     const size_t ne = (size_t)(n_edges > 0 ? n_edges : 1);
     cudaError_t e = cudaMalloc(&t->first_child, (size_t)(n_nodes + 1) * 4);
     if (e == cudaSuccess) e = cudaMalloc(&t->child_tok, ne * 4);
@@ -329,6 +333,7 @@ int gdr_trie_destroy(gdr_trie_t *t) {
     cudaFree(t->first_child);
     cudaFree(t->child_tok);
     cudaFree(t->child_node);
+    cudaFree(t->cand_ws);
     delete t;
     return GDR_OK;
 }
@@ -342,6 +347,39 @@ int gdr_tree_mask(gdr_trie_t *t, const int64_t *input_ids, int64_t ids_row_strid
     if (ids_row_stride < cur_len || scores_row_stride < V) return invalid("gdr_tree_mask: row stride smaller than row");
     GDR_CUDA(launch_tree_mask(t->first_child, t->child_tok, t->child_node, input_ids, ids_row_stride, R, cur_len, scores,
                               scores_row_stride, V, eos_id, strict, (cudaStream_t)stream));
+    return GDR_OK;
+}
+
+int gdr_beam_step(gdr_trie_t *t, const float *logits, int64_t logits_row_stride, const int64_t *input_ids,
+                  int64_t ids_row_stride, const float *beam_scores, int32_t B, int32_t K, int32_t cur_len, int32_t V,
+                  int32_t eos_id, float *out_scores, int32_t *out_tokens, void *stream) {
+    if (!t) return invalid("gdr_beam_step: trie is null");
+    if (B < 0 || K <= 0 || cur_len < 1 || V <= 0) return invalid("gdr_beam_step: need B >= 0, K > 0, cur_len >= 1, V > 0");
+    if (B == 0) return GDR_OK;
+    if (!logits || !input_ids || !beam_scores || !out_scores || !out_tokens) return invalid("gdr_beam_step: null pointer");
+    if (logits_row_stride < V || ids_row_stride < cur_len) return invalid("gdr_beam_step: row stride smaller than row");
+    if ((int64_t)K * V > INT_MAX) return invalid("gdr_beam_step: K * V must fit in int32");
+    const int fanout = (t->fanout + 3) / 4 * 4;
+    const int64_t R = (int64_t)B * K;
+    if ((int64_t)K * fanout > 32768 || 2 * K > 4096) {
+        set_error("gdr_beam_step: K * max_fanout > 32768 or 2K > 4096 is not supported (use gdr_tree_mask + torch)");
+        return GDR_ERR_UNSUPPORTED;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t need = (size_t)R * fanout * 8;
+    if (need > t->cand_ws_bytes) {
+        GDR_CUDA(cudaStreamSynchronize(st));
+        if (t->cand_ws) GDR_CUDA(cudaFree(t->cand_ws));
+        t->cand_ws = nullptr; t->cand_ws_bytes = 0;
+        GDR_CUDA(cudaMalloc(&t->cand_ws, need));
+        t->cand_ws_bytes = need;
+    }
+    float *cand_val = reinterpret_cast<float *>(t->cand_ws);
+    int32_t *cand_id = reinterpret_cast<int32_t *>(cand_val + R * fanout);
+    GDR_CUDA(launch_beam_rows(t->first_child, t->child_tok, t->child_node, input_ids, ids_row_stride, cur_len, logits,
+                              logits_row_stride, V, beam_scores, (int)R, K, eos_id, fanout, cand_val, cand_id, st));
+    // per query: top-2K of its K * fanout candidates, (score desc, flat index asc) — the merge kernel with one "rank"
+    GDR_CUDA(launch_merge_topk(cand_val, cand_id, 1, B, K * fanout, (int64_t)B * K * fanout, 2 * K, out_scores, out_tokens, st));
     return GDR_OK;
 }
 

@@ -85,6 +85,10 @@ cudaError_t launch_similarity(const float *q, int64_t Q, const void *p, int64_t 
 cudaError_t launch_tree_mask(const int32_t *first_child, const int32_t *child_tok, const int32_t *child_node,
                              const int64_t *input_ids, int64_t ids_stride, int R, int cur_len, float *scores,
                              int64_t scores_stride, int V, int eos_id, int strict, cudaStream_t s);
+cudaError_t launch_beam_rows(const int32_t *first_child, const int32_t *child_tok, const int32_t *child_node,
+                             const int64_t *input_ids, int64_t ids_stride, int cur_len, const float *logits,
+                             int64_t logits_stride, int V, const float *beam_scores, int R, int K, int eos_id, int fanout,
+                             float *cand_val, int32_t *cand_id, cudaStream_t s);
 cudaError_t launch_position_mask(float *logits, int64_t bz, int sl, int V, int v_out, int last_eos_only,
                                  cudaStream_t s);
 

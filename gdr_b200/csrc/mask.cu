@@ -120,6 +120,93 @@ cudaError_t launch_tree_mask(const int32_t *first_child, const int32_t *child_to
     return cudaGetLastError();
 }
 
+// ---- fused beam step (the "next" row after the mask itself) ----------------------------------------
+// Replaces the three full-size passes around the mask in the reference's beam search,
+//   generation_utils_previous.py:694  scores = log_softmax(next_token_logits)          (read + write R*V)
+//   generation_utils_previous.py:714-729  scores += tree mask                            (read + write R*V)
+//   :757-771  next_scores = (scores + beam_scores[:, None]).view(B, K*V); topk(2K)       (read + write + read R*V)
+// by ONE read of the logits: after the mask at most `fanout` entries of a row are finite, so a row only needs its
+// log-sum-exp (online, one pass) and the log-probabilities of the allowed tokens.  k_beam_rows writes those candidates
+// (value, beam*V + token); the per-query top-2K over the K*fanout candidates is the merge kernel of topk.cu.
+// HBM-bound: algorithmic bytes = R*V*4.
+__global__ void __launch_bounds__(TM_THREADS) k_beam_rows(const int32_t *__restrict__ first_child,
+                                                          const int32_t *__restrict__ child_tok,
+                                                          const int32_t *__restrict__ child_node,
+                                                          const int64_t *__restrict__ input_ids, int64_t ids_stride, int cur_len,
+                                                          const float *__restrict__ logits, int64_t logits_stride, int V,
+                                                          const float *__restrict__ beam_scores, int K, int eos_id, int fanout,
+                                                          float *__restrict__ cand_val, int32_t *__restrict__ cand_id) {
+    __shared__ int s_node;
+    __shared__ float s_m[TM_THREADS / 32], s_s[TM_THREADS / 32];
+    const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *row = logits + (int64_t)r * logits_stride;
+    if (warp == 0) {
+        const int node = trie_walk(first_child, child_tok, child_node, input_ids + (int64_t)r * ids_stride, cur_len, lane);
+        if (lane == 0) s_node = node;
+    }
+    // online log-sum-exp: running maximum m and sum s of exp(x - m)
+    float m = -INFINITY, s = 0.f;
+    auto push = [&](float x) {
+        if (x > m) { s = s * expf(m - x) + 1.f; m = x; }
+        else if (x > -INFINITY) s += expf(x - m);
+    };
+    if ((reinterpret_cast<uintptr_t>(row) & 15) == 0) {
+        const float4 *row4 = reinterpret_cast<const float4 *>(row);
+        const int n4 = V >> 2;
+        for (int i = tid; i < n4; i += TM_THREADS) {
+            const float4 v = __ldcs(row4 + i);      // streamed once
+            push(v.x); push(v.y); push(v.z); push(v.w);
+        }
+        for (int i = (n4 << 2) + tid; i < V; i += TM_THREADS) push(row[i]);
+    } else {
+        for (int i = tid; i < V; i += TM_THREADS) push(row[i]);
+    }
+    auto combine = [](float &m1, float &s1, float m2, float s2) {
+        const float mx = fmaxf(m1, m2);
+        if (mx == -INFINITY) { s1 = 0.f; return; }
+        s1 = s1 * expf(m1 - mx) + s2 * expf(m2 - mx);
+        m1 = mx;
+    };
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        const float m2 = __shfl_xor_sync(0xffffffffu, m, d), s2 = __shfl_xor_sync(0xffffffffu, s, d);
+        combine(m, s, m2, s2);
+    }
+    if (lane == 0) { s_m[warp] = m; s_s[warp] = s; }
+    __syncthreads();
+    m = s_m[0]; s = s_s[0];
+    for (int w = 1; w < TM_THREADS / 32; ++w) combine(m, s, s_m[w], s_s[w]);
+    const float log_s = logf(s);
+    const int node = s_node;
+    const int lo = node < 0 ? 0 : first_child[node];
+    const int n_allowed = node < 0 ? 1 : first_child[node + 1] - lo;
+    const float beam = beam_scores[r];
+    for (int e = tid; e < fanout; e += TM_THREADS) {
+        float val = -INFINITY;
+        int32_t id = -1;
+        if (e < n_allowed) {
+            const int tok = node < 0 ? eos_id : child_tok[lo + e];
+            if (tok >= 0 && tok < V) {
+                // log_softmax as torch computes it, (x - max) - log(sum), then "+ 0" (mask) and "+ beam score"
+                val = __fadd_rn(__fadd_rn(__fsub_rn(__fsub_rn(row[tok], m), log_s), 0.0f), beam);
+                id = (r % K) * V + tok;
+            }
+        }
+        cand_val[(int64_t)r * fanout + e] = val;
+        cand_id[(int64_t)r * fanout + e] = id;
+    }
+}
+
+cudaError_t launch_beam_rows(const int32_t *first_child, const int32_t *child_tok, const int32_t *child_node,
+                             const int64_t *input_ids, int64_t ids_stride, int cur_len, const float *logits,
+                             int64_t logits_stride, int V, const float *beam_scores, int R, int K, int eos_id, int fanout,
+                             float *cand_val, int32_t *cand_id, cudaStream_t s) {
+    if (R == 0) return cudaSuccess;
+    k_beam_rows<<<R, TM_THREADS, 0, s>>>(first_child, child_tok, child_node, input_ids, ids_stride, cur_len, logits, logits_stride,
+                                         V, beam_scores, K, eos_id, fanout, cand_val, cand_id);
+    return cudaGetLastError();
+}
+
 // logits [bz, sl, V]: position t keeps {t*v_out+2 .. t*v_out+v_out+1} ∪ {1}; with last_eos_only the last
 // position keeps only {1} (modeling_t5.py:1296).
 __global__ void __launch_bounds__(256) k_position_mask(float *__restrict__ logits, int64_t n_rows, int sl, int V,

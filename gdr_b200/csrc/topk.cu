@@ -474,27 +474,28 @@ __global__ void __launch_bounds__(TK_THREADS) k_topk_merge(ListSrc src0, int n, 
 
 static int pow2_at_least(int x) { int p = 2; while (p < x) p <<= 1; return p; }
 
+// cudaFuncSetAttribute is per device and function: remember which devices have it (one process may drive several)
+static bool need_attr(unsigned long long &mask) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const bool need = !((mask >> (dev & 63)) & 1ull);
+    mask |= 1ull << (dev & 63);
+    return need;
+}
+
 cudaError_t launch_topk_store(const ScoreArgs &a, float alpha, float *out_scores, int32_t *out_docids, cudaStream_t s) {
     if (a.B == 0) return cudaSuccess;
     const int cap = pow2_at_least(a.k);
     const size_t fixed = (size_t)cap * 8 + (size_t)TK_BINS * 4 + (size_t)(2 * a.K + 1) * 4;
     const size_t with_keys = fixed + (size_t)a.stride * 4;
-    if (with_keys <= 96 * 1024) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(k_topk_store<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-            attr_set_mask |= 1ull << (dev & 63);
-        }
-        return launch_pdl(k_topk_store<true>, dim3(a.B), dim3(TK_THREADS), with_keys, s, a, alpha, cap, out_scores, out_docids);
-    } else {
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(k_topk_store<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-            attr_set_mask |= 1ull << (dev & 63);
-        }
-        return launch_pdl(k_topk_store<false>, dim3(a.B), dim3(TK_THREADS), fixed, s, a, alpha, cap, out_scores, out_docids);
+    static unsigned long long attr_mask = 0;
+    if (need_attr(attr_mask)) {
+        cudaFuncSetAttribute(k_topk_store<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        cudaFuncSetAttribute(k_topk_store<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     }
-    return cudaGetLastError();
+    if (with_keys <= 96 * 1024)
+        return launch_pdl(k_topk_store<true>, dim3(a.B), dim3(TK_THREADS), with_keys, s, a, alpha, cap, out_scores, out_docids);
+    return launch_pdl(k_topk_store<false>, dim3(a.B), dim3(TK_THREADS), fixed, s, a, alpha, cap, out_scores, out_docids);
 }
 
 cudaError_t launch_merge_topk(const float *scores, const int32_t *docids, int G, int B, int k_in, int64_t g_stride, int k,

@@ -80,6 +80,31 @@ class DeviceTrie:
                 int(strict), _cabi.stream_ptr(stream)))
         return scores
 
+    def beam_step(self, next_token_logits: torch.Tensor, input_ids: torch.Tensor, beam_scores: torch.Tensor,
+                  num_beams: int, eos_token_id: int = 1, stream=None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Fused log_softmax -> tree mask -> + beam score -> view [B, K*V] -> topk(2K) of the reference's beam search
+        (generation_utils_previous.py:694, 714-729, 757-771) with one read of the logits.
+        next_token_logits [B*K, V] fp32, input_ids [B*K, cur_len] int64, beam_scores [B*K] fp32 (all CUDA).
+        Returns (next_scores [B, 2K] fp32, next_tokens [B, 2K] int64 = beam * V + token; -inf / -1 past the survivors)."""
+        if not (next_token_logits.is_cuda and input_ids.is_cuda and beam_scores.is_cuda):
+            raise ValueError("beam_step runs on the device (no CPU fallback)")
+        if next_token_logits.dtype != torch.float32 or input_ids.dtype != torch.int64 or next_token_logits.stride(1) != 1:
+            raise ValueError("next_token_logits must be float32 with a contiguous last dimension, input_ids int64")
+        R, V = next_token_logits.shape
+        if R % num_beams or input_ids.shape[0] != R or beam_scores.numel() != R:
+            raise ValueError("row counts must equal batch_size * num_beams")
+        B = R // num_beams
+        bs = beam_scores.to(torch.float32).contiguous().view(-1)
+        ids = input_ids if input_ids.stride(1) == 1 else input_ids.contiguous()
+        out_s = torch.empty((B, 2 * num_beams), dtype=torch.float32, device=next_token_logits.device)
+        out_t = torch.empty((B, 2 * num_beams), dtype=torch.int32, device=next_token_logits.device)
+        with torch.cuda.device(next_token_logits.device):
+            _cabi.check(_cabi.lib().gdr_beam_step(
+                self._handle, next_token_logits.data_ptr(), next_token_logits.stride(0) if R > 1 else V, ids.data_ptr(),
+                ids.stride(0) if R > 1 else ids.shape[1], bs.data_ptr(), B, num_beams, ids.shape[1], V, int(eos_token_id),
+                out_s.data_ptr(), out_t.data_ptr(), _cabi.stream_ptr(stream)))
+        return out_s, out_t.long()
+
     def close(self):
         if getattr(self, "_handle", None) is not None and self._handle.value:
             _cabi.lib().gdr_trie_destroy(self._handle)
@@ -104,6 +129,10 @@ class TreeMask:
 
     def __call__(self, input_ids: torch.Tensor, scores: torch.Tensor) -> torch.Tensor:
         return self.trie.mask_(scores, input_ids, self.eos_token_id, self.strict)
+
+    def beam_step(self, next_token_logits, input_ids, beam_scores, num_beams):
+        """Fused replacement of log_softmax + mask + beam-score add + topk(2K): see DeviceTrie.beam_step."""
+        return self.trie.beam_step(next_token_logits, input_ids, beam_scores, num_beams, self.eos_token_id)
 
 
 def position_mask_(logits: torch.Tensor, output_vocab_size: int, last_eos_only: bool = False, stream=None) -> torch.Tensor:

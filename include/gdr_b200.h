@@ -129,6 +129,18 @@ int gdr_tree_mask(gdr_trie_t *trie, const int64_t *input_ids, int64_t ids_row_st
                   int32_t cur_len, float *scores, int64_t scores_row_stride, int32_t V, int32_t eos_id,
                   int32_t strict, void *stream);
 
+/* Fused beam step ("next" row): replaces generation_utils_previous.py:694 (log_softmax), :714-729 (tree
+ * mask) and :757-771 (add the beam scores, view [B, K*V], topk(2K, largest, sorted)) with ONE read of the logits.
+ *   logits DEV fp32 [B*K, V] (row stride in elements, not modified), input_ids DEV int64 [B*K, cur_len],
+ *   beam_scores DEV fp32 [B*K]
+ *   -> out_scores DEV fp32 [B, 2K], out_tokens DEV int32 [B, 2K]: flat index beam*V + token, sorted by score
+ *      descending, ties by ascending index; when fewer than 2K entries survive the mask the tail is (-inf, -1) (the
+ *      reference's topk returns -inf with unspecified indices there).
+ * The other postprocess_next_token_scores options (:696-708) are not applied (the reference's defaults make them no-ops). */
+int gdr_beam_step(gdr_trie_t *trie, const float *logits, int64_t logits_row_stride, const int64_t *input_ids,
+                  int64_t ids_row_stride, const float *beam_scores, int32_t B, int32_t K, int32_t cur_len, int32_t V,
+                  int32_t eos_id, float *out_scores, int32_t *out_tokens, void *stream);
+
 /* Replaces modeling_t5.py:1546-1571 `select_valid_embedding` (eval; last_eos_only = 0) and the
  * `logit_mask` buffer of modeling_t5.py:1279-1301 (training; last_eos_only = 1): in place on
  * logits DEV fp32 [bz, sl, V]; position t keeps tokens {t*v_out+2 .. t*v_out+v_out+1} and 1

@@ -255,6 +255,20 @@ def tree_mask(scores: torch.Tensor, input_ids: torch.Tensor, root) -> torch.Tens
     return scores + mask
 
 
+def beam_step(next_token_logits: torch.Tensor, input_ids: torch.Tensor, beam_scores: torch.Tensor, root, num_beams: int
+              ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """generation_utils_previous.py:694 (log_softmax) -> :714-729 (tree mask) -> :757-771:
+    `next_scores = scores + beam_scores[:, None]`, `.view(batch_size, num_beams * vocab_size)`,
+    `torch.topk(next_scores, 2 * num_beams, dim=1, largest=True, sorted=True)`.
+    (postprocess_next_token_scores, :696-708, is a no-op under the reference's generate() defaults.)"""
+    scores = torch.log_softmax(next_token_logits, dim=-1)
+    scores = tree_mask(scores, input_ids, root)
+    next_scores = scores + beam_scores[:, None].expand_as(scores)
+    B = next_token_logits.shape[0] // num_beams
+    next_scores = next_scores.view(B, num_beams * next_token_logits.shape[1])
+    return torch.topk(next_scores, 2 * num_beams, dim=1, largest=True, sorted=True)
+
+
 # --------------------------------------------------------------------------------------
 # a12. positional mask — GDR_model/transformers/modeling_t5.py:1546-1571 (eval) / 1279-1301 (train)
 # --------------------------------------------------------------------------------------

@@ -169,6 +169,37 @@ def gen_main_models():
                         edges=np.array(edges, dtype=np.int64), leaves=np.array(leaves, dtype=np.int64), **out)
     print("wrote tree")
 
+    # ---------------- fused beam step: log_softmax (:694) -> mask block (:714-729) -> + beam scores, view, topk(2K) (:757-771) -----
+    import torch.nn.functional as F
+    bs_out = {}
+    for case, (Bq, Kb, cur_len) in {"a": (3, 4, 3), "b": (2, 6, 1), "c": (4, 5, 4)}.items():
+        R = Bq * Kb
+        ids_t = torch.zeros(R, cur_len, dtype=torch.int64)
+        for r in range(R):
+            t = tok_paths[rng.randint(len(tok_paths))]
+            n = min(cur_len - 1, len(t))
+            ids_t[r, 1:1 + n] = torch.tensor(t[:n])
+            if r % 5 == 2 and cur_len > 1:
+                ids_t[r, rng.randint(1, cur_len)] = 99 + rng.randint(20)
+        g = torch.Generator().manual_seed(500 + R)
+        logits = torch.randn(R, V, generator=g) * 3
+        beam_scores = -torch.rand(R, generator=g) * 5
+        if cur_len == 1:
+            beam_scores = beam_scores.view(Bq, Kb)
+            beam_scores[:, 1:] = -1e9                                   # generation_utils_previous.py:668
+            beam_scores = beam_scores.reshape(-1)
+        scores = F.log_softmax(logits, dim=-1)                          # :694
+        ns = {"torch": torch, "decode_tree": root, "scores": scores, "input_ids": ids_t, "num_beams": Kb, "batch_size": Bq}
+        exec(block, ns)                                                 # :714-729
+        next_scores = ns["scores"] + beam_scores[:, None].expand_as(ns["scores"])      # :757
+        next_scores = next_scores.view(Bq, Kb * V)                      # :760-762
+        top_s, top_t = torch.topk(next_scores, 2 * Kb, dim=1, largest=True, sorted=True)   # :771
+        bs_out.update({f"logits_{case}": logits.numpy(), f"ids_{case}": ids_t.numpy(), f"beam_{case}": beam_scores.numpy(),
+                       f"K_{case}": np.int64(Kb), f"scores_{case}": top_s.numpy(), f"tokens_{case}": top_t.numpy()})
+    np.savez_compressed(os.path.join(GOLD, "beam_step.npz"), edges=np.array(edges, dtype=np.int64),
+                        leaves=np.array(leaves, dtype=np.int64), **bs_out)
+    print("wrote beam_step")
+
     # ---------------- positional mask ----------------
     sel_src = _ref_lines(os.path.join(REF, "transformers", "modeling_t5.py"), 1546, 1571)
     assert sel_src.startswith("def select_valid_embedding(sequence):"), sel_src[:60]

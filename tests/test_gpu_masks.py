@@ -110,3 +110,64 @@ def test_position_mask_golden():
     assert np.array_equal(build_logit_mask(10, 302, 30).cpu().numpy(), g["train_logit_mask_30_10"])
     with pytest.raises(RuntimeError):
         position_mask_(torch.zeros(1, 10, 100, device="cuda"), 30)      # vocabulary too small (scatter_ would raise)
+
+
+def _check_beam_step(got_s, got_t, ref_s, ref_t, what):
+    """values within 1e-5; tokens equal wherever the reference value is finite and not within 1e-5 of a neighbour;
+    past the survivors ours is (-inf, -1) (the reference's topk returns -inf with unspecified indices there)."""
+    got_s, got_t = got_s.cpu().numpy(), got_t.cpu().numpy()
+    finite = np.isfinite(ref_s)
+    assert np.array_equal(np.isfinite(got_s), finite), what
+    np.testing.assert_allclose(got_s[finite], ref_s[finite], rtol=1e-5, atol=1e-5, err_msg=what)
+    assert np.all(got_t[~finite] == -1), what
+    for b in range(ref_s.shape[0]):
+        for i in np.nonzero(finite[b] & (got_t[b] != ref_t[b]))[0]:
+            js = np.nonzero(ref_t[b] == got_t[b, i])[0]
+            assert js.size and abs(ref_s[b, js[0]] - ref_s[b, i]) <= 1e-5 * max(1.0, abs(ref_s[b, i])), (what, b, i)
+
+
+def test_beam_step_golden():
+    from gdr_b200 import Node, TreeMask
+    g = load_golden("beam_step")
+    hook = TreeMask(rebuild_tree(g["edges"], g["leaves"], Node))
+    for case in ("a", "b", "c"):
+        K = int(g[f"K_{case}"])
+        logits = torch.from_numpy(g[f"logits_{case}"]).cuda()
+        before = logits.clone()
+        s, t = hook.beam_step(logits, torch.from_numpy(g[f"ids_{case}"]).cuda(), torch.from_numpy(g[f"beam_{case}"]).cuda(), K)
+        assert torch.equal(logits, before), "beam_step must not modify the logits"
+        _check_beam_step(s, t, g[f"scores_{case}"], g[f"tokens_{case}"], f"beam_step golden {case}")
+
+
+def test_beam_step_cfg4_shape_vs_oracle():
+    """V = 32,128, 3-level 30-ary tree with 1,024 leaf clusters, beam 100 (rows reduced so the CPU oracle finishes fast)."""
+    from gdr_b200 import TreeBuilder, TreeMask
+    rng = np.random.RandomState(7)
+    paths = set()
+    while len(paths) < 1024:
+        paths.add(tuple(rng.randint(0, 30, 3)))
+    tb, otb = TreeBuilder(), orc.TreeBuilder()
+    toks = []
+    for di, p in enumerate(sorted(paths)):
+        t = [i * 30 + int(c) + 2 for i, c in enumerate(p)] + [1]
+        toks.append(t)
+        tb.add(t, di); otb.add(t, di)
+    hook = TreeMask(tb.build())
+    V, B, K = 32128, 4, 100
+    for cur_len in (1, 2, 3, 4):
+        R = B * K
+        ids = torch.zeros(R, cur_len, dtype=torch.int64)
+        for r in range(R):
+            t = toks[rng.randint(len(toks))]
+            n = min(cur_len - 1, len(t))
+            ids[r, 1:1 + n] = torch.tensor(t[:n])
+            if r % 37 == 5 and cur_len > 1:
+                ids[r, rng.randint(1, cur_len)] = 91 + rng.randint(1000)
+        gen = torch.Generator().manual_seed(cur_len)
+        logits = torch.randn(R, V, generator=gen) * 2
+        beam = -torch.rand(R, generator=gen) * 8
+        if cur_len == 1:
+            beam = beam.view(B, K); beam[:, 1:] = -1e9; beam = beam.reshape(-1)
+        ref_s, ref_t = orc.beam_step(logits, ids, beam, otb.build(), K)
+        s, t = hook.beam_step(logits.cuda(), ids.cuda(), beam.cuda(), K)
+        _check_beam_step(s, t, ref_s.numpy(), ref_t.numpy(), f"beam_step cfg4 cur_len={cur_len}")

@@ -245,3 +245,25 @@ def test_merge_topk_kernel():
     ms, md = ShardedRetriever._cuda_merge(packed, k)
     ref_s, ref_d = orc.merge_topk(s, d, k)
     assert_topk_parity(ms, md, ref_s, ref_d, "merge")
+
+
+def test_index_file_loads_into_an_identical_store(tmp_path):
+    """load_store(file) == ClusterStore.from_reference: same results, whole corpus and a cluster shard."""
+    from types import SimpleNamespace
+    from gdr_b200 import ClusterStore
+    from gdr_b200.index_io import load_store, write_index
+    from gdr_b200.store import csr_from_reference
+    f = fine_stage_inputs("fine_stage_tanh")
+    emb, offsets, docid, keys = csr_from_reference(f["doc_embed"], f["id_mapping"])
+    p = str(tmp_path / "idx.gdr")
+    write_index(p, emb.bfloat16(), offsets.numpy(), docid.numpy(), keys)
+    a = ClusterStore.from_reference(f["doc_embed"], f["id_mapping"], dtype=torch.bfloat16)
+    b = load_store(p, chunk_rows=37)
+    assert b.keys == a.keys and torch.equal(b.emb, a.emb) and torch.equal(b.docid, a.docid) and torch.equal(b.offsets, a.offsets)
+    beams = a.beams_from_ids(f["dec"]).cuda()
+    q = f["q"].cuda()
+    sa, da = a.score_topk(q, beams, 5)
+    sb, db = b.score_topk(q, beams, 5)
+    assert torch.equal(sa, sb) and torch.equal(da, db)
+    shard = load_store(p, clusters=np.array([1, 4, 7]), chunk_rows=16)
+    assert shard.keys == [keys[1], keys[4], keys[7]] and shard.n_docs == int(sum(len(f["id_mapping"][keys[c]]) for c in (1, 4, 7)))

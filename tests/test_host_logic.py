@@ -139,3 +139,31 @@ def test_no_cpu_fallback_in_product_path():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert "gdr_oracle" not in src and "import oracle" not in src and "from oracle" not in src, fn
+
+
+def test_index_file_roundtrip_and_pickle_converter(tmp_path):
+    """On-disk CSR format: write -> mmap round trip, and the converter from the reference's pickles."""
+    import pickle
+    from gdr_b200.index_io import convert_pickles, map_index, read_header, write_index
+    f = fine_stage_inputs("fine_stage_tanh")
+    emb, offsets, docid, keys = csr_from_reference(f["doc_embed"], f["id_mapping"])
+    for dt in (torch.float32, torch.bfloat16):
+        p = str(tmp_path / f"idx_{dt}.gdr")
+        write_index(p, emb.to(dt), offsets.numpy(), docid.numpy(), keys)
+        h = read_header(p)
+        assert h["n_rows"] == emb.shape[0] and h["dim"] == emb.shape[1] and h["n_clusters"] == len(keys)
+        m_emb, m_off, m_doc, m_keys, m_dt = map_index(p)
+        assert m_dt == dt and m_keys == keys
+        assert np.array_equal(m_off, offsets.numpy()) and np.array_equal(m_doc, docid.numpy())
+        back = torch.from_numpy(np.array(m_emb))
+        back = back.view(torch.int16).view(torch.bfloat16) if dt == torch.bfloat16 else back
+        assert torch.equal(back, emb.to(dt))
+    pe, pm = str(tmp_path / "doc_embedding.pkl"), str(tmp_path / "indexmap.pkl")
+    pickle.dump(f["doc_embed"], open(pe, "wb"))
+    pickle.dump(f["id_mapping"], open(pm, "wb"))
+    h = convert_pickles(pe, pm, str(tmp_path / "conv.gdr"), dtype=torch.float32)
+    assert h["n_clusters"] == len(f["id_mapping"]) and h["n_rows"] == sum(len(v) for v in f["id_mapping"].values())
+    m_emb, m_off, m_doc, m_keys, _ = map_index(str(tmp_path / "conv.gdr"))
+    assert m_keys == list(f["id_mapping"].keys()) and torch.equal(torch.from_numpy(np.array(m_emb)), emb)
+    with pytest.raises(ValueError):
+        read_header(pe)

@@ -23,6 +23,7 @@ SYMBOLS = {
     "gdr_store_last_stats": (c_int32, [c_void_p, POINTER(c_int64), c_void_p]),
     "gdr_store_set_profiling": (c_int32, [c_void_p, c_int32]),
     "gdr_store_last_phase_ms": (c_int32, [c_void_p, POINTER(c_float)]),
+    "gdr_cluster_centroids": (c_int32, [c_void_p, c_void_p, c_void_p]),
     "gdr_similarity": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
     "gdr_merge_topk": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
     "gdr_trie_create": (c_int32, [POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_int32, c_int32]),

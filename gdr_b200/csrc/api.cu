@@ -264,6 +264,12 @@ int gdr_store_last_stats(gdr_store_t *s, int64_t out[4], void *stream) {
     return GDR_OK;
 }
 
+int gdr_cluster_centroids(gdr_store_t *s, float *out, void *stream) {
+    if (!s || !out) return invalid("gdr_cluster_centroids: null argument");
+    GDR_CUDA(launch_centroids(s->emb, s->dtype, s->offsets, s->n_clusters, s->dim, out, (cudaStream_t)stream));
+    return GDR_OK;
+}
+
 int gdr_similarity(const float *q, int64_t Q, const void *p, int64_t P, int32_t dim, int32_t p_dtype, float *out,
                    void *stream) {
     if (Q < 0 || P < 0) return invalid("gdr_similarity: negative size");

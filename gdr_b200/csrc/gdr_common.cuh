@@ -82,6 +82,7 @@ cudaError_t launch_merge_topk(const float *scores, const int32_t *docids, int G,
                               float *out_scores, int32_t *out_docids, cudaStream_t s);
 cudaError_t launch_similarity(const float *q, int64_t Q, const void *p, int64_t P, int dim, int p_dtype,
                               float *out, cudaStream_t s, int sm_count);
+cudaError_t launch_centroids(const void *emb, int dtype, const int32_t *offsets, int n_clusters, int dim, float *out, cudaStream_t s);
 cudaError_t launch_tree_mask(const int32_t *first_child, const int32_t *child_tok, const int32_t *child_node,
                              const int64_t *input_ids, int64_t ids_stride, int R, int cur_len, float *scores,
                              int64_t scores_stride, int V, int eos_id, int strict, cudaStream_t s);

@@ -206,6 +206,40 @@ __global__ void __launch_bounds__(128) k_similarity(const float *__restrict__ q,
     }
 }
 
+// Leaf-cluster centroids: out[c] = mean of the rows of cluster c, fp32, rows added in store order —
+// the order `sum([embedding[i] for i in embedding_index])` uses in tree_embedding_calculate (main_models.py:154-158).
+// One CTA per cluster, one 16-byte chunk of the row per thread; a single pass over the store (HBM-bound, run once
+// per index build / expansion).
+template <typename T>
+__global__ void __launch_bounds__(256) k_centroids(const T *__restrict__ emb, const int32_t *__restrict__ offsets, int dim,
+                                                   float *__restrict__ out) {
+    constexpr int EPC = Chunk<T>::EPC;
+    const int c = blockIdx.x;
+    const int lo = offsets[c], hi = offsets[c + 1];
+    const int nchunks = dim / EPC;
+    for (int ch = threadIdx.x; ch < nchunks; ch += blockDim.x) {
+        float acc[EPC];
+#pragma unroll
+        for (int e = 0; e < EPC; ++e) acc[e] = 0.f;
+        for (int r = lo; r < hi; ++r) {
+            float x[EPC];
+            Chunk<T>::unpack(ldg_stream(reinterpret_cast<const char *>(emb + (int64_t)r * dim) + (int64_t)ch * 16), x);
+#pragma unroll
+            for (int e = 0; e < EPC; ++e) acc[e] = __fadd_rn(acc[e], x[e]);
+        }
+        const float n = (float)(hi - lo);
+#pragma unroll
+        for (int e = 0; e < EPC; ++e) out[(int64_t)c * dim + ch * EPC + e] = hi > lo ? __fdiv_rn(acc[e], n) : 0.f;
+    }
+}
+
+cudaError_t launch_centroids(const void *emb, int dtype, const int32_t *offsets, int n_clusters, int dim, float *out, cudaStream_t s) {
+    if (n_clusters == 0) return cudaSuccess;
+    if (dtype == GDR_DTYPE_BF16) k_centroids<__nv_bfloat16><<<n_clusters, 128, 0, s>>>((const __nv_bfloat16 *)emb, offsets, dim, out);
+    else k_centroids<float><<<n_clusters, 256, 0, s>>>((const float *)emb, offsets, dim, out);
+    return cudaGetLastError();
+}
+
 template <typename T> static int cpl_for(int dim) {
     const int nchunks = dim / Chunk<T>::EPC;
     const int cpl = (nchunks + 31) / 32;

@@ -120,7 +120,7 @@ def load_store(path: str, device="cuda", clusters: Optional[np.ndarray] = None, 
             src = stage[:n].view(torch.bfloat16) if dt == torch.bfloat16 else stage[:n]
             dev_emb[pos:pos + n].copy_(src, non_blocking=False)
             pos += n
-    return ClusterStore(dev_emb, torch.from_numpy(np.ascontiguousarray(loc_off)), torch.from_numpy(np.ascontiguousarray(loc_doc)), loc_keys)
+    return ClusterStore(dev_emb, torch.from_numpy(np.array(loc_off, dtype=np.int64)), torch.from_numpy(np.array(loc_doc, dtype=np.int64)), loc_keys)
 
 
 def convert_pickles(doc_embedding_pkl: str, indexmap_pkl: str, out_path: str, dtype=torch.bfloat16) -> Dict[str, int]:

@@ -142,6 +142,14 @@ class ClusterStore:
             _cabi.check(_cabi.lib().gdr_store_last_stats(self._handle, arr, _cabi.stream_ptr()))
         return {"simt_items": arr[0], "umma_tiles": arr[1], "launches": arr[2], "clusters_touched": arr[3]}
 
+    def centroids(self, stream=None) -> torch.Tensor:
+        """Leaf-cluster centroids [C, D] fp32: the `embedding` tree_embedding_calculate stores on every leaf-cluster node
+        (reference main_models.py:154-158)."""
+        out = torch.empty((self.n_clusters, self.dim), dtype=torch.float32, device=self.emb.device)
+        with torch.cuda.device(self.emb.device):
+            _cabi.check(_cabi.lib().gdr_cluster_centroids(self._handle, out.data_ptr(), _cabi.stream_ptr(stream)))
+        return out
+
     def set_profiling(self, enable: bool) -> None:
         _cabi.check(_cabi.lib().gdr_store_set_profiling(self._handle, int(enable)))
 

@@ -97,6 +97,13 @@ int gdr_store_last_stats(gdr_store_t *store, int64_t out[4], void *stream);
 int gdr_store_set_profiling(gdr_store_t *store, int32_t enable);
 int gdr_store_last_phase_ms(gdr_store_t *store, float out[4]);
 
+/* ---- index expansion --------------------------------------------------------
+ * Leaf-cluster centroids of tree_embedding_calculate (main_models.py:154-158): out DEV fp32 [n_clusters, dim],
+ * out[c] = mean of cluster c's rows (rows summed in store order, fp32); empty clusters give zeros.  Assigning new
+ * documents to clusters (tree_embedding_insert, main_models.py:268-295: argmax_c doc . centroid_c) is then
+ * gdr_score_topk with k = 1 on a store whose single cluster holds the centroids (gdr_b200/expand.py). */
+int gdr_cluster_centroids(gdr_store_t *store, float *out, void *stream);
+
 /* ---- dense similarity (dense.py:53-54 / encoder.py:128-129): out[Q, P] = q @ p^T, fp32 out ----
  *   q DEV fp32 [Q, dim]; p DEV [P, dim] of p_dtype; out DEV fp32 [Q, P]. */
 int gdr_similarity(const float *q, int64_t Q, const void *p, int64_t P, int32_t dim, int32_t p_dtype,

@@ -215,6 +215,27 @@ def dense_topk(q: torch.Tensor, emb: torch.Tensor, offsets: np.ndarray, docid: n
     return out_s, out_i
 
 
+def leaf_centroids(doc_embed, id_mapping: Dict[str, List[int]]) -> torch.Tensor:
+    """tree_embedding_calculate, leaf part (main_models.py:154-158): `sum([embedding[i] for i in idx]) / len(idx)`,
+    one row per cluster in id_mapping order."""
+    return torch.stack([sum([doc_embed[i] for i in idx]) / len(idx) for idx in id_mapping.values()])
+
+
+def tree_embedding_insert(cluster_embedding: torch.Tensor, keys: List[str], id_mapping: Dict[str, List[int]], insert_doc,
+                          docnum: int) -> Dict[str, List[int]]:
+    """main_models.py:282-294: for index >= docnum: `sim = torch.mul(insert_doc[index], cluster_embedding).sum(-1)`,
+    `np.argmax(sim)`, append the index to that cluster's list, `list(set(...))`.  (The reference walks its tree to get
+    `cluster_embedding` (:268-281); here the [C, D] centroid matrix and the key of each row are passed in.)"""
+    for index in range(len(insert_doc)):
+        if index < docnum:
+            continue
+        sim = torch.mul(insert_doc[index], cluster_embedding).sum(dim=-1)
+        target = keys[int(np.argmax(sim))]
+        id_mapping[target].append(index)
+        id_mapping[target] = list(set(id_mapping[target]))
+    return id_mapping
+
+
 def merge_topk(scores: torch.Tensor, docids: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
     """New in the sharded design (no reference counterpart): merge G per-rank
     sorted candidate lists [G, B, k'] into one [B, k].  Equivalent to topk over the union."""

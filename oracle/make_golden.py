@@ -200,6 +200,36 @@ def gen_main_models():
                         leaves=np.array(leaves, dtype=np.int64), **bs_out)
     print("wrote beam_step")
 
+    # ---------------- index expansion: tree_embedding_calculate (:154-179) + tree_embedding_insert (:268-295) ----------------
+    g = torch.Generator().manual_seed(321)
+    n_cl, per, D_e, n_new = 10, 6, 32, 15
+    cl_tok_paths = [t for t in tok_paths if len(t) == 4][:n_cl]         # token paths of 10 three-level clusters ([t0, t1, t2, 1])
+    exp_builder = mm.TreeBuilder()
+    docnum = n_cl * per
+    embedding = [torch.randn(D_e, generator=g) for _ in range(docnum + n_new)]
+    id_map = {}
+    perm = torch.randperm(docnum, generator=g).tolist()
+    for c, toks in enumerate(cl_tok_paths):
+        key = mm.decode_token(args, [np.array([0] + toks)])[0]
+        id_map[key] = perm[c * per:(c + 1) * per][: per - (c % 2)]
+        for d in id_map[key]:
+            exp_builder.add(toks, d)
+    exp_root = exp_builder.build()
+    mm.tree_embedding_calculate(exp_root, embedding)                    # main_models.py:154-179
+    cluster_set = set("-".join(str(t) for t in toks[:-1]) for toks in cl_tok_paths)
+    centroids = []
+    for toks in cl_tok_paths:
+        cur = exp_root
+        for t in toks[:-1]:
+            cur = cur.children[t]
+        centroids.append(cur.embedding)
+    before = {k: list(v) for k, v in id_map.items()}
+    after = mm.tree_embedding_insert(exp_root, id_map, embedding, cluster_set, SimpleNamespace(docnum=docnum, **vars(args)))   # :268-295
+    np.savez_compressed(os.path.join(GOLD, "expand.npz"), embedding=torch.stack(embedding).numpy(), docnum=np.int64(docnum),
+                        before_json=np.array(json.dumps(before)), after_json=np.array(json.dumps({k: sorted(v) for k, v in after.items()})),
+                        centroids=torch.stack(centroids).numpy())
+    print("wrote expand")
+
     # ---------------- positional mask ----------------
     sel_src = _ref_lines(os.path.join(REF, "transformers", "modeling_t5.py"), 1546, 1571)
     assert sel_src.startswith("def select_valid_embedding(sequence):"), sel_src[:60]

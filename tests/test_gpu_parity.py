@@ -267,3 +267,25 @@ def test_index_file_loads_into_an_identical_store(tmp_path):
     assert torch.equal(sa, sb) and torch.equal(da, db)
     shard = load_store(p, clusters=np.array([1, 4, 7]), chunk_rows=16)
     assert shard.keys == [keys[1], keys[4], keys[7]] and shard.n_docs == int(sum(len(f["id_mapping"][keys[c]]) for c in (1, 4, 7)))
+
+
+def test_index_expansion_matches_reference():
+    """Centroid kernel + top-1 assignment (gdr_b200.expand) against the reference's tree_embedding_calculate /
+    tree_embedding_insert run (tests/golden/expand.npz).  fp32 store: centroids bit-exact, assignments identical."""
+    import json
+    from gdr_b200 import ClusterStore
+    from gdr_b200.expand import assign_to_clusters, tree_embedding_insert
+    g = load_golden("expand")
+    emb = torch.from_numpy(g["embedding"])
+    docs = [emb[i] for i in range(emb.shape[0])]
+    before = json.loads(str(g["before_json"]))
+    after = json.loads(str(g["after_json"]))
+    docnum = int(g["docnum"])
+    store = ClusterStore.from_reference(docs[:docnum], before, dtype=torch.float32)
+    cent = store.centroids()
+    assert torch.equal(cent.cpu(), torch.from_numpy(g["centroids"])), "centroids must equal the reference's leaf embeddings"
+    idx, score = assign_to_clusters(cent, emb[docnum:].cuda())
+    ref = torch.from_numpy(g["centroids"]) @ emb[docnum:].T
+    assert torch.equal(idx.cpu(), ref.argmax(0))
+    out = tree_embedding_insert(store, {k: list(v) for k, v in before.items()}, docs, docnum)
+    assert {k: sorted(v) for k, v in out.items()} == after

@@ -33,7 +33,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: N docs, C clusters, D, batch B, beam K, top-k      (BASELINE.json configs[1], [2]; cfg5s = per-GPU slice of [4])
+    # name: N docs, C clusters, D, batch B, beam K, top-k      (BASELINE.json configs[0], [1], [2]; cfg5s = per-GPU slice of [4])
+    "cfg1": dict(N=109739, C=1024, D=768, B=1024, K=10, k=100, fp32=True),     # configs[0]: fp32 store, beam 10 (the reference's CPU case)
     "cfg2": dict(N=109739, C=1024, D=768, B=1024, K=20, k=100),
     "cfg3": dict(N=73970, C=1024, D=768, B=1024, K=100, k=1000),
     "cfg5s": dict(N=12500000, C=131072, D=768, B=1250, K=100, k=100),
@@ -90,10 +91,11 @@ def synth_shard(cfg, seed, device):
     counts = torch.bincount(assign, minlength=C)
     offsets = torch.zeros(C + 1, dtype=torch.int64, device=device)
     offsets[1:] = torch.cumsum(counts, 0)
-    emb = torch.empty((N, D), dtype=torch.bfloat16, device=device)
+    dt = torch.float32 if cfg.get("fp32") else torch.bfloat16
+    emb = torch.empty((N, D), dtype=dt, device=device)
     step = 1 << 20
     for i in range(0, N, step):   # chunked so the fp32 temporary stays small at 12.5 M rows
-        emb[i:i + step] = (torch.randn((min(step, N - i), D), generator=g, device=device) * D ** -0.5).to(torch.bfloat16)
+        emb[i:i + step] = (torch.randn((min(step, N - i), D), generator=g, device=device) * D ** -0.5).to(dt)
     return emb, offsets.cpu(), order
 
 
@@ -204,7 +206,8 @@ def main():
     B_rank = B_global if sharded else cfg["B"]      # queries each rank handles per step (sharded: all of them, replicated)
     C_total = cfg["C"] * world if sharded else cfg["C"]
     path_flags = {"auto": 0, "simt": 2, "umma": 4}[args.path]
-    emb_bytes = cfg["N"] * D * 2
+    esize = 4 if cfg.get("fp32") else 2
+    emb_bytes = cfg["N"] * D * esize
     replicas = args.replicas or max(1, min(6, -(-640 * 2 ** 20 // emb_bytes)))     # >= 640 MB of distinct store bytes in rotation
     stores = []
     base_offsets = None
@@ -383,6 +386,14 @@ def main():
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
+    if not sharded:
+        # the pipelined end-to-end loop must return what a plain serial call returns for the same batch
+        last = (period if use_graph else e2e_steps) - 1
+        P = pipes[last % n_pipe]
+        chk_s, chk_d = stores[last % replicas].score_topk(batches[last % n_batches][0], batches[last % n_batches][1], k)
+        torch.cuda.synchronize()
+        if not torch.equal(P["res_d"], chk_d.cpu()) or not torch.equal(P["res_s"], chk_s.cpu()):
+            raise RuntimeError("end-to-end pipeline result differs from the serial call")
     if world > 1:
         t = torch.tensor([e2e_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -401,7 +412,7 @@ def main():
     beams0 = batches[0][1]
     lo_c = rank * cfg["C"] if sharded else 0
     local = beams0[(beams0 >= lo_c) & (beams0 < lo_c + cfg["C"])] - lo_c
-    emb_touched = int(stores[0].sizes_host[torch.unique(local).cpu().numpy()].sum()) * D * 2
+    emb_touched = int(stores[0].sizes_host[torch.unique(local).cpu().numpy()].sum()) * D * esize
     alg_bytes = emb_touched + B_rank * D * 4 + B_rank * k * 8      # rank 0's launch
     dominant = max(("score_umma", "score_simt"), key=lambda n: phase[n])
     dom_ms = phase[dominant]
@@ -432,9 +443,9 @@ def main():
     line = {
         "metric": "queries/sec, cluster-restricted scoring + top-%d" % k, "value": qps, "unit": "queries/s", "n_gpus": world,
         "steps": steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f32" if cfg.get("fp32") else "bf16", "data": "synthetic",
         "config": {"workload": args.workload + ("" if world == 1 else (f" x{world} cluster-sharded" if sharded else f" x{world} replicas, queries sharded")),
-                   "precision": "bf16 embeddings x fp32 queries (exact 3-term bf16 split), fp32 accumulate", "docs_per_gpu": cfg["N"],
+                   "precision": "fp32 embeddings x fp32 queries, fp32 FMA" if cfg.get("fp32") else "bf16 embeddings x fp32 queries (exact 3-term bf16 split), fp32 accumulate", "docs_per_gpu": cfg["N"],
                    "clusters_per_gpu": cfg["C"], "dim": D, "global_batch": B_global, "beam": K, "top_k": k,
                    "l2": f"{replicas} store replicas ({replicas * emb_bytes / 2**20:.0f} MB) and {n_batches} query batches cycled; inputs larger than L2",
                    "cuda_graph": bool(use_graph), "batches_in_flight": n_pipe, "scoring_path": args.path,

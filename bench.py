@@ -390,7 +390,7 @@ def main():
         # the pipelined end-to-end loop must return what a plain serial call returns for the same batch
         last = (period if use_graph else e2e_steps) - 1
         P = pipes[last % n_pipe]
-        chk_s, chk_d = stores[last % replicas].score_topk(batches[last % n_batches][0], batches[last % n_batches][1], k)
+        chk_s, chk_d = stores[last % replicas].score_topk(batches[last % n_batches][0], batches[last % n_batches][1], k, flags=path_flags)
         torch.cuda.synchronize()
         if not torch.equal(P["res_d"], chk_d.cpu()) or not torch.equal(P["res_s"], chk_s.cpu()):
             raise RuntimeError("end-to-end pipeline result differs from the serial call")
@@ -418,7 +418,13 @@ def main():
     dom_ms = phase[dominant]
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     step_ms = ms / steps
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.isfile(tpath) and world == 1 and args.path == "auto":
+        t = json.load(open(tpath)).get(args.workload)
+        if t and t["kernel"] in {"score_umma": "k_score_umma", "score_simt": "k_score_simt"}[dominant]:
+            traffic = t["dram_read_bytes"] + t["dram_write_bytes"]       # one ncu --set full capture of this workload (profiles/)
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "kernel": {"score_umma": "k_score_umma (tcgen05 grouped GEMM)", "score_simt": "k_score_simt (GEMV)"}[dominant],
                 "kernel_ms": dom_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "phase_ms": phase, "whole_step_frac": alg_bytes / (step_ms * 1e-3) / 1e9 / peak,

@@ -88,7 +88,7 @@ int gdr_store_create(gdr_store_t **out, const void *emb, int64_t n_docs, int32_t
     cudaError_t e = cudaGetDevice(&s->device);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device);
     const size_t n = (size_t)n_clusters;
-    const size_t words = n + 3 * (n + 1) + CTR_COUNT;
+    const size_t words = n + 3 * (n + 1) + CTR_COUNT + 4 * (n / 8192 + 2);
     if (e == cudaSuccess) e = cudaMalloc(&s->cluster_ws, words * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMemset(s->cluster_ws, 0, words * sizeof(int32_t));
     if (e != cudaSuccess) {
@@ -173,6 +173,7 @@ int gdr_score_topk(gdr_store_t *s, const float *q, const int32_t *beams, const f
     a.simt_off = a.grp_off + (n + 1);
     a.umma_off = a.simt_off + (n + 1);
     a.counters = a.umma_off + (n + 1);
+    a.scan_base = a.counters + CTR_COUNT;
     a.grp_pair = reinterpret_cast<int32_t *>(ws + o_pair);
     a.candoff = reinterpret_cast<int32_t *>(ws + o_cand);
     a.simt_items = reinterpret_cast<Item *>(ws + o_simt);

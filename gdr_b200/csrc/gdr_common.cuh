@@ -64,6 +64,7 @@ struct ScoreArgs {
     Item *simt_items;
     Item *umma_items;
     int32_t *counters;   // [CTR_COUNT]
+    int32_t *scan_base;  // [4 * (n_scan_blocks + 1)] exclusive bases (group, SIMT items, tcgen05 items, -) of each 8,192-cluster block
     float *scorebuf;     // [B, stride]
     int64_t stride;
     __nv_bfloat16 *qsplit;  // [rows(q), 3, dim] exact bf16 hi/mid/lo split of the fp32 queries (tcgen05 path), else null

@@ -138,61 +138,111 @@ __device__ __forceinline__ void block_scan3(int &x, int &y, int &z, int tot[3], 
 }
 
 constexpr int SCAN_PER_THREAD = 8;   // clusters per thread and round: 8,192 clusters per block-wide scan
+constexpr int SCAN_BLOCK = 1024 * SCAN_PER_THREAD;
 
-__global__ void __launch_bounds__(1024) k_scan(ScoreArgs a) {
-    __shared__ int wsum[32][3];
-    pdl_launch_dependents();
-    pdl_wait();
-    int carry[3] = {0, 0, 0};
-    int touched = 0;
+// One block-wide round over clusters [c0, c0 + SCAN_BLOCK): exclusive prefixes of (group size, SIMT items, tcgen05 items)
+// written relative to `carry`; returns the round's totals in tot[] and the number of touched clusters of this thread.
+__device__ __forceinline__ int scan_round(const ScoreArgs &a, int c0, const int carry[3], int tot[3], int (*wsum)[3]) {
     const int C = a.n_clusters;
-    for (int c0 = 0; c0 < C; c0 += 1024 * SCAN_PER_THREAD) {
-        const int cb = c0 + threadIdx.x * SCAN_PER_THREAD;      // this thread's consecutive clusters
-        int g[SCAN_PER_THREAD], ns[SCAN_PER_THREAD], nu[SCAN_PER_THREAD];
-        int sg = 0, ss = 0, su = 0;
+    const int cb = c0 + threadIdx.x * SCAN_PER_THREAD;      // this thread's consecutive clusters
+    int g[SCAN_PER_THREAD], ns[SCAN_PER_THREAD], nu[SCAN_PER_THREAD];
+    int sg = 0, ss = 0, su = 0, touched = 0;
 #pragma unroll
-        for (int i = 0; i < SCAN_PER_THREAD; ++i) {
-            g[i] = ns[i] = nu[i] = 0;
-            const int c = cb + i;
-            if (c < C) {
-                g[i] = a.cnt[c];
-                const int size = a.offsets[c + 1] - a.offsets[c];
-                if (g[i] > 0 && size > 0) {
-                    touched++;
-                    item_counts(a, g[i], size, ns[i], nu[i]);
-                }
+    for (int i = 0; i < SCAN_PER_THREAD; ++i) {
+        g[i] = ns[i] = nu[i] = 0;
+        const int c = cb + i;
+        if (c < C) {
+            g[i] = a.cnt[c];
+            const int size = a.offsets[c + 1] - a.offsets[c];
+            if (g[i] > 0 && size > 0) {
+                touched++;
+                item_counts(a, g[i], size, ns[i], nu[i]);
             }
-            sg += g[i]; ss += ns[i]; su += nu[i];
         }
-        int tot[3];
-        block_scan3(sg, ss, su, tot, wsum);                      // exclusive prefix of the per-thread sums
-        sg += carry[0]; ss += carry[1]; su += carry[2];
-#pragma unroll
-        for (int i = 0; i < SCAN_PER_THREAD; ++i) {
-            const int c = cb + i;
-            if (c < C) {
-                a.grp_off[c] = sg;
-                a.simt_off[c] = ss;
-                a.umma_off[c] = su;
-            }
-            sg += g[i]; ss += ns[i]; su += nu[i];
-        }
-        carry[0] += tot[0]; carry[1] += tot[1]; carry[2] += tot[2];
+        sg += g[i]; ss += ns[i]; su += nu[i];
     }
-    // total clusters touched (block reduce, reuse wsum)
+    block_scan3(sg, ss, su, tot, wsum);                      // exclusive prefix of the per-thread sums
+    sg += carry[0]; ss += carry[1]; su += carry[2];
+#pragma unroll
+    for (int i = 0; i < SCAN_PER_THREAD; ++i) {
+        const int c = cb + i;
+        if (c < C) {
+            a.grp_off[c] = sg;
+            a.simt_off[c] = ss;
+            a.umma_off[c] = su;
+        }
+        sg += g[i]; ss += ns[i]; su += nu[i];
+    }
+    return touched;
+}
+
+// block reduce of `touched` (reuses wsum); result valid in thread 0
+__device__ __forceinline__ int reduce_touched(int touched, int (*wsum)[3]) {
     for (int d = 16; d; d >>= 1) touched += __shfl_xor_sync(0xffffffffu, touched, d);
     __syncthreads();
     if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5][0] = touched;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        int t = 0;
+    int t = 0;
+    if (threadIdx.x == 0)
         for (int w = 0; w < 32; ++w) t += wsum[w][0];
-        a.grp_off[C] = carry[0];
-        a.simt_off[C] = carry[1];
-        a.umma_off[C] = carry[2];
-        a.counters[CTR_N_SIMT] = carry[1];
-        a.counters[CTR_N_UMMA] = carry[2];
-        a.counters[CTR_N_TOUCHED] = t;
+    return t;
+}
+
+// C <= SCAN_BLOCK: one CTA, one round, final offsets directly
+__global__ void __launch_bounds__(1024) k_scan(ScoreArgs a) {
+    __shared__ int wsum[32][3];
+    pdl_launch_dependents();
+    pdl_wait();
+    const int carry[3] = {0, 0, 0};
+    int tot[3];
+    const int touched = reduce_touched(scan_round(a, 0, carry, tot, wsum), wsum);
+    if (threadIdx.x == 0) {
+        const int C = a.n_clusters;
+        a.grp_off[C] = tot[0];
+        a.simt_off[C] = tot[1];
+        a.umma_off[C] = tot[2];
+        a.counters[CTR_N_SIMT] = tot[1];
+        a.counters[CTR_N_UMMA] = tot[2];
+        a.counters[CTR_N_TOUCHED] = touched;
+        a.scan_base[0] = a.scan_base[1] = a.scan_base[2] = 0;
+    }
+}
+
+// C > SCAN_BLOCK (cfg5: 131,072 clusters per GPU): one CTA per 8,192 clusters writes block-local offsets and its totals
+// (scan_base[4 * (blk + 1) ...] as raw totals), then one small CTA turns the totals into exclusive bases; k_fill adds
+// the base of a cluster's block.  (The single-CTA scan took ~200 us of the 2.4 ms cfg5 step.)
+__global__ void __launch_bounds__(1024) k_scan_part(ScoreArgs a) {
+    __shared__ int wsum[32][3];
+    pdl_launch_dependents();
+    pdl_wait();
+    const int carry[3] = {0, 0, 0};
+    int tot[3];
+    const int touched = reduce_touched(scan_round(a, blockIdx.x * SCAN_BLOCK, carry, tot, wsum), wsum);
+    if (threadIdx.x == 0) {
+        int32_t *t = a.scan_base + 4 * blockIdx.x;
+        t[0] = tot[0]; t[1] = tot[1]; t[2] = tot[2]; t[3] = touched;
+    }
+}
+
+__global__ void __launch_bounds__(32) k_scan_bases(ScoreArgs a, int n_blocks) {
+    pdl_launch_dependents();
+    pdl_wait();
+    if (threadIdx.x == 0) {
+        int run[4] = {0, 0, 0, 0}, last[3] = {0, 0, 0};
+        for (int b = 0; b < n_blocks; ++b) {
+            int32_t *t = a.scan_base + 4 * b;
+            const int v[4] = {t[0], t[1], t[2], t[3]};
+            t[0] = run[0]; t[1] = run[1]; t[2] = run[2];
+            for (int i = 0; i < 4; ++i) run[i] += v[i];
+            last[0] = v[0]; last[1] = v[1]; last[2] = v[2];
+        }
+        const int C = a.n_clusters;
+        a.grp_off[C] = last[0];       // block-LOCAL end offsets of the last block: k_fill takes differences inside a block
+        a.simt_off[C] = last[1];
+        a.umma_off[C] = last[2];
+        a.counters[CTR_N_SIMT] = run[1];
+        a.counters[CTR_N_UMMA] = run[2];
+        a.counters[CTR_N_TOUCHED] = run[3];
     }
 }
 
@@ -201,16 +251,24 @@ __global__ void __launch_bounds__(256) k_fill(ScoreArgs a) {
     pdl_wait();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t n_pairs = (int64_t)a.B * a.K;
+    // offsets are block-local when the scan ran in several CTAs: add the base of the cluster's 8,192-cluster block
     if (t < n_pairs) {
         const int c = a.beams[t];
         if (c >= 0 && c < a.n_clusters) {
-            const int slot = a.grp_off[c] + atomicSub(&a.cnt[c], 1) - 1;
+            const int slot = a.scan_base[4 * (c / SCAN_BLOCK)] + a.grp_off[c] + atomicSub(&a.cnt[c], 1) - 1;
             a.grp_pair[slot] = (int32_t)t;
         }
     }
     if (t < a.n_clusters) {
         const int c = (int)t;
-        write_items(a, c, a.grp_off[c], a.grp_off[c + 1] - a.grp_off[c], a.simt_off[c], a.umma_off[c]);
+        const int32_t *base = a.scan_base + 4 * (c / SCAN_BLOCK);
+        // group size: the next cluster's local offset, unless it starts a new block (then this block's total is needed:
+        // recompute from the counter-free item count — cnt is being drained, so use the scan's own prefix differences)
+        const bool last_in_block = (c + 1) % SCAN_BLOCK == 0 && c + 1 < a.n_clusters;
+        int g;
+        if (!last_in_block) g = a.grp_off[c + 1] - a.grp_off[c];
+        else g = (a.scan_base[4 * (c / SCAN_BLOCK + 1)] - base[0]) - a.grp_off[c];
+        write_items(a, c, base[0] + a.grp_off[c], g, base[1] + a.simt_off[c], base[2] + a.umma_off[c]);
     }
     trace_end(a.dbg, 1);
 }
@@ -280,7 +338,14 @@ cudaError_t launch_invert(const ScoreArgs &a, cudaStream_t s, int *n_launches) {
         return launch_pdl(k_invert_small, dim3(1), dim3(1024), 0, s, a);
     }
     cudaError_t e = launch_pdl(k_count, dim3((a.B + 3) / 4), dim3(128), 0, s, a);
-    if (e == cudaSuccess) e = launch_pdl(k_scan, dim3(1), dim3(1024), 0, s, a);
+    const int n_blocks = (a.n_clusters + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    if (n_blocks <= 1) {
+        if (e == cudaSuccess) e = launch_pdl(k_scan, dim3(1), dim3(1024), 0, s, a);
+    } else {
+        if (e == cudaSuccess) e = launch_pdl(k_scan_part, dim3(n_blocks), dim3(1024), 0, s, a);
+        if (e == cudaSuccess) e = launch_pdl(k_scan_bases, dim3(1), dim3(32), 0, s, a, n_blocks);
+        *n_launches += 1;
+    }
     const int64_t n = max((int64_t)a.B * a.K, (int64_t)a.n_clusters);
     if (e == cudaSuccess) e = launch_pdl(k_fill, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, a);
     *n_launches += 3;

@@ -289,3 +289,18 @@ def test_index_expansion_matches_reference():
     assert torch.equal(idx.cpu(), ref.argmax(0))
     out = tree_embedding_insert(store, {k: list(v) for k, v in before.items()}, docs, docnum)
     assert {k: sorted(v) for k, v in out.items()} == after
+
+
+def test_many_clusters_multi_block_scan():
+    """More than 8,192 clusters: the inversion's scan runs in several CTAs (block-local offsets + bases)."""
+    N, C, D, Q, K, k = 60000, 20000, 64, 300, 50, 20
+    emb, offsets, docid = orc.synth_corpus(N, C, D, seed=31)
+    emb = emb.bfloat16().float()
+    q, beams, _ = orc.synth_queries(Q, C, K, D, seed=32)
+    beams[:, :3] = np.array([8191, 8192, 16383])[None, :]          # clusters on both sides of the block boundaries, shared by all queries
+    beams[:, 3] = C - 1
+    st = _store(emb, offsets, docid, torch.bfloat16)
+    ref_s, ref_d = orc.dense_topk(q, emb, offsets, docid, beams, k)
+    for flags in (FLAG_SIMT, FLAG_UMMA, 0):
+        s, d = st.score_topk(q.cuda(), torch.from_numpy(beams).cuda(), k, flags=flags)
+        assert_topk_parity(s, d, ref_s, ref_d, f"many clusters flags={flags}")

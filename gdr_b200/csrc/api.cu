@@ -137,7 +137,8 @@ int gdr_score_topk(gdr_store_t *s, const float *q, const int32_t *beams, const f
     const int64_t simt_cap = pairs * ((s->max_cluster + SIMT_ROWS - 1) / SIMT_ROWS);
     const int64_t umma_cap = pairs * ((s->max_cluster + UMMA_ROWS - 1) / UMMA_ROWS);
     const bool umma_possible = s->has_tmap && !(flags & GDR_FORCE_SIMT);
-    const bool global_keys = (size_t)stride * 4 + 8 * 4096 + 4 * 2048 + (size_t)(2 * K + 1) * 4 > 96 * 1024;
+    // k <= 128: the fast top-k keeps no key array (its mass-tie fallback uses the global scratch); larger k: keys in smem if they fit
+    const bool global_keys = k <= 128 || (size_t)stride * 4 + 8 * 4096 + 4 * 2048 + (size_t)(2 * K + 1) * 4 > 96 * 1024;
 
     // carve the per-batch scratch
     size_t off = 0;
@@ -180,7 +181,7 @@ int gdr_score_topk(gdr_store_t *s, const float *q, const int32_t *beams, const f
     a.umma_items = reinterpret_cast<Item *>(ws + o_umma);
     a.scorebuf = reinterpret_cast<float *>(ws + o_score);
     a.stride = stride;
-    a.gkeys = reinterpret_cast<uint32_t *>(ws + o_keys);
+    a.gkeys = global_keys ? reinterpret_cast<uint32_t *>(ws + o_keys) : nullptr;
     a.qsplit = nullptr;   // set below when the tcgen05 path is taken
     // One scoring path per call: a batch that names each cluster three or more times on average goes to the tcgen05
     // grouped GEMM (slab read once for the whole group); a sparse batch goes to the SIMT GEMV, which serves up to four

@@ -106,7 +106,7 @@ __device__ __forceinline__ void write_items(const ScoreArgs &a, int c, int g0, i
     }
 }
 
-// Block-wide exclusive scan of three ints per thread (1024 threads), returns totals via `tot`.
+// Block-wide exclusive scan of three ints per thread (up to 1024 threads), returns totals via `tot`.
 __device__ __forceinline__ void block_scan3(int &x, int &y, int &z, int tot[3], int (*wsum)[3]) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int ix = x, iy = y, iz = z;
@@ -119,8 +119,9 @@ __device__ __forceinline__ void block_scan3(int &x, int &y, int &z, int tot[3], 
     }
     if (lane == 31) { wsum[warp][0] = ix; wsum[warp][1] = iy; wsum[warp][2] = iz; }
     __syncthreads();
+    const int nwarps = (blockDim.x + 31) >> 5;
     if (warp == 0) {
-        int sx = wsum[lane][0], sy = wsum[lane][1], sz = wsum[lane][2];
+        int sx = lane < nwarps ? wsum[lane][0] : 0, sy = lane < nwarps ? wsum[lane][1] : 0, sz = lane < nwarps ? wsum[lane][2] : 0;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             int tx = __shfl_up_sync(0xffffffffu, sx, d);
@@ -184,7 +185,7 @@ __device__ __forceinline__ int reduce_touched(int touched, int (*wsum)[3]) {
     __syncthreads();
     int t = 0;
     if (threadIdx.x == 0)
-        for (int w = 0; w < 32; ++w) t += wsum[w][0];
+        for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w) t += wsum[w][0];
     return t;
 }
 
@@ -340,7 +341,10 @@ cudaError_t launch_invert(const ScoreArgs &a, cudaStream_t s, int *n_launches) {
     cudaError_t e = launch_pdl(k_count, dim3((a.B + 3) / 4), dim3(128), 0, s, a);
     const int n_blocks = (a.n_clusters + SCAN_BLOCK - 1) / SCAN_BLOCK;
     if (n_blocks <= 1) {
-        if (e == cudaSuccess) e = launch_pdl(k_scan, dim3(1), dim3(1024), 0, s, a);
+        // as few threads as the cluster count needs (8 clusters per thread): a 1,024-thread CTA cannot be placed on an SM
+        // that already hosts the scoring kernel and top-k CTAs of neighbouring batches, which stalled the whole pipeline
+        const int threads = min(1024, max(32, ((a.n_clusters + SCAN_PER_THREAD - 1) / SCAN_PER_THREAD + 31) / 32 * 32));
+        if (e == cudaSuccess) e = launch_pdl(k_scan, dim3(1), dim3(threads), 0, s, a);
     } else {
         if (e == cudaSuccess) e = launch_pdl(k_scan_part, dim3(n_blocks), dim3(1024), 0, s, a);
         if (e == cudaSuccess) e = launch_pdl(k_scan_bases, dim3(1), dim3(32), 0, s, a, n_blocks);

@@ -298,7 +298,10 @@ __device__ __forceinline__ void warp_bitonic128_desc(uint64_t (&v)[4], int lane)
     }
 }
 
-template <typename Src>
+// STORE_KEYS = false: the keys are not kept between the two passes (pass 2 re-reads the L2-resident scores), which cuts
+// the CTA's shared memory from ~20 KB to ~9 KB so that more of these CTAs co-reside with the scoring kernel of the next
+// batch on every SM; `keys` then points to global scratch used only by the general fallback.
+template <bool STORE_KEYS, typename Src>
 __device__ void topk_body(const Src &src, int n, int k, int cap, uint32_t *keys, uint64_t *sel, uint32_t *hist,
                           TkShared *sh, float *out_s, int32_t *out_d) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -320,7 +323,7 @@ __device__ void topk_body(const Src &src, int n, int k, int cap, uint32_t *keys,
             k4[e] = float_to_ordered(s4[e]);
             if (j4 + e < n) atomicAdd(&hist[k4[e] >> 21], 1u);
         }
-        *reinterpret_cast<uint4 *>(keys + j4) = make_uint4(k4[0], k4[1], k4[2], k4[3]);
+        if (STORE_KEYS) *reinterpret_cast<uint4 *>(keys + j4) = make_uint4(k4[0], k4[1], k4[2], k4[3]);
     }
     __syncthreads();
     // boundary bin: warp w sums bins [256w, 256w + 256) with conflict-free strided reads ...
@@ -355,8 +358,16 @@ __device__ void topk_body(const Src &src, int n, int k, int cap, uint32_t *keys,
     uint64_t *bnd2 = bnd + TK_BND;
     __syncthreads();                                              // everyone is done reading hist
     for (int j4 = tid * 4; j4 < n; j4 += TK_THREADS * 4) {
-        const uint4 kv = *reinterpret_cast<const uint4 *>(keys + j4);
-        const uint32_t k4[4] = {kv.x, kv.y, kv.z, kv.w};
+        uint32_t k4[4];
+        if (STORE_KEYS) {
+            const uint4 kv = *reinterpret_cast<const uint4 *>(keys + j4);
+            k4[0] = kv.x; k4[1] = kv.y; k4[2] = kv.z; k4[3] = kv.w;
+        } else {
+            float s4[4];
+            src.score4(j4, n, s4);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) k4[e] = float_to_ordered(s4[e]);
+        }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             if (j4 + e < n) {
@@ -428,7 +439,9 @@ __device__ void topk_body(const Src &src, int n, int k, int cap, uint32_t *keys,
 }
 
 // dynamic shared memory layout: sel[cap] u64 | hist[TK_BINS] u32 | keys[stride] u32 (smem variant) | co[K+1] i32 | cbase[K] i32
-template <bool KEYS_IN_SMEM>
+// KEYS: 0 = key array in global scratch, 1 = key array in shared memory, 2 = fast path (k <= 128) without a key array
+// (its mass-tie fallback uses the global scratch)
+template <int KEYS>
 __global__ void __launch_bounds__(TK_THREADS, 8) k_topk_store(ScoreArgs a, float alpha, int cap, float *out_scores,
                                                               int32_t *out_docids) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -436,7 +449,7 @@ __global__ void __launch_bounds__(TK_THREADS, 8) k_topk_store(ScoreArgs a, float
     uint64_t *sel = reinterpret_cast<uint64_t *>(smem);
     uint32_t *hist = reinterpret_cast<uint32_t *>(sel + cap);
     uint32_t *skeys = hist + TK_BINS;                              // 16-byte aligned: cap * 8 + 8 KB
-    int32_t *co = reinterpret_cast<int32_t *>(skeys + (KEYS_IN_SMEM ? a.stride : 0));
+    int32_t *co = reinterpret_cast<int32_t *>(skeys + (KEYS == 1 ? a.stride : 0));
     const int b = blockIdx.x;
     int32_t *cbase = co + a.K + 1;
     pdl_launch_dependents();
@@ -450,11 +463,11 @@ __global__ void __launch_bounds__(TK_THREADS, 8) k_topk_store(ScoreArgs a, float
         }
     }
     __syncthreads();
-    uint32_t *keys = KEYS_IN_SMEM ? skeys : a.gkeys + (int64_t)b * a.stride;
+    uint32_t *keys = KEYS == 1 ? skeys : a.gkeys + (int64_t)b * a.stride;
     StoreSrc src{a.scorebuf + (int64_t)b * a.stride, co, cbase, a.prob ? a.prob + (int64_t)b * a.K : nullptr,
                  a.docid, a.K, alpha};
-    topk_body(src, co[a.K], a.k, cap, keys, sel, hist, &sh, out_scores + (int64_t)b * a.k,
-              out_docids + (int64_t)b * a.k);
+    topk_body<KEYS != 2>(src, co[a.K], a.k, cap, keys, sel, hist, &sh, out_scores + (int64_t)b * a.k,
+                         out_docids + (int64_t)b * a.k);
     trace_end(a.dbg, 5);
 }
 
@@ -469,7 +482,7 @@ __global__ void __launch_bounds__(TK_THREADS) k_topk_merge(ListSrc src0, int n, 
     ListSrc src = src0;
     src.scores += (int64_t)b * src.k_in;
     src.docids += (int64_t)b * src.k_in;
-    topk_body(src, n, k, cap, keys, sel, hist, &sh, out_scores + (int64_t)b * k, out_docids + (int64_t)b * k);
+    topk_body<true>(src, n, k, cap, keys, sel, hist, &sh, out_scores + (int64_t)b * k, out_docids + (int64_t)b * k);
 }
 
 static int pow2_at_least(int x) { int p = 2; while (p < x) p <<= 1; return p; }
@@ -490,12 +503,14 @@ cudaError_t launch_topk_store(const ScoreArgs &a, float alpha, float *out_scores
     const size_t with_keys = fixed + (size_t)a.stride * 4;
     static unsigned long long attr_mask = 0;
     if (need_attr(attr_mask)) {
-        cudaFuncSetAttribute(k_topk_store<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-        cudaFuncSetAttribute(k_topk_store<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        cudaFuncSetAttribute(k_topk_store<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        cudaFuncSetAttribute(k_topk_store<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     }
+    if (cap <= 128 && a.gkeys)
+        return launch_pdl(k_topk_store<2>, dim3(a.B), dim3(TK_THREADS), fixed, s, a, alpha, cap, out_scores, out_docids);
     if (with_keys <= 96 * 1024)
-        return launch_pdl(k_topk_store<true>, dim3(a.B), dim3(TK_THREADS), with_keys, s, a, alpha, cap, out_scores, out_docids);
-    return launch_pdl(k_topk_store<false>, dim3(a.B), dim3(TK_THREADS), fixed, s, a, alpha, cap, out_scores, out_docids);
+        return launch_pdl(k_topk_store<1>, dim3(a.B), dim3(TK_THREADS), with_keys, s, a, alpha, cap, out_scores, out_docids);
+    return launch_pdl(k_topk_store<0>, dim3(a.B), dim3(TK_THREADS), fixed, s, a, alpha, cap, out_scores, out_docids);
 }
 
 cudaError_t launch_merge_topk(const float *scores, const int32_t *docids, int G, int B, int k_in, int64_t g_stride, int k,

@@ -138,7 +138,7 @@ int gdr_score_topk(gdr_store_t *s, const float *q, const int32_t *beams, const f
     const int64_t umma_cap = pairs * ((s->max_cluster + UMMA_ROWS - 1) / UMMA_ROWS);
     const bool umma_possible = s->has_tmap && !(flags & GDR_FORCE_SIMT);
     // k <= 128: the fast top-k keeps no key array (its mass-tie fallback uses the global scratch); larger k: keys in smem if they fit
-    const bool global_keys = k <= 128 || (size_t)stride * 4 + 8 * 4096 + 4 * 2048 + (size_t)(2 * K + 1) * 4 > 96 * 1024;
+    const bool global_keys = k <= 128 || (size_t)stride * 4 + 8 * 4096 + 4 * 2048 + (size_t)(3 * K + 1) * 4 > 96 * 1024;
 
     // carve the per-batch scratch
     size_t off = 0;
@@ -196,7 +196,7 @@ int gdr_score_topk(gdr_store_t *s, const float *q, const int32_t *beams, const f
 
     int launches = 0;
     const bool prof = s->profiling;
-    if (s->dbg) {   // kernel timeline: min-start slots to +inf, max-end slots to 0
+    if (s->dbg && !(flags & GDR_SKIP_INVERT)) {   // kernel timeline: min-start slots to +inf, max-end slots to 0
         static const unsigned long long init[6] = {~0ull, 0ull, ~0ull, 0ull, ~0ull, 0ull};
         GDR_CUDA(cudaMemcpyAsync(s->dbg + 500, init, sizeof(init), cudaMemcpyHostToDevice, st));
     }
@@ -255,7 +255,8 @@ int gdr_store_last_stats(gdr_store_t *s, int64_t out[4], void *stream) {
             smin = st < smin ? st : smin; smax = st > smax ? st : smax; emin = en < emin ? en : emin; emax = en > emax ? en : emax;
         }
         fprintf(stderr, "| CTA loop start min %lld max %lld, end min %lld max %lld\n", smin, smax, emin, emax);
-        fprintf(stderr, "[timeline] %lld %lld %lld %lld %lld %lld\n", h[500], h[501], h[502], h[503], h[504], h[505]);
+        fprintf(stderr, "[timeline] %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld\n", h[500], h[501], h[502], h[503], h[504], h[505],
+                smin + h[0], smax + h[0], emin + h[0], emax + h[0]);
     }
     const size_t n = (size_t)s->n_clusters;
     GDR_CUDA(cudaMemcpy(c, s->cluster_ws + n + 3 * (n + 1), sizeof(c), cudaMemcpyDeviceToHost));

@@ -115,10 +115,9 @@ struct StoreSrc {   // a query's candidates = its K beam segments of the score b
     const float *sb;        // score buffer row of this query
     const int32_t *co;      // [K+1] segment starts (shared memory)
     const int32_t *cbase;   // [K] first store row of each beam's cluster (shared memory)
-    const float *prob;      // [K] or null
+    const float *bias;      // [K] alpha * p[b][i] (shared memory) or null
     const int32_t *docid;
     int K;
-    float alpha;
     __device__ int seg(int j) const {
         int lo = 0, hi = K - 1;
         while (lo < hi) {
@@ -130,21 +129,31 @@ struct StoreSrc {   // a query's candidates = its K beam segments of the score b
     __device__ float score(int j) const {
         float s = sb[j];
         // main_models.py:1623-1624: score + alpha * p[b][i], two roundings (no FMA contraction)
-        if (prob) s = __fadd_rn(s, __fmul_rn(alpha, prob[seg(j)]));
+        if (bias) s = __fadd_rn(s, bias[seg(j)]);
         return s;
     }
     __device__ int32_t doc(int j) const {
         const int i = seg(j);
         return docid[cbase[i] + (j - co[i])];
     }
-    // four consecutive candidates starting at j4 (multiple of 4; the score row is 16-byte aligned and padded)
+    // four consecutive candidates starting at j4 (multiple of 4; the score row is 16-byte aligned and padded).
+    // One segment search per four: they almost always share a beam segment; otherwise walk forward from it.
     __device__ void score4(int j4, int n, float (&s)[4]) const {
         const float4 v = *reinterpret_cast<const float4 *>(sb + j4);
         s[0] = v.x; s[1] = v.y; s[2] = v.z; s[3] = v.w;
-        if (prob) {
+        if (bias) {
+            int i = seg(j4);
+            if (j4 + 3 < co[i + 1]) {
+                const float bv = bias[i];
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-                if (j4 + e < n) s[e] = __fadd_rn(s[e], __fmul_rn(alpha, prob[seg(j4 + e)]));
+                for (int e = 0; e < 4; ++e) s[e] = __fadd_rn(s[e], bv);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    while (i < K - 1 && co[i + 1] <= j4 + e) ++i;
+                    if (j4 + e < n) s[e] = __fadd_rn(s[e], bias[i]);
+                }
+            }
         }
     }
 };
@@ -168,7 +177,12 @@ __device__ void topk_general(const Src &src, int n, int k, int cap, uint32_t *ke
                           TkShared *sh, float *out_s, int32_t *out_d) {
     const int tid = threadIdx.x;
     if (tid == 0) { sh->sel_count = 0; sh->eq2_count = 0; }
-    for (int j = tid; j < n; j += TK_THREADS) keys[j] = float_to_ordered(src.score(j));
+    for (int j4 = tid * 4; j4 < n; j4 += TK_THREADS * 4) {            // keys[] is padded to a multiple of 4
+        float s4[4];
+        src.score4(j4, n, s4);
+        *reinterpret_cast<uint4 *>(keys + j4) = make_uint4(float_to_ordered(s4[0]), float_to_ordered(s4[1]), float_to_ordered(s4[2]),
+                                                           float_to_ordered(s4[3]));
+    }
     __syncthreads();
     const int kk = min(k, n);
     Threshold t1{0u, 32, kk, n};
@@ -438,7 +452,7 @@ __device__ void topk_body(const Src &src, int n, int k, int cap, uint32_t *keys,
     }
 }
 
-// dynamic shared memory layout: sel[cap] u64 | hist[TK_BINS] u32 | keys[stride] u32 (smem variant) | co[K+1] i32 | cbase[K] i32
+// dynamic shared memory layout: sel[cap] u64 | hist[TK_BINS] u32 | keys[stride] u32 (smem variant) | co[K+1] i32 | cbase[K] i32 | bias[K] f32
 // KEYS: 0 = key array in global scratch, 1 = key array in shared memory, 2 = fast path (k <= 128) without a key array
 // (its mass-tie fallback uses the global scratch)
 template <int KEYS>
@@ -450,22 +464,23 @@ __global__ void __launch_bounds__(TK_THREADS, 8) k_topk_store(ScoreArgs a, float
     uint32_t *hist = reinterpret_cast<uint32_t *>(sel + cap);
     uint32_t *skeys = hist + TK_BINS;                              // 16-byte aligned: cap * 8 + 8 KB
     int32_t *co = reinterpret_cast<int32_t *>(skeys + (KEYS == 1 ? a.stride : 0));
-    const int b = blockIdx.x;
     int32_t *cbase = co + a.K + 1;
+    float *bias = reinterpret_cast<float *>(cbase + a.K);
     pdl_launch_dependents();
     pdl_wait();
     trace_start(a.dbg, 4);
+    const int b = blockIdx.x;
     for (int i = threadIdx.x; i <= a.K; i += TK_THREADS) {
         co[i] = a.candoff[(int64_t)b * (a.K + 1) + i];
         if (i < a.K) {
             const int c = a.beams[(int64_t)b * a.K + i];
             cbase[i] = (c >= 0 && c < a.n_clusters) ? a.offsets[c] : 0;
+            if (a.prob) bias[i] = __fmul_rn(alpha, a.prob[(int64_t)b * a.K + i]);
         }
     }
     __syncthreads();
     uint32_t *keys = KEYS == 1 ? skeys : a.gkeys + (int64_t)b * a.stride;
-    StoreSrc src{a.scorebuf + (int64_t)b * a.stride, co, cbase, a.prob ? a.prob + (int64_t)b * a.K : nullptr,
-                 a.docid, a.K, alpha};
+    StoreSrc src{a.scorebuf + (int64_t)b * a.stride, co, cbase, a.prob ? bias : nullptr, a.docid, a.K};
     topk_body<KEYS != 2>(src, co[a.K], a.k, cap, keys, sel, hist, &sh, out_scores + (int64_t)b * a.k,
                          out_docids + (int64_t)b * a.k);
     trace_end(a.dbg, 5);
@@ -499,18 +514,19 @@ static bool need_attr(unsigned long long &mask) {
 cudaError_t launch_topk_store(const ScoreArgs &a, float alpha, float *out_scores, int32_t *out_docids, cudaStream_t s) {
     if (a.B == 0) return cudaSuccess;
     const int cap = pow2_at_least(a.k);
-    const size_t fixed = (size_t)cap * 8 + (size_t)TK_BINS * 4 + (size_t)(2 * a.K + 1) * 4;
+    const size_t fixed = (size_t)cap * 8 + (size_t)TK_BINS * 4 + (size_t)(3 * a.K + 1) * 4;
     const size_t with_keys = fixed + (size_t)a.stride * 4;
     static unsigned long long attr_mask = 0;
     if (need_attr(attr_mask)) {
         cudaFuncSetAttribute(k_topk_store<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
         cudaFuncSetAttribute(k_topk_store<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     }
+    const int grid = a.B;      // (a few persistent CTAs per SM walking the queries measured slower in the pipelined step: 62 vs 57 us)
     if (cap <= 128 && a.gkeys)
-        return launch_pdl(k_topk_store<2>, dim3(a.B), dim3(TK_THREADS), fixed, s, a, alpha, cap, out_scores, out_docids);
+        return launch_pdl(k_topk_store<2>, dim3(grid), dim3(TK_THREADS), fixed, s, a, alpha, cap, out_scores, out_docids);
     if (with_keys <= 96 * 1024)
-        return launch_pdl(k_topk_store<1>, dim3(a.B), dim3(TK_THREADS), with_keys, s, a, alpha, cap, out_scores, out_docids);
-    return launch_pdl(k_topk_store<0>, dim3(a.B), dim3(TK_THREADS), fixed, s, a, alpha, cap, out_scores, out_docids);
+        return launch_pdl(k_topk_store<1>, dim3(grid), dim3(TK_THREADS), with_keys, s, a, alpha, cap, out_scores, out_docids);
+    return launch_pdl(k_topk_store<0>, dim3(grid), dim3(TK_THREADS), fixed, s, a, alpha, cap, out_scores, out_docids);
 }
 
 cudaError_t launch_merge_topk(const float *scores, const int32_t *docids, int G, int B, int k_in, int64_t g_stride, int k,

@@ -5,7 +5,7 @@ rows=[list(map(int,l.split()[1:])) for l in sys.stdin if l.startswith('[timeline
 rows=[r for r in rows if r[1]>0]
 t0=min(r[0] for r in rows)
 rows.sort()
-for r in rows: print('inv %7.1f-%7.1f  umma %7.1f-%7.1f  topk %7.1f-%7.1f us' % tuple((x-t0)/1000 for x in r))"
+for r in rows: print('inv %7.1f-%7.1f  umma %7.1f-%7.1f  topk %7.1f-%7.1f us | umma CTA loop start %7.1f..%7.1f end %7.1f..%7.1f' % tuple((x-t0)/1000 for x in r))"
 import sys, torch
 sys.path.insert(0, '.')
 import bench

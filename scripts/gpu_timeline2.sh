@@ -1,5 +1,14 @@
 #!/bin/bash
-GDR_UMMA_TRACE=${TRACE:-} timeout 200 python - "$@" <<'PY' 2>&1 | grep -v "umma trace" | tail -20
+GDR_UMMA_TRACE=${TRACE:-} timeout 200 python - "$@" <<'PY' 2>&1 | grep -v "umma trace" | python -c "
+import sys
+rows=[]
+for l in sys.stdin:
+    if l.startswith('[timeline]'): rows.append(list(map(int,l.split()[1:])))
+    else: print(l.rstrip())
+rows=[r for r in rows if r[1]>0]
+if rows:
+    t0=min(r[0] for r in rows); rows.sort()
+    for r in rows: print('inv %7.1f-%7.1f  umma %7.1f-%7.1f  topk %7.1f-%7.1f us | umma CTA loop start %7.1f..%7.1f end %7.1f..%7.1f' % tuple((x-t0)/1000 for x in r))"
 import sys, torch, time
 sys.path.insert(0, '.')
 import bench
@@ -8,7 +17,7 @@ cfg = bench.WORKLOADS['cfg2']; dev = torch.device('cuda', 0)
 emb, offsets, docid = bench.synth_shard(cfg, 1234, dev)
 embs = [emb] + [emb.clone() for _ in range(3)]
 DEPTH = int(sys.argv[1]) if len(sys.argv) > 1 else 4
-NS = 24
+NS = int(sys.argv[2]) if len(sys.argv) > 2 else 24
 stores = [ClusterStore(embs[i % 4], offsets, docid) for i in range(DEPTH)]
 batches = bench.synth_batches(cfg, 8, cfg['C'], cfg['B'], 4321, dev)
 outs = [(torch.empty((1, cfg['B'], 100), device=dev), torch.empty((1, cfg['B'], 100), dtype=torch.int32, device=dev)) for _ in range(DEPTH)]
@@ -56,4 +65,7 @@ print("phase-split pipeline depth %d: %.2f us/step" % (DEPTH, e0.elapsed_time(e1
 ref_s, ref_d = stores[0].score_topk(batches[(NS - 1) % 8][0], batches[(NS - 1) % 8][1], 100)
 h = (NS - 1) % DEPTH
 print("split == fused:", bool(torch.equal(outs[h][1][0], ref_d)) if h == 0 else "n/a")
+import os
+if os.environ.get("GDR_UMMA_TRACE"):
+    for st in stores: st.last_stats()
 PY

@@ -332,6 +332,28 @@ def main():
     for s in stores:
         s.set_profiling(False)
 
+    # ---- average launch duration of the scoring kernel: the scoring phase alone (GDR_SKIP_INVERT | GDR_SKIP_TOPK), launched
+    # back to back on one stream over alternating store replicas (each launch streams a replica the previous one did not),
+    # between two CUDA events.  The GPU is first parked on a spin kernel so the host's launch rate cannot show up in the number.
+    kernel_ms = None
+    if not sharded:
+        SK_I, SK_T = 256, 1024
+        P0 = pipes[0]
+        for r in range(replicas):                # leaves batch r's inversion in replica r's scratch
+            P0["stores"][r].score_topk(batches[r % n_batches][0], batches[r % n_batches][1], k, out=(P0["out_s"], P0["out_d"]), flags=path_flags)
+        torch.cuda.synchronize()
+        n_rep = 40 * replicas
+        torch.cuda._sleep(4_000_000)
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        for i in range(n_rep):
+            r = i % replicas
+            q_, b_ = batches[r % n_batches]
+            P0["stores"][r].score_topk(q_, b_, k, out=(P0["out_s"], P0["out_d"]), flags=path_flags | SK_I | SK_T)
+        k1.record()
+        torch.cuda.synchronize()
+        kernel_ms = k0.elapsed_time(k1) / n_rep
+
     # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region.
     # Every step copies ITS inputs host->device and ITS results device->host; steps are issued round-robin on
     # `n_pipe` CUDA streams (each with its own device/host buffers and its own store handle = its own scratch),
@@ -377,15 +399,19 @@ def main():
         e2e_graph.replay()
         barrier()
     e2e_steps = max(period, (min(steps, 960) // period) * period) if use_graph else max(12, min(steps, 96))
-    e0.record()
-    if use_graph:
-        for _ in range(e2e_steps // period):
-            e2e_graph.replay()
-    else:
-        run_e2e(e2e_steps, cur)
-    e1.record()
-    barrier()
-    e2e_ms = e0.elapsed_time(e1)
+    # PCIe on a shared host is noisy: the timed region is repeated five times and the median segment reported
+    e2e_segments = []
+    for _ in range(5):
+        e0.record()
+        if use_graph:
+            for _ in range(e2e_steps // period):
+                e2e_graph.replay()
+        else:
+            run_e2e(e2e_steps, cur)
+        e1.record()
+        barrier()
+        e2e_segments.append(e0.elapsed_time(e1))
+    e2e_ms = sorted(e2e_segments)[len(e2e_segments) // 2]
     if not sharded:
         # the pipelined end-to-end loop must return what a plain serial call returns for the same batch
         last = (period if use_graph else e2e_steps) - 1
@@ -415,7 +441,7 @@ def main():
     emb_touched = int(stores[0].sizes_host[torch.unique(local).cpu().numpy()].sum()) * D * esize
     alg_bytes = emb_touched + B_rank * D * 4 + B_rank * k * 8      # rank 0's launch
     dominant = max(("score_umma", "score_simt"), key=lambda n: phase[n])
-    dom_ms = phase[dominant]
+    dom_ms = kernel_ms if kernel_ms else phase[dominant]     # phase[]: one event-bracketed launch inside a full call (includes launch gaps)
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     step_ms = ms / steps
     traffic = None
@@ -426,7 +452,8 @@ def main():
             traffic = t["dram_read_bytes"] + t["dram_write_bytes"]       # one ncu --set full capture of this workload (profiles/)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "kernel": {"score_umma": "k_score_umma (tcgen05 grouped GEMM)", "score_simt": "k_score_simt (GEMV)"}[dominant],
-                "kernel_ms": dom_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                "kernel_ms": dom_ms, "kernel_ms_method": "mean of 40+ back-to-back launches of the scoring phase between two CUDA events" if kernel_ms else
+                "one event-bracketed launch inside a full call", "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "phase_ms": phase, "whole_step_frac": alg_bytes / (step_ms * 1e-3) / 1e9 / peak,
                 "frac_of_nominal_8TBs": achieved / 8000.0}
 
@@ -459,6 +486,7 @@ def main():
                                                                    if sharded else f"corpus replicated on {world} GPUs, queries sharded, no data-path collective")},
         "clocks": clocks, "gpu_launches": (int(stats["launches"]) * steps + (steps if sharded else 0)) * (1 if sharded else world),
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "segments_ms_per_step": [round(x / e2e_steps, 5) for x in e2e_segments], "estimator": "median of 5 timed segments",
                 "pipeline": f"{n_pipe} batches in flight on {n_pipe} CUDA streams, pinned host buffers, per-step H2D of q+beams and D2H of (score, docid)"},
         "roofline": roofline, "cpu_baseline": cpu,
         "path": {"simt_items": int(stats["simt_items"]), "umma_tiles": int(stats["umma_tiles"]), "clusters_touched": int(stats["clusters_touched"])},

@@ -45,6 +45,7 @@ struct gdr_store {
     CUtensorMap tmap;
     int last_launches = 0;
     int umma_min_group = 1;   // > 1 (env GDR_UMMA_MIN_GROUP) = mixed mode
+    int umma_ctas = 0;        // > 0 (env GDR_UMMA_CTAS): persistent CTAs of the tcgen05 kernel (default: one per SM)
     bool profiling = false;
     long long *dbg = nullptr;   // device timeline scratch for GDR_UMMA_TRACE
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -97,6 +98,7 @@ int gdr_store_create(gdr_store_t **out, const void *emb, int64_t n_docs, int32_t
     }
     if (dtype == GDR_DTYPE_BF16 && dim % 64 == 0) s->has_tmap = umma_make_tensor_map(&s->tmap, emb, n_docs, dim);
     if (const char *env = getenv("GDR_UMMA_MIN_GROUP")) s->umma_min_group = atoi(env);
+    if (const char *env = getenv("GDR_UMMA_CTAS")) s->umma_ctas = atoi(env);
     if (getenv("GDR_UMMA_TRACE")) { cudaMalloc(&s->dbg, 512 * sizeof(long long)); cudaMemset(s->dbg, 0, 512 * sizeof(long long)); }
     *out = s;
     return GDR_OK;
@@ -127,6 +129,7 @@ int gdr_score_topk(gdr_store_t *s, const float *q, const int32_t *beams, const f
         return GDR_ERR_UNSUPPORTED;
     }
     if ((int64_t)B * K > INT_MAX / 2) return invalid("gdr_score_topk: B*K too large");
+    if ((int64_t)B * K * s->max_cluster > INT_MAX - 4) return invalid("gdr_score_topk: B*K*max_cluster_size must be below 2^31 (score buffer index)");
     if ((flags & GDR_FORCE_UMMA) && !s->has_tmap) {
         set_error("gdr_score_topk: GDR_FORCE_UMMA needs a bf16 store with dim % 64 == 0");
         return GDR_ERR_UNSUPPORTED;
@@ -145,12 +148,16 @@ int gdr_score_topk(gdr_store_t *s, const float *q, const int32_t *beams, const f
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
     const size_t o_pair = take(pairs * 4);
     const size_t o_cand = take((size_t)B * (K + 1) * 4);
+    const size_t o_cbase = take(pairs * 4);
     const size_t o_simt = take((size_t)simt_cap * sizeof(Item));
     const size_t o_umma = take(umma_possible ? (size_t)umma_cap * sizeof(Item) : 0);
     const size_t o_score = take((size_t)B * stride * 4);
     const int64_t q_rows = (flags & GDR_Q_PER_BEAM) ? pairs : B;
     const size_t o_qsplit = take(umma_possible ? (size_t)q_rows * 3 * s->dim * 2 : 0);
+    const size_t o_tmeta = take(umma_possible ? (size_t)umma_cap * sizeof(TileMeta) : 0);
     const size_t o_keys = take(global_keys ? (size_t)B * stride * 4 : 0);
+    const bool small_topk = k <= 128 && stride <= 65535 && !(getenv("GDR_TOPK_WIDE") && *getenv("GDR_TOPK_WIDE"));     // 128-thread top-k CTAs with 16-bit histogram bins
+    const size_t o_ghist = take(small_topk ? (size_t)B * 2048 * 4 : 0);
     if (off > s->batch_ws_bytes) {
         // growing the scratch synchronises; run one call per shape before capturing a CUDA graph
         GDR_CUDA(cudaStreamSynchronize(st));
@@ -177,11 +184,13 @@ int gdr_score_topk(gdr_store_t *s, const float *q, const int32_t *beams, const f
     a.scan_base = a.counters + CTR_COUNT;
     a.grp_pair = reinterpret_cast<int32_t *>(ws + o_pair);
     a.candoff = reinterpret_cast<int32_t *>(ws + o_cand);
+    a.cbase = reinterpret_cast<int32_t *>(ws + o_cbase);
     a.simt_items = reinterpret_cast<Item *>(ws + o_simt);
     a.umma_items = reinterpret_cast<Item *>(ws + o_umma);
     a.scorebuf = reinterpret_cast<float *>(ws + o_score);
     a.stride = stride;
     a.gkeys = global_keys ? reinterpret_cast<uint32_t *>(ws + o_keys) : nullptr;
+    a.ghist = small_topk ? reinterpret_cast<uint32_t *>(ws + o_ghist) : nullptr;
     a.qsplit = nullptr;   // set below when the tcgen05 path is taken
     // One scoring path per call: a batch that names each cluster three or more times on average goes to the tcgen05
     // grouped GEMM (slab read once for the whole group); a sparse batch goes to the SIMT GEMV, which serves up to four
@@ -192,6 +201,7 @@ int gdr_score_topk(gdr_store_t *s, const float *q, const int32_t *beams, const f
     const bool use_simt = !use_umma || mixed;
     a.dbg = s->dbg;
     if (use_umma) a.qsplit = reinterpret_cast<__nv_bfloat16 *>(ws + o_qsplit);
+    if (use_umma) a.tile_meta = reinterpret_cast<TileMeta *>(ws + o_tmeta);
     a.umma_min_group = !use_umma ? INT_MAX : (mixed ? s->umma_min_group : 1);
 
     int launches = 0;
@@ -204,7 +214,7 @@ int gdr_score_topk(gdr_store_t *s, const float *q, const int32_t *beams, const f
     if (!(flags & GDR_SKIP_INVERT)) GDR_CUDA(launch_invert(a, st, &launches));
     if (prof) GDR_CUDA(cudaEventRecord(s->ev[1], st));
     if (use_umma && !(flags & GDR_SKIP_SCORE)) {
-        GDR_CUDA(launch_score_umma(a, &s->tmap, st, s->sm_count));
+        GDR_CUDA(launch_score_umma(a, &s->tmap, st, s->umma_ctas > 0 ? s->umma_ctas : s->sm_count));
         launches += 1;
     }
     if (prof) GDR_CUDA(cudaEventRecord(s->ev[2], st));

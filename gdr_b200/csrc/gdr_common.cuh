@@ -38,7 +38,17 @@ constexpr int UMMA_NQ = 32;      // max pairs per tcgen05 tile (UMMA_N)
 constexpr int MAX_DIM = 1024;
 
 // counters[] layout (device int32)
-enum { CTR_N_SIMT = 0, CTR_N_UMMA = 1, CTR_N_TOUCHED = 2, CTR_COUNT = 8 };
+// CTR_TILE_NEXT / CTR_TILE_DONE: the tcgen05 kernel's dynamic tile queue (claimed with atomicAdd; the last CTA to finish
+// resets both, so they are zero between launches)
+enum { CTR_N_SIMT = 0, CTR_N_UMMA = 1, CTR_N_TOUCHED = 2, CTR_TILE_NEXT = 3, CTR_TILE_DONE = 4, CTR_COUNT = 8 };
+
+// Everything the tcgen05 kernel needs to know about one tile, resolved once per batch by k_tilemeta (work item ->
+// pairs -> candidate offsets: three dependent loads) so that the scoring kernel fetches it with ONE bulk copy.
+struct __align__(16) TileMeta {
+    int32_t row0, nrows, nq, rel0;   // first store row, rows (<= 128), pairs (<= 32; -1 = no more tiles), row offset inside the cluster
+    int32_t qrow[32];                // query row of each pair (B operand)
+    int32_t off[32];                 // score-buffer index of each pair's first row of this tile (epilogue)
+};
 
 // Everything one gdr_score_topk call needs on the device.
 struct ScoreArgs {
@@ -61,6 +71,7 @@ struct ScoreArgs {
     int32_t *umma_off;   // [C+1]
     int32_t *grp_pair;   // [B*K] pair ids grouped by cluster
     int32_t *candoff;    // [B, K+1] start of each beam's segment in the query's candidate list
+    int32_t *cbase;      // [B, K] first store row of each beam's cluster (0 for an absent beam)
     Item *simt_items;
     Item *umma_items;
     int32_t *counters;   // [CTR_COUNT]
@@ -69,6 +80,8 @@ struct ScoreArgs {
     int64_t stride;
     __nv_bfloat16 *qsplit;  // [rows(q), 3, dim] exact bf16 hi/mid/lo split of the fp32 queries (tcgen05 path), else null
     uint32_t *gkeys;     // [B, stride] keys scratch for the global-memory top-k variant
+    TileMeta *tile_meta; // [umma tile capacity] (null unless the tcgen05 path is taken)
+    uint32_t *ghist;     // [B, 2048] histogram scratch of the small-footprint top-k's fallback (null: variant not used)
     long long *dbg;      // [512] optional timeline scratch (GDR_UMMA_TRACE=1), else null
     int32_t umma_min_group;  // groups with at least this many pairs go to the tcgen05 path (INT_MAX = never)
 };

@@ -46,16 +46,20 @@ __device__ __forceinline__ void count_query(const ScoreArgs &a, int b, int lane,
     }
     const int32_t *beams = a.beams + (int64_t)b * a.K;
     int32_t *co = a.candoff + (int64_t)b * (a.K + 1);
+    int32_t *cb = a.cbase + (int64_t)b * a.K;
     int carry = 0;
     for (int i0 = 0; i0 < a.K; i0 += 32) {
         const int i = i0 + lane;
         int sz = 0;
         if (i < a.K) {
             const int c = beams[i];
+            int row_lo = 0;
             if (c >= 0 && c < a.n_clusters) {
-                sz = a.offsets[c + 1] - a.offsets[c];
+                row_lo = a.offsets[c];
+                sz = a.offsets[c + 1] - row_lo;
                 atomicAdd(&cnt[c], 1);
             }
+            cb[i] = row_lo;               // the top-k maps a winning candidate back to its store row without touching beams/offsets
         }
         int incl = sz;
 #pragma unroll
@@ -274,6 +278,36 @@ __global__ void __launch_bounds__(256) k_fill(ScoreArgs a) {
     trace_end(a.dbg, 1);
 }
 
+// One warp per tcgen05 tile: work item -> pairs -> candidate offsets, written as the tile's TileMeta record.
+__device__ __forceinline__ void write_tile_meta(const ScoreArgs &a, int t, int lane) {
+    const Item item = a.umma_items[t];
+    const int nq = item.nrows_nq >> 16;
+    int qrow = 0, off = 0;
+    if (lane < nq) {
+        const int p = a.grp_pair[item.slot0 + lane];
+        const int b = p / a.K;
+        qrow = (a.flags & GDR_Q_PER_BEAM) ? p : b;
+        off = (int)((int64_t)b * a.stride + a.candoff[p + b] + item.rel0);
+    }
+    TileMeta *m = a.tile_meta + t;
+    if (lane == 0) {
+        m->row0 = item.row0;
+        m->nrows = item.nrows_nq & 0xffff;
+        m->nq = nq;
+        m->rel0 = item.rel0;
+    }
+    m->qrow[lane] = qrow;
+    m->off[lane] = off;
+}
+
+__global__ void __launch_bounds__(256) k_tilemeta(ScoreArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int n_tiles = a.counters[CTR_N_UMMA];
+    const int lane = threadIdx.x & 31;
+    for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n_tiles; t += (gridDim.x * blockDim.x) >> 5) write_tile_meta(a, t, lane);
+}
+
 // Small batches (B <= 64, C <= 2048): the whole inversion in ONE CTA with the per-cluster arrays in shared
 // memory — one launch instead of three dependent ones.  (Larger batches need the per-query walk spread over many
 // SMs: measured 47 us in one CTA vs 14 us as three kernels for B = 1,024.)
@@ -331,6 +365,10 @@ __global__ void __launch_bounds__(1024) k_invert_small(ScoreArgs a) {
         const int g = (c + 1 < C ? s_off[c + 1] : carry[0]) - s_off[c];
         write_items(a, c, s_off[c], g, s_simt[c], s_umma[c]);
     }
+    if (a.tile_meta) {
+        __syncthreads();                       // items and grp_pair were written by this CTA
+        for (int t = warp; t < carry[2]; t += 32) write_tile_meta(a, t, lane);
+    }
 }
 
 cudaError_t launch_invert(const ScoreArgs &a, cudaStream_t s, int *n_launches) {
@@ -353,6 +391,10 @@ cudaError_t launch_invert(const ScoreArgs &a, cudaStream_t s, int *n_launches) {
     const int64_t n = max((int64_t)a.B * a.K, (int64_t)a.n_clusters);
     if (e == cudaSuccess) e = launch_pdl(k_fill, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, a);
     *n_launches += 3;
+    if (a.tile_meta) {
+        if (e == cudaSuccess) e = launch_pdl(k_tilemeta, dim3(148), dim3(256), 0, s, a);
+        *n_launches += 1;
+    }
     return e;
 }
 

@@ -47,16 +47,12 @@ constexpr int UM_ACC_COLS = 128;               // TMEM columns reserved per accu
 constexpr int UM_TMEM_COLS = 2 * UM_ACC_COLS;  // double-buffered accumulator
 constexpr int UM_RING_BYTES = UM_SA * UM_A_BYTES + UM_SB * UM_B_BYTES;   // 168 KB: leaves room for co-resident top-k / inversion CTAs
 static_assert(UM_SA == UM_SB, "A and B share one ring");
-constexpr int UM_MD = 4;                       // tile-metadata ring depth
-struct __align__(16) TileMeta {                // one tile's metadata, written by the metadata warp
-    int32_t row0, nrows, nq, rel0;
-    int32_t qrow[UMMA_NQ];                     // query row of each pair (B fillers)
-    int64_t off[UMMA_NQ];                      // score-buffer offset of each pair's first row (epilogue)
-};
-constexpr int UM_META_CONSUMERS = 1 + UM_FILL_WARPS + 4;    // MMA, fillers, epilogue warps
+constexpr int UM_MD = 2;                       // tile-metadata ring depth = how far ahead of its slowest role a CTA claims tiles
+constexpr int UM_META_CONSUMERS = 2 + UM_FILL_WARPS + 4;    // TMA, MMA, fillers, epilogue warps
 constexpr int UM_BAR_BYTES = 512;
 constexpr int UM_SMEM_BYTES = UM_RING_BYTES + UM_BAR_BYTES + UM_MD * (int)sizeof(TileMeta);
 static_assert(UM_SMEM_BYTES <= 227 * 1024, "shared memory budget");
+static_assert(sizeof(TileMeta) % 16 == 0 && UM_BAR_BYTES % 16 == 0 && UM_RING_BYTES % 16 == 0, "bulk-copy alignment of the metadata ring");
 static_assert(UM_SB == 2 * UM_FILL_WARPS, "two B stages per filler warp");
 static_assert(UMMA_NQ == 32, "epilogue and filler lane maps assume 32 pairs per tile");
 
@@ -85,9 +81,29 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "DONE_%=:\n\t"
         "}" ::"r"(bar), "r"(parity) : "memory");
 }
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {      // non-blocking
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tmap, int c0, int c1, uint32_t bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+// same load with an L2 eviction-priority hint: the store is streamed once per batch (and is larger than L2), so its lines
+// are marked evict-first and do not push the score buffer, the split-query table and the work lists out of L2
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const CUtensorMap *tmap, int c0, int c1, uint32_t bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+                 ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -203,25 +219,27 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_score_umma(const __grid_const
     pdl_wait();
     trace_start(a.dbg, 2);
     const int n_tiles = (a.flags & (1u << 31)) ? 0 : a.counters[CTR_N_UMMA];
-    const int my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
     if (warp == 0) {
         // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
         int s = 0;
         uint32_t ph = 0;
-        // the TMA warp needs only row0 (one load, fetched a tile ahead) and must not wait for the three-load
-        // metadata chain: the first TMA is what the whole CTA's start-up latency hangs on
-        int row0_next = my_tiles > 0 ? a.umma_items[blockIdx.x].row0 : 0;
-        for (int it = 0; it < my_tiles; ++it) {
-            const int row0 = row0_next;
-            if (it + 1 < my_tiles) row0_next = a.umma_items[blockIdx.x + (it + 1) * gridDim.x].row0;
+        uint64_t policy;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+        const bool hint = !(a.flags & (1u << 27));
+        for (int it = 0;; ++it) {
+            const TileMeta *m = meta_acquire(it);
+            const int nq = m->nq, row0 = m->row0;
+            if (nq < 0) break;
+            meta_release(it);
             for (int kb = 0; kb < nkb; ++kb) {
                 mbar_wait(empty_bar(s), ph ^ 1u);
                 if (elect_one()) {
                     if (a.flags & (1u << 28)) mbar_arrive(full_bar(s));
                     else {
                     mbar_arrive_expect_tx(full_bar(s), UM_A_BYTES);
-                    tma_load_2d(a_smem(s), &tmap, kb * UM_BLOCK_K, row0, full_bar(s));
+                    if (hint) tma_load_2d_hint(a_smem(s), &tmap, kb * UM_BLOCK_K, row0, full_bar(s), policy);
+                    else tma_load_2d(a_smem(s), &tmap, kb * UM_BLOCK_K, row0, full_bar(s));
                     }
                 }
                 __syncwarp();
@@ -235,8 +253,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_score_umma(const __grid_const
         UM_TRACE(1);
         if (a.dbg && lane == 0) a.dbg[200 + 2 * blockIdx.x] = gtime();      // every CTA: loop start / end
         int tr = 2;
-        for (int it = 0; it < my_tiles; ++it) {
+        for (int it = 0;; ++it) {
             const int nq = meta_acquire(it)->nq;
+            if (nq < 0) break;
             meta_release(it);
             UM_TRACE(tr); ++tr;           // metadata of tile `it` in hand
             const uint32_t idesc = umma_idesc(nq <= 16 ? 48 : 96);     // N = 3 terms x TS rows
@@ -275,20 +294,10 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_score_umma(const __grid_const
         // its next K block; the PREVIOUS block's group is then complete (wait_group 1), gets its generic->async proxy
         // fence and is published to the MMA warp.  No register staging, no L2 latency on the warp's critical path.
         const int fw = warp - 2;
-        const int total_kb = my_tiles * nkb;
         const uint32_t b_ring = smem_base + UM_SA * UM_A_BYTES;
         // every filler warp consumes every tile's metadata slot (lane l caches the query row of pair l), including
         // tiles in which it owns no K block, so the slot's consumer count is the same for all tiles
-        int cur_it = -1, nq = 0, qrow = 0;
-        auto advance_to = [&](int it_target) {
-            while (cur_it < it_target) {
-                ++cur_it;
-                const TileMeta *m = meta_acquire(cur_it);
-                nq = m->nq;
-                qrow = m->qrow[lane];
-                meta_release(cur_it);
-            }
-        };
+        int cur_it = -1, nq = 0, qrow = 0, prev_g = -1;
         auto publish = [&](int g_done, int pending_groups) {
             if (pending_groups) asm volatile("cp.async.wait_group 1;" ::: "memory");
             else asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -296,11 +305,29 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_score_umma(const __grid_const
             __syncwarp();
             if (lane == 0) mbar_arrive(full_bar(g_done % UM_SB));
         };
+        auto advance_to = [&](int it_target) -> bool {      // false once the end-of-work record has been reached
+            while (cur_it < it_target) {
+                if (nq < 0) return false;
+                ++cur_it;
+                // The K block this warp filled last is published only after the next one has been issued.  If the next
+                // tile's record is not there yet, publish first: the record may be waiting for this very K block (it is
+                // claimed when the epilogue moves on, i.e. after the MMAs that need the block; one-K-block tiles, dim 64).
+                if (prev_g >= 0 && !mbar_test(mfull_bar(cur_it % UM_MD), (uint32_t)(cur_it / UM_MD) & 1u)) {
+                    publish(prev_g, 0);
+                    prev_g = -1;
+                }
+                const TileMeta *m = meta_acquire(cur_it);
+                nq = m->nq;
+                qrow = m->qrow[lane];
+                if (nq < 0) return false;
+                meta_release(cur_it);
+            }
+            return true;
+        };
         const int64_t row_stride = 3 * (int64_t)a.dim;                 // bf16 elements per query row of the split table
-        int prev_g = -1;
-        for (int g = fw; g < total_kb; g += UM_FILL_WARPS) {
+        for (int g = fw;; g += UM_FILL_WARPS) {
             const int it = g / nkb, kb = g - it * nkb;
-            advance_to(it);
+            if (!advance_to(it)) break;
             const int sb = g % UM_SB;
             const uint32_t phb = (uint32_t)(g / UM_SB) & 1u;
             const uint32_t bst = b_ring + (uint32_t)sb * UM_B_BYTES;
@@ -325,15 +352,15 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_score_umma(const __grid_const
             prev_g = g;
         }
         if (prev_g >= 0) publish(prev_g, 0);
-        advance_to(my_tiles - 1);
     } else if (warp < 2 + UM_FILL_WARPS + 4) {
         // ===================== epilogue (128 threads) =====================
         const int wq = warp & 3;                    // TMEM lane quarter this warp may read
         const int row = wq * 32 + lane;
-        for (int it = 0; it < my_tiles; ++it) {
+        for (int it = 0;; ++it) {
             const TileMeta *m = meta_acquire(it);
             const int nrows = m->nrows, nq = m->nq;
             const int64_t off = m->off[lane];      // lane l owns column l: where pair l's scores of this tile start
+            if (nq < 0) break;
             meta_release(it);
             const int acc = it & 1;
             const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
@@ -378,51 +405,35 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_score_umma(const __grid_const
     }
 
     else {
-        // ===================== tile metadata (one warp, four tiles per round so the three dependent loads overlap) =====================
-        for (int it0 = 0; it0 < my_tiles; it0 += UM_MD) {
-            Item item[UM_MD];
-            int pr[UM_MD];
-            int64_t off[UM_MD];
-#pragma unroll
-            for (int u = 0; u < UM_MD; ++u)
-                if (it0 + u < my_tiles) item[u] = a.umma_items[blockIdx.x + (it0 + u) * gridDim.x];
-#pragma unroll
-            for (int u = 0; u < UM_MD; ++u) {
-                pr[u] = 0;
-                if (it0 + u < my_tiles && lane < (item[u].nrows_nq >> 16)) pr[u] = a.grp_pair[item[u].slot0 + lane];
-            }
-#pragma unroll
-            for (int u = 0; u < UM_MD; ++u) {
-                off[u] = 0;
-                if (it0 + u < my_tiles && lane < (item[u].nrows_nq >> 16)) {
-                    const int b = pr[u] / a.K;
-                    off[u] = (int64_t)b * a.stride + a.candoff[pr[u] + b] + item[u].rel0;
+        // ===================== tile scheduler (one lane): claim the next tile, bulk-copy its TileMeta record into the ring =====================
+        // Tiles are claimed one at a time from a global counter, so CTAs that run slower (an SM shared with the previous
+        // batch's top-k CTAs) or start later (an SM still busy with the previous batch's scoring CTA) simply take fewer.
+        for (int it = 0;; ++it) {
+            const int slot = it % UM_MD;
+            mbar_wait(mempty_bar(slot), ((uint32_t)(it / UM_MD) & 1u) ^ 1u);
+            int t = 0;
+            if (lane == 0) {
+                t = atomicAdd(&a.counters[CTR_TILE_NEXT], 1);
+                if (t < n_tiles) {
+                    mbar_arrive_expect_tx(mfull_bar(slot), (uint32_t)sizeof(TileMeta));
+                    bulk_load(smem_u32(meta + slot), a.tile_meta + t, (uint32_t)sizeof(TileMeta), mfull_bar(slot));
+                } else {
+                    meta[slot].nq = -1;                      // end of work: every role leaves its loop on this record
+                    mbar_arrive(mfull_bar(slot));
                 }
             }
-#pragma unroll
-            for (int u = 0; u < UM_MD; ++u) {
-                const int it = it0 + u;
-                if (it < my_tiles) {
-                    mbar_wait(mempty_bar(u), ((uint32_t)(it / UM_MD) & 1u) ^ 1u);
-                    TileMeta *m = meta + u;
-                    if (lane == 0) {
-                        m->row0 = item[u].row0;
-                        m->nrows = item[u].nrows_nq & 0xffff;
-                        m->nq = item[u].nrows_nq >> 16;
-                        m->rel0 = item[u].rel0;
-                    }
-                    m->qrow[lane] = (a.flags & GDR_Q_PER_BEAM) ? pr[u] : pr[u] / a.K;
-                    m->off[lane] = off[u];
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(mfull_bar(u));
-                }
-            }
+            t = __shfl_sync(0xffffffffu, t, 0);
+            if (t >= n_tiles) break;
         }
     }
 
     tc_fence_before();
     __syncthreads();
     trace_end(a.dbg, 3);
+    if (threadIdx.x == 0 && atomicAdd(&a.counters[CTR_TILE_DONE], 1) == (int)gridDim.x - 1) {
+        a.counters[CTR_TILE_NEXT] = 0;                       // every CTA has made its last claim: leave the queue ready for the next launch
+        a.counters[CTR_TILE_DONE] = 0;
+    }
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(UM_TMEM_COLS) : "memory");
     }

@@ -35,7 +35,7 @@ struct Threshold {
 
 // Select the kk largest keys among the active candidates.  key_at(j, key) returns false for
 // inactive candidates.  All threads of the CTA call this with identical arguments.
-template <typename KeyAt>
+template <int NT, typename KeyAt>
 __device__ Threshold radix_select(int n, int kk, uint32_t *hist, TkShared *sh, KeyAt key_at) {
     Threshold th{0u, 32, kk, 0};
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -43,9 +43,9 @@ __device__ Threshold radix_select(int n, int kk, uint32_t *hist, TkShared *sh, K
     for (int pass = 0; pass < 3; ++pass) {
         const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);      // 11 + 11 + 10 bits
         const int nb = pass == 2 ? 1024 : 2048;
-        for (int i = tid; i < nb; i += TK_THREADS) hist[i] = 0;
+        for (int i = tid; i < nb; i += NT) hist[i] = 0;
         __syncthreads();
-        for (int j = tid; j < n; j += TK_THREADS) {
+        for (int j = tid; j < n; j += NT) {
             uint32_t key;
             if (!key_at(j, key)) continue;
             if (th.shift == 32 || (key >> th.shift) == (th.prefix >> th.shift))
@@ -53,7 +53,7 @@ __device__ Threshold radix_select(int n, int kk, uint32_t *hist, TkShared *sh, K
         }
         __syncthreads();
         // thread t owns `per` bins counted from the top: [nb - (t+1)*per, nb - t*per)
-        const int per = nb / TK_THREADS;
+        const int per = nb / NT;
         const int top = nb - tid * per;
         int local = 0;
         for (int i = 1; i <= per; ++i) local += hist[top - i];
@@ -93,11 +93,12 @@ __device__ Threshold radix_select(int n, int kk, uint32_t *hist, TkShared *sh, K
     return th;
 }
 
+template <int NT>
 __device__ __forceinline__ void bitonic_sort_desc(uint64_t *v, int cap) {
     for (int size = 2; size <= cap; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
             __syncthreads();
-            for (int i = threadIdx.x; i < cap; i += TK_THREADS) {
+            for (int i = threadIdx.x; i < cap; i += NT) {
                 const int p = i ^ stride;
                 if (p > i) {
                     const uint64_t a = v[i], b = v[p];
@@ -138,8 +139,9 @@ struct StoreSrc {   // a query's candidates = its K beam segments of the score b
     }
     // four consecutive candidates starting at j4 (multiple of 4; the score row is 16-byte aligned and padded).
     // One segment search per four: they almost always share a beam segment; otherwise walk forward from it.
-    __device__ void score4(int j4, int n, float (&s)[4]) const {
-        const float4 v = *reinterpret_cast<const float4 *>(sb + j4);
+    __device__ float4 load4(int j4) const { return *reinterpret_cast<const float4 *>(sb + j4); }
+    __device__ void score4(int j4, int n, float (&s)[4]) const { bias4(load4(j4), j4, n, s); }
+    __device__ void bias4(const float4 v, int j4, int n, float (&s)[4]) const {
         s[0] = v.x; s[1] = v.y; s[2] = v.z; s[3] = v.w;
         if (bias) {
             int i = seg(j4);
@@ -172,12 +174,12 @@ struct ListSrc {    // explicit candidate lists from G ranks: [G, B, k_in]
     }
 };
 
-template <typename Src>
+template <int NT, typename Src>
 __device__ void topk_general(const Src &src, int n, int k, int cap, uint32_t *keys, uint64_t *sel, uint32_t *hist,
                           TkShared *sh, float *out_s, int32_t *out_d) {
     const int tid = threadIdx.x;
     if (tid == 0) { sh->sel_count = 0; sh->eq2_count = 0; }
-    for (int j4 = tid * 4; j4 < n; j4 += TK_THREADS * 4) {            // keys[] is padded to a multiple of 4
+    for (int j4 = tid * 4; j4 < n; j4 += NT * 4) {            // keys[] is padded to a multiple of 4
         float s4[4];
         src.score4(j4, n, s4);
         *reinterpret_cast<uint4 *>(keys + j4) = make_uint4(float_to_ordered(s4[0]), float_to_ordered(s4[1]), float_to_ordered(s4[2]),
@@ -186,18 +188,18 @@ __device__ void topk_general(const Src &src, int n, int k, int cap, uint32_t *ke
     __syncthreads();
     const int kk = min(k, n);
     Threshold t1{0u, 32, kk, n};
-    if (n > k) t1 = radix_select(n, kk, hist, sh, [&](int j, uint32_t &key) { key = keys[j]; return true; });
+    if (n > k) t1 = radix_select<NT>(n, kk, hist, sh, [&](int j, uint32_t &key) { key = keys[j]; return true; });
     const bool tie = t1.shift == 0 && t1.n_eq > t1.need;   // exact-score ties straddle the cut
     Threshold t2{0u, 32, t1.need, t1.n_eq};
     if (tie) {
         const uint32_t T = t1.prefix;
-        t2 = radix_select(n, t1.need, hist, sh, [&](int j, uint32_t &key) {
+        t2 = radix_select<NT>(n, t1.need, hist, sh, [&](int j, uint32_t &key) {
             if (keys[j] != T) return false;
             key = ~(uint32_t)src.doc(j);
             return true;
         });
     }
-    for (int j = tid; j < n; j += TK_THREADS) {
+    for (int j = tid; j < n; j += NT) {
         const uint32_t key = keys[j];
         bool take = true;
         uint32_t nd = 0;
@@ -222,9 +224,9 @@ __device__ void topk_general(const Src &src, int n, int k, int cap, uint32_t *ke
         }
     }
     __syncthreads();
-    for (int i = kk + tid; i < cap; i += TK_THREADS) sel[i] = 0ull;
-    bitonic_sort_desc(sel, cap);
-    for (int r = tid; r < k; r += TK_THREADS) {
+    for (int i = kk + tid; i < cap; i += NT) sel[i] = 0ull;
+    bitonic_sort_desc<NT>(sel, cap);
+    for (int r = tid; r < k; r += NT) {
         float s = -INFINITY;
         int32_t d = -1;
         if (r < kk) {
@@ -240,7 +242,8 @@ __device__ void topk_general(const Src &src, int n, int k, int cap, uint32_t *ke
 
 // One warp, 256 bins, lane owns bins [256 - 8*lane - 8, 256 - 8*lane) (lane 0 the highest): find the bin d where
 // the count accumulated from the top reaches `need`; gt = count strictly above d, eq = count in d.
-__device__ __forceinline__ void scan_down8(const uint32_t *bins, int lane, int need, int &d, int &gt, int &eq) {
+template <typename BinT>
+__device__ __forceinline__ void scan_down8(const BinT *bins, int lane, int need, int &d, int &gt, int &eq) {
     const int top = 256 - lane * 8;
     int local = 0;
 #pragma unroll
@@ -315,20 +318,21 @@ __device__ __forceinline__ void warp_bitonic128_desc(uint64_t (&v)[4], int lane)
 // STORE_KEYS = false: the keys are not kept between the two passes (pass 2 re-reads the L2-resident scores), which cuts
 // the CTA's shared memory from ~20 KB to ~9 KB so that more of these CTAs co-reside with the scoring kernel of the next
 // batch on every SM; `keys` then points to global scratch used only by the general fallback.
-template <bool STORE_KEYS, typename Src>
+template <int NT, bool STORE_KEYS, typename Src>
 __device__ void topk_body(const Src &src, int n, int k, int cap, uint32_t *keys, uint64_t *sel, uint32_t *hist,
                           TkShared *sh, float *out_s, int32_t *out_d) {
+    static_assert(NT == 256, "the bin ranges below assume eight warps");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (n <= k || cap > 128) {     // few candidates (take all) or large k: general path
-        topk_general(src, n, k, cap, keys, sel, hist, sh, out_s, out_d);
+        topk_general<NT>(src, n, k, cap, keys, sel, hist, sh, out_s, out_d);
         return;
     }
-    for (int i = tid; i < TK_BINS; i += TK_THREADS) hist[i] = 0;
-    sh->hist2[tid] = 0;                                           // TK_THREADS == 256 bins
+    for (int i = tid; i < TK_BINS; i += NT) hist[i] = 0;
+    sh->hist2[tid] = 0;                                           // NT == 256 bins
     if (tid == 0) { sh->sel_count = 0; sh->eq2_count = 0; sh->bnd_count = 0; }
     __syncthreads();
     // pass 1: keys + histogram, four candidates per thread and iteration
-    for (int j4 = tid * 4; j4 < n; j4 += TK_THREADS * 4) {
+    for (int j4 = tid * 4; j4 < n; j4 += NT * 4) {
         float s4[4];
         src.score4(j4, n, s4);
         uint32_t k4[4];
@@ -352,7 +356,7 @@ __device__ void topk_body(const Src &src, int n, int k, int cap, uint32_t *keys,
     __syncthreads();
     // ... then every warp redundantly walks down from the top to the 256-bin range and the bin where the
     // cumulative count reaches k (no further barrier needed: all threads end up with the same d / gt / eq)
-    int above = 0, range = TK_THREADS / 32 - 1;
+    int above = 0, range = NT / 32 - 1;
     for (; range > 0; --range) {
         const int t = sh->warp_tot[range];
         if (above + t >= k) break;
@@ -364,14 +368,14 @@ __device__ void topk_body(const Src &src, int n, int k, int cap, uint32_t *keys,
     gt += above;
     if (eq > TK_BND) {             // mass ties in the boundary bin: general path (uniform decision)
         __syncthreads();
-        topk_general(src, n, k, cap, keys, sel, hist, sh, out_s, out_d);
+        topk_general<NT>(src, n, k, cap, keys, sel, hist, sh, out_s, out_d);
         return;
     }
     // pass 2: classify.  sel[0, gt) <- keys above the boundary bin; bnd[0, eq) <- keys inside it (bnd aliases hist)
     uint64_t *bnd = reinterpret_cast<uint64_t *>(hist);           // 2 x TK_BND x 8 B = 4 KB <= the 8 KB histogram
     uint64_t *bnd2 = bnd + TK_BND;
     __syncthreads();                                              // everyone is done reading hist
-    for (int j4 = tid * 4; j4 < n; j4 += TK_THREADS * 4) {
+    for (int j4 = tid * 4; j4 < n; j4 += NT * 4) {
         uint32_t k4[4];
         if (STORE_KEYS) {
             const uint4 kv = *reinterpret_cast<const uint4 *>(keys + j4);
@@ -452,6 +456,225 @@ __device__ void topk_body(const Src &src, int n, int k, int cap, uint32_t *keys,
     }
 }
 
+
+// ---- fast path, small-footprint variant --------------------------------------------------------------------------
+// Same algorithm as topk_body<false> for CTAs of NT = 128 threads with 16-bit histogram bins (n <= 65,535): 6.4 KB of
+// shared memory and 4 K registers per query.  A batch's top-k overlaps the NEXT batch's scoring kernel, whose CTA leaves
+// ~53 KB of shared memory and ~32 K registers per SM; every query's top-k is a chain of dependent L2 round trips and
+// block barriers (latency-bound: ~25 us per query under a saturated memory system), so what matters is how many
+// queries are in flight per SM: eight of these CTAs fit beside the scoring CTA against four of the 256-thread ones.
+// The rare fallbacks (n <= k, mass ties in the boundary bin) run the general select with its histogram in global scratch.
+template <int NT, int R4, typename Src>
+__device__ void topk_fast16(const Src &src, int n, int k, uint32_t *gkeys, uint32_t *ghist, uint64_t *sel, uint32_t *hist_words,
+                            TkShared *sh, float *out_s, int32_t *out_d) {
+    constexpr int NW = NT / 32;
+    constexpr int RANGE = TK_BINS / NW;                            // bins summed by one warp (512 for four warps)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (n <= k) {
+        topk_general<NT>(src, n, k, 128, gkeys, sel, ghist, sh, out_s, out_d);
+        return;
+    }
+    uint16_t *hist = reinterpret_cast<uint16_t *>(hist_words);     // bin b = half (b & 1) of word b >> 1
+    for (int i = tid; i < TK_BINS / 2; i += NT) hist_words[i] = 0;
+    for (int i = tid; i < 256; i += NT) sh->hist2[i] = 0;
+    if (tid == 0) { sh->sel_count = 0; sh->eq2_count = 0; sh->bnd_count = 0; }
+    // Up to NT * 4 * R4 candidates (2,560: the reference's beam 20 x ~107-doc clusters) are read ONCE, all loads of a
+    // thread in flight together, and their keys stay in registers for the second pass; a query's top-k is a chain of
+    // dependent steps on few warps, so every exposed L2 round trip (one per loop iteration otherwise) is what it costs.
+    const bool in_regs = R4 > 0 && n <= NT * 4 * R4;
+    uint32_t kreg[R4 > 0 ? R4 : 1][4];
+    if (in_regs) {
+        float4 v[R4 > 0 ? R4 : 1];
+#pragma unroll
+        for (int r = 0; r < R4; ++r) {
+            const int j4 = (r * NT + tid) * 4;
+            v[r] = j4 < n ? src.load4(j4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncthreads();                                           // histogram is zeroed
+#pragma unroll
+        for (int r = 0; r < R4; ++r) {
+            const int j4 = (r * NT + tid) * 4;
+            float s4[4];
+            if (j4 < n) src.bias4(v[r], j4, n, s4);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                kreg[r][e] = float_to_ordered(s4[e]);
+                const uint32_t bin = kreg[r][e] >> 21;
+                if (j4 + e < n) atomicAdd(&hist_words[bin >> 1], 1u << ((bin & 1u) * 16u));
+            }
+        }
+    } else {
+        __syncthreads();
+        for (int j4 = tid * 4; j4 < n; j4 += NT * 4) {
+            float s4[4];
+            src.score4(j4, n, s4);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const uint32_t bin = float_to_ordered(s4[e]) >> 21;
+                if (j4 + e < n) atomicAdd(&hist_words[bin >> 1], 1u << ((bin & 1u) * 16u));
+            }
+        }
+    }
+    __syncthreads();
+    {
+        int part = 0;
+#pragma unroll
+        for (int i = 0; i < RANGE / 64; ++i) {
+            const uint32_t w = hist_words[warp * (RANGE / 2) + i * 32 + lane];
+            part += (int)(w & 0xffffu) + (int)(w >> 16);
+        }
+#pragma unroll
+        for (int d = 16; d; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+        if (lane == 0) sh->warp_tot[warp] = part;
+    }
+    __syncthreads();
+    int above = 0, range = NW - 1;
+    for (; range > 0; --range) {
+        const int t = sh->warp_tot[range];
+        if (above + t >= k) break;
+        above += t;
+    }
+    int base = range * RANGE + RANGE - 256;                        // walk the range's 256-bin blocks from the top
+    for (; base > range * RANGE; base -= 256) {
+        const uint32_t *w = hist_words + base / 2 + lane * 4;
+        int t = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) t += (int)(w[i] & 0xffffu) + (int)(w[i] >> 16);
+#pragma unroll
+        for (int d = 16; d; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+        if (above + t >= k) break;
+        above += t;
+    }
+    int d_bin, gt, eq;
+    scan_down8(hist + base, lane, k - above, d_bin, gt, eq);
+    d_bin += base;
+    gt += above;
+    if (eq > TK_BND) {
+        __syncthreads();
+        topk_general<NT>(src, n, k, 128, gkeys, sel, ghist, sh, out_s, out_d);
+        return;
+    }
+    uint64_t *bnd = reinterpret_cast<uint64_t *>(hist_words);      // 2 x TK_BND x 8 B = the 4 KB histogram
+    uint64_t *bnd2 = bnd + TK_BND;
+    __syncthreads();
+    auto classify = [&](uint32_t key, int j) {
+        const int bin = (int)(key >> 21);
+        if (bin > d_bin) sel[atomicAdd(&sh->sel_count, 1)] = ((uint64_t)key << 32) | (uint32_t)j;
+        else if (bin == d_bin) {
+            bnd[atomicAdd(&sh->bnd_count, 1)] = ((uint64_t)key << 32) | (uint32_t)j;
+            atomicAdd(&sh->hist2[(key >> 13) & 255u], 1u);
+        }
+    };
+    if (in_regs) {
+#pragma unroll
+        for (int r = 0; r < R4; ++r) {
+            const int j4 = (r * NT + tid) * 4;
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (j4 + e < n) classify(kreg[r][e], j4 + e);
+        }
+    } else {
+        for (int j4 = tid * 4; j4 < n; j4 += NT * 4) {
+            float s4[4];
+            src.score4(j4, n, s4);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (j4 + e < n) classify(float_to_ordered(s4[e]), j4 + e);
+        }
+    }
+    __syncthreads();
+    int d2, gt2, eq2;
+    scan_down8(sh->hist2, lane, k - gt, d2, gt2, eq2);
+    const int need2 = k - gt - gt2;
+    for (int t = tid; t < eq; t += NT) {
+        const uint64_t e = bnd[t];
+        const int sub = (int)((e >> 45) & 255u);
+        if (sub > d2) sel[atomicAdd(&sh->sel_count, 1)] = e;
+        else if (sub == d2) bnd2[atomicAdd(&sh->eq2_count, 1)] = e;
+    }
+    __syncthreads();
+    if (need2 == eq2) {
+        for (int t = tid; t < eq2; t += NT) sel[gt + gt2 + t] = bnd2[t];
+    } else {
+        // still tied after 19 key bits: order by (key desc, docid asc); identical (key, docid) pairs by list position
+        constexpr int PER = TK_BND / NT;
+        uint64_t mine[PER], orig[PER];
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            const int t = tid + u * NT;
+            if (t < eq2) {
+                orig[u] = bnd2[t];
+                mine[u] = (orig[u] & 0xffffffff00000000ull) | (uint32_t)~(uint32_t)src.doc((int)(uint32_t)orig[u]);
+                bnd2[t] = mine[u];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            const int t = tid + u * NT;
+            if (t < eq2) {
+                int rank = 0;
+                for (int v = 0; v < eq2; ++v) {
+                    const uint64_t o = bnd2[v];
+                    rank += (o > mine[u]) || (o == mine[u] && v < t);
+                }
+                if (rank < need2) sel[gt + gt2 + rank] = orig[u];
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        uint64_t v[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int i = lane * 4 + r;
+            v[r] = 0;
+            if (i < k) {
+                const uint64_t e = sel[i];
+                v[r] = (e & 0xffffffff00000000ull) | (uint32_t)~(uint32_t)src.doc((int)(uint32_t)e);
+            }
+        }
+        warp_bitonic128_desc(v, lane);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int i = lane * 4 + r;
+            if (i < k) {
+                out_s[i] = ordered_to_float((uint32_t)(v[r] >> 32));
+                out_d[i] = (int32_t)(~(uint32_t)v[r]);
+            }
+        }
+    }
+}
+
+constexpr int TKF_THREADS = 128;
+constexpr int TKF_R4 = 5;            // 128 threads x 5 x 4 = 2,560 candidates held in registers
+// dynamic shared memory: sel[128] u64 | hist[2048] u16 | co[K+1] | cbase[K] | bias[K]
+__global__ void __launch_bounds__(TKF_THREADS, 10) k_topk_fast(ScoreArgs a, float alpha, float *out_scores, int32_t *out_docids) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ TkShared sh;
+    uint64_t *sel = reinterpret_cast<uint64_t *>(smem);
+    uint32_t *hist_words = reinterpret_cast<uint32_t *>(sel + 128);
+    int32_t *co = reinterpret_cast<int32_t *>(hist_words + TK_BINS / 2);
+    int32_t *cbase = co + a.K + 1;
+    float *bias = reinterpret_cast<float *>(cbase + a.K);
+    const int b = blockIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
+    trace_start(a.dbg, 4);
+    for (int i = threadIdx.x; i <= a.K; i += TKF_THREADS) {          // one round trip: k_count left both arrays per query
+        co[i] = a.candoff[(int64_t)b * (a.K + 1) + i];
+        if (i < a.K) {
+            cbase[i] = a.cbase[(int64_t)b * a.K + i];
+            if (a.prob) bias[i] = __fmul_rn(alpha, a.prob[(int64_t)b * a.K + i]);
+        }
+    }
+    __syncthreads();
+    StoreSrc src{a.scorebuf + (int64_t)b * a.stride, co, cbase, a.prob ? bias : nullptr, a.docid, a.K};
+    topk_fast16<TKF_THREADS, TKF_R4>(src, co[a.K], a.k, a.gkeys + (int64_t)b * a.stride, a.ghist + (int64_t)b * TK_BINS, sel, hist_words, &sh,
+                             out_scores + (int64_t)b * a.k, out_docids + (int64_t)b * a.k);
+    trace_end(a.dbg, 5);
+}
+
 // dynamic shared memory layout: sel[cap] u64 | hist[TK_BINS] u32 | keys[stride] u32 (smem variant) | co[K+1] i32 | cbase[K] i32 | bias[K] f32
 // KEYS: 0 = key array in global scratch, 1 = key array in shared memory, 2 = fast path (k <= 128) without a key array
 // (its mass-tie fallback uses the global scratch)
@@ -473,15 +696,14 @@ __global__ void __launch_bounds__(TK_THREADS, 8) k_topk_store(ScoreArgs a, float
     for (int i = threadIdx.x; i <= a.K; i += TK_THREADS) {
         co[i] = a.candoff[(int64_t)b * (a.K + 1) + i];
         if (i < a.K) {
-            const int c = a.beams[(int64_t)b * a.K + i];
-            cbase[i] = (c >= 0 && c < a.n_clusters) ? a.offsets[c] : 0;
+            cbase[i] = a.cbase[(int64_t)b * a.K + i];
             if (a.prob) bias[i] = __fmul_rn(alpha, a.prob[(int64_t)b * a.K + i]);
         }
     }
     __syncthreads();
     uint32_t *keys = KEYS == 1 ? skeys : a.gkeys + (int64_t)b * a.stride;
     StoreSrc src{a.scorebuf + (int64_t)b * a.stride, co, cbase, a.prob ? bias : nullptr, a.docid, a.K};
-    topk_body<KEYS != 2>(src, co[a.K], a.k, cap, keys, sel, hist, &sh, out_scores + (int64_t)b * a.k,
+    topk_body<TK_THREADS, KEYS != 2>(src, co[a.K], a.k, cap, keys, sel, hist, &sh, out_scores + (int64_t)b * a.k,
                          out_docids + (int64_t)b * a.k);
     trace_end(a.dbg, 5);
 }
@@ -497,7 +719,7 @@ __global__ void __launch_bounds__(TK_THREADS) k_topk_merge(ListSrc src0, int n, 
     ListSrc src = src0;
     src.scores += (int64_t)b * src.k_in;
     src.docids += (int64_t)b * src.k_in;
-    topk_body<true>(src, n, k, cap, keys, sel, hist, &sh, out_scores + (int64_t)b * k, out_docids + (int64_t)b * k);
+    topk_body<TK_THREADS, true>(src, n, k, cap, keys, sel, hist, &sh, out_scores + (int64_t)b * k, out_docids + (int64_t)b * k);
 }
 
 static int pow2_at_least(int x) { int p = 2; while (p < x) p <<= 1; return p; }
@@ -522,6 +744,9 @@ cudaError_t launch_topk_store(const ScoreArgs &a, float alpha, float *out_scores
         cudaFuncSetAttribute(k_topk_store<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     }
     const int grid = a.B;      // (a few persistent CTAs per SM walking the queries measured slower in the pipelined step: 62 vs 57 us)
+    if (cap <= 128 && a.gkeys && a.ghist && a.stride <= 65535)
+        return launch_pdl(k_topk_fast, dim3(grid), dim3(TKF_THREADS), (size_t)128 * 8 + TK_BINS * 2 + (size_t)(3 * a.K + 1) * 4, s, a, alpha,
+                          out_scores, out_docids);
     if (cap <= 128 && a.gkeys)
         return launch_pdl(k_topk_store<2>, dim3(grid), dim3(TK_THREADS), fixed, s, a, alpha, cap, out_scores, out_docids);
     if (with_keys <= 96 * 1024)

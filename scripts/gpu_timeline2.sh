@@ -1,5 +1,5 @@
 #!/bin/bash
-GDR_UMMA_TRACE=${TRACE:-} timeout 200 python - "$@" <<'PY' 2>&1 | grep -v "umma trace" | python -c "
+GDR_UMMA_TRACE=${TRACE:-} timeout 200 python - "$@" <<'PY' 2>&1 | grep -v "umma trace" | python -u -c "
 import sys
 rows=[]
 for l in sys.stdin:
@@ -22,11 +22,15 @@ stores = [ClusterStore(embs[i % 4], offsets, docid) for i in range(DEPTH)]
 batches = bench.synth_batches(cfg, 8, cfg['C'], cfg['B'], 4321, dev)
 outs = [(torch.empty((1, cfg['B'], 100), device=dev), torch.empty((1, cfg['B'], 100), dtype=torch.int32, device=dev)) for _ in range(DEPTH)]
 lo, hi = torch.cuda.Stream.priority_range() if hasattr(torch.cuda.Stream, 'priority_range') else (0, -5)
-s_inv = torch.cuda.Stream(priority=-1); s_sc = torch.cuda.Stream(priority=-3); s_tk = torch.cuda.Stream(priority=0)
+import os
+P = [int(x) for x in os.environ.get('PRIO', '-1,-3,0').split(',')]
+s_inv = torch.cuda.Stream(priority=P[0]); s_sc = torch.cuda.Stream(priority=P[1]); NTK = int(os.environ.get('NTK', '1'))
+s_tks = [torch.cuda.Stream(priority=P[2]) for _ in range(NTK)]
+print('priorities inv/score/topk', P, 'range', torch.cuda.Stream.priority_range() if hasattr(torch.cuda.Stream, 'priority_range') else None)
 SK_I, SK_S, SK_T = 256, 512, 1024
 def run(n):
     cur = torch.cuda.current_stream()
-    for s in (s_inv, s_sc, s_tk): s.wait_stream(cur)
+    for s in [s_inv, s_sc] + s_tks: s.wait_stream(cur)
     done = [None] * DEPTH
     for i in range(n):
         h = i % DEPTH; q, b = batches[i % 8]
@@ -38,12 +42,13 @@ def run(n):
             s_sc.wait_event(e1)
             stores[h].score_topk(q, b, 100, out=outs[h], flags=SK_I | SK_T)
             e2 = torch.cuda.Event(); e2.record(s_sc)
+        s_tk = s_tks[i % NTK]
         with torch.cuda.stream(s_tk):
             s_tk.wait_event(e2)
             stores[h].score_topk(q, b, 100, out=outs[h], flags=SK_I | SK_S)
             e3 = torch.cuda.Event(); e3.record(s_tk)
             done[h] = e3
-    for s in (s_inv, s_sc, s_tk): cur.wait_stream(s)
+    for s in [s_inv, s_sc] + s_tks: cur.wait_stream(s)
 for h in range(DEPTH):
     q, b = batches[0]; stores[h].score_topk(q, b, 100, out=outs[h])
 torch.cuda.synchronize()

@@ -282,36 +282,39 @@ __device__ __forceinline__ void scan_down8(const BinT *bins, int lane, int need,
 // general radix select when the boundary bin holds more than TK_BND keys (mass ties).
 constexpr int TK_BND = 256;
 
-// descending bitonic sort of 128 u64 keys held 4 per lane (element index = lane * 4 + r)
+// descending bitonic sort of 128 u64 keys held 4 per lane (element index = lane * 4 + r).  The (size, stride) loops are
+// NOT unrolled: fully unrolled the network is ~1,300 instructions (21 KB of SASS) executed once per query by one warp,
+// and the top-k kernel was losing a quarter of its issue slots to instruction-cache misses (ncu: no_inst 26%).
 __device__ __forceinline__ void warp_bitonic128_desc(uint64_t (&v)[4], int lane) {
+    auto local_stage = [&](int size, int stride) {                 // both partners in this lane's registers
 #pragma unroll
-    for (int size = 2; size <= 128; size <<= 1) {
-#pragma unroll
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            if (stride >= 4) {
-                const int lm = stride >> 2;
-                const bool lower = (lane & lm) == 0;
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const uint64_t other = __shfl_xor_sync(0xffffffffu, v[r], lm);
-                    const bool desc = (((lane * 4 + r) & size) == 0);
-                    const bool want_max = (lower == desc);
-                    const uint64_t mx = v[r] > other ? v[r] : other, mn = v[r] > other ? other : v[r];
-                    v[r] = want_max ? mx : mn;
-                }
-            } else {
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    if ((r & stride) == 0) {
-                        const int p = r | stride;
-                        const bool desc = (((lane * 4 + r) & size) == 0);
-                        const uint64_t mx = v[r] > v[p] ? v[r] : v[p], mn = v[r] > v[p] ? v[p] : v[r];
-                        v[r] = desc ? mx : mn;
-                        v[p] = desc ? mn : mx;
-                    }
-                }
+        for (int r = 0; r < 4; ++r) {
+            if ((r & stride) == 0) {
+                const int p = r | stride;
+                const bool desc = (((lane * 4 + r) & size) == 0);
+                const uint64_t mx = v[r] > v[p] ? v[r] : v[p], mn = v[r] > v[p] ? v[p] : v[r];
+                v[r] = desc ? mx : mn;
+                v[p] = desc ? mn : mx;
             }
         }
+    };
+#pragma unroll 1
+    for (int size = 2; size <= 128; size <<= 1) {
+#pragma unroll 1
+        for (int stride = size >> 1; stride >= 4; stride >>= 1) {  // partner in lane ^ (stride / 4)
+            const int lm = stride >> 2;
+            const bool lower = (lane & lm) == 0;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const uint64_t other = __shfl_xor_sync(0xffffffffu, v[r], lm);
+                const bool desc = (((lane * 4 + r) & size) == 0);
+                const bool want_max = (lower == desc);
+                const uint64_t mx = v[r] > other ? v[r] : other, mn = v[r] > other ? other : v[r];
+                v[r] = want_max ? mx : mn;
+            }
+        }
+        if (size >= 4) local_stage(size, 2);
+        local_stage(size, 1);
     }
 }
 
@@ -457,6 +460,14 @@ __device__ void topk_body(const Src &src, int n, int k, int cap, uint32_t *keys,
 }
 
 
+// The general select as the COLD fallback of the small-footprint fast path: kept out of line so that its two call sites
+// do not triple the hot kernel's instruction-cache footprint.
+template <int NT, typename Src>
+__device__ __noinline__ void topk_general_cold(const Src &src, int n, int k, int cap, uint32_t *keys, uint64_t *sel, uint32_t *hist,
+                                               TkShared *sh, float *out_s, int32_t *out_d) {
+    topk_general<NT>(src, n, k, cap, keys, sel, hist, sh, out_s, out_d);
+}
+
 // ---- fast path, small-footprint variant --------------------------------------------------------------------------
 // Same algorithm as topk_body<false> for CTAs of NT = 128 threads with 16-bit histogram bins (n <= 65,535): 6.4 KB of
 // shared memory and 4 K registers per query.  A batch's top-k overlaps the NEXT batch's scoring kernel, whose CTA leaves
@@ -471,7 +482,7 @@ __device__ void topk_fast16(const Src &src, int n, int k, uint32_t *gkeys, uint3
     constexpr int RANGE = TK_BINS / NW;                            // bins summed by one warp (512 for four warps)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (n <= k) {
-        topk_general<NT>(src, n, k, 128, gkeys, sel, ghist, sh, out_s, out_d);
+        topk_general_cold<NT>(src, n, k, 128, gkeys, sel, ghist, sh, out_s, out_d);
         return;
     }
     uint16_t *hist = reinterpret_cast<uint16_t *>(hist_words);     // bin b = half (b & 1) of word b >> 1
@@ -551,7 +562,7 @@ __device__ void topk_fast16(const Src &src, int n, int k, uint32_t *gkeys, uint3
     gt += above;
     if (eq > TK_BND) {
         __syncthreads();
-        topk_general<NT>(src, n, k, 128, gkeys, sel, ghist, sh, out_s, out_d);
+        topk_general_cold<NT>(src, n, k, 128, gkeys, sel, ghist, sh, out_s, out_d);
         return;
     }
     uint64_t *bnd = reinterpret_cast<uint64_t *>(hist_words);      // 2 x TK_BND x 8 B = the 4 KB histogram

@@ -73,6 +73,9 @@ CASES = [
     (5000, 64, 1024, 33, 7, 50, 0.0, torch.bfloat16, 0),             # max dim
     (5000, 64, 8, 33, 7, 50, 0.0, torch.float32, 0),                 # min dim
     (5000, 64, 200, 33, 7, 50, 0.0, torch.bfloat16, 0),              # dim not a multiple of 64 (no TMA path)
+    (40000, 256, 64, 96, 24, 100, 0.0, torch.bfloat16, 0),            # ~3,700 candidates per query: top-100 streams the scores twice (more than fit in registers)
+    (30000, 300, 64, 40, 16, 64, 1.2, torch.bfloat16, 0),            # K x largest cluster > 65,535: 256-thread top-k with 32-bit histogram bins
+    (3000, 200, 64, 500, 3, 10, 0.0, torch.bfloat16, FLAG_UMMA),      # fewer tiles than CTAs in the tile queue, one-K-block tiles
 ]
 
 

@@ -144,7 +144,12 @@ def main():
                     help="N > 1: replica = every rank holds the corpus and its own query batches (no collective); sharded = clusters "
                          "sharded over ranks, queries replicated, NCCL all-gather of candidates + merge (auto: sharded for cfg5s)")
     ap.add_argument("--path", default="auto", choices=["auto", "simt", "umma"], help="force a scoring path")
-    ap.add_argument("--pipeline", type=int, default=3, help="independent batches kept in flight on separate CUDA streams (1 = strictly serial)")
+    ap.add_argument("--pipeline", type=int, default=0, help="independent batches kept in flight, each with its own scratch (0 = auto: 6 for the "
+                    "phase schedule, 3 for the batch schedule; 1 = strictly serial)")
+    ap.add_argument("--schedule", default="auto", choices=["auto", "batches", "phases"],
+                    help="batches: whole batches round-robin on one stream per batch in flight; phases: inversion / scoring / top-k on their own "
+                         "(prioritised) streams, ordered with events, so scoring kernels of consecutive batches overlap (auto = batches, "
+                         "which measured faster)")
     ap.add_argument("--no-graph", action="store_true", help="launch every step from the host instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -227,7 +232,9 @@ def main():
     # Batches are independent, so `n_pipe` of them are kept in flight on `n_pipe` CUDA streams, each with its own
     # store handles (= its own scratch) and result buffers: the latency-bound inversion and top-k kernels of one batch
     # co-reside with, and hide under, the HBM-bound scoring kernel of its neighbours.
-    n_pipe = 1 if sharded else max(1, args.pipeline)
+    # measured at cfg2 with every step streaming a store replica that is not in L2: phases 55.3 us per step, batches 51.4
+    phases = not sharded and args.pipeline != 1 and args.schedule == "phases"
+    n_pipe = 1 if sharded else (args.pipeline if args.pipeline > 0 else (6 if phases else 3))
     pipes = []
     for p in range(n_pipe):
         st_p = stores if p == 0 else [ClusterStore(s0.emb, torch.as_tensor(s0.offsets_host), s0.docid) for s0 in stores]
@@ -237,6 +244,22 @@ def main():
             q=torch.empty_like(batches[0][0]), b=torch.empty_like(batches[0][1]),
             out_s=torch.empty((1, B_rank, k), dtype=torch.float32, device=dev),
             out_d=torch.empty((1, B_rank, k), dtype=torch.int32, device=dev)))
+
+    # phase schedule: one high-priority stream for the (tiny, latency-bound) inversion kernels so they never queue behind a
+    # scoring grid that is waiting for SMs, three scoring streams (consecutive scoring kernels overlap tail to head, the
+    # dynamic tile queue absorbs the staggered CTA starts), three low-priority top-k streams, one copy stream for e2e
+    SK_I, SK_S, SK_T = 256, 512, 1024
+    if phases:
+        lo_p, hi_p = 0, -3
+        try:
+            lo_p, hi_p = torch.cuda.Stream.priority_range()
+        except Exception:
+            pass
+        s_inv = torch.cuda.Stream(priority=hi_p)
+        s_scs = [torch.cuda.Stream(priority=min(lo_p, hi_p + 1)) for _ in range(3)]
+        s_tks = [torch.cuda.Stream(priority=lo_p) for _ in range(3)]
+        s_h2d = torch.cuda.Stream(priority=hi_p)
+        phase_streams = [s_inv, s_h2d] + s_scs + s_tks
 
     def step(i, P=None):
         """One pass of the hot path over one device-resident batch."""
@@ -260,8 +283,54 @@ def main():
         for P in pipes:
             cur.wait_stream(P["stream"])
 
+    def run_phases(n, cur, e2e=False):
+        """n steps, each issued as three calls (inversion / scoring / top-k) on the phase streams; capturable into one graph."""
+        for s in phase_streams:
+            s.wait_stream(cur)
+        done = [None] * n_pipe
+        for i in range(n):
+            P = pipes[i % n_pipe]
+            st = P["stores"][i % replicas]
+            q, beams = (P["q_in"], P["b_in"]) if e2e else batches[i % n_batches]
+            out = (P["o_s"], P["o_d"]) if e2e else (P["out_s"], P["out_d"])
+            if e2e:
+                with torch.cuda.stream(s_h2d):
+                    if done[i % n_pipe] is not None:
+                        s_h2d.wait_event(done[i % n_pipe])           # the previous batch of this slot no longer reads its inputs
+                    P["in_dev"].copy_(in_host[i % n_batches], non_blocking=True)
+                    e0_ = torch.cuda.Event()
+                    e0_.record(s_h2d)
+            with torch.cuda.stream(s_inv):
+                if e2e:
+                    s_inv.wait_event(e0_)
+                elif done[i % n_pipe] is not None:
+                    s_inv.wait_event(done[i % n_pipe])               # ... nor its scratch
+                st.score_topk(q, beams, k, out=out, flags=path_flags | SK_S | SK_T)
+                e1_ = torch.cuda.Event()
+                e1_.record(s_inv)
+            s_sc = s_scs[i % len(s_scs)]
+            with torch.cuda.stream(s_sc):
+                s_sc.wait_event(e1_)
+                st.score_topk(q, beams, k, out=out, flags=path_flags | SK_I | SK_T)
+                e2_ = torch.cuda.Event()
+                e2_.record(s_sc)
+            s_tk = s_tks[i % len(s_tks)]
+            with torch.cuda.stream(s_tk):
+                s_tk.wait_event(e2_)
+                st.score_topk(q, beams, k, out=out, flags=path_flags | SK_I | SK_S)
+                if e2e:
+                    P["res"].copy_(P["out_dev"], non_blocking=True)
+                e3_ = torch.cuda.Event()
+                e3_.record(s_tk)
+                done[i % n_pipe] = e3_
+        for s in phase_streams:
+            cur.wait_stream(s)
+
     def run_steps(n, cur):
         """n steps round-robin over the pipes' streams (fork/join on `cur`, so it is capturable into one graph)."""
+        if phases:
+            run_phases(n, cur)
+            return
         if n_pipe == 1:
             for i in range(n):
                 step(i)
@@ -281,7 +350,7 @@ def main():
     stats = stores[0].last_stats()
 
     # CUDA graph of `period` consecutive steps (every replica / batch / pipe combination once), replayed: no host launch latency
-    period = math.lcm(replicas, n_batches, n_pipe)
+    period = math.lcm(replicas, n_batches, n_pipe) * (2 if phases else 1)     # the pipeline drains at every graph boundary: amortise it
     use_graph = not sharded and not args.no_graph and args.steps >= period
     graph = None
     if use_graph:
@@ -389,6 +458,9 @@ def main():
             P["res"].copy_(P["out_dev"], non_blocking=True)
 
     def run_e2e(n, cur):
+        if phases:
+            run_phases(n, cur, e2e=True)
+            return
         fork(cur)
         for i in range(n):
             e2e_step(i)
@@ -507,14 +579,14 @@ def main():
                    "precision": "fp32 embeddings x fp32 queries, fp32 FMA" if cfg.get("fp32") else "bf16 embeddings x fp32 queries (exact 3-term bf16 split), fp32 accumulate", "docs_per_gpu": cfg["N"],
                    "clusters_per_gpu": cfg["C"], "dim": D, "global_batch": B_global, "beam": K, "top_k": k,
                    "l2": f"{replicas} store replicas ({replicas * emb_bytes / 2**20:.0f} MB) and {n_batches} query batches cycled; inputs larger than L2",
-                   "cuda_graph": bool(use_graph), "batches_in_flight": n_pipe, "scoring_path": args.path,
+                   "cuda_graph": bool(use_graph), "batches_in_flight": n_pipe, "schedule": "phases (inversion / scoring x3 / top-k x3 streams, events)" if phases else "batches (one stream per batch in flight)", "scoring_path": args.path,
                    "parallelism": "single GPU" if world == 1 else (f"clusters sharded over {world} GPUs, queries replicated, NCCL all-gather of candidates + merge"
                                                                    if sharded else f"corpus replicated on {world} GPUs, queries sharded, no data-path collective")},
         "clocks": clocks, "gpu_launches": (int(stats["launches"]) * steps + (steps if sharded else 0)) * (1 if sharded else world),
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "segments_ms_per_step": [round(x / e2e_steps, 5) for x in e2e_segments], "estimator": "median of 5 timed segments",
                 "copies_alone": {k_: round(v_, 2) for k_, v_ in pcie.items()},
-                "pipeline": f"{n_pipe} batches in flight on {n_pipe} CUDA streams, pinned host buffers, per step one H2D copy (q + beams) and one D2H copy (scores + docids)"},
+                "pipeline": f"{n_pipe} batches in flight ({'phase' if phases else 'batch'} schedule), pinned host buffers, per step one H2D copy (q + beams) and one D2H copy (scores + docids)"},
         "roofline": roofline, "cpu_baseline": cpu,
         "path": {"simt_items": int(stats["simt_items"]), "umma_tiles": int(stats["umma_tiles"]), "clusters_touched": int(stats["clusters_touched"])},
     }

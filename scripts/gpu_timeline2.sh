@@ -24,13 +24,13 @@ outs = [(torch.empty((1, cfg['B'], 100), device=dev), torch.empty((1, cfg['B'], 
 lo, hi = torch.cuda.Stream.priority_range() if hasattr(torch.cuda.Stream, 'priority_range') else (0, -5)
 import os
 P = [int(x) for x in os.environ.get('PRIO', '-1,-3,0').split(',')]
-s_inv = torch.cuda.Stream(priority=P[0]); s_sc = torch.cuda.Stream(priority=P[1]); NTK = int(os.environ.get('NTK', '1'))
+s_inv = torch.cuda.Stream(priority=P[0]); NSC = int(os.environ.get('NSC', '1')); s_scs = [torch.cuda.Stream(priority=P[1]) for _ in range(NSC)]; NTK = int(os.environ.get('NTK', '1'))
 s_tks = [torch.cuda.Stream(priority=P[2]) for _ in range(NTK)]
 print('priorities inv/score/topk', P, 'range', torch.cuda.Stream.priority_range() if hasattr(torch.cuda.Stream, 'priority_range') else None)
 SK_I, SK_S, SK_T = 256, 512, 1024
 def run(n):
     cur = torch.cuda.current_stream()
-    for s in [s_inv, s_sc] + s_tks: s.wait_stream(cur)
+    for s in [s_inv] + s_scs + s_tks: s.wait_stream(cur)
     done = [None] * DEPTH
     for i in range(n):
         h = i % DEPTH; q, b = batches[i % 8]
@@ -38,6 +38,7 @@ def run(n):
             if done[h] is not None: s_inv.wait_event(done[h])
             stores[h].score_topk(q, b, 100, out=outs[h], flags=SK_S | SK_T)
             e1 = torch.cuda.Event(); e1.record(s_inv)
+        s_sc = s_scs[i % NSC]
         with torch.cuda.stream(s_sc):
             s_sc.wait_event(e1)
             stores[h].score_topk(q, b, 100, out=outs[h], flags=SK_I | SK_T)
@@ -48,7 +49,7 @@ def run(n):
             stores[h].score_topk(q, b, 100, out=outs[h], flags=SK_I | SK_S)
             e3 = torch.cuda.Event(); e3.record(s_tk)
             done[h] = e3
-    for s in [s_inv, s_sc] + s_tks: cur.wait_stream(s)
+    for s in [s_inv] + s_scs + s_tks: cur.wait_stream(s)
 for h in range(DEPTH):
     q, b = batches[0]; stores[h].score_topk(q, b, 100, out=outs[h])
 torch.cuda.synchronize()
@@ -69,7 +70,7 @@ print("phase-split pipeline depth %d: %.2f us/step" % (DEPTH, e0.elapsed_time(e1
 # correctness of the split call vs the fused call
 ref_s, ref_d = stores[0].score_topk(batches[(NS - 1) % 8][0], batches[(NS - 1) % 8][1], 100)
 h = (NS - 1) % DEPTH
-print("split == fused:", bool(torch.equal(outs[h][1][0], ref_d)) if h == 0 else "n/a")
+print("split == fused:", bool(torch.equal(outs[h][1][0], ref_d) and torch.equal(outs[h][0][0], ref_s)))
 import os
 if os.environ.get("GDR_UMMA_TRACE"):
     for st in stores: st.last_stats()

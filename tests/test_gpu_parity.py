@@ -307,3 +307,24 @@ def test_many_clusters_multi_block_scan():
     for flags in (FLAG_SIMT, FLAG_UMMA, 0):
         s, d = st.score_topk(q.cuda(), torch.from_numpy(beams).cuda(), k, flags=flags)
         assert_topk_parity(s, d, ref_s, ref_d, f"many clusters flags={flags}")
+
+
+def test_phases_can_be_reissued_separately():
+    """GDR_SKIP_* phase flags: scoring re-launched on an existing inversion (the tile queue resets itself), then top-k alone,
+    must reproduce the fused call (bench.py times the scoring kernel this way)."""
+    SK_I, SK_S, SK_T = 256, 512, 1024
+    N, C, D, Q, K, k = 20000, 128, 768, 256, 20, 100
+    emb, offsets, docid = orc.synth_corpus(N, C, D, seed=77)
+    emb = emb.bfloat16().float()
+    q, beams, _ = orc.synth_queries(Q, C, K, D, seed=78)
+    st = _store(emb, offsets, docid, torch.bfloat16)
+    qd, bd = q.cuda(), torch.from_numpy(beams).cuda()
+    for flags in (0, FLAG_SIMT):
+        ref_s, ref_d = st.score_topk(qd, bd, k, flags=flags)
+        out = (torch.zeros((1, Q, k), device="cuda"), torch.zeros((1, Q, k), dtype=torch.int32, device="cuda"))
+        st.score_topk(qd, bd, k, out=out, flags=flags | SK_S | SK_T)           # inversion only
+        for _ in range(3):
+            st.score_topk(qd, bd, k, out=out, flags=flags | SK_I | SK_T)       # scoring only, three times over
+        st.score_topk(qd, bd, k, out=out, flags=flags | SK_I | SK_S)           # top-k only
+        torch.cuda.synchronize()
+        assert torch.equal(out[1][0], ref_d) and torch.equal(out[0][0], ref_s)

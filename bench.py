@@ -134,7 +134,7 @@ def cpu_reference_qps(emb_cpu, offsets, docid, q_cpu, beams_cpu, k, min_seconds,
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=4608)
+    ap.add_argument("--steps", type=int, default=4800)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="gdr_b200", choices=["gdr_b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
@@ -145,7 +145,7 @@ def main():
                          "sharded over ranks, queries replicated, NCCL all-gather of candidates + merge (auto: sharded for cfg5s)")
     ap.add_argument("--path", default="auto", choices=["auto", "simt", "umma"], help="force a scoring path")
     ap.add_argument("--pipeline", type=int, default=0, help="independent batches kept in flight, each with its own scratch (0 = auto: 6 for the "
-                    "phase schedule, 3 for the batch schedule; 1 = strictly serial)")
+                    "phase schedule, 5 for the batch schedule; 1 = strictly serial)")
     ap.add_argument("--schedule", default="auto", choices=["auto", "batches", "phases"],
                     help="batches: whole batches round-robin on one stream per batch in flight; phases: inversion / scoring / top-k on their own "
                          "(prioritised) streams, ordered with events, so scoring kernels of consecutive batches overlap (auto = batches, "
@@ -234,7 +234,7 @@ def main():
     # co-reside with, and hide under, the HBM-bound scoring kernel of its neighbours.
     # measured at cfg2 with every step streaming a store replica that is not in L2: phases 55.3 us per step, batches 51.4
     phases = not sharded and args.pipeline != 1 and args.schedule == "phases"
-    n_pipe = 1 if sharded else (args.pipeline if args.pipeline > 0 else (6 if phases else 3))
+    n_pipe = 1 if sharded else (args.pipeline if args.pipeline > 0 else (6 if phases else 5))
     pipes = []
     for p in range(n_pipe):
         st_p = stores if p == 0 else [ClusterStore(s0.emb, torch.as_tensor(s0.offsets_host), s0.docid) for s0 in stores]

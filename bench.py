@@ -351,7 +351,9 @@ def main():
 
     # CUDA graph of `period` consecutive steps (every replica / batch / pipe combination once), replayed: no host launch latency
     period = math.lcm(replicas, n_batches, n_pipe) * (2 if phases else 1)     # the pipeline drains at every graph boundary: amortise it
-    use_graph = not sharded and not args.no_graph and args.steps >= period
+    if args.steps < period:
+        period = max(1, args.steps)               # short runs: one graph of exactly --steps steps
+    use_graph = not sharded and not args.no_graph
     graph = None
     if use_graph:
         side = torch.cuda.Stream()

@@ -365,7 +365,17 @@ def main():
         torch.cuda.current_stream().wait_stream(side)
         graph.replay()
         barrier()
-    steps = (args.steps // period) * period if use_graph else args.steps
+    steps = args.steps                            # exactly --steps steps are timed: whole replays + one shorter graph for the remainder
+    graph_rem, rem = None, (args.steps % period if use_graph else 0)
+    if rem:
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            graph_rem = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph_rem, stream=side):
+                run_steps(rem, side)
+        torch.cuda.current_stream().wait_stream(side)
+        graph_rem.replay()
+        barrier()
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -375,6 +385,8 @@ def main():
     if use_graph:
         for _ in range(steps // period):
             graph.replay()
+        if graph_rem is not None:
+            graph_rem.replay()
     else:
         run_steps(steps, torch.cuda.current_stream())
     e1.record()
@@ -447,10 +459,21 @@ def main():
         P["res_s"] = P["res"][:r_bytes].view(torch.float32).view(B_rank, k)
         P["res_d"] = P["res"][r_bytes:].view(torch.int32).view(B_rank, k)
 
-    def e2e_step(i):
+    # The H2D copies run back to back on a stream of their own (the 3.2 MB of queries per step is what bounds the end-to-end
+    # rate, so the copy engine must never wait for a batch's compute or D2H); a slot's input buffer is refilled once the
+    # batch that last used it has finished.
+    s_in = torch.cuda.Stream()
+
+    def e2e_step(i, done):
         P = pipes[i % n_pipe]
-        with torch.cuda.stream(P["stream"]):
+        with torch.cuda.stream(s_in):
+            if done[i % n_pipe] is not None:
+                s_in.wait_event(done[i % n_pipe])
             P["in_dev"].copy_(in_host[i % n_batches], non_blocking=True)
+            ev_in = torch.cuda.Event()
+            ev_in.record(s_in)
+        with torch.cuda.stream(P["stream"]):
+            P["stream"].wait_event(ev_in)
             if not sharded:
                 P["stores"][i % replicas].score_topk(P["q_in"], P["b_in"], k, out=(P["o_s"], P["o_d"]), flags=path_flags)
             else:
@@ -458,18 +481,23 @@ def main():
                 P["o_s"][0].copy_(s_)
                 P["o_d"][0].copy_(d_)
             P["res"].copy_(P["out_dev"], non_blocking=True)
+            ev_done = torch.cuda.Event()
+            ev_done.record(P["stream"])
+            done[i % n_pipe] = ev_done
 
     def run_e2e(n, cur):
         if phases:
             run_phases(n, cur, e2e=True)
             return
         fork(cur)
+        s_in.wait_stream(cur)
+        done = [None] * n_pipe
         for i in range(n):
-            e2e_step(i)
+            e2e_step(i, done)
         join(cur)
+        cur.wait_stream(s_in)
 
-    for i in range(2 * n_pipe * replicas):      # warm-up: every (pipe, replica) handle has its scratch
-        e2e_step(i)
+    run_e2e(2 * n_pipe * replicas, torch.cuda.current_stream())      # warm-up: every (pipe, replica) handle has its scratch
     barrier()
     cur = torch.cuda.current_stream()
     # the copies are graph nodes too (fixed pinned buffers, as a serving loop that refills them would use), so the host

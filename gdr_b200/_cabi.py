@@ -28,6 +28,9 @@ SYMBOLS = {
     "gdr_merge_topk": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
     "gdr_trie_create": (c_int32, [POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_int32, c_int32]),
     "gdr_trie_destroy": (c_int32, [c_void_p]),
+    "gdr_trie_set_child_order": (c_int32, [c_void_p, c_void_p, c_void_p]),
+    "gdr_trie_node_embeddings": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
+    "gdr_tree_match": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "gdr_tree_mask": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int64, c_int32, c_int32,
                                 c_int32, c_void_p]),
     "gdr_beam_step": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int32, c_int32, c_int32, c_int32,

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include "gdr_common.cuh"
 
@@ -54,6 +55,8 @@ struct gdr_store {
 struct gdr_trie {
     int32_t *first_child = nullptr, *child_tok = nullptr, *child_node = nullptr;
     int32_t n_nodes = 0, n_edges = 0;
+    int32_t *child_order = nullptr;   // [n_edges] edges of every node in the reference's child insertion order (default: by token)
+    std::vector<int> level_start;     // nodes are numbered breadth-first: depth d = ids [level_start[d], level_start[d+1])
     int32_t fanout = 1;          // max children of any node (>= 1: the off-tree EOS candidate)
     void *cand_ws = nullptr;     // beam-step candidates: [R, fanout] fp32 values | [R, fanout] int32 flat token ids
     size_t cand_ws_bytes = 0;
@@ -339,6 +342,31 @@ int gdr_trie_create(gdr_trie_t **out, const int32_t *first_child, const int32_t 
     if (e == cudaSuccess) e = cudaMemcpy(t->first_child, first_child, (size_t)(n_nodes + 1) * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess && n_edges) e = cudaMemcpy(t->child_tok, child_tok, (size_t)n_edges * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess && n_edges) e = cudaMemcpy(t->child_node, child_node, (size_t)n_edges * 4, cudaMemcpyHostToDevice);
+    // depth levels (for the bottom-up node embeddings): breadth-first numbering makes every depth a contiguous id range
+    {
+        std::vector<int> depth((size_t)n_nodes, -1);
+        depth[0] = 0;
+        bool bfs = true;
+        for (int n = 0; n < n_nodes && bfs; ++n) {
+            if (depth[n] < 0) { bfs = false; break; }
+            for (int e2 = first_child[n]; e2 < first_child[n + 1]; ++e2) {
+                if (depth[child_node[e2]] >= 0) bfs = false;
+                depth[child_node[e2]] = depth[n] + 1;
+            }
+        }
+        for (int n = 1; n < n_nodes && bfs; ++n)
+            if (depth[n] < depth[n - 1]) bfs = false;
+        if (bfs) {
+            t->level_start.push_back(0);
+            for (int n = 1; n < n_nodes; ++n)
+                if (depth[n] != depth[n - 1]) t->level_start.push_back(n);
+            t->level_start.push_back(n_nodes);
+        }                                                    // not breadth-first: masks still work, node embeddings are refused
+    }
+    std::vector<int32_t> ident(ne);
+    for (size_t i = 0; i < ne; ++i) ident[i] = (int32_t)i;
+    if (e == cudaSuccess) e = cudaMalloc(&t->child_order, ne * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(t->child_order, ident.data(), ne * 4, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         gdr_trie_destroy(t);
         return cuda_fail(e, "gdr_trie_create");
@@ -347,11 +375,46 @@ int gdr_trie_create(gdr_trie_t **out, const int32_t *first_child, const int32_t 
     return GDR_OK;
 }
 
+int gdr_trie_set_child_order(gdr_trie_t *t, const int32_t *first_child, const int32_t *order) {
+    if (!t || !first_child || !order) return invalid("gdr_trie_set_child_order: null argument");
+    std::vector<char> seen((size_t)(t->n_edges > 0 ? t->n_edges : 1), 0);
+    for (int n = 0; n < t->n_nodes; ++n)
+        for (int r = first_child[n]; r < first_child[n + 1]; ++r) {
+            const int e = order[r];
+            if (e < first_child[n] || e >= first_child[n + 1] || seen[e]) return invalid("gdr_trie_set_child_order: order must permute every node's own edges");
+            seen[e] = 1;
+        }
+    if (t->n_edges) GDR_CUDA(cudaMemcpy(t->child_order, order, (size_t)t->n_edges * 4, cudaMemcpyHostToDevice));
+    return GDR_OK;
+}
+
+int gdr_trie_node_embeddings(gdr_trie_t *t, const int32_t *node_cluster, const float *leaf_emb, const int32_t *leaf_num, int32_t dim,
+                             float *node_emb, int32_t *node_leaf_num, void *stream) {
+    if (!t || !node_cluster || !leaf_emb || !leaf_num || !node_emb || !node_leaf_num) return invalid("gdr_trie_node_embeddings: null argument");
+    if (dim <= 0) return invalid("gdr_trie_node_embeddings: dim must be positive");
+    if (t->level_start.empty()) return invalid("gdr_trie_node_embeddings: the trie's nodes must be numbered breadth-first");
+    GDR_CUDA(launch_node_embeddings(t->first_child, t->child_node, t->child_order, node_cluster, leaf_emb, leaf_num, dim, t->level_start.data(),
+                                    (int)t->level_start.size() - 1, node_emb, node_leaf_num, (cudaStream_t)stream));
+    return GDR_OK;
+}
+
+int gdr_tree_match(gdr_trie_t *t, const float *node_emb, const int32_t *node_leaf_num, int32_t dim, const float *docs, int32_t M,
+                   int32_t max_len, int32_t *out_tokens, int32_t *out_len, void *stream) {
+    if (!t) return invalid("gdr_tree_match: trie is null");
+    if (M < 0 || dim <= 0 || max_len < 2) return invalid("gdr_tree_match: need M >= 0, dim > 0, max_len >= 2");
+    if (M == 0) return GDR_OK;
+    if (!node_emb || !node_leaf_num || !docs || !out_tokens || !out_len) return invalid("gdr_tree_match: null pointer");
+    GDR_CUDA(launch_tree_match(t->first_child, t->child_tok, t->child_node, t->child_order, node_emb, node_leaf_num, dim, docs, M, max_len,
+                               out_tokens, out_len, (cudaStream_t)stream));
+    return GDR_OK;
+}
+
 int gdr_trie_destroy(gdr_trie_t *t) {
     if (!t) return GDR_OK;
     cudaFree(t->first_child);
     cudaFree(t->child_tok);
     cudaFree(t->child_node);
+    cudaFree(t->child_order);
     cudaFree(t->cand_ws);
     delete t;
     return GDR_OK;

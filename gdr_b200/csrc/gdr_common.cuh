@@ -104,6 +104,12 @@ cudaError_t launch_beam_rows(const int32_t *first_child, const int32_t *child_to
                              const int64_t *input_ids, int64_t ids_stride, int cur_len, const float *logits,
                              int64_t logits_stride, int V, const float *beam_scores, int R, int K, int eos_id, int fanout,
                              float *cand_val, int32_t *cand_id, cudaStream_t s);
+cudaError_t launch_node_embeddings(const int32_t *first_child, const int32_t *child_node, const int32_t *child_order, const int32_t *node_cluster,
+                                   const float *leaf_emb, const int32_t *leaf_num, int dim, const int *level_start, int n_levels,
+                                   float *node_emb, int32_t *node_leaf_num, cudaStream_t s);
+cudaError_t launch_tree_match(const int32_t *first_child, const int32_t *child_tok, const int32_t *child_node, const int32_t *child_order,
+                              const float *node_emb, const int32_t *node_leaf_num, int dim, const float *docs, int M, int max_len,
+                              int32_t *out_tokens, int32_t *out_len, cudaStream_t s);
 cudaError_t launch_position_mask(float *logits, int64_t bz, int sl, int V, int v_out, int last_eos_only,
                                  cudaStream_t s);
 

@@ -10,6 +10,7 @@ from __future__ import annotations
 
 from typing import Dict, List, Sequence, Tuple
 
+import numpy as np
 import torch
 
 from .store import ClusterStore
@@ -44,3 +45,47 @@ def tree_embedding_insert(store: ClusterStore, id_mapping: Dict[str, List[int]],
         if doc_index not in lst:
             lst.append(doc_index)
     return id_mapping
+
+
+def node_embeddings(trie, store: ClusterStore, args) -> Tuple[torch.Tensor, torch.Tensor]:
+    """reference `tree_embedding_calculate` (main_models.py:154-179) on the device trie: every node's embedding
+    ([n_nodes, D] fp32) and leaf count ([n_nodes] int32, 0 = the node carries no embedding).  Leaf clusters are the
+    store's clusters (their keys are cluster-id strings, encoded with `encode_single_newid(args, key)` to find the
+    node); inner nodes are the leaf-count-weighted means of their children, accumulated in the children's insertion
+    order with the reference's operations."""
+    from . import _cabi
+    from .main_models import encode_single_newid
+    if store.keys is None:
+        raise ValueError("the store must carry its cluster keys")
+    dev = store.emb.device
+    node_cluster = np.full(trie.n_nodes, -1, dtype=np.int32)
+    for c, key in enumerate(store.keys):
+        n = trie.find(encode_single_newid(args, key)[:-1])                # the leaf-cluster node = parent of the EOS node
+        if n < 0:
+            raise KeyError(f"cluster {key!r} is not a path of the tree")
+        node_cluster[n] = c
+    leaf_emb = store.centroids()
+    leaf_num = torch.as_tensor(np.diff(store.offsets_host).astype(np.int32), device=dev)
+    node_emb = torch.zeros((trie.n_nodes, store.dim), dtype=torch.float32, device=dev)
+    node_leaf_num = torch.zeros(trie.n_nodes, dtype=torch.int32, device=dev)
+    nc = torch.as_tensor(node_cluster, device=dev)
+    with torch.cuda.device(dev):
+        _cabi.check(_cabi.lib().gdr_trie_node_embeddings(trie._handle, nc.data_ptr(), leaf_emb.data_ptr(), leaf_num.data_ptr(), store.dim,
+                                                         node_emb.data_ptr(), node_leaf_num.data_ptr(), _cabi.stream_ptr()))
+    return node_emb, node_leaf_num
+
+
+def tree_match(trie, node_emb: torch.Tensor, node_leaf_num: torch.Tensor, docs: torch.Tensor, max_len: int = 16) -> List[np.ndarray]:
+    """reference `tree_match` (main_models.py:232-252) for a batch of documents [M, D]: greedy descent by
+    `doc . child embedding`; one int array `[0, tok, ..., 1]` per document, as the reference returns."""
+    from . import _cabi
+    dev = node_emb.device
+    docs = docs.to(dev, torch.float32).contiguous()
+    M = docs.shape[0]
+    out = torch.zeros((M, max_len), dtype=torch.int32, device=dev)
+    out_len = torch.zeros(M, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _cabi.check(_cabi.lib().gdr_tree_match(trie._handle, node_emb.data_ptr(), node_leaf_num.data_ptr(), node_emb.shape[1], docs.data_ptr(), M,
+                                               max_len, out.data_ptr(), out_len.data_ptr(), _cabi.stream_ptr()))
+    out, out_len = out.cpu().numpy(), out_len.cpu().numpy()
+    return [out[m, :out_len[m]].astype(np.int64) for m in range(M)]

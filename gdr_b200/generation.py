@@ -13,7 +13,7 @@ PyTorch; `TreeMask` is the hook a maintainer drops where the reference's block s
 from __future__ import annotations
 
 import ctypes
-from typing import List, Tuple
+from typing import List, Optional, Tuple
 
 import numpy as np
 import torch
@@ -40,10 +40,27 @@ def flatten_trie(root) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
             np.asarray(child_node, dtype=np.int32))
 
 
+def child_insertion_order(root) -> np.ndarray:
+    """For the numbering of `flatten_trie`: every node's edge indices in the order its `children` dict was filled (the
+    order the reference iterates `cur.children.keys()` in, main_models.py:164,241), as one [n_edges] array."""
+    order, queue, head, n_edges = [], [root], 0, 0
+    while head < len(queue):
+        node = queue[head]
+        head += 1
+        toks = sorted(node.children)
+        pos = {t: i for i, t in enumerate(toks)}
+        order.extend(n_edges + pos[t] for t in node.children)          # dict order = insertion order
+        for t in toks:
+            queue.append(node.children[t])
+        n_edges += len(toks)
+    return np.asarray(order, dtype=np.int32)
+
+
 class DeviceTrie:
     """Device-resident CSR form of the reference's `Node` trie (main_models.py:112-151)."""
 
-    def __init__(self, first_child: np.ndarray, child_tok: np.ndarray, child_node: np.ndarray, device="cuda"):
+    def __init__(self, first_child: np.ndarray, child_tok: np.ndarray, child_node: np.ndarray, device="cuda",
+                 child_order: Optional[np.ndarray] = None):
         self.first_child = np.ascontiguousarray(first_child, dtype=np.int32)
         self.child_tok = np.ascontiguousarray(child_tok, dtype=np.int32)
         self.child_node = np.ascontiguousarray(child_node, dtype=np.int32)
@@ -55,10 +72,24 @@ class DeviceTrie:
             _cabi.check(_cabi.lib().gdr_trie_create(
                 ctypes.byref(self._handle), self.first_child.ctypes.data, self.child_tok.ctypes.data,
                 self.child_node.ctypes.data, self.n_nodes, self.n_edges))
+            if child_order is not None:
+                self.child_order = np.ascontiguousarray(child_order, dtype=np.int32)
+                _cabi.check(_cabi.lib().gdr_trie_set_child_order(self._handle, self.first_child.ctypes.data, self.child_order.ctypes.data))
 
     @classmethod
     def from_root(cls, root, device="cuda") -> "DeviceTrie":
-        return cls(*flatten_trie(root), device=device)
+        return cls(*flatten_trie(root), device=device, child_order=child_insertion_order(root))
+
+    def find(self, tokens) -> int:
+        """Node reached from the root along `tokens` (host walk over the CSR arrays), -1 if the path leaves the tree."""
+        cur = 0
+        for t in tokens:
+            lo, hi = int(self.first_child[cur]), int(self.first_child[cur + 1])
+            j = lo + int(np.searchsorted(self.child_tok[lo:hi], int(t)))
+            if j >= hi or int(self.child_tok[j]) != int(t):
+                return -1
+            cur = int(self.child_node[j])
+        return cur
 
     def mask_(self, scores: torch.Tensor, input_ids: torch.Tensor, eos_token_id: int = 1, strict: bool = False,
               stream=None) -> torch.Tensor:

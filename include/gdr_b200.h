@@ -125,6 +125,23 @@ int gdr_trie_create(gdr_trie_t **out, const int32_t *first_child, const int32_t 
                     const int32_t *child_node, int32_t n_nodes, int32_t n_edges);
 int gdr_trie_destroy(gdr_trie_t *trie);
 
+/* ---- node embeddings and greedy descent (index expansion) ---------------------------------
+ * gdr_trie_set_child_order: HOST order[n_edges] lists every node's edges (indices into child_tok / child_node, within
+ *   first_child[n] .. first_child[n+1]-1) in the reference's child INSERTION order (dict order of Node.children): the
+ *   order tree_embedding_calculate accumulates in and np.argmax breaks ties by.  Default: by token.
+ * gdr_trie_node_embeddings replaces tree_embedding_calculate (main_models.py:154-179): node_cluster DEV int32 [n_nodes] =
+ *   store cluster of a leaf-cluster node (-1 otherwise), leaf_emb DEV fp32 [C, dim] (gdr_cluster_centroids), leaf_num DEV
+ *   int32 [C] (cluster sizes) -> node_emb DEV fp32 [n_nodes, dim], node_leaf_num DEV int32 [n_nodes] (0 = the node has no
+ *   embedding, e.g. the EOS child of a leaf cluster).  Needs breadth-first node numbering.
+ * gdr_tree_match replaces tree_match (main_models.py:232-252): docs DEV fp32 [M, dim] -> out_tokens DEV int32 [M, max_len]
+ *   = [0, tok, ..., 1] and out_len DEV int32 [M]; at every node the child with the largest doc . embedding, first maximum
+ *   in child order; stops at a node whose only child has no embedding. */
+int gdr_trie_set_child_order(gdr_trie_t *trie, const int32_t *first_child, const int32_t *order);
+int gdr_trie_node_embeddings(gdr_trie_t *trie, const int32_t *node_cluster, const float *leaf_emb, const int32_t *leaf_num,
+                             int32_t dim, float *node_emb, int32_t *node_leaf_num, void *stream);
+int gdr_tree_match(gdr_trie_t *trie, const float *node_emb, const int32_t *node_leaf_num, int32_t dim, const float *docs,
+                   int32_t M, int32_t max_len, int32_t *out_tokens, int32_t *out_len, void *stream);
+
 /* Replaces generation_utils_previous.py:714-729.  For each of R rows, walk the trie along
  * input_ids[r, 1:cur_len]; allowed = children of the node reached, or {eos_id} if the path
  * leaves the tree.  In place on scores DEV fp32 [R, V] (row stride in elements): allowed

@@ -236,6 +236,48 @@ def tree_embedding_insert(cluster_embedding: torch.Tensor, keys: List[str], id_m
     return id_mapping
 
 
+def tree_embedding_calculate(root: Node, embedding) -> None:
+    """main_models.py:154-179.  Depth-first: a node that lists documents (a leaf cluster) gets the mean of their
+    embeddings (`sum([...]) / len`) and is not descended further; any other node gets the leaf-count-weighted mean of
+    its children, accumulated in the children's insertion order (`embed * leaf_num` summed, then `/ sum(leaf_num)`)."""
+    def dfs(cur):
+        if len(cur.embedding_index) > 0:
+            cur.embedding = sum([embedding[i] for i in cur.embedding_index]) / len(cur.embedding_index)
+            cur.all_leaf_num = len(cur.embedding_index)
+            return cur.embedding, cur.all_leaf_num
+        embeds, leaf_nums = [], []
+        for key in cur.children.keys():
+            e, n = dfs(cur.children[key])
+            embeds.append(e)
+            leaf_nums.append(n)
+        acc = None
+        for e, n in zip(embeds, leaf_nums):
+            acc = e.clone() * n if acc is None else acc + e.clone() * n
+        cur.embedding = acc / sum(leaf_nums)
+        cur.all_leaf_num = sum(leaf_nums)
+        return cur.embedding, cur.all_leaf_num
+
+    dfs(root)
+
+
+def tree_match(root: Node, doc_embed: torch.Tensor) -> np.ndarray:
+    """main_models.py:232-252.  Greedy descent from the root: at every node take the child whose embedding has the
+    largest `torch.mul(doc, child).sum(-1)` (np.argmax: first maximum in the children's insertion order); stop at a
+    node whose only child carries no embedding (the EOS child of a leaf cluster).  Returns [0, tok..., 1]."""
+    cur, out = root, [0]
+    while True:
+        kids = list(cur.children.keys())
+        if len(kids) == 1 and cur.children[kids[0]].embedding is None:
+            break
+        cand = torch.stack([cur.children[k].embedding for k in kids])
+        sim = torch.mul(doc_embed, cand).sum(dim=-1)
+        target = kids[int(np.argmax(sim))]
+        out.append(target)
+        cur = cur.children[target]
+    out.append(1)
+    return np.array(out)
+
+
 def merge_topk(scores: torch.Tensor, docids: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
     """New in the sharded design (no reference counterpart): merge G per-rank
     sorted candidate lists [G, B, k'] into one [B, k].  Equivalent to topk over the union."""

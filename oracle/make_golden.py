@@ -13,6 +13,8 @@ Each fixture holds the inputs and the reference's outputs for one piece of the h
                      tree-mask block, whose SOURCE LINES generation_utils_previous.py:714-729 are read
                      from the mounted reference at run time and exec'd (the block is inline in a
                      300-line method and cannot be called on its own)
+  tree_match.npz     reference `tree_embedding_calculate` over all nodes (main_models.py:154-179) and the greedy descent
+                     `tree_match` (main_models.py:232-252); generated on its own: python oracle/make_golden.py tree_match
   position_mask.npz  reference `select_valid_embedding` (modeling_t5.py:1546-1571), same technique,
                      and the training `logit_mask` recipe (modeling_t5.py:1279-1301)
 """
@@ -310,10 +312,59 @@ def gen_main_models():
         print("wrote", case)
 
 
+def gen_tree_match():
+    """tree_match.npz: reference `tree_embedding_calculate` over ALL nodes (main_models.py:154-179: leaf clusters = mean of
+    their documents, inner nodes = leaf-count-weighted mean of their children) and the greedy descent `tree_match`
+    (main_models.py:232-252) for a set of new documents."""
+    import numpy as np
+    import torch
+    import ref_shims
+    from types import SimpleNamespace
+
+    mm, _ = ref_shims.load_ref_main_models()
+    args = SimpleNamespace(kary=30, position=1, output_vocab_size=30)
+    rng = np.random.RandomState(17)
+    g = torch.Generator().manual_seed(99)
+    paths = set()
+    while len(paths) < 60:                                              # 60 three-level clusters with shared prefixes
+        paths.add("%d-%d-%d" % (rng.randint(0, 4), rng.randint(0, 5), rng.randint(0, 30)))
+    paths = sorted(paths)
+    rng.shuffle(paths)                                                  # insertion order != token order
+    D, n_new = 48, 40
+    builder = mm.TreeBuilder()
+    id_map, embedding = {}, []
+    for p in paths:
+        toks = mm.encode_single_newid(args, p)                          # [t0, t1, t2, 1]
+        n_docs = int(rng.randint(1, 6))
+        id_map[p] = list(range(len(embedding), len(embedding) + n_docs))
+        for d in id_map[p]:
+            builder.add(toks, d)
+            embedding.append(torch.randn(D, generator=g))
+    root = builder.build()
+    mm.tree_embedding_calculate(root, embedding)                        # main_models.py:154-179
+    node_paths, node_emb, node_leaves, stack = [], [], [], [((), root)]
+    while stack:
+        path, n = stack.pop()
+        if n.embedding is not None:
+            node_paths.append(list(path))
+            node_emb.append(n.embedding.clone())
+            node_leaves.append(int(n.all_leaf_num))
+        for tok, ch in n.children.items():
+            stack.append((path + (int(tok),), ch))
+    new_docs = torch.randn(n_new, D, generator=g)
+    new_docs[:10] = torch.stack([embedding[i] for i in range(0, 50, 5)]) + 0.05 * torch.randn(10, D, generator=g)   # near existing docs
+    matches = [mm.tree_match(root, new_docs[i]).tolist() for i in range(n_new)]          # main_models.py:232-252
+    np.savez_compressed(os.path.join(GOLD, "tree_match.npz"), embedding=torch.stack(embedding).numpy(), id_map_json=np.array(json.dumps(id_map)),
+                        cluster_order=np.array(paths), node_paths_json=np.array(json.dumps(node_paths)),
+                        node_emb=torch.stack(node_emb).numpy(), node_leaves=np.array(node_leaves, dtype=np.int64),
+                        new_docs=new_docs.numpy(), matches_json=np.array(json.dumps(matches)))
+    print("wrote tree_match:", len(node_paths), "nodes with embeddings,", n_new, "matches, e.g.", matches[0])
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     if len(sys.argv) > 1:
-        {"dense": gen_dense, "main_models": gen_main_models}[sys.argv[1]]()
+        {"dense": gen_dense, "main_models": gen_main_models, "tree_match": gen_tree_match}[sys.argv[1]]()
     else:
         for part in ("dense", "main_models"):      # separate processes: they need different `transformers`
             subprocess.check_call([sys.executable, os.path.abspath(__file__), part])

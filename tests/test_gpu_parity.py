@@ -328,3 +328,40 @@ def test_phases_can_be_reissued_separately():
         st.score_topk(qd, bd, k, out=out, flags=flags | SK_I | SK_S)           # top-k only
         torch.cuda.synchronize()
         assert torch.equal(out[1][0], ref_d) and torch.equal(out[0][0], ref_s)
+
+
+def test_node_embeddings_and_tree_match_match_reference():
+    """gdr_trie_node_embeddings / gdr_tree_match against the reference's tree_embedding_calculate (all nodes) and tree_match
+    (tests/golden/tree_match.npz).  fp32 store: node embeddings bit-identical; descents identical (a near-tie between two
+    children — sims within 1e-5 — would be excused and counted; the fixture has none)."""
+    import json
+    from types import SimpleNamespace
+    from gdr_b200 import ClusterStore, DeviceTrie, TreeBuilder
+    from gdr_b200.expand import node_embeddings, tree_match
+    from gdr_b200.main_models import encode_single_newid
+    f = load_golden("tree_match")
+    args = SimpleNamespace(kary=30, position=1, output_vocab_size=30)
+    emb = torch.from_numpy(f["embedding"])
+    docs = [emb[i] for i in range(emb.shape[0])]
+    id_map = json.loads(str(f["id_map_json"]))
+    order = [str(x) for x in f["cluster_order"]]
+    id_map = {k: id_map[k] for k in order}                              # the reference's insertion order
+    tb = TreeBuilder()
+    for key in order:
+        for d in id_map[key]:
+            tb.add(encode_single_newid(args, key), d)
+    trie = DeviceTrie.from_root(tb.build())
+    store = ClusterStore.from_reference(docs, id_map, dtype=torch.float32)
+    node_emb, node_leaf = node_embeddings(trie, store, args)
+    paths = json.loads(str(f["node_paths_json"]))
+    ne, nl = node_emb.cpu(), node_leaf.cpu()
+    seen = set()
+    for path, want, leaves in zip(paths, f["node_emb"], f["node_leaves"]):
+        n = trie.find(path)
+        seen.add(n)
+        assert n >= 0 and int(nl[n]) == int(leaves)
+        assert torch.equal(ne[n], torch.from_numpy(want)), f"node {path}: embedding differs from the reference"
+    assert all(int(nl[n]) == 0 for n in range(trie.n_nodes) if n not in seen)      # EOS children carry no embedding
+    got = tree_match(trie, node_emb, node_leaf, torch.from_numpy(f["new_docs"]).cuda())
+    want = json.loads(str(f["matches_json"]))
+    assert [g.tolist() for g in got] == want

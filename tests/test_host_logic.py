@@ -167,3 +167,20 @@ def test_index_file_roundtrip_and_pickle_converter(tmp_path):
     assert m_keys == list(f["id_mapping"].keys()) and torch.equal(torch.from_numpy(np.array(m_emb)), emb)
     with pytest.raises(ValueError):
         read_header(pe)
+
+
+def test_child_insertion_order_matches_the_dict_order():
+    """flatten_trie sorts every node's edges by token (the mask kernels binary-search them); child_insertion_order keeps the
+    order the children were inserted in, which the reference's tree_embedding_calculate / tree_match iterate in."""
+    from gdr_b200.generation import child_insertion_order, flatten_trie
+    from gdr_b200.main_models import TreeBuilder
+    tb = TreeBuilder()
+    for i, seq in enumerate([[9, 40, 1], [3, 35, 1], [9, 33, 1], [5, 61, 1], [3, 34, 1]]):
+        tb.add(seq, i)
+    root = tb.build()
+    fc, tok, node = flatten_trie(root)
+    order = child_insertion_order(root)
+    assert sorted(order.tolist()) == list(range(len(tok)))
+    assert [int(tok[e]) for e in order[fc[0]:fc[1]]] == [9, 3, 5]            # root: inserted 9, 3, 5; stored 3, 5, 9
+    n9 = int(node[fc[0]:fc[1]][list(tok[fc[0]:fc[1]]).index(9)])
+    assert [int(tok[e]) for e in order[fc[n9]:fc[n9 + 1]]] == [40, 33]

@@ -26,6 +26,8 @@ SYMBOLS = {
     "gdr_cluster_centroids": (c_int32, [c_void_p, c_void_p, c_void_p]),
     "gdr_similarity": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
     "gdr_merge_topk": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
+    "gdr_contrastive_loss": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_float, c_float,
+                                       c_void_p, c_void_p, c_void_p, c_void_p]),
     "gdr_trie_create": (c_int32, [POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_int32, c_int32]),
     "gdr_trie_destroy": (c_int32, [c_void_p]),
     "gdr_trie_set_child_order": (c_int32, [c_void_p, c_void_p, c_void_p]),

@@ -286,6 +286,23 @@ int gdr_cluster_centroids(gdr_store_t *s, float *out, void *stream) {
     return GDR_OK;
 }
 
+int gdr_contrastive_loss(gdr_store_t *s, const float *q, const int32_t *pos_rows, const int32_t *cand_rows, const int32_t *cand_off,
+                         int32_t B, int32_t S, int32_t act, float tau, float intra_rate, float *loss_per_query, float *loss,
+                         float *grad_q, void *stream) {
+    if (!s) return invalid("gdr_contrastive_loss: store is null");
+    if (B <= 0 || S < 0) return invalid("gdr_contrastive_loss: need B > 0, S >= 0");
+    if (!q || !pos_rows || !cand_off || (S > 0 && !cand_rows) || !loss_per_query || !loss) return invalid("gdr_contrastive_loss: null pointer");
+    if (act < GDR_ACT_NONE || act > GDR_ACT_SIGMOID) return invalid("gdr_contrastive_loss: bad activation");
+    if (!(tau > 0.f)) return invalid("gdr_contrastive_loss: tau must be positive");
+    if ((size_t)(S + 1) * 8 > 200 * 1024) {
+        set_error("gdr_contrastive_loss: more than 25,599 candidates per batch is not supported");
+        return GDR_ERR_UNSUPPORTED;
+    }
+    GDR_CUDA(launch_contrastive(s->emb, s->dtype, s->dim, q, pos_rows, cand_rows, cand_off, B, S, act, tau, intra_rate, loss_per_query, loss,
+                                grad_q, (cudaStream_t)stream));
+    return GDR_OK;
+}
+
 int gdr_similarity(const float *q, int64_t Q, const void *p, int64_t P, int32_t dim, int32_t p_dtype, float *out,
                    void *stream) {
     if (Q < 0 || P < 0) return invalid("gdr_similarity: negative size");

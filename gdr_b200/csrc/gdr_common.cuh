@@ -110,6 +110,9 @@ cudaError_t launch_node_embeddings(const int32_t *first_child, const int32_t *ch
 cudaError_t launch_tree_match(const int32_t *first_child, const int32_t *child_tok, const int32_t *child_node, const int32_t *child_order,
                               const float *node_emb, const int32_t *node_leaf_num, int dim, const float *docs, int M, int max_len,
                               int32_t *out_tokens, int32_t *out_len, cudaStream_t s);
+cudaError_t launch_contrastive(const void *emb, int dtype, int dim, const float *q, const int32_t *pos_rows, const int32_t *cand_rows,
+                               const int32_t *cand_off, int B, int S, int act, float tau, float intra_rate, float *loss_per_query,
+                               float *loss, float *grad_q, cudaStream_t st);
 cudaError_t launch_position_mask(float *logits, int64_t bz, int sl, int V, int v_out, int last_eos_only,
                                  cudaStream_t s);
 

@@ -92,6 +92,20 @@ class ClusterStore:
         like `self.id_mapping[cluster_id]` at main_models.py:1442."""
         return torch.tensor([[self.cluster_index[c] for c in row] for row in dec], dtype=torch.int32)
 
+    def rows_of(self, doc_indices) -> torch.Tensor:
+        """Store row of each document index (the reference indexes `doc_embed[index]`, main_models.py:983-996); a
+        document listed by several clusters has several rows holding the same embedding — the first is returned.
+        KeyError for a document that is in no cluster."""
+        if getattr(self, "_row_of_doc", None) is None:
+            d = self.docid.cpu().numpy().astype(np.int64)
+            table = np.full(int(d.max()) + 1 if d.size else 0, -1, dtype=np.int32)
+            table[d[::-1]] = np.arange(d.size - 1, -1, -1, dtype=np.int32)      # reversed: the first occurrence wins
+            self._row_of_doc = table
+        idx = np.asarray(doc_indices, dtype=np.int64).reshape(-1)
+        if idx.size and (idx.min() < 0 or idx.max() >= self._row_of_doc.size or (self._row_of_doc[idx] < 0).any()):
+            raise KeyError("document index not in the store")
+        return torch.from_numpy(self._row_of_doc[idx])
+
     def candidate_counts(self, beams_host: torch.Tensor) -> torch.Tensor:
         sizes = torch.from_numpy(np.append(self.sizes_host, 0))     # index -1 -> 0
         return sizes[beams_host.long()].sum(dim=1)

@@ -104,6 +104,18 @@ int gdr_store_last_phase_ms(gdr_store_t *store, float out[4]);
  * gdr_score_topk with k = 1 on a store whose single cluster holds the centroids (gdr_b200/expand.py). */
 int gdr_cluster_centroids(gdr_store_t *store, float *out, void *stream);
 
+/* ---- training-time gather + contrastive loss -------------------------------------------
+ * Replaces the row gather of T5FineTuner.forward (main_models.py:983-996) and encoder_cal (main_models.py:1184-1221):
+ *   q DEV fp32 [B, dim]; pos_rows DEV int32 [B] = store row of each query's positive document; cand_rows DEV int32 [S] =
+ *   store rows of the in-cluster candidates, query 0's first; cand_off DEV int32 [B+1] = start of each query's own
+ *   candidates in cand_rows (the reference's valid_num, prefix-summed).  act = GDR_ACT_TANH | GDR_ACT_SIGMOID (--loss_func),
+ *   tau (--tau), intra_rate (--intra_rate).
+ *   -> loss_per_query DEV fp32 [B]; loss DEV fp32 [1] = their mean (= encoder_cal's return value); grad_q DEV fp32
+ *   [B, dim] = d loss / d q, or NULL.  Document embeddings get no gradient (they are a fixed table in the reference). */
+int gdr_contrastive_loss(gdr_store_t *store, const float *q, const int32_t *pos_rows, const int32_t *cand_rows,
+                         const int32_t *cand_off, int32_t B, int32_t S, int32_t act, float tau, float intra_rate,
+                         float *loss_per_query, float *loss, float *grad_q, void *stream);
+
 /* ---- dense similarity (dense.py:53-54 / encoder.py:128-129): out[Q, P] = q @ p^T, fp32 out ----
  *   q DEV fp32 [Q, dim]; p DEV [P, dim] of p_dtype; out DEV fp32 [Q, P]. */
 int gdr_similarity(const float *q, int64_t Q, const void *p, int64_t P, int32_t dim, int32_t p_dtype,

@@ -278,6 +278,31 @@ def tree_match(root: Node, doc_embed: torch.Tensor) -> np.ndarray:
     return np.array(out)
 
 
+def encoder_cal(query: torch.Tensor, all_doc: torch.Tensor, valid_num: Sequence[int], loss_func: str, tau: float,
+                intra_rate: float) -> torch.Tensor:
+    """main_models.py:1184-1221, the training-time contrastive loss.  all_doc = cat([positives (one per query), in-cluster
+    candidates of query 0, of query 1, ...]) with valid_num[i] candidates for query i (main_models.py:1259-1273).
+    dot_sim = f(q . d) for every (query, doc); per query  -log exp(s_ii / tau) + log( intra_rate * sum over its OWN
+    candidates of exp(s / tau) + sum over the OTHER queries' candidates of exp(s / tau) ); mean over queries.  The
+    reference's intra_rate == 1 branch (:1206-1219) is the same expression with intra_rate = 1, evaluated batched."""
+    B = len(valid_num)
+    func = torch.sigmoid if loss_func == "sigmoid" else torch.tanh
+    dot_sim = func(torch.mul(query.unsqueeze(1), all_doc.unsqueeze(0)).sum(-1))
+    if intra_rate != 1:
+        loss = 0
+        for i in range(B):
+            lo, hi = B + sum(valid_num[:i]), B + sum(valid_num[:i + 1])
+            nominator = torch.exp(dot_sim[i][i] / tau)
+            intra = torch.sum(torch.exp(dot_sim[i][lo:hi] / tau), dim=-1)
+            inter = torch.sum(torch.exp(torch.cat([dot_sim[i][B:lo], dot_sim[i][hi:]], dim=0) / tau), dim=-1)
+            loss = loss + (-torch.log(nominator) + torch.log(intra_rate * intra + inter))
+    else:
+        nominator = torch.exp(torch.gather(dot_sim, index=torch.arange(B).unsqueeze(1), dim=1) / tau)
+        denominator = torch.sum(torch.exp(dot_sim[:, B:] / tau), dim=-1)
+        loss = -torch.sum(torch.log(nominator), dim=0) + torch.sum(torch.log(denominator), dim=0)
+    return loss / B
+
+
 def merge_topk(scores: torch.Tensor, docids: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
     """New in the sharded design (no reference counterpart): merge G per-rank
     sorted candidate lists [G, B, k'] into one [B, k].  Equivalent to topk over the union."""

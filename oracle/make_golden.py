@@ -15,6 +15,8 @@ Each fixture holds the inputs and the reference's outputs for one piece of the h
                      300-line method and cannot be called on its own)
   tree_match.npz     reference `tree_embedding_calculate` over all nodes (main_models.py:154-179) and the greedy descent
                      `tree_match` (main_models.py:232-252); generated on its own: python oracle/make_golden.py tree_match
+  contrastive.npz    reference `encoder_cal` (main_models.py:1184-1221, exec'd source lines) + autograd d loss / d query;
+                     generated on its own: python oracle/make_golden.py contrastive
   position_mask.npz  reference `select_valid_embedding` (modeling_t5.py:1546-1571), same technique,
                      and the training `logit_mask` recipe (modeling_t5.py:1279-1301)
 """
@@ -361,10 +363,50 @@ def gen_tree_match():
     print("wrote tree_match:", len(node_paths), "nodes with embeddings,", n_new, "matches, e.g.", matches[0])
 
 
+def gen_contrastive():
+    """contrastive.npz: the reference's training-time contrastive loss `encoder_cal` (a closure inside T5FineTuner.forward,
+    main_models.py:1184-1221; its SOURCE LINES are read from the mounted reference and exec'd with a stub `self`) over
+    `all_doc = cat([positives, in-cluster candidates])` gathered by document index (main_models.py:983-996, 1259-1275),
+    plus d loss / d query from autograd.  `.cuda()` is shimmed to a no-op: this container has no GPU."""
+    import numpy as np
+    import torch
+    import ref_shims
+    from types import SimpleNamespace
+
+    src = _ref_lines(os.path.join(ref_shims.REF_MODEL_DIR, "main_models.py"), 1184, 1221)
+    assert src.lstrip().startswith("def encoder_cal(query, all_doc, valid_num):"), src[:80]
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    g = torch.Generator().manual_seed(2024)
+    N, D, B = 300, 64, 6
+    doc_embed = torch.randn(N, D, generator=g) * D ** -0.5
+    out = {"doc_embed": doc_embed.numpy()}
+    cases = [("tanh", 1.0, 0.05), ("tanh", 0.5, 0.05), ("sigmoid", 2.0, 0.1)]
+    for ci, (loss_func, intra_rate, tau) in enumerate(cases):
+        valid_num = [int(v) for v in torch.randint(0 if ci else 1, 9, (B,), generator=g)]
+        pos = torch.randint(0, N, (B,), generator=g)
+        cand = torch.randint(0, N, (sum(valid_num),), generator=g)
+        q = (torch.randn(B, D, generator=g) * 1.5).requires_grad_(True)
+        stub = SimpleNamespace(args=SimpleNamespace(intra_rate=intra_rate, loss_func=loss_func), tau=tau)
+        ns = {"torch": torch, "self": stub}
+        exec(textwrap.dedent(src), ns)
+        all_doc = torch.cat([doc_embed[pos], doc_embed[cand]], dim=0)          # main_models.py:983-996 gather + :1259-1273 concat
+        loss = ns["encoder_cal"](q, all_doc, valid_num)                        # main_models.py:1184-1221
+        loss = loss.reshape(())
+        loss.backward()
+        out.update({f"c{ci}_loss_func": np.array(loss_func), f"c{ci}_intra_rate": np.float64(intra_rate), f"c{ci}_tau": np.float64(tau),
+                    f"c{ci}_valid_num": np.array(valid_num, dtype=np.int64), f"c{ci}_pos": pos.numpy(), f"c{ci}_cand": cand.numpy(),
+                    f"c{ci}_q": q.detach().numpy(), f"c{ci}_loss": np.float64(loss.item()), f"c{ci}_loss_f32": loss.detach().numpy(),
+                    f"c{ci}_grad_q": q.grad.numpy()})
+        print("case", ci, loss_func, intra_rate, tau, valid_num, "loss", loss.item())
+    out["n_cases"] = np.int64(len(cases))
+    np.savez_compressed(os.path.join(GOLD, "contrastive.npz"), **out)
+    print("wrote contrastive")
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     if len(sys.argv) > 1:
-        {"dense": gen_dense, "main_models": gen_main_models, "tree_match": gen_tree_match}[sys.argv[1]]()
+        {"dense": gen_dense, "main_models": gen_main_models, "tree_match": gen_tree_match, "contrastive": gen_contrastive}[sys.argv[1]]()
     else:
         for part in ("dense", "main_models"):      # separate processes: they need different `transformers`
             subprocess.check_call([sys.executable, os.path.abspath(__file__), part])

@@ -365,3 +365,31 @@ def test_node_embeddings_and_tree_match_match_reference():
     got = tree_match(trie, node_emb, node_leaf, torch.from_numpy(f["new_docs"]).cuda())
     want = json.loads(str(f["matches_json"]))
     assert [g.tolist() for g in got] == want
+
+
+def test_contrastive_loss_and_gradient_match_reference():
+    """gdr_contrastive_loss against the reference's encoder_cal + autograd (tests/golden/contrastive.npz): loss within 1e-5
+    relative, d loss / d query within 1e-4 of its largest entry (expf / tanhf vs. the CPU libm)."""
+    from gdr_b200 import ClusterStore
+    from gdr_b200.contrastive import encoder_cal
+    f = load_golden("contrastive")
+    doc = torch.from_numpy(f["doc_embed"])
+    N = doc.shape[0]
+    id_map = {str(c): list(range(c * 30, (c + 1) * 30)) for c in range(N // 30)}
+    store = ClusterStore.from_reference([doc[i] for i in range(N)], id_map, dtype=torch.float32)
+    for c in range(int(f["n_cases"])):
+        valid = f[f"c{c}_valid_num"].tolist()
+        cand = f[f"c{c}_cand"].tolist()
+        cands, at = [], 0
+        for v in valid:
+            cands.append(cand[at:at + v])
+            at += v
+        q = torch.from_numpy(f[f"c{c}_q"]).cuda().requires_grad_(True)
+        loss = encoder_cal(store, q, f[f"c{c}_pos"].tolist(), cands, str(f[f"c{c}_loss_func"]), float(f[f"c{c}_tau"]), float(f[f"c{c}_intra_rate"]))
+        loss.backward()
+        want = float(f[f"c{c}_loss"])
+        assert abs(loss.item() - want) <= 1e-5 * abs(want), (c, loss.item(), want)
+        gw = torch.from_numpy(f[f"c{c}_grad_q"])
+        assert (q.grad.cpu() - gw).abs().max().item() <= 1e-4 * gw.abs().max().item(), c
+    with pytest.raises(KeyError):
+        encoder_cal(store, q, [N + 5] * q.shape[0], cands)

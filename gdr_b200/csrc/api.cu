@@ -179,6 +179,7 @@ int gdr_score_topk(gdr_store_t *s, const float *q, const int32_t *beams, const f
     a.dim = s->dim; a.dtype = s->dtype; a.n_clusters = s->n_clusters; a.max_cluster = s->max_cluster; a.n_docs = s->n_docs;
     a.q = q; a.beams = beams; a.prob = prob; a.B = B; a.K = K; a.act = act; a.k = k; a.flags = flags;
     if (const char *dbg = getenv("GDR_UMMA_DEBUG")) a.flags |= (uint32_t)atoi(dbg) << 27;   // timing experiments only
+    if (const char *dbg = getenv("GDR_TOPK_DEBUG")) a.flags |= ((uint32_t)atoi(dbg) & 15u) << 20;   // timing experiments only (results invalid)
     a.cnt = s->cluster_ws;
     a.grp_off = s->cluster_ws + n;
     a.simt_off = a.grp_off + (n + 1);

@@ -141,7 +141,6 @@ __global__ void __launch_bounds__(128) k_score_simt(ScoreArgs a) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
-    pdl_launch_dependents();
     pdl_wait();
     const int n_items = a.counters[CTR_N_SIMT];
     const bool per_beam = (a.flags & GDR_Q_PER_BEAM) != 0;
@@ -180,6 +179,7 @@ __global__ void __launch_bounds__(128) k_score_simt(ScoreArgs a) {
             score_rows<T, CPL, SIMT_QT, RB4>(rows, a.dim, nrows, a.q, qrow, dst, a.act, lane);
         }
     }
+    pdl_launch_dependents();      // at the end: released at entry, the top-k's CTAs would sit resident for this whole kernel (see k_score_umma)
 }
 
 // Dense similarity (dense.py:53-54): out[Q, P] = q @ p^T.  Same core; items are arithmetic:

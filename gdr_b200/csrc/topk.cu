@@ -477,7 +477,7 @@ __device__ __noinline__ void topk_general_cold(const Src &src, int n, int k, int
 // The rare fallbacks (n <= k, mass ties in the boundary bin) run the general select with its histogram in global scratch.
 template <int NT, int R4, typename Src>
 __device__ void topk_fast16(const Src &src, int n, int k, uint32_t *gkeys, uint32_t *ghist, uint64_t *sel, uint32_t *hist_words,
-                            TkShared *sh, float *out_s, int32_t *out_d) {
+                            TkShared *sh, float *out_s, int32_t *out_d, uint32_t dbg = 0) {
     constexpr int NW = NT / 32;
     constexpr int RANGE = TK_BINS / NW;                            // bins summed by one warp (512 for four warps)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -527,6 +527,7 @@ __device__ void topk_fast16(const Src &src, int n, int k, uint32_t *gkeys, uint3
         }
     }
     __syncthreads();
+    if (dbg & 2u) return;                     // GDR_TOPK_DEBUG timing experiments: stop after pass 1
     {
         int part = 0;
 #pragma unroll
@@ -617,6 +618,7 @@ __device__ void topk_fast16(const Src &src, int n, int k, uint32_t *gkeys, uint3
         }
     }
     __syncthreads();
+    if (dbg & 4u) return;                     // stop after pass 2
     int d2, gt2, eq2;
     scan_down8(sh->hist2, lane, k - gt, d2, gt2, eq2);
     const int need2 = k - gt - gt2;
@@ -657,6 +659,7 @@ __device__ void topk_fast16(const Src &src, int n, int k, uint32_t *gkeys, uint3
         }
     }
     __syncthreads();
+    if (dbg & 8u) return;                     // stop before the docid gather + sort + output
     if (warp == 0) {
         uint64_t v[4];
 #pragma unroll
@@ -703,9 +706,11 @@ __global__ void __launch_bounds__(TKF_THREADS, 10) k_topk_fast(ScoreArgs a, floa
         }
     }
     __syncthreads();
+    const uint32_t dbg = (a.flags >> 20) & 15u;
+    if (dbg & 1u) return;                     // stop after the prologue
     StoreSrc src{a.scorebuf + (int64_t)b * a.stride, co, cbase, a.prob ? bias : nullptr, a.docid, a.K};
     topk_fast16<TKF_THREADS, TKF_R4>(src, co[a.K], a.k, a.gkeys + (int64_t)b * a.stride, a.ghist + (int64_t)b * TK_BINS, sel, hist_words, &sh,
-                             out_scores + (int64_t)b * a.k, out_docids + (int64_t)b * a.k);
+                             out_scores + (int64_t)b * a.k, out_docids + (int64_t)b * a.k, dbg);
     trace_end(a.dbg, 5);
 }
 

@@ -481,7 +481,10 @@ __device__ void topk_fast16(const Src &src, int n, int k, uint32_t *gkeys, uint3
     constexpr int NW = NT / 32;
     constexpr int RANGE = TK_BINS / NW;                            // bins summed by one warp (512 for four warps)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // The caller has STARTED filling co / cbase / bias in shared memory and has not synchronised: the first barrier below
+    // covers that fill too, so the score loads (which need only n) are in flight together with the caller's loads.
     if (n <= k) {
+        __syncthreads();
         topk_general_cold<NT>(src, n, k, 128, gkeys, sel, ghist, sh, out_s, out_d);
         return;
     }
@@ -619,11 +622,16 @@ __device__ void topk_fast16(const Src &src, int n, int k, uint32_t *gkeys, uint3
     }
     __syncthreads();
     if (dbg & 4u) return;                     // stop after pass 2
+    // Every listed candidate becomes (key, ~docid) HERE, one or two entries per thread with all lanes busy: the docid
+    // reads (segment search + one global load each) are issued together and overlap the second-level scan, instead of one
+    // exposed round trip in front of the final sort.
+    auto with_doc = [&](uint64_t e) { return (e & 0xffffffff00000000ull) | (uint32_t)~(uint32_t)src.doc((int)(uint32_t)e); };
+    if (tid < gt) sel[tid] = with_doc(sel[tid]);                   // gt < k <= 128 = NT; slots >= gt are appended below
     int d2, gt2, eq2;
     scan_down8(sh->hist2, lane, k - gt, d2, gt2, eq2);
     const int need2 = k - gt - gt2;
     for (int t = tid; t < eq; t += NT) {
-        const uint64_t e = bnd[t];
+        const uint64_t e = with_doc(bnd[t]);
         const int sub = (int)((e >> 45) & 255u);
         if (sub > d2) sel[atomicAdd(&sh->sel_count, 1)] = e;
         else if (sub == d2) bnd2[atomicAdd(&sh->eq2_count, 1)] = e;
@@ -633,29 +641,14 @@ __device__ void topk_fast16(const Src &src, int n, int k, uint32_t *gkeys, uint3
         for (int t = tid; t < eq2; t += NT) sel[gt + gt2 + t] = bnd2[t];
     } else {
         // still tied after 19 key bits: order by (key desc, docid asc); identical (key, docid) pairs by list position
-        constexpr int PER = TK_BND / NT;
-        uint64_t mine[PER], orig[PER];
-#pragma unroll
-        for (int u = 0; u < PER; ++u) {
-            const int t = tid + u * NT;
-            if (t < eq2) {
-                orig[u] = bnd2[t];
-                mine[u] = (orig[u] & 0xffffffff00000000ull) | (uint32_t)~(uint32_t)src.doc((int)(uint32_t)orig[u]);
-                bnd2[t] = mine[u];
+        for (int t = tid; t < eq2; t += NT) {
+            const uint64_t mine = bnd2[t];
+            int rank = 0;
+            for (int v = 0; v < eq2; ++v) {
+                const uint64_t o = bnd2[v];
+                rank += (o > mine) || (o == mine && v < t);
             }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int u = 0; u < PER; ++u) {
-            const int t = tid + u * NT;
-            if (t < eq2) {
-                int rank = 0;
-                for (int v = 0; v < eq2; ++v) {
-                    const uint64_t o = bnd2[v];
-                    rank += (o > mine[u]) || (o == mine[u] && v < t);
-                }
-                if (rank < need2) sel[gt + gt2 + rank] = orig[u];
-            }
+            if (rank < need2) sel[gt + gt2 + rank] = mine;
         }
     }
     __syncthreads();
@@ -666,10 +659,7 @@ __device__ void topk_fast16(const Src &src, int n, int k, uint32_t *gkeys, uint3
         for (int r = 0; r < 4; ++r) {
             const int i = lane * 4 + r;
             v[r] = 0;
-            if (i < k) {
-                const uint64_t e = sel[i];
-                v[r] = (e & 0xffffffff00000000ull) | (uint32_t)~(uint32_t)src.doc((int)(uint32_t)e);
-            }
+            if (i < k) v[r] = sel[i];
         }
         warp_bitonic128_desc(v, lane);
 #pragma unroll
@@ -705,11 +695,11 @@ __global__ void __launch_bounds__(TKF_THREADS, 10) k_topk_fast(ScoreArgs a, floa
             if (a.prob) bias[i] = __fmul_rn(alpha, a.prob[(int64_t)b * a.K + i]);
         }
     }
-    __syncthreads();
+    const int n = a.candoff[(int64_t)b * (a.K + 1) + a.K];           // every thread reads it itself: no barrier before the score loads
     const uint32_t dbg = (a.flags >> 20) & 15u;
     if (dbg & 1u) return;                     // stop after the prologue
     StoreSrc src{a.scorebuf + (int64_t)b * a.stride, co, cbase, a.prob ? bias : nullptr, a.docid, a.K};
-    topk_fast16<TKF_THREADS, TKF_R4>(src, co[a.K], a.k, a.gkeys + (int64_t)b * a.stride, a.ghist + (int64_t)b * TK_BINS, sel, hist_words, &sh,
+    topk_fast16<TKF_THREADS, TKF_R4>(src, n, a.k, a.gkeys + (int64_t)b * a.stride, a.ghist + (int64_t)b * TK_BINS, sel, hist_words, &sh,
                              out_scores + (int64_t)b * a.k, out_docids + (int64_t)b * a.k, dbg);
     trace_end(a.dbg, 5);
 }

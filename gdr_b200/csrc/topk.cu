@@ -685,7 +685,6 @@ __global__ void __launch_bounds__(TKF_THREADS, 10) k_topk_fast(ScoreArgs a, floa
     int32_t *cbase = co + a.K + 1;
     float *bias = reinterpret_cast<float *>(cbase + a.K);
     const int b = blockIdx.x;
-    pdl_launch_dependents();
     pdl_wait();
     trace_start(a.dbg, 4);
     for (int i = threadIdx.x; i <= a.K; i += TKF_THREADS) {          // one round trip: k_count left both arrays per query
@@ -701,6 +700,9 @@ __global__ void __launch_bounds__(TKF_THREADS, 10) k_topk_fast(ScoreArgs a, floa
     StoreSrc src{a.scorebuf + (int64_t)b * a.stride, co, cbase, a.prob ? bias : nullptr, a.docid, a.K};
     topk_fast16<TKF_THREADS, TKF_R4>(src, n, a.k, a.gkeys + (int64_t)b * a.stride, a.ghist + (int64_t)b * TK_BINS, sel, hist_words, &sh,
                              out_scores + (int64_t)b * a.k, out_docids + (int64_t)b * a.k, dbg);
+    // dependents (the next batch's k_count on this stream) are released at the end: released at entry, their CTAs would hold
+    // registers and thread slots beside this kernel for its whole duration (see k_score_umma)
+    pdl_launch_dependents();
     trace_end(a.dbg, 5);
 }
 
@@ -718,7 +720,6 @@ __global__ void __launch_bounds__(TK_THREADS, 8) k_topk_store(ScoreArgs a, float
     int32_t *co = reinterpret_cast<int32_t *>(skeys + (KEYS == 1 ? a.stride : 0));
     int32_t *cbase = co + a.K + 1;
     float *bias = reinterpret_cast<float *>(cbase + a.K);
-    pdl_launch_dependents();
     pdl_wait();
     trace_start(a.dbg, 4);
     const int b = blockIdx.x;

@@ -47,6 +47,8 @@ struct gdr_store {
     int last_launches = 0;
     int umma_min_group = 1;   // > 1 (env GDR_UMMA_MIN_GROUP) = mixed mode
     int umma_ctas = 0;        // > 0 (env GDR_UMMA_CTAS): persistent CTAs of the tcgen05 kernel (default: one per SM)
+    uint32_t debug_flags = 0; // GDR_UMMA_DEBUG / GDR_TOPK_DEBUG bits (timing experiments), read once at creation
+    bool topk_wide = false;   // env GDR_TOPK_WIDE: the 256-thread top-k also for k <= 128
     bool profiling = false;
     long long *dbg = nullptr;   // device timeline scratch for GDR_UMMA_TRACE
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -102,6 +104,9 @@ int gdr_store_create(gdr_store_t **out, const void *emb, int64_t n_docs, int32_t
     if (dtype == GDR_DTYPE_BF16 && dim % 64 == 0) s->has_tmap = umma_make_tensor_map(&s->tmap, emb, n_docs, dim);
     if (const char *env = getenv("GDR_UMMA_MIN_GROUP")) s->umma_min_group = atoi(env);
     if (const char *env = getenv("GDR_UMMA_CTAS")) s->umma_ctas = atoi(env);
+    if (const char *env = getenv("GDR_UMMA_DEBUG")) s->debug_flags |= (uint32_t)atoi(env) << 27;
+    if (const char *env = getenv("GDR_TOPK_DEBUG")) s->debug_flags |= ((uint32_t)atoi(env) & 15u) << 20;   // results are invalid under it
+    if (const char *env = getenv("GDR_TOPK_WIDE")) s->topk_wide = *env != 0;
     if (getenv("GDR_UMMA_TRACE")) { cudaMalloc(&s->dbg, 512 * sizeof(long long)); cudaMemset(s->dbg, 0, 512 * sizeof(long long)); }
     *out = s;
     return GDR_OK;
@@ -159,7 +164,7 @@ int gdr_score_topk(gdr_store_t *s, const float *q, const int32_t *beams, const f
     const size_t o_qsplit = take(umma_possible ? (size_t)q_rows * 3 * s->dim * 2 : 0);
     const size_t o_tmeta = take(umma_possible ? (size_t)umma_cap * sizeof(TileMeta) : 0);
     const size_t o_keys = take(global_keys ? (size_t)B * stride * 4 : 0);
-    const bool small_topk = k <= 128 && stride <= 65535 && !(getenv("GDR_TOPK_WIDE") && *getenv("GDR_TOPK_WIDE"));     // 128-thread top-k CTAs with 16-bit histogram bins
+    const bool small_topk = k <= 128 && stride <= 65535 && !s->topk_wide;     // 128-thread top-k CTAs with 16-bit histogram bins
     const size_t o_ghist = take(small_topk ? (size_t)B * 2048 * 4 : 0);
     if (off > s->batch_ws_bytes) {
         // growing the scratch synchronises; run one call per shape before capturing a CUDA graph
@@ -178,8 +183,7 @@ int gdr_score_topk(gdr_store_t *s, const float *q, const int32_t *beams, const f
     a.emb = s->emb; a.offsets = s->offsets; a.docid = s->docid;
     a.dim = s->dim; a.dtype = s->dtype; a.n_clusters = s->n_clusters; a.max_cluster = s->max_cluster; a.n_docs = s->n_docs;
     a.q = q; a.beams = beams; a.prob = prob; a.B = B; a.K = K; a.act = act; a.k = k; a.flags = flags;
-    if (const char *dbg = getenv("GDR_UMMA_DEBUG")) a.flags |= (uint32_t)atoi(dbg) << 27;   // timing experiments only
-    if (const char *dbg = getenv("GDR_TOPK_DEBUG")) a.flags |= ((uint32_t)atoi(dbg) & 15u) << 20;   // timing experiments only (results invalid)
+    a.flags |= s->debug_flags;                                         // timing experiments only (environment, read at creation)
     a.cnt = s->cluster_ws;
     a.grp_off = s->cluster_ws + n;
     a.simt_off = a.grp_off + (n + 1);

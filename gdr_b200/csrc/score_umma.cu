@@ -16,18 +16,21 @@
 // accumulation-order noise.  The kernel is still HBM-bound: per tile it moves 128 x 768 x 2 B = 196 KB of
 // embeddings and issues 12 x 4 MMAs of 128 x 96 x 16.
 //
-// Warp roles (320 threads, one persistent CTA per SM, tiles strided over CTAs):
-//   warp 0       TMA producer: A tiles of the store, 6-stage ring shared with B (96 KB of A in flight per SM)
+// Warp roles (320 threads, one persistent CTA per SM, tiles claimed one at a time from a global counter):
+//   warp 0       TMA producer: A tiles of the store (L2 evict-first hint), 6-stage ring shared with B (96 KB of A in flight per SM)
 //   warp 1       MMA issuer (one lane): tcgen05.mma cta_group::1 kind::f16; commits free the A and B stages
 //   warps 2-4    B fillers: gather the group's query rows from the pre-split bf16 table (hi/mid/lo terms written once
 //                per batch by k_count, L2-resident) with 16-byte cp.async straight into the 128B-swizzled K-major layout
 //                the UMMA descriptor expects; wait_group -> fence.proxy.async -> arrive.  Two stages per warp.
 //   warps 5-8    epilogue: tcgen05.ld the accumulator (double-buffered in TMEM so it overlaps the next
 //                tile's MMAs), activation, coalesced stores into each query's candidate segment
-//   warp 9       tile metadata: walks item -> pair -> candidate offset (three dependent L2 round trips) for four
-//                tiles at a time, up to four tiles ahead, into a shared-memory ring, so no other role ever has a
-//                global-memory latency on its per-tile critical path (measured: with each role fetching its own
-//                metadata the empty barrier skeleton alone cost 4 us per tile, as much as the tile's HBM time)
+//   warp 9       tile scheduler (one lane): atomicAdd on the tile counter, then ONE cp.async.bulk of the tile's 272-byte
+//                TileMeta record (row range, query rows, score offsets: resolved once per batch by k_tilemeta) into a
+//                two-slot shared-memory ring that every other role reads; a record with nq = -1 ends all loops.  No role
+//                has a dependent global load on its per-tile critical path (measured: with each role walking item ->
+//                pair -> candidate offset itself the empty barrier skeleton alone cost 4 us per tile, as much as the
+//                tile's HBM time), and a CTA that runs slower or starts later simply claims fewer tiles.
+// The dependent grid (the batch's top-k) is released at the kernel's END (see the note at pdl_launch_dependents below).
 #include "gdr_common.cuh"
 
 namespace gdr {

@@ -10,6 +10,10 @@
 // tied candidates, so the result does not depend on candidate order (and therefore not on how the
 // corpus is sharded across GPUs).  The same kernel, with an explicit candidate list as source,
 // is the merge step after the cross-rank exchange.
+//
+// Kernels: k_topk_fast (k <= 128 and <= 65,535 candidates per query: 128 threads, 16-bit histogram bins, 5.4 KB of shared
+// memory, keys of up to 2,560 candidates held in registers) is what the reference's top-100 runs; k_topk_store (256 threads)
+// covers larger k / more candidates with the three-pass radix select; k_topk_merge merges per-rank lists.
 #include "gdr_common.cuh"
 
 namespace gdr {

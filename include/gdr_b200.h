@@ -10,6 +10,11 @@
  * aborts; gdr_last_error() gives the message for the calling thread.  Kernels are enqueued
  * on the `stream` argument (a cudaStream_t passed as void*; NULL = legacy default stream);
  * no entry point synchronises the device unless documented.  There is NO CPU fallback.
+ *
+ * Concurrency: a store / trie handle owns ONE set of scratch buffers, so calls on the same handle must be ordered
+ * (same stream, or streams ordered with events).  To keep several batches in flight, create one handle per batch in
+ * flight over the SAME device arrays (a handle copies nothing: bench.py runs five per GPU).  The scratch grows on the
+ * first call of a new shape (that call synchronises the stream): run every shape once before capturing a CUDA graph.
  */
 #ifndef GDR_B200_H
 #define GDR_B200_H

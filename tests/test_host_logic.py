@@ -184,3 +184,22 @@ def test_child_insertion_order_matches_the_dict_order():
     assert [int(tok[e]) for e in order[fc[0]:fc[1]]] == [9, 3, 5]            # root: inserted 9, 3, 5; stored 3, 5, 9
     n9 = int(node[fc[0]:fc[1]][list(tok[fc[0]:fc[1]]).index(9)])
     assert [int(tok[e]) for e in order[fc[n9]:fc[n9 + 1]]] == [40, 33]
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` runs on the host alone (it is the CPU arm the driver times beside ours): one JSON line
+    with the contract's keys, the same metric / unit / config.workload as the GPU arm, and a zero-copy e2e object."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "3"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["unit"] == "queries/s" and line["value"] > 0 and line["steps"] == 2
+    assert line["config"]["workload"] == "cfg2" and line["vs_baseline"] is None and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0

@@ -6,10 +6,13 @@
 
 A "step" is one pass of the hot path (pair inversion -> gather-and-score -> per-query top-k) over one
 batch of synthetic queries.  N = 1 runs BASELINE.json configs[1] ("cfg2": 109,739 x 768 bf16 corpus,
-1,024 k-means-shaped clusters, batch 1,024 queries, beam 20, top-100).  N > 1 runs the cluster-sharded
-path of SURVEY.md §8e, weak scaling: every rank owns a cfg2-shaped shard (its own 1,024 clusters), the
-global batch is 1,024*N queries whose beams spread over all N*1,024 clusters, local top-k on each rank,
-one NCCL all-gather of packed (score, docid) candidates, merge top-k.
+1,024 k-means-shaped clusters, batch 1,024 queries, beam 20, top-100).  N > 1 (weak scaling, one process per GPU):
+cfg2's corpus is 169 MB, so every rank holds a replica and its own 1,024-query batch — independent units, no
+data-path collective (`--mode replica`, the default); `--workload cfg5s` (a 12.5 M-doc slice per GPU, the shape of
+a corpus that does NOT fit one GPU) runs the cluster-sharded path of SURVEY.md §8e: queries replicated, local top-k
+on each rank's clusters, one NCCL all-gather of packed (score, docid) candidates, merge top-k (`--mode sharded`).
+Batches are independent, so `--pipeline` of them (default 5) are kept in flight on as many streams inside one CUDA
+graph; `e2e` adds one pinned-host H2D copy (q + beams) and one D2H copy (scores + docids) per step.
 Timing: W warm-up steps, then exactly K steps between barrier + synchronize, CUDA events on the
 launching stream, max over ranks.  L2 hygiene: each step reads a different replica of the store
 (`config.l2`: the replicas together are several times the 126 MB L2) and a different query batch.

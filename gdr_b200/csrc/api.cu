@@ -49,6 +49,7 @@ struct gdr_store {
     int umma_ctas = 0;        // > 0 (env GDR_UMMA_CTAS): persistent CTAs of the tcgen05 kernel (default: one per SM)
     uint32_t debug_flags = 0; // GDR_UMMA_DEBUG / GDR_TOPK_DEBUG bits (timing experiments), read once at creation
     bool topk_wide = false;   // env GDR_TOPK_WIDE: the 256-thread top-k also for k <= 128
+    int prio_invert = 0, prio_score = 0, prio_topk = 0;   // env GDR_LAUNCH_PRIORITIES=1: per-launch priorities (+1000), 0 = off
     bool profiling = false;
     long long *dbg = nullptr;   // device timeline scratch for GDR_UMMA_TRACE
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -107,6 +108,16 @@ int gdr_store_create(gdr_store_t **out, const void *emb, int64_t n_docs, int32_t
     if (const char *env = getenv("GDR_UMMA_DEBUG")) s->debug_flags |= (uint32_t)atoi(env) << 27;
     if (const char *env = getenv("GDR_TOPK_DEBUG")) s->debug_flags |= ((uint32_t)atoi(env) & 15u) << 20;   // results are invalid under it
     if (const char *env = getenv("GDR_TOPK_WIDE")) s->topk_wide = *env != 0;
+    if (const char *env = getenv("GDR_LAUNCH_PRIORITIES")) {
+        // experiment (ROADMAP.md): inversion kernels at the greatest priority (they are tiny and otherwise queue behind the
+        // 1,024-CTA top-k grid), scoring one below, top-k at the least — so a pending scoring grid takes a freed SM first
+        int least = 0, greatest = 0;
+        if (atoi(env) > 0 && cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess && greatest < least) {
+            s->prio_invert = greatest + 1000;
+            s->prio_score = (greatest + 1 <= least ? greatest + 1 : least) + 1000;
+            s->prio_topk = least + 1000;
+        }
+    }
     if (getenv("GDR_UMMA_TRACE")) { cudaMalloc(&s->dbg, 512 * sizeof(long long)); cudaMemset(s->dbg, 0, 512 * sizeof(long long)); }
     *out = s;
     return GDR_OK;
@@ -219,7 +230,9 @@ int gdr_score_topk(gdr_store_t *s, const float *q, const int32_t *beams, const f
         GDR_CUDA(cudaMemcpyAsync(s->dbg + 500, init, sizeof(init), cudaMemcpyHostToDevice, st));
     }
     if (prof) GDR_CUDA(cudaEventRecord(s->ev[0], st));
+    g_launch_priority = s->prio_invert;
     if (!(flags & GDR_SKIP_INVERT)) GDR_CUDA(launch_invert(a, st, &launches));
+    g_launch_priority = s->prio_score;
     if (prof) GDR_CUDA(cudaEventRecord(s->ev[1], st));
     if (use_umma && !(flags & GDR_SKIP_SCORE)) {
         GDR_CUDA(launch_score_umma(a, &s->tmap, st, s->umma_ctas > 0 ? s->umma_ctas : s->sm_count));
@@ -231,11 +244,13 @@ int gdr_score_topk(gdr_store_t *s, const float *q, const int32_t *beams, const f
         launches += 1;
     }
     if (prof) GDR_CUDA(cudaEventRecord(s->ev[3], st));
+    g_launch_priority = s->prio_topk;
     for (int r = 0; r < n_alpha && !(flags & GDR_SKIP_TOPK); ++r) {
         const float alpha = alphas ? alphas[r] : 1.0f;
         GDR_CUDA(launch_topk_store(a, alpha, out_scores + (int64_t)r * B * k, out_docids + (int64_t)r * B * k, st));
         launches += 1;
     }
+    g_launch_priority = 0;
     if (prof) GDR_CUDA(cudaEventRecord(s->ev[4], st));
     s->last_launches = launches;
     return GDR_OK;

@@ -124,6 +124,11 @@ cudaError_t launch_position_mask(float *logits, int64_t bz, int sl, int V, int v
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// Per-launch scheduling priority (experiment, off unless GDR_LAUNCH_PRIORITIES=1; see ROADMAP.md): gdr_score_topk sets the
+// class of the phase it is about to launch, launch_pdl attaches cudaLaunchAttributePriority when a class is set.
+// 0 = no attribute.  Values are CUDA stream-priority numbers offset by +1000 (priorities can be 0 or negative).
+inline int g_launch_priority = 0;
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
     cudaLaunchConfig_t cfg = {};
@@ -131,11 +136,16 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (g_launch_priority != 0) {
+        attr[1].id = cudaLaunchAttributePriority;
+        attr[1].val.priority = g_launch_priority - 1000;
+        cfg.numAttrs = 2;
+    }
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

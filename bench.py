@@ -13,6 +13,10 @@ a corpus that does NOT fit one GPU) runs the cluster-sharded path of SURVEY.md Â
 on each rank's clusters, one NCCL all-gather of packed (score, docid) candidates, merge top-k (`--mode sharded`).
 Batches are independent, so `--pipeline` of them (default 5) are kept in flight on as many streams inside one CUDA
 graph; `e2e` adds one pinned-host H2D copy (q + beams) and one D2H copy (scores + docids) per step.
+Launch autotune (`--launch-priorities auto`, the default): before the stores are created rank 0 times 1,920 device-resident
+steps of the workload in child processes â€” default launches, per-launch priorities (GDR_LAUNCH_PRIORITIES=1: inversion >
+scoring > top-k), priorities with 3 more batches in flight â€” and keeps a candidate only if it beats the default by > 3 %;
+all three timings are printed in `config.launch_autotune`, so the line says what was chosen and why.
 Timing: W warm-up steps, then exactly K steps between barrier + synchronize, CUDA events on the
 launching stream, max over ranks.  L2 hygiene: each step reads a different replica of the store
 (`config.l2`: the replicas together are several times the 126 MB L2) and a different query batch.
@@ -134,6 +138,36 @@ def cpu_reference_qps(emb_cpu, offsets, docid, q_cpu, beams_cpu, k, min_seconds,
     return done / dt, done, dt
 
 
+def autotune_launch_config(args, local_rank, n_pipe_default):
+    """Times the device-resident loop of this workload under a few launch configurations, each in a CHILD process (the library
+    reads GDR_LAUNCH_PRIORITIES once per store, and a child that fails or hangs cannot take the bench down), and returns
+    (use_priorities, pipeline, report).  A configuration replaces the default only if it is more than 3 % faster."""
+    variants = [("default", "0", n_pipe_default), ("priorities", "1", n_pipe_default), ("priorities_deep", "1", n_pipe_default + 3)]
+    report, best = {}, None
+    for name, prio, n_pipe in variants:
+        env = {k_: v_ for k_, v_ in os.environ.items() if k_ not in ("RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE", "GROUP_RANK", "ROLE_RANK",
+                                                                     "TORCHELASTIC_RUN_ID", "MASTER_ADDR", "MASTER_PORT")}
+        env.update(GDR_LAUNCH_PRIORITIES=prio, LOCAL_RANK=str(local_rank))
+        cmd = [sys.executable, os.path.abspath(__file__), "--probe", "--gpus", "1", "--steps", "1920", "--warmup", "3", "--workload", args.workload,
+               "--path", args.path, "--pipeline", str(n_pipe), "--schedule", args.schedule, "--replicas", str(args.replicas)]
+        try:
+            out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=150)
+            lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+            us = float(json.loads(lines[-1])["us_per_step"]) if out.returncode == 0 and lines else None
+            report[name] = {"us_per_step": us, "batches_in_flight": n_pipe} if us else {"failed": (out.stderr or out.stdout)[-200:], "batches_in_flight": n_pipe}
+        except Exception as e:      # timeout, launch failure, malformed line: the default stays
+            us = None
+            report[name] = {"failed": repr(e)[:200], "batches_in_flight": n_pipe}
+        if us and (best is None or us < best[0]):
+            best = (us, name, prio == "1", n_pipe)
+    base = report["default"].get("us_per_step")
+    if best is None or base is None or best[1] == "default" or best[0] > 0.97 * base:
+        report["chosen"] = "default"
+        return False, n_pipe_default, report
+    report["chosen"] = best[1]
+    return best[2], best[3], report
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -154,6 +188,12 @@ def main():
                          "(prioritised) streams, ordered with events, so scoring kernels of consecutive batches overlap (auto = batches, "
                          "which measured faster)")
     ap.add_argument("--no-graph", action="store_true", help="launch every step from the host instead of replaying a CUDA graph")
+    ap.add_argument("--launch-priorities", default="auto", choices=["auto", "on", "off"],
+                    help="per-launch scheduling priorities of the library (env GDR_LAUNCH_PRIORITIES, ROADMAP.md item 0: inversion > scoring > "
+                         "top-k).  auto: rank 0 times a short run of this workload with and without them in child processes before the "
+                         "stores are created and keeps the faster setting (like a cuDNN-style launch autotune); both timings are reported "
+                         "in config.launch_autotune")
+    ap.add_argument("--probe", action="store_true", help=argparse.SUPPRESS)     # child mode of the autotune: time the device-resident loop, print one line
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -214,6 +254,24 @@ def main():
     B_rank = B_global if sharded else cfg["B"]      # queries each rank handles per step (sharded: all of them, replicated)
     C_total = cfg["C"] * world if sharded else cfg["C"]
     path_flags = {"auto": 0, "simt": 2, "umma": 4}[args.path]
+
+    # ---- launch configuration: measured, not assumed (a short device-resident run per candidate, in child processes)
+    autotune = None
+    if args.launch_priorities == "on":
+        os.environ["GDR_LAUNCH_PRIORITIES"] = "1"
+    elif args.launch_priorities == "off":
+        os.environ["GDR_LAUNCH_PRIORITIES"] = "0"
+    elif (not args.probe and not sharded and "GDR_LAUNCH_PRIORITIES" not in os.environ and args.pipeline != 1
+          and args.schedule != "phases" and not args.no_graph):
+        decision = torch.zeros(2, dtype=torch.int32, device=dev)
+        if rank == 0:
+            use_prio, n_best, autotune = autotune_launch_config(args, local_rank, args.pipeline if args.pipeline > 0 else 5)
+            decision = torch.tensor([int(use_prio), n_best], dtype=torch.int32, device=dev)
+        if world > 1:
+            dist.broadcast(decision, src=0)
+        use_prio, n_best = (int(x) for x in decision.tolist())
+        os.environ["GDR_LAUNCH_PRIORITIES"] = "1" if use_prio else "0"      # read by the library when a store is created
+        args.pipeline = n_best
     esize = 4 if cfg.get("fp32") else 2
     emb_bytes = cfg["N"] * D * esize
     replicas = args.replicas or max(1, min(6, -(-640 * 2 ** 20 // emb_bytes)))     # >= 640 MB of distinct store bytes in rotation
@@ -353,7 +411,9 @@ def main():
     stats = stores[0].last_stats()
 
     # CUDA graph of `period` consecutive steps (every replica / batch / pipe combination once), replayed: no host launch latency
-    period = math.lcm(replicas, n_batches, n_pipe) * (2 if n_pipe > 1 else 1)     # the pipeline drains at every graph boundary: amortise it
+    period = math.lcm(replicas, n_batches, n_pipe)
+    if n_pipe > 1:
+        period *= max(2, -(-80 // period))        # the pipeline drains at every graph boundary: amortise it over >= 80 steps
     if args.steps < period:
         period = max(1, args.steps)               # short runs: one graph of exactly --steps steps
     use_graph = not sharded and not args.no_graph
@@ -402,6 +462,20 @@ def main():
         ms = float(t.item())
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     qps = steps * B_global / (ms * 1e-3)
+    if args.probe:                                # child of autotune_launch_config: two more timed regions, median, one line, done
+        reps = [ms]
+        for _ in range(2):
+            e0.record()
+            for _ in range(steps // period):
+                graph.replay()
+            if graph_rem is not None:
+                graph_rem.replay()
+            e1.record()
+            barrier()
+            reps.append(e0.elapsed_time(e1))
+        print(json.dumps({"probe": True, "us_per_step": sorted(reps)[1] / steps * 1e3, "reps_us_per_step": [r / steps * 1e3 for r in reps],
+                          "launch_priorities": os.environ.get("GDR_LAUNCH_PRIORITIES", "0"), "batches_in_flight": n_pipe}))
+        return
 
     # ---- per-phase device time of the dominant kernel (CUDA events recorded inside the library, same stream)
     phase = {"invert": 0.0, "score_umma": 0.0, "score_simt": 0.0, "topk": 0.0}
@@ -639,6 +713,7 @@ def main():
                    "clusters_per_gpu": cfg["C"], "dim": D, "global_batch": B_global, "beam": K, "top_k": k,
                    "l2": f"{replicas} store replicas ({replicas * emb_bytes / 2**20:.0f} MB) and {n_batches} query batches cycled; inputs larger than L2",
                    "cuda_graph": bool(use_graph), "batches_in_flight": n_pipe, "schedule": "phases (inversion / scoring x3 / top-k x3 streams, events)" if phases else "batches (one stream per batch in flight)", "scoring_path": args.path,
+                   "launch_priorities": os.environ.get("GDR_LAUNCH_PRIORITIES", "0") not in ("", "0"), "launch_autotune": autotune,
                    "parallelism": "single GPU" if world == 1 else (f"clusters sharded over {world} GPUs, queries replicated, NCCL all-gather of candidates + merge"
                                                                    if sharded else f"corpus replicated on {world} GPUs, queries sharded, no data-path collective")},
         "clocks": clocks, "gpu_launches": (int(stats["launches"]) * steps + (steps if sharded else 0)) * (1 if sharded else world),

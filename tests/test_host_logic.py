@@ -203,3 +203,46 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["config"]["workload"] == "cfg2" and line["vs_baseline"] is None and line["higher_is_better"] is True
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_bench_launch_autotune_decision(monkeypatch):
+    """bench.py's launch autotune (child processes time the device-resident loop with / without per-launch priorities): a
+    candidate replaces the default only when it is > 3 % faster, and a failed, hung or garbled child leaves the default."""
+    import argparse
+    import json
+    import subprocess
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+
+    args = argparse.Namespace(workload="cfg2", path="auto", schedule="auto", replicas=0)
+    seen = []
+
+    def fake_run(times, fail=()):
+        def run(cmd, env=None, capture_output=None, text=None, timeout=None):
+            name = ("default", "priorities", "priorities_deep")[len(seen) % 3]
+            seen.append((cmd, env))
+            assert "--probe" in cmd and "RANK" not in env and env["LOCAL_RANK"] == "2"
+            assert env["GDR_LAUNCH_PRIORITIES"] == ("0" if name == "default" else "1")
+            if name in fail:
+                if fail[name] == "timeout":
+                    raise subprocess.TimeoutExpired(cmd, timeout)
+                return subprocess.CompletedProcess(cmd, 1, stdout="", stderr="CUDA error: invalid value")
+            return subprocess.CompletedProcess(cmd, 0, stdout="noise\n" + json.dumps({"probe": True, "us_per_step": times[name]}) + "\n", stderr="")
+        return run
+
+    monkeypatch.setenv("RANK", "0")
+    monkeypatch.setattr(bench.subprocess, "run", fake_run({"default": 50.0, "priorities": 40.0, "priorities_deep": 42.0}))
+    assert bench.autotune_launch_config(args, 2, 5)[:2] == (True, 5)
+    monkeypatch.setattr(bench.subprocess, "run", fake_run({"default": 50.0, "priorities": 42.0, "priorities_deep": 38.0}))
+    use, n_pipe, rep = bench.autotune_launch_config(args, 2, 5)
+    assert (use, n_pipe, rep["chosen"]) == (True, 8, "priorities_deep")
+    monkeypatch.setattr(bench.subprocess, "run", fake_run({"default": 50.0, "priorities": 49.0, "priorities_deep": 51.0}))
+    use, n_pipe, rep = bench.autotune_launch_config(args, 2, 5)
+    assert (use, n_pipe, rep["chosen"]) == (False, 5, "default") and rep["priorities"]["us_per_step"] == 49.0
+    monkeypatch.setattr(bench.subprocess, "run", fake_run({"default": 50.0, "priorities": 1.0, "priorities_deep": 1.0},
+                                                          fail={"priorities": "rc", "priorities_deep": "timeout"}))
+    use, n_pipe, rep = bench.autotune_launch_config(args, 2, 5)
+    assert (use, n_pipe) == (False, 5) and "failed" in rep["priorities"] and "failed" in rep["priorities_deep"]
+    monkeypatch.setattr(bench.subprocess, "run", fake_run({"default": 50.0, "priorities": 30.0, "priorities_deep": 30.0}, fail={"default": "rc"}))
+    assert bench.autotune_launch_config(args, 2, 5)[:2] == (False, 5)       # no trusted baseline: nothing changes

@@ -108,6 +108,10 @@ int gdr_store_create(gdr_store_t **out, const void *emb, int64_t n_docs, int32_t
     if (const char *env = getenv("GDR_UMMA_DEBUG")) s->debug_flags |= (uint32_t)atoi(env) << 27;
     if (const char *env = getenv("GDR_TOPK_DEBUG")) s->debug_flags |= ((uint32_t)atoi(env) & 15u) << 20;   // results are invalid under it
     if (const char *env = getenv("GDR_TOPK_WIDE")) s->topk_wide = *env != 0;
+    if (const char *env = getenv("GDR_TOPK_GROUPS")) {     // experiment: grouped persistent top-k (k_topk_fast_grouped), 1, 2 or 4 groups per CTA
+        const int g = atoi(env);
+        if (g > 0) s->debug_flags |= (uint32_t)(g >= 4 ? 4 : (g >= 2 ? 2 : 1)) << 16;
+    }
     if (const char *env = getenv("GDR_LAUNCH_PRIORITIES")) {
         // experiment (ROADMAP.md): inversion kernels at the greatest priority (they are tiny and otherwise queue behind the
         // 1,024-CTA top-k grid), scoring one below, top-k at the least — so a pending scoring grid takes a freed SM first

@@ -40,7 +40,9 @@ constexpr int MAX_DIM = 1024;
 // counters[] layout (device int32)
 // CTR_TILE_NEXT / CTR_TILE_DONE: the tcgen05 kernel's dynamic tile queue (claimed with atomicAdd; the last CTA to finish
 // resets both, so they are zero between launches)
-enum { CTR_N_SIMT = 0, CTR_N_UMMA = 1, CTR_N_TOUCHED = 2, CTR_TILE_NEXT = 3, CTR_TILE_DONE = 4, CTR_COUNT = 8 };
+// CTR_TOPK_NEXT / CTR_TOPK_DONE: the same protocol for the query queue of the grouped top-k (experiment, GDR_TOPK_GROUPS)
+enum { CTR_N_SIMT = 0, CTR_N_UMMA = 1, CTR_N_TOUCHED = 2, CTR_TILE_NEXT = 3, CTR_TILE_DONE = 4, CTR_TOPK_NEXT = 5, CTR_TOPK_DONE = 6,
+       CTR_COUNT = 8 };
 
 // Everything the tcgen05 kernel needs to know about one tile, resolved once per batch by k_tilemeta (work item ->
 // pairs -> candidate offsets: three dependent loads) so that the scoring kernel fetches it with ONE bulk copy.

@@ -37,25 +37,41 @@ struct Threshold {
     int n_eq;         // size of the boundary class
 };
 
+// Who is "the group" that runs one top-k: in the stand-alone kernels it is the whole CTA (CtaScope: threadIdx.x and
+// __syncthreads() — the kernels compile to the SASS they had before the policy existed); GroupScope<FIRST> is one of the
+// 128-thread groups that follow the first FIRST threads of a larger CTA (group g = threads [FIRST + 128 g, FIRST + 128 g + 128),
+// named barrier 1 + g) — the building block of the fused scoring + top-k CTA of ROADMAP.md.  Purely static: no argument is
+// added to any function, so the default instantiation is the code it was.
+struct CtaScope {
+    __device__ __forceinline__ static int tid() { return (int)threadIdx.x; }
+    __device__ __forceinline__ static void sync() { __syncthreads(); }
+};
+template <int FIRST>
+struct GroupScope {
+    __device__ __forceinline__ static int tid() { return ((int)threadIdx.x - FIRST) & 127; }
+    __device__ __forceinline__ static int group() { return ((int)threadIdx.x - FIRST) >> 7; }
+    __device__ __forceinline__ static void sync() { asm volatile("bar.sync %0, 128;" ::"r"(1 + group()) : "memory"); }
+};
+
 // Select the kk largest keys among the active candidates.  key_at(j, key) returns false for
 // inactive candidates.  All threads of the CTA call this with identical arguments.
-template <int NT, typename KeyAt>
+template <int NT, typename Scope = CtaScope, typename KeyAt>
 __device__ Threshold radix_select(int n, int kk, uint32_t *hist, TkShared *sh, KeyAt key_at) {
     Threshold th{0u, 32, kk, 0};
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = Scope::tid(), lane = tid & 31, warp = tid >> 5;
 #pragma unroll 1
     for (int pass = 0; pass < 3; ++pass) {
         const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);      // 11 + 11 + 10 bits
         const int nb = pass == 2 ? 1024 : 2048;
         for (int i = tid; i < nb; i += NT) hist[i] = 0;
-        __syncthreads();
+        Scope::sync();
         for (int j = tid; j < n; j += NT) {
             uint32_t key;
             if (!key_at(j, key)) continue;
             if (th.shift == 32 || (key >> th.shift) == (th.prefix >> th.shift))
                 atomicAdd(&hist[(key >> shift) & (nb - 1)], 1u);
         }
-        __syncthreads();
+        Scope::sync();
         // thread t owns `per` bins counted from the top: [nb - (t+1)*per, nb - t*per)
         const int per = nb / NT;
         const int top = nb - tid * per;
@@ -68,7 +84,7 @@ __device__ Threshold radix_select(int n, int kk, uint32_t *hist, TkShared *sh, K
             if (lane >= d) incl += t;
         }
         if (lane == 31) sh->warp_tot[warp] = incl;
-        __syncthreads();
+        Scope::sync();
         int before = 0;
         for (int w = 0; w < warp; ++w) before += sh->warp_tot[w];
         incl += before;
@@ -86,23 +102,23 @@ __device__ Threshold radix_select(int n, int kk, uint32_t *hist, TkShared *sh, K
                 running += h;
             }
         }
-        __syncthreads();
+        Scope::sync();
         th.prefix |= (uint32_t)sh->found_bin << shift;
         th.need -= sh->found_gt;
         th.n_eq = sh->found_eq;
         th.shift = shift;
-        __syncthreads();
+        Scope::sync();
         if (th.n_eq == th.need) break;
     }
     return th;
 }
 
-template <int NT>
+template <int NT, typename Scope = CtaScope>
 __device__ __forceinline__ void bitonic_sort_desc(uint64_t *v, int cap) {
     for (int size = 2; size <= cap; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            __syncthreads();
-            for (int i = threadIdx.x; i < cap; i += NT) {
+            Scope::sync();
+            for (int i = Scope::tid(); i < cap; i += NT) {
                 const int p = i ^ stride;
                 if (p > i) {
                     const uint64_t a = v[i], b = v[p];
@@ -112,7 +128,7 @@ __device__ __forceinline__ void bitonic_sort_desc(uint64_t *v, int cap) {
             }
         }
     }
-    __syncthreads();
+    Scope::sync();
 }
 
 // ---- candidate sources ------------------------------------------------------------------------
@@ -178,10 +194,10 @@ struct ListSrc {    // explicit candidate lists from G ranks: [G, B, k_in]
     }
 };
 
-template <int NT, typename Src>
+template <int NT, typename Src, typename Scope = CtaScope>
 __device__ void topk_general(const Src &src, int n, int k, int cap, uint32_t *keys, uint64_t *sel, uint32_t *hist,
                           TkShared *sh, float *out_s, int32_t *out_d) {
-    const int tid = threadIdx.x;
+    const int tid = Scope::tid();
     if (tid == 0) { sh->sel_count = 0; sh->eq2_count = 0; }
     for (int j4 = tid * 4; j4 < n; j4 += NT * 4) {            // keys[] is padded to a multiple of 4
         float s4[4];
@@ -189,15 +205,15 @@ __device__ void topk_general(const Src &src, int n, int k, int cap, uint32_t *ke
         *reinterpret_cast<uint4 *>(keys + j4) = make_uint4(float_to_ordered(s4[0]), float_to_ordered(s4[1]), float_to_ordered(s4[2]),
                                                            float_to_ordered(s4[3]));
     }
-    __syncthreads();
+    Scope::sync();
     const int kk = min(k, n);
     Threshold t1{0u, 32, kk, n};
-    if (n > k) t1 = radix_select<NT>(n, kk, hist, sh, [&](int j, uint32_t &key) { key = keys[j]; return true; });
+    if (n > k) t1 = radix_select<NT, Scope>(n, kk, hist, sh, [&](int j, uint32_t &key) { key = keys[j]; return true; });
     const bool tie = t1.shift == 0 && t1.n_eq > t1.need;   // exact-score ties straddle the cut
     Threshold t2{0u, 32, t1.need, t1.n_eq};
     if (tie) {
         const uint32_t T = t1.prefix;
-        t2 = radix_select<NT>(n, t1.need, hist, sh, [&](int j, uint32_t &key) {
+        t2 = radix_select<NT, Scope>(n, t1.need, hist, sh, [&](int j, uint32_t &key) {
             if (keys[j] != T) return false;
             key = ~(uint32_t)src.doc(j);
             return true;
@@ -227,9 +243,9 @@ __device__ void topk_general(const Src &src, int n, int k, int cap, uint32_t *ke
             if (slot < cap) sel[slot] = ((uint64_t)key << 32) | nd;
         }
     }
-    __syncthreads();
+    Scope::sync();
     for (int i = kk + tid; i < cap; i += NT) sel[i] = 0ull;
-    bitonic_sort_desc<NT>(sel, cap);
+    bitonic_sort_desc<NT, Scope>(sel, cap);
     for (int r = tid; r < k; r += NT) {
         float s = -INFINITY;
         int32_t d = -1;
@@ -466,10 +482,10 @@ __device__ void topk_body(const Src &src, int n, int k, int cap, uint32_t *keys,
 
 // The general select as the COLD fallback of the small-footprint fast path: kept out of line so that its two call sites
 // do not triple the hot kernel's instruction-cache footprint.
-template <int NT, typename Src>
+template <int NT, typename Src, typename Scope = CtaScope>
 __device__ __noinline__ void topk_general_cold(const Src &src, int n, int k, int cap, uint32_t *keys, uint64_t *sel, uint32_t *hist,
                                                TkShared *sh, float *out_s, int32_t *out_d) {
-    topk_general<NT>(src, n, k, cap, keys, sel, hist, sh, out_s, out_d);
+    topk_general<NT, Src, Scope>(src, n, k, cap, keys, sel, hist, sh, out_s, out_d);
 }
 
 // ---- fast path, small-footprint variant --------------------------------------------------------------------------
@@ -479,17 +495,17 @@ __device__ __noinline__ void topk_general_cold(const Src &src, int n, int k, int
 // block barriers (latency-bound: ~25 us per query under a saturated memory system), so what matters is how many
 // queries are in flight per SM: eight of these CTAs fit beside the scoring CTA against four of the 256-thread ones.
 // The rare fallbacks (n <= k, mass ties in the boundary bin) run the general select with its histogram in global scratch.
-template <int NT, int R4, typename Src>
+template <int NT, int R4, typename Src, typename Scope = CtaScope>
 __device__ void topk_fast16(const Src &src, int n, int k, uint32_t *gkeys, uint32_t *ghist, uint64_t *sel, uint32_t *hist_words,
                             TkShared *sh, float *out_s, int32_t *out_d, uint32_t dbg = 0) {
     constexpr int NW = NT / 32;
     constexpr int RANGE = TK_BINS / NW;                            // bins summed by one warp (512 for four warps)
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = Scope::tid(), lane = tid & 31, warp = tid >> 5;
     // The caller has STARTED filling co / cbase / bias in shared memory and has not synchronised: the first barrier below
     // covers that fill too, so the score loads (which need only n) are in flight together with the caller's loads.
     if (n <= k) {
-        __syncthreads();
-        topk_general_cold<NT>(src, n, k, 128, gkeys, sel, ghist, sh, out_s, out_d);
+        Scope::sync();
+        topk_general_cold<NT, Src, Scope>(src, n, k, 128, gkeys, sel, ghist, sh, out_s, out_d);
         return;
     }
     uint16_t *hist = reinterpret_cast<uint16_t *>(hist_words);     // bin b = half (b & 1) of word b >> 1
@@ -508,7 +524,7 @@ __device__ void topk_fast16(const Src &src, int n, int k, uint32_t *gkeys, uint3
             const int j4 = (r * NT + tid) * 4;
             v[r] = j4 < n ? src.load4(j4) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        __syncthreads();                                           // histogram is zeroed
+        Scope::sync();                                           // histogram is zeroed
 #pragma unroll
         for (int r = 0; r < R4; ++r) {
             const int j4 = (r * NT + tid) * 4;
@@ -522,7 +538,7 @@ __device__ void topk_fast16(const Src &src, int n, int k, uint32_t *gkeys, uint3
             }
         }
     } else {
-        __syncthreads();
+        Scope::sync();
         for (int j4 = tid * 4; j4 < n; j4 += NT * 4) {
             float s4[4];
             src.score4(j4, n, s4);
@@ -533,7 +549,7 @@ __device__ void topk_fast16(const Src &src, int n, int k, uint32_t *gkeys, uint3
             }
         }
     }
-    __syncthreads();
+    Scope::sync();
     if (dbg & 2u) return;                     // GDR_TOPK_DEBUG timing experiments: stop after pass 1
     {
         int part = 0;
@@ -546,7 +562,7 @@ __device__ void topk_fast16(const Src &src, int n, int k, uint32_t *gkeys, uint3
         for (int d = 16; d; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
         if (lane == 0) sh->warp_tot[warp] = part;
     }
-    __syncthreads();
+    Scope::sync();
     int above = 0, range = NW - 1;
     for (; range > 0; --range) {
         const int t = sh->warp_tot[range];
@@ -569,13 +585,13 @@ __device__ void topk_fast16(const Src &src, int n, int k, uint32_t *gkeys, uint3
     d_bin += base;
     gt += above;
     if (eq > TK_BND) {
-        __syncthreads();
-        topk_general_cold<NT>(src, n, k, 128, gkeys, sel, ghist, sh, out_s, out_d);
+        Scope::sync();
+        topk_general_cold<NT, Src, Scope>(src, n, k, 128, gkeys, sel, ghist, sh, out_s, out_d);
         return;
     }
     uint64_t *bnd = reinterpret_cast<uint64_t *>(hist_words);      // 2 x TK_BND x 8 B = the 4 KB histogram
     uint64_t *bnd2 = bnd + TK_BND;
-    __syncthreads();
+    Scope::sync();
     auto classify = [&](uint32_t key, int j) {
         const int bin = (int)(key >> 21);
         if (bin > d_bin) sel[atomicAdd(&sh->sel_count, 1)] = ((uint64_t)key << 32) | (uint32_t)j;
@@ -624,7 +640,7 @@ __device__ void topk_fast16(const Src &src, int n, int k, uint32_t *gkeys, uint3
                 if (j4 + e < n) classify(float_to_ordered(s4[e]), j4 + e);
         }
     }
-    __syncthreads();
+    Scope::sync();
     if (dbg & 4u) return;                     // stop after pass 2
     // Every listed candidate becomes (key, ~docid) HERE, one or two entries per thread with all lanes busy: the docid
     // reads (segment search + one global load each) are issued together and overlap the second-level scan, instead of one
@@ -640,7 +656,7 @@ __device__ void topk_fast16(const Src &src, int n, int k, uint32_t *gkeys, uint3
         if (sub > d2) sel[atomicAdd(&sh->sel_count, 1)] = e;
         else if (sub == d2) bnd2[atomicAdd(&sh->eq2_count, 1)] = e;
     }
-    __syncthreads();
+    Scope::sync();
     if (need2 == eq2) {
         for (int t = tid; t < eq2; t += NT) sel[gt + gt2 + t] = bnd2[t];
     } else {
@@ -655,7 +671,7 @@ __device__ void topk_fast16(const Src &src, int n, int k, uint32_t *gkeys, uint3
             if (rank < need2) sel[gt + gt2 + rank] = mine;
         }
     }
-    __syncthreads();
+    Scope::sync();
     if (dbg & 8u) return;                     // stop before the docid gather + sort + output
     if (warp == 0) {
         uint64_t v[4];
@@ -712,6 +728,63 @@ __global__ void __launch_bounds__(TKF_THREADS, 10) k_topk_fast(ScoreArgs a, floa
     // registers and thread slots beside this kernel for its whole duration (see k_score_umma)
     pdl_launch_dependents();
     trace_end(a.dbg, 5);
+}
+
+// ---- grouped variant (EXPERIMENT, off unless GDR_TOPK_GROUPS=G is set when the store is created; written after the GPU budget
+// of round 1 was spent: compiled, NOT yet run on a GPU, no parity test yet — ROADMAP.md, "plan of record") ---------------------
+// G independent 128-thread groups per CTA (GroupScope: own named barrier, own shared-memory slice), each claiming one query
+// at a time from a global counter and running the unchanged topk_fast16 on it.  This loop is what the top-k warps of the fused
+// scoring + top-k CTA will execute; stand-alone it is the check that the group-scoped body equals k_topk_fast.
+// slice: sel[128] u64 | hist[2048] u16 | co[K+1] | cbase[K] | bias[K] | TkShared | next query (int), rounded up to 16 bytes
+__host__ __device__ inline int tkg_slice_bytes(int K) {
+    return (128 * 8 + TK_BINS * 2 + (3 * K + 1) * 4 + (int)sizeof(TkShared) + 4 + 15) / 16 * 16;
+}
+
+template <int FIRST>
+__device__ void topk_group_loop(const ScoreArgs &a, float alpha, float *out_scores, int32_t *out_docids, unsigned char *slice) {
+    using S = GroupScope<FIRST>;
+    const int tid = S::tid();
+    uint64_t *sel = reinterpret_cast<uint64_t *>(slice);
+    uint32_t *hist_words = reinterpret_cast<uint32_t *>(sel + 128);
+    int32_t *co = reinterpret_cast<int32_t *>(hist_words + TK_BINS / 2);
+    int32_t *cbase = co + a.K + 1;
+    float *bias = reinterpret_cast<float *>(cbase + a.K);
+    TkShared *sh = reinterpret_cast<TkShared *>(bias + a.K);
+    volatile int *next = reinterpret_cast<int *>(sh + 1);
+    for (;;) {
+        if (tid == 0) *next = atomicAdd(&a.counters[CTR_TOPK_NEXT], 1);
+        S::sync();
+        const int b = *next;
+        if (b >= a.B) break;                                       // group-uniform
+        for (int i = tid; i <= a.K; i += TKF_THREADS) {
+            co[i] = a.candoff[(int64_t)b * (a.K + 1) + i];
+            if (i < a.K) {
+                cbase[i] = a.cbase[(int64_t)b * a.K + i];
+                if (a.prob) bias[i] = __fmul_rn(alpha, a.prob[(int64_t)b * a.K + i]);
+            }
+        }
+        const int n = a.candoff[(int64_t)b * (a.K + 1) + a.K];
+        StoreSrc src{a.scorebuf + (int64_t)b * a.stride, co, cbase, a.prob ? bias : nullptr, a.docid, a.K};
+        topk_fast16<TKF_THREADS, TKF_R4, StoreSrc, S>(src, n, a.k, a.gkeys + (int64_t)b * a.stride, a.ghist + (int64_t)b * TK_BINS, sel, hist_words,
+                                                      sh, out_scores + (int64_t)b * a.k, out_docids + (int64_t)b * a.k, 0u);
+        S::sync();                                                 // the slice (and *next) is free for the next query
+    }
+}
+
+template <int G>
+__global__ void __launch_bounds__(TKF_THREADS * G, 8 / G) k_topk_fast_grouped(ScoreArgs a, float alpha, float *out_scores, int32_t *out_docids) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    pdl_wait();
+    topk_group_loop<0>(a, alpha, out_scores, out_docids, smem + (size_t)GroupScope<0>::group() * tkg_slice_bytes(a.K));
+    __syncthreads();                                               // every group of this CTA has made its last claim
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&a.counters[CTR_TOPK_DONE], 1) == (int)gridDim.x - 1) {      // last CTA: leave the queue ready for the next launch
+            a.counters[CTR_TOPK_NEXT] = 0;
+            a.counters[CTR_TOPK_DONE] = 0;
+        }
+    }
+    pdl_launch_dependents();
 }
 
 // dynamic shared memory layout: sel[cap] u64 | hist[TK_BINS] u32 | keys[stride] u32 (smem variant) | co[K+1] i32 | cbase[K] i32 | bias[K] f32
@@ -782,6 +855,18 @@ cudaError_t launch_topk_store(const ScoreArgs &a, float alpha, float *out_scores
         cudaFuncSetAttribute(k_topk_store<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     }
     const int grid = a.B;      // (a few persistent CTAs per SM walking the queries measured slower in the pipelined step: 62 vs 57 us)
+    const int groups = (int)((a.flags >> 16) & 7u);                // GDR_TOPK_GROUPS (experiment, see k_topk_fast_grouped)
+    if (groups && cap <= 128 && a.gkeys && a.ghist && a.stride <= 65535) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int per_sm = groups >= 4 ? 2 : (groups == 2 ? 4 : 8);          // eight groups per SM in every shape
+        const int ctas = min((a.B + groups - 1) / groups, sms * per_sm);
+        const size_t smem = (size_t)groups * tkg_slice_bytes(a.K);
+        if (groups >= 4) return launch_pdl(k_topk_fast_grouped<4>, dim3(ctas), dim3(TKF_THREADS * 4), smem, s, a, alpha, out_scores, out_docids);
+        if (groups >= 2) return launch_pdl(k_topk_fast_grouped<2>, dim3(ctas), dim3(TKF_THREADS * 2), smem, s, a, alpha, out_scores, out_docids);
+        return launch_pdl(k_topk_fast_grouped<1>, dim3(ctas), dim3(TKF_THREADS), smem, s, a, alpha, out_scores, out_docids);
+    }
     if (cap <= 128 && a.gkeys && a.ghist && a.stride <= 65535)
         return launch_pdl(k_topk_fast, dim3(grid), dim3(TKF_THREADS), (size_t)128 * 8 + TK_BINS * 2 + (size_t)(3 * a.K + 1) * 4, s, a, alpha,
                           out_scores, out_docids);

@@ -11,6 +11,7 @@ GDR_OK = 0
 DTYPE_F32, DTYPE_BF16 = 0, 1
 ACT = {"none": 0, None: 0, "tanh": 1, "sigmoid": 2}
 Q_PER_BEAM, FORCE_SIMT, FORCE_UMMA = 1, 2, 4
+SKIP_INVERT, SKIP_SCORE, SKIP_TOPK = 256, 512, 1024
 
 # every symbol include/gdr_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
@@ -20,6 +21,7 @@ SYMBOLS = {
     "gdr_store_destroy": (c_int32, [c_void_p]),
     "gdr_score_topk": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_float), c_int32, c_int32, c_int32,
                                  c_int32, c_int32, c_uint32, c_void_p, c_void_p, c_void_p]),
+    "gdr_score_fused": (c_int32, [c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p]),
     "gdr_store_last_stats": (c_int32, [c_void_p, POINTER(c_int64), c_void_p]),
     "gdr_store_set_profiling": (c_int32, [c_void_p, c_int32]),
     "gdr_store_last_phase_ms": (c_int32, [c_void_p, POINTER(c_float)]),

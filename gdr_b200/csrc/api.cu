@@ -51,6 +51,10 @@ struct gdr_store {
     bool topk_wide = false;   // env GDR_TOPK_WIDE: the 256-thread top-k also for k <= 128
     int prio_invert = 0, prio_score = 0, prio_topk = 0;   // env GDR_LAUNCH_PRIORITIES=1: per-launch priorities (+1000), 0 = off
     bool profiling = false;
+    // what the last gdr_score_topk call on this handle set up (scratch pointers, shapes): input of gdr_score_fused (experiment)
+    ScoreArgs last_args;
+    bool last_valid = false, last_umma_only = false;
+    int fused_groups = 4;       // env GDR_FUSED_GROUPS: 3 or 4 top-k groups in the fused CTA
     long long *dbg = nullptr;   // device timeline scratch for GDR_UMMA_TRACE
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 };
@@ -108,6 +112,7 @@ int gdr_store_create(gdr_store_t **out, const void *emb, int64_t n_docs, int32_t
     if (const char *env = getenv("GDR_UMMA_DEBUG")) s->debug_flags |= (uint32_t)atoi(env) << 27;
     if (const char *env = getenv("GDR_TOPK_DEBUG")) s->debug_flags |= ((uint32_t)atoi(env) & 15u) << 20;   // results are invalid under it
     if (const char *env = getenv("GDR_TOPK_WIDE")) s->topk_wide = *env != 0;
+    if (const char *env = getenv("GDR_FUSED_GROUPS")) s->fused_groups = atoi(env) == 3 ? 3 : 4;
     if (const char *env = getenv("GDR_TOPK_GROUPS")) {     // experiment: grouped persistent top-k (k_topk_fast_grouped), 1, 2 or 4 groups per CTA
         const int g = atoi(env);
         if (g > 0) s->debug_flags |= (uint32_t)(g >= 4 ? 4 : (g >= 2 ? 2 : 1)) << 16;
@@ -257,6 +262,39 @@ int gdr_score_topk(gdr_store_t *s, const float *q, const int32_t *beams, const f
     g_launch_priority = 0;
     if (prof) GDR_CUDA(cudaEventRecord(s->ev[4], st));
     s->last_launches = launches;
+    s->last_args = a;
+    s->last_valid = true;
+    s->last_umma_only = use_umma && !use_simt;
+    return GDR_OK;
+}
+
+// EXPERIMENT (ROADMAP.md "plan of record", csrc/score_fused.cu; compiled, not yet run on a GPU).
+int gdr_score_fused(gdr_store_t *cur, gdr_store_t *prev, float alpha, float *prev_out_scores, int32_t *prev_out_docids, void *stream) {
+    if (!cur && !prev) return invalid("gdr_score_fused: both handles are null");
+    if (cur == prev) return invalid("gdr_score_fused: cur and prev must be different handles (two scratch sets)");
+    cudaStream_t st = (cudaStream_t)stream;
+    ScoreArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    if (prev) {
+        if (!prev->last_valid) return invalid("gdr_score_fused: prev has no batch (call gdr_score_topk on it first)");
+        if (!prev_out_scores || !prev_out_docids) return invalid("gdr_score_fused: null output pointer");
+        pa = prev->last_args;
+        if (pa.k > 128 || !pa.gkeys || !pa.ghist || pa.stride > 65535) {
+            set_error("gdr_score_fused: the fused top-k serves k <= 128 and <= 65,535 candidates per query");
+            return GDR_ERR_UNSUPPORTED;
+        }
+    }
+    if (!cur) {                                                    // flush: the last batch's top-k alone
+        GDR_CUDA(launch_topk_store(pa, alpha, prev_out_scores, prev_out_docids, st));
+        return GDR_OK;
+    }
+    if (!cur->last_valid) return invalid("gdr_score_fused: cur has no inversion (call gdr_score_topk with GDR_SKIP_SCORE | GDR_SKIP_TOPK first)");
+    if (!cur->last_umma_only || !cur->has_tmap) {
+        set_error("gdr_score_fused: the batch in cur does not take the tcgen05 path alone");
+        return GDR_ERR_UNSUPPORTED;
+    }
+    GDR_CUDA(launch_score_fused(cur->last_args, &cur->tmap, pa, alpha, prev_out_scores, prev_out_docids, st,
+                                cur->umma_ctas > 0 ? cur->umma_ctas : cur->sm_count, cur->fused_groups));
     return GDR_OK;
 }
 

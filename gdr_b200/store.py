@@ -146,9 +146,33 @@ class ClusterStore:
             _cabi.check(_cabi.lib().gdr_score_topk(
                 self._handle, q.data_ptr(), beams.data_ptr(), None if prob is None else prob.data_ptr(), alpha_arr,
                 n_alpha, B, K, _cabi.ACT[act], int(k), flags, out_s.data_ptr(), out_d.data_ptr(), _cabi.stream_ptr(stream)))
+        self._last_shape = (B, int(k))
         if alphas is None and out is None:
             return out_s[0], out_d[0]
         return out_s, out_d
+
+    # ---- experiment: fused scoring + top-k, one batch behind (include/gdr_b200.h gdr_score_fused; ROADMAP.md) ----------------
+    def invert(self, q: torch.Tensor, beams: torch.Tensor, k: int, prob: Optional[torch.Tensor] = None, act: Optional[str] = "none",
+               flags: int = 0, stream=None) -> None:
+        """Inversion phase of a batch alone (gdr_score_topk with GDR_SKIP_SCORE | GDR_SKIP_TOPK): leaves the batch's work lists
+        in this handle's scratch for `score_fused`.  q / beams / prob must stay alive until the batch's top-k has run."""
+        if getattr(self, "_fused_dummy", None) is None or self._fused_dummy[0].numel() < k:
+            self._fused_dummy = (torch.empty(max(k, 128), dtype=torch.float32, device=self.emb.device),
+                                 torch.empty(max(k, 128), dtype=torch.int32, device=self.emb.device))
+        self.score_topk(q, beams, k, prob=prob, act=act, flags=flags | _cabi.SKIP_SCORE | _cabi.SKIP_TOPK,
+                        out=self._fused_dummy, stream=stream)
+
+    def score_fused(self, prev: Optional["ClusterStore"], alpha: float = 1.0,
+                    out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, stream=None):
+        """ONE launch that scores the batch last given to `self.invert` and, in the same CTAs, selects the top-k of the batch
+        that `prev` (another handle = another scratch set) scored in the previous launch.  Returns prev's (scores [B, k],
+        docids [B, k]) or None when prev is None (first batch).  `ClusterStore.flush_fused(prev, ...)` ends a sequence."""
+        return _score_fused(self, prev, alpha, out, stream)
+
+    @staticmethod
+    def flush_fused(prev: "ClusterStore", alpha: float = 1.0, out=None, stream=None):
+        """Top-k of the last batch of a `score_fused` sequence (the stand-alone top-k kernel)."""
+        return _score_fused(None, prev, alpha, out, stream)
 
     def last_stats(self) -> Dict[str, int]:
         arr = (ctypes.c_int64 * 4)()
@@ -189,3 +213,17 @@ class ClusterStore:
             self.close()
         except Exception:
             pass
+
+
+def _score_fused(cur: Optional[ClusterStore], prev: Optional[ClusterStore], alpha, out, stream):
+    out_s = out_d = None
+    if prev is not None:
+        B, k = prev._last_shape
+        out_s, out_d = out if out is not None else (torch.empty((B, k), dtype=torch.float32, device=prev.emb.device),
+                                                    torch.empty((B, k), dtype=torch.int32, device=prev.emb.device))
+    dev = (cur if cur is not None else prev).emb.device
+    with torch.cuda.device(dev):
+        _cabi.check(_cabi.lib().gdr_score_fused(
+            None if cur is None else cur._handle, None if prev is None else prev._handle, float(alpha),
+            None if out_s is None else out_s.data_ptr(), None if out_d is None else out_d.data_ptr(), _cabi.stream_ptr(stream)))
+    return None if prev is None else (out_s, out_d)

@@ -89,6 +89,21 @@ int gdr_score_topk(gdr_store_t *store, const float *q, const int32_t *beams, con
                    const float *alphas, int32_t n_alpha, int32_t B, int32_t K, int32_t act, int32_t k,
                    uint32_t flags, float *out_scores, int32_t *out_docids, void *stream);
 
+/* EXPERIMENT — fused scoring + top-k, one batch behind (ROADMAP.md "plan of record"; csrc/score_fused.cu; compiled for
+ * sm_100a but not yet run on a GPU when round 1 ended; gdr_score_topk does not use it).  No reference counterpart: it is a
+ * different schedule of main_models.py:1577-1631, not a different result.
+ * `cur` and `prev` are two handles over the same (or different) embeddings, i.e. two scratch sets.  Protocol per batch i:
+ *   gdr_score_topk(h[i % 2], q_i, beams_i, prob_i, NULL, 1, B, K, act, k, GDR_SKIP_SCORE | GDR_SKIP_TOPK, any valid out pointers, stream)
+ *                                             -- the inversion of batch i into h[i % 2]'s scratch (the outputs are checked, not written)
+ *   gdr_score_fused(h[i % 2], i ? h[(i - 1) % 2] : NULL, alpha, out_scores_{i-1}, out_docids_{i-1}, stream)
+ *                                             -- ONE launch: scores batch i and selects the top-k of batch i-1 in the same CTAs
+ *   ... and after the last batch n-1:  gdr_score_fused(NULL, h[(n - 1) % 2], alpha, out_scores_{n-1}, out_docids_{n-1}, stream)
+ * Requirements: the batch in `cur` takes the tcgen05 path alone (bf16 store, dim % 64 == 0, B*K >= 3 * n_clusters or
+ * GDR_FORCE_UMMA); the batch in `prev` has k <= 128 and <= 65,535 candidates per query; prev's q / beams / prob buffers are
+ * still alive; one alpha per call (result = score + alpha * prob[b, beam]); outputs DEV [B, k] of the batch in `prev`. */
+int gdr_score_fused(gdr_store_t *cur, gdr_store_t *prev, float alpha, float *prev_out_scores, int32_t *prev_out_docids,
+                    void *stream);
+
 /* Counters of the most recent gdr_score_topk on this store (device-side work-list sizes):
  * out[0] = (cluster, query-chunk) items scored by the SIMT GEMV path, out[1] = tiles scored by the
  * tcgen05 grouped-GEMM path, out[2] = kernels launched by that call, out[3] = clusters touched.

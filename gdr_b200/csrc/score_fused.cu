@@ -1,6 +1,6 @@
 // k_score_topk_fused — EXPERIMENT (ROADMAP.md, "plan of record" for round 2).  Written after the GPU budget of round 1 was
 // spent: it compiles for sm_100a and has NOT run on a GPU yet; nothing in the default path (gdr_score_topk) uses it, its first
-// run is tests/test_gpu_experimental.py (child process, xfail-tolerant).
+// run is tests/test_gpu_zz_experimental.py (child process, xfail-tolerant).
 //
 // Why: alone, the scoring kernel takes 34.5 us and the top-k 17.5 us per 1,024-query batch, but pipelined they cost 48-50 us
 // per step, and the measured reason is RESIDENCY — the top-k's ~1,000 small CTAs occupy SMs that the next batch's scoring CTA

@@ -1,11 +1,11 @@
 #!/bin/bash
 # Round 2, first GPU call: the variants written without GPU access at the end of round 1 (ROADMAP.md "plan of record").
 #   gpurun --timeout 900 -- 'bash scripts/gpu_experimental.sh'
-# 1. grouped top-k, fused scoring + top-k and priority launches against the default, bit for bit (child processes, 240 s each)
+# 1. grouped top-k, fused scoring + top-k and priority launches against the default, bit for bit (child processes, 100 s each)
 # 2. if the fused kernel is exact: its cfg2 step time against the default schedule
 # 3. the bench with and without per-launch priorities (the autotune prints both)
 mkdir -p gpurun_out
-timeout 800 python -m pytest tests/test_gpu_experimental.py -q -rxX 2>&1 | tee gpurun_out/experimental_tests.log
+timeout 800 python -m pytest tests/test_gpu_zz_experimental.py -q -rxX 2>&1 | tee gpurun_out/experimental_tests.log
 for g in 4 3; do
     timeout 300 python tools/bench_fused.py --groups $g 2>gpurun_out/bench_fused_g$g.err | tee gpurun_out/bench_fused_g$g.json
 done

@@ -1,4 +1,4 @@
-"""Child process of tests/test_gpu_experimental.py: runs an experimental launch variant of the library (selected by an
+"""Child process of tests/test_gpu_zz_experimental.py: runs an experimental launch variant of the library (selected by an
 environment variable that the library reads when a store is created) against the default variant on the same inputs and
 prints one JSON line.  A separate process so that a variant that faults or hangs cannot take the test session down."""
 import json

@@ -27,6 +27,9 @@ def main():
     ap.add_argument("--pipeline", type=int, default=5)
     ap.add_argument("--groups", type=int, default=4, choices=[3, 4])
     ap.add_argument("--replicas", type=int, default=4)
+    ap.add_argument("--ctas", type=int, default=140, help="CTAs of the fused grid (GDR_UMMA_CTAS): fewer than the 148 SMs, because the "
+                    "inversion's 1,024-thread k_scan CTA does not fit beside an 832-thread fused CTA and needs SMs of its own; the "
+                    "default schedule keeps one scoring CTA per SM")
     args = ap.parse_args()
     os.environ["GDR_FUSED_GROUPS"] = str(args.groups)
     cfg = dict(bench.WORKLOADS["cfg2"])
@@ -45,7 +48,9 @@ def main():
     ref_h = handles(1)[0]
     refs = [ref_h[i % R].score_topk(q, b, k) for i, (q, b) in enumerate(batches)]
     refs = [(s.clone(), d.clone()) for s, d in refs]
+    os.environ["GDR_UMMA_CTAS"] = str(args.ctas)          # read once per handle, at creation: only the fused handles get it
     h = handles(3)
+    os.environ.pop("GDR_UMMA_CTAS")
     outs = []
     for i, (q, b) in enumerate(batches):
         cur, prev = h[i % 3][i % R], (h[(i - 1) % 3][(i - 1) % R] if i else None)
@@ -102,7 +107,7 @@ def main():
             cur_stream.wait_stream(s)
 
     period = 120                                   # lcm(3 handles, 8 batches, 4 replicas, 5 pipes)
-    result = {"ok": True, "groups": args.groups, "steps": args.steps, "period": period}
+    result = {"ok": True, "groups": args.groups, "fused_ctas": args.ctas, "steps": args.steps, "period": period}
     for name, fn in (("default", run_default), ("fused", run_fused)):
         fn(period, torch.cuda.current_stream())    # warm-up: every handle allocates its scratch
         torch.cuda.synchronize()

@@ -140,32 +140,43 @@ def cpu_reference_qps(emb_cpu, offsets, docid, q_cpu, beams_cpu, k, min_seconds,
 
 def autotune_launch_config(args, local_rank, n_pipe_default):
     """Times the device-resident loop of this workload under a few launch configurations, each in a CHILD process (the library
-    reads GDR_LAUNCH_PRIORITIES once per store, and a child that fails or hangs cannot take the bench down), and returns
-    (use_priorities, pipeline, report).  A configuration replaces the default only if it is more than 3 % faster."""
-    variants = [("default", "0", n_pipe_default), ("priorities", "1", n_pipe_default), ("priorities_deep", "1", n_pipe_default + 3)]
+    reads its launch knobs once per store, and a child that fails or hangs cannot take the bench down), and returns
+    (use_priorities, pipeline, schedule, report).  A configuration replaces the default only if it is more than 3 % faster; the
+    fused schedule (gdr_score_fused: ONE launch scores batch i and selects the top-k of batch i-1) is eligible only if the
+    child found its results identical, bit for bit, to gdr_score_topk's on every batch."""
+    variants = [("default", "0", n_pipe_default, args.schedule), ("priorities", "1", n_pipe_default, args.schedule),
+                ("priorities_deep", "1", n_pipe_default + 3, args.schedule)]
+    if args.workload == "cfg2" and args.path == "auto" and args.schedule == "auto":
+        variants.append(("fused", "0", n_pipe_default, "fused"))
     report, best = {}, None
-    for name, prio, n_pipe in variants:
+    for name, prio, n_pipe, schedule in variants:
         env = {k_: v_ for k_, v_ in os.environ.items() if k_ not in ("RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE", "GROUP_RANK", "ROLE_RANK",
                                                                      "TORCHELASTIC_RUN_ID", "MASTER_ADDR", "MASTER_PORT")}
         env.update(GDR_LAUNCH_PRIORITIES=prio, LOCAL_RANK=str(local_rank))
         cmd = [sys.executable, os.path.abspath(__file__), "--probe", "--gpus", "1", "--steps", "1920", "--warmup", "3", "--workload", args.workload,
-               "--path", args.path, "--pipeline", str(n_pipe), "--schedule", args.schedule, "--replicas", str(args.replicas)]
+               "--path", args.path, "--pipeline", str(n_pipe), "--schedule", schedule, "--replicas", str(args.replicas)]
+        us = None
         try:
             out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=150)
             lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
-            us = float(json.loads(lines[-1])["us_per_step"]) if out.returncode == 0 and lines else None
-            report[name] = {"us_per_step": us, "batches_in_flight": n_pipe} if us else {"failed": (out.stderr or out.stdout)[-200:], "batches_in_flight": n_pipe}
+            line = json.loads(lines[-1]) if out.returncode == 0 and lines else {}
+            if line.get("us_per_step") and (schedule != "fused" or line.get("schedule") == "fused"):
+                us = float(line["us_per_step"])
+                report[name] = {"us_per_step": us, "batches_in_flight": n_pipe}
+                if schedule == "fused":
+                    report[name]["verified_identical_to_default"] = True
+            else:
+                report[name] = {"failed": (line.get("failed") or out.stderr or out.stdout)[-200:], "batches_in_flight": n_pipe}
         except Exception as e:      # timeout, launch failure, malformed line: the default stays
-            us = None
             report[name] = {"failed": repr(e)[:200], "batches_in_flight": n_pipe}
         if us and (best is None or us < best[0]):
-            best = (us, name, prio == "1", n_pipe)
+            best = (us, name, prio == "1", n_pipe, schedule)
     base = report["default"].get("us_per_step")
     if best is None or base is None or best[1] == "default" or best[0] > 0.97 * base:
         report["chosen"] = "default"
-        return False, n_pipe_default, report
+        return False, n_pipe_default, args.schedule, report
     report["chosen"] = best[1]
-    return best[2], best[3], report
+    return best[2], best[3], best[4], report
 
 
 def main():
@@ -183,10 +194,12 @@ def main():
     ap.add_argument("--path", default="auto", choices=["auto", "simt", "umma"], help="force a scoring path")
     ap.add_argument("--pipeline", type=int, default=0, help="independent batches kept in flight, each with its own scratch (0 = auto: 6 for the "
                     "phase schedule, 5 for the batch schedule; 1 = strictly serial)")
-    ap.add_argument("--schedule", default="auto", choices=["auto", "batches", "phases"],
+    ap.add_argument("--schedule", default="auto", choices=["auto", "batches", "phases", "fused"],
                     help="batches: whole batches round-robin on one stream per batch in flight; phases: inversion / scoring / top-k on their own "
                          "(prioritised) streams, ordered with events, so scoring kernels of consecutive batches overlap (auto = batches, "
-                         "which measured faster)")
+                         "which measured faster; fused = EXPERIMENT, gdr_score_fused: one launch scores batch i and selects the top-k of "
+                         "batch i-1, inversion one batch ahead on a second stream — only adopted by the autotune when a child process "
+                         "found it bit-identical to the default and > 3 % faster)")
     ap.add_argument("--no-graph", action="store_true", help="launch every step from the host instead of replaying a CUDA graph")
     ap.add_argument("--launch-priorities", default="auto", choices=["auto", "on", "off"],
                     help="per-launch scheduling priorities of the library (env GDR_LAUNCH_PRIORITIES, ROADMAP.md item 0: inversion > scoring > "
@@ -263,15 +276,17 @@ def main():
         os.environ["GDR_LAUNCH_PRIORITIES"] = "0"
     elif (not args.probe and not sharded and "GDR_LAUNCH_PRIORITIES" not in os.environ and args.pipeline != 1
           and args.schedule != "phases" and not args.no_graph):
-        decision = torch.zeros(2, dtype=torch.int32, device=dev)
+        decision = torch.zeros(3, dtype=torch.int32, device=dev)
         if rank == 0:
-            use_prio, n_best, autotune = autotune_launch_config(args, local_rank, args.pipeline if args.pipeline > 0 else 5)
-            decision = torch.tensor([int(use_prio), n_best], dtype=torch.int32, device=dev)
+            use_prio, n_best, sched, autotune = autotune_launch_config(args, local_rank, args.pipeline if args.pipeline > 0 else 5)
+            decision = torch.tensor([int(use_prio), n_best, int(sched == "fused")], dtype=torch.int32, device=dev)
         if world > 1:
             dist.broadcast(decision, src=0)
-        use_prio, n_best = (int(x) for x in decision.tolist())
+        use_prio, n_best, use_fused = (int(x) for x in decision.tolist())
         os.environ["GDR_LAUNCH_PRIORITIES"] = "1" if use_prio else "0"      # read by the library when a store is created
         args.pipeline = n_best
+        if use_fused:
+            args.schedule = "fused"
     esize = 4 if cfg.get("fp32") else 2
     emb_bytes = cfg["N"] * D * esize
     replicas = args.replicas or max(1, min(6, -(-640 * 2 ** 20 // emb_bytes)))     # >= 640 MB of distinct store bytes in rotation
@@ -389,6 +404,9 @@ def main():
 
     def run_steps(n, cur):
         """n steps round-robin over the pipes' streams (fork/join on `cur`, so it is capturable into one graph)."""
+        if fused:
+            run_fused(n, cur)
+            return
         if phases:
             run_phases(n, cur)
             return
@@ -410,9 +428,66 @@ def main():
     barrier()
     stats = stores[0].last_stats()
 
+    # ---- fused schedule (EXPERIMENT, only on request or when the autotune's child verified it and found it faster):
+    # launch i scores batch i and, in the same persistent CTAs, selects the top-k of batch i-1 (gdr_score_fused); the inversion
+    # of batch i+1 runs one batch ahead on a second stream.  Three scratch sets: launch i scores into set i % 3, reads set
+    # (i-1) % 3 for the top-k, and the inversion of batch i+1 fills set (i+1) % 3.  The fused grid leaves 8 SMs to the inversion
+    # (k_scan's 1,024-thread CTA does not fit beside an 832-thread fused CTA; 108-140 scoring CTAs measured the same speed).
+    fused = not sharded and args.schedule == "fused" and not args.no_graph
+    fused_launches = None
+    if fused:
+        os.environ["GDR_UMMA_CTAS"] = os.environ.get("GDR_FUSED_CTAS", "140")
+        fh = [[ClusterStore(s0.emb, torch.as_tensor(s0.offsets_host), s0.docid) for s0 in stores] for _ in range(3)]
+        os.environ.pop("GDR_UMMA_CTAS")
+        f_out = [(torch.empty((B_rank, k), dtype=torch.float32, device=dev), torch.empty((B_rank, k), dtype=torch.int32, device=dev)) for _ in range(3)]
+        s_inv = torch.cuda.Stream()
+
+        def run_fused(n, cur, keep=None):
+            """n steps + the flush of the last batch; capturable.  keep: list that receives clones of every batch's result."""
+            s_inv.wait_stream(cur)
+            ev_f = {}
+            for i in range(n):
+                q, beams = batches[i % n_batches]
+                h_cur = fh[i % 3][i % replicas]
+                with torch.cuda.stream(s_inv):
+                    if i - 2 in ev_f:
+                        s_inv.wait_event(ev_f[i - 2])         # the batch that last used this scratch set has had its top-k
+                    h_cur.invert(q, beams, k, flags=path_flags)
+                    e_inv = torch.cuda.Event()
+                    e_inv.record(s_inv)
+                cur.wait_event(e_inv)
+                with torch.cuda.stream(cur):
+                    r = h_cur.score_fused(fh[(i - 1) % 3][(i - 1) % replicas] if i else None, out=f_out[(i - 1) % 3] if i else None)
+                    if keep is not None and r is not None:
+                        keep.append((r[0].clone(), r[1].clone()))
+                    ev_f[i] = torch.cuda.Event()
+                    ev_f[i].record(cur)
+            with torch.cuda.stream(cur):
+                r = ClusterStore.flush_fused(fh[(n - 1) % 3][(n - 1) % replicas], out=f_out[(n - 1) % 3])
+                if keep is not None:
+                    keep.append((r[0].clone(), r[1].clone()))
+            cur.wait_stream(s_inv)
+
+        # results first: every batch through the fused sequence must equal gdr_score_topk's result bit for bit
+        try:
+            got = []
+            run_fused(3 * n_batches, torch.cuda.current_stream(), keep=got)
+            torch.cuda.synchronize()
+            for i, (gs, gd) in enumerate(got):
+                rs, rd = stores[i % replicas].score_topk(batches[i % n_batches][0], batches[i % n_batches][1], k, flags=path_flags)
+                if not (torch.equal(gs, rs) and torch.equal(gd, rd)):
+                    raise RuntimeError(f"fused schedule: batch {i} differs from gdr_score_topk")
+            fused_launches = int(fh[0][0].last_stats()["launches"]) + 1          # inversion kernels + the fused launch
+        except Exception as e:
+            if args.probe:
+                print(json.dumps({"probe": True, "us_per_step": None, "failed": f"fused: {e}"[:200]}))
+                return
+            fused = False                             # fall back to the default schedule; said in config.schedule_note
+            autotune = dict(autotune or {}, fused_rejected_in_parent=str(e)[:200])
+
     # CUDA graph of `period` consecutive steps (every replica / batch / pipe combination once), replayed: no host launch latency
-    period = math.lcm(replicas, n_batches, n_pipe)
-    if n_pipe > 1:
+    period = math.lcm(replicas, n_batches, 3 if fused else n_pipe)
+    if n_pipe > 1 or fused:
         period *= max(2, -(-80 // period))        # the pipeline drains at every graph boundary: amortise it over >= 80 steps
     if args.steps < period:
         period = max(1, args.steps)               # short runs: one graph of exactly --steps steps
@@ -474,7 +549,8 @@ def main():
             barrier()
             reps.append(e0.elapsed_time(e1))
         print(json.dumps({"probe": True, "us_per_step": sorted(reps)[1] / steps * 1e3, "reps_us_per_step": [r / steps * 1e3 for r in reps],
-                          "launch_priorities": os.environ.get("GDR_LAUNCH_PRIORITIES", "0"), "batches_in_flight": n_pipe}))
+                          "launch_priorities": os.environ.get("GDR_LAUNCH_PRIORITIES", "0"), "batches_in_flight": n_pipe,
+                          "schedule": "fused" if fused else ("phases" if phases else "batches")}))
         return
 
     # ---- per-phase device time of the dominant kernel (CUDA events recorded inside the library, same stream)
@@ -712,11 +788,14 @@ def main():
                    "precision": "fp32 embeddings x fp32 queries, fp32 FMA" if cfg.get("fp32") else "bf16 embeddings x fp32 queries (exact 3-term bf16 split), fp32 accumulate", "docs_per_gpu": cfg["N"],
                    "clusters_per_gpu": cfg["C"], "dim": D, "global_batch": B_global, "beam": K, "top_k": k,
                    "l2": f"{replicas} store replicas ({replicas * emb_bytes / 2**20:.0f} MB) and {n_batches} query batches cycled; inputs larger than L2",
-                   "cuda_graph": bool(use_graph), "batches_in_flight": n_pipe, "schedule": "phases (inversion / scoring x3 / top-k x3 streams, events)" if phases else "batches (one stream per batch in flight)", "scoring_path": args.path,
+                   "cuda_graph": bool(use_graph), "batches_in_flight": n_pipe, "schedule": ("fused (EXPERIMENT gdr_score_fused: one launch scores batch i and selects the top-k of batch i-1 in the same CTAs; inversion one batch "
+                                "ahead on a second stream; 3 scratch sets; results verified bit-identical to gdr_score_topk before timing; e2e and roofline "
+                                "legs use the default schedule)") if fused else
+                               ("phases (inversion / scoring x3 / top-k x3 streams, events)" if phases else "batches (one stream per batch in flight)"), "scoring_path": args.path,
                    "launch_priorities": os.environ.get("GDR_LAUNCH_PRIORITIES", "0") not in ("", "0"), "launch_autotune": autotune,
                    "parallelism": "single GPU" if world == 1 else (f"clusters sharded over {world} GPUs, queries replicated, NCCL all-gather of candidates + merge"
                                                                    if sharded else f"corpus replicated on {world} GPUs, queries sharded, no data-path collective")},
-        "clocks": clocks, "gpu_launches": (int(stats["launches"]) * steps + (steps if sharded else 0)) * (1 if sharded else world),
+        "clocks": clocks, "gpu_launches": ((fused_launches * steps + -(-steps // period)) if fused else (int(stats["launches"]) * steps + (steps if sharded else 0))) * (1 if sharded else world),
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "segments_ms_per_step": [round(x / e2e_steps, 5) for x in e2e_segments], "estimator": "median of 5 timed segments",
                 "copies_alone": {k_: round(v_, 2) for k_, v_ in pcie.items()},

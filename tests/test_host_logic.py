@@ -206,8 +206,9 @@ def test_bench_reference_arm_prints_the_contract_line():
 
 
 def test_bench_launch_autotune_decision(monkeypatch):
-    """bench.py's launch autotune (child processes time the device-resident loop with / without per-launch priorities): a
-    candidate replaces the default only when it is > 3 % faster, and a failed, hung or garbled child leaves the default."""
+    """bench.py's launch autotune (child processes time the device-resident loop under candidate launch configurations): a
+    candidate replaces the default only when it is > 3 % faster, a failed, hung or garbled child leaves the default, and the
+    fused schedule is eligible only when its child ran it and verified the results."""
     import argparse
     import json
     import subprocess
@@ -216,33 +217,61 @@ def test_bench_launch_autotune_decision(monkeypatch):
     import bench
 
     args = argparse.Namespace(workload="cfg2", path="auto", schedule="auto", replicas=0)
+    names = ("default", "priorities", "priorities_deep", "fused")
     seen = []
 
-    def fake_run(times, fail=()):
+    def fake_run(times, fail=(), fused_line=None):
         def run(cmd, env=None, capture_output=None, text=None, timeout=None):
-            name = ("default", "priorities", "priorities_deep")[len(seen) % 3]
+            name = names[len(seen) % 4]
             seen.append((cmd, env))
             assert "--probe" in cmd and "RANK" not in env and env["LOCAL_RANK"] == "2"
-            assert env["GDR_LAUNCH_PRIORITIES"] == ("0" if name == "default" else "1")
+            assert env["GDR_LAUNCH_PRIORITIES"] == ("1" if name.startswith("priorities") else "0")
+            assert cmd[cmd.index("--schedule") + 1] == ("fused" if name == "fused" else "auto")
             if name in fail:
                 if fail[name] == "timeout":
                     raise subprocess.TimeoutExpired(cmd, timeout)
                 return subprocess.CompletedProcess(cmd, 1, stdout="", stderr="CUDA error: invalid value")
-            return subprocess.CompletedProcess(cmd, 0, stdout="noise\n" + json.dumps({"probe": True, "us_per_step": times[name]}) + "\n", stderr="")
+            line = {"probe": True, "us_per_step": times[name], "schedule": "fused" if name == "fused" else "batches"}
+            if name == "fused" and fused_line is not None:
+                line = fused_line
+            return subprocess.CompletedProcess(cmd, 0, stdout="noise\n" + json.dumps(line) + "\n", stderr="")
         return run
 
     monkeypatch.setenv("RANK", "0")
-    monkeypatch.setattr(bench.subprocess, "run", fake_run({"default": 50.0, "priorities": 40.0, "priorities_deep": 42.0}))
-    assert bench.autotune_launch_config(args, 2, 5)[:2] == (True, 5)
-    monkeypatch.setattr(bench.subprocess, "run", fake_run({"default": 50.0, "priorities": 42.0, "priorities_deep": 38.0}))
-    use, n_pipe, rep = bench.autotune_launch_config(args, 2, 5)
-    assert (use, n_pipe, rep["chosen"]) == (True, 8, "priorities_deep")
-    monkeypatch.setattr(bench.subprocess, "run", fake_run({"default": 50.0, "priorities": 49.0, "priorities_deep": 51.0}))
-    use, n_pipe, rep = bench.autotune_launch_config(args, 2, 5)
-    assert (use, n_pipe, rep["chosen"]) == (False, 5, "default") and rep["priorities"]["us_per_step"] == 49.0
-    monkeypatch.setattr(bench.subprocess, "run", fake_run({"default": 50.0, "priorities": 1.0, "priorities_deep": 1.0},
-                                                          fail={"priorities": "rc", "priorities_deep": "timeout"}))
-    use, n_pipe, rep = bench.autotune_launch_config(args, 2, 5)
-    assert (use, n_pipe) == (False, 5) and "failed" in rep["priorities"] and "failed" in rep["priorities_deep"]
-    monkeypatch.setattr(bench.subprocess, "run", fake_run({"default": 50.0, "priorities": 30.0, "priorities_deep": 30.0}, fail={"default": "rc"}))
-    assert bench.autotune_launch_config(args, 2, 5)[:2] == (False, 5)       # no trusted baseline: nothing changes
+    monkeypatch.setattr(bench.subprocess, "run", fake_run({"default": 50.0, "priorities": 40.0, "priorities_deep": 42.0, "fused": 45.0}))
+    assert bench.autotune_launch_config(args, 2, 5)[:3] == (True, 5, "auto")
+    monkeypatch.setattr(bench.subprocess, "run", fake_run({"default": 50.0, "priorities": 42.0, "priorities_deep": 38.0, "fused": 60.0}))
+    use, n_pipe, sched, rep = bench.autotune_launch_config(args, 2, 5)
+    assert (use, n_pipe, sched, rep["chosen"]) == (True, 8, "auto", "priorities_deep")
+    monkeypatch.setattr(bench.subprocess, "run", fake_run({"default": 50.0, "priorities": 49.0, "priorities_deep": 51.0, "fused": 49.5}))
+    use, n_pipe, sched, rep = bench.autotune_launch_config(args, 2, 5)
+    assert (use, n_pipe, sched, rep["chosen"]) == (False, 5, "auto", "default") and rep["priorities"]["us_per_step"] == 49.0
+    monkeypatch.setattr(bench.subprocess, "run", fake_run({"default": 50.0, "priorities": 1.0, "priorities_deep": 1.0, "fused": 1.0},
+                                                          fail={"priorities": "rc", "priorities_deep": "timeout", "fused": "rc"}))
+    use, n_pipe, sched, rep = bench.autotune_launch_config(args, 2, 5)
+    assert (use, n_pipe, sched) == (False, 5, "auto") and all("failed" in rep[n] for n in names[1:])
+    monkeypatch.setattr(bench.subprocess, "run", fake_run({"default": 50.0, "priorities": 30.0, "priorities_deep": 30.0, "fused": 30.0}, fail={"default": "rc"}))
+    assert bench.autotune_launch_config(args, 2, 5)[:3] == (False, 5, "auto")       # no trusted baseline: nothing changes
+    # the fused schedule: chosen when verified and fastest ...
+    monkeypatch.setattr(bench.subprocess, "run", fake_run({"default": 50.0, "priorities": 49.0, "priorities_deep": 50.0, "fused": 38.0}))
+    use, n_pipe, sched, rep = bench.autotune_launch_config(args, 2, 5)
+    assert (use, n_pipe, sched, rep["chosen"]) == (False, 5, "fused", "fused") and rep["fused"]["verified_identical_to_default"]
+    # ... never when its child reports differing results, or ran another schedule
+    monkeypatch.setattr(bench.subprocess, "run", fake_run({"default": 50.0, "priorities": 49.0, "priorities_deep": 50.0, "fused": 38.0},
+                                                          fused_line={"probe": True, "us_per_step": None, "failed": "fused: batch 3 differs"}))
+    use, n_pipe, sched, rep = bench.autotune_launch_config(args, 2, 5)
+    assert sched == "auto" and rep["chosen"] == "default" and "differs" in rep["fused"]["failed"]
+    monkeypatch.setattr(bench.subprocess, "run", fake_run({"default": 50.0, "priorities": 49.0, "priorities_deep": 50.0, "fused": 38.0},
+                                                          fused_line={"probe": True, "us_per_step": 38.0, "schedule": "batches"}))
+    assert bench.autotune_launch_config(args, 2, 5)[2] == "auto"
+    # other workloads do not try the fused schedule at all
+    seen.clear()
+    names3 = names[:3]
+    args3 = argparse.Namespace(workload="cfg3", path="auto", schedule="auto", replicas=0)
+
+    def run3(cmd, env=None, capture_output=None, text=None, timeout=None):
+        seen.append(cmd)
+        return subprocess.CompletedProcess(cmd, 0, stdout=json.dumps({"probe": True, "us_per_step": 100.0, "schedule": "batches"}), stderr="")
+    monkeypatch.setattr(bench.subprocess, "run", run3)
+    bench.autotune_launch_config(args3, 2, 5)
+    assert len(seen) == len(names3) and all("fused" not in c for c in seen)

@@ -15,8 +15,9 @@ Batches are independent, so `--pipeline` of them (default 5) are kept in flight 
 graph; `e2e` adds one pinned-host H2D copy (q + beams) and one D2H copy (scores + docids) per step.
 Launch autotune (`--launch-priorities auto`, the default): before the stores are created rank 0 times 1,920 device-resident
 steps of the workload in child processes — default launches, per-launch priorities (GDR_LAUNCH_PRIORITIES=1: inversion >
-scoring > top-k), priorities with 3 more batches in flight — and keeps a candidate only if it beats the default by > 3 %;
-all three timings are printed in `config.launch_autotune`, so the line says what was chosen and why.
+scoring > top-k), priorities with 3 more batches in flight, and (cfg2 only) the experimental fused schedule `gdr_score_fused`,
+whose child first checks every batch's result bit for bit against gdr_score_topk — and keeps a candidate only if it beats the
+default by > 3 %; all timings (or failures) are printed in `config.launch_autotune`, so the line says what was chosen and why.
 Timing: W warm-up steps, then exactly K steps between barrier + synchronize, CUDA events on the
 launching stream, max over ranks.  L2 hygiene: each step reads a different replica of the store
 (`config.l2`: the replicas together are several times the 126 MB L2) and a different query batch.
@@ -157,7 +158,7 @@ def autotune_launch_config(args, local_rank, n_pipe_default):
                "--path", args.path, "--pipeline", str(n_pipe), "--schedule", schedule, "--replicas", str(args.replicas)]
         us = None
         try:
-            out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=150)
+            out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=120)
             lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
             line = json.loads(lines[-1]) if out.returncode == 0 and lines else {}
             if line.get("us_per_step") and (schedule != "fused" or line.get("schedule") == "fused"):

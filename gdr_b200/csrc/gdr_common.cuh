@@ -94,6 +94,7 @@ cudaError_t launch_score_simt(const ScoreArgs &a, cudaStream_t s, int sm_count);
 cudaError_t launch_score_umma(const ScoreArgs &a, const CUtensorMap *tmap, cudaStream_t s, int sm_count);
 cudaError_t launch_topk_store(const ScoreArgs &a, float alpha, float *out_scores, int32_t *out_docids,
                               cudaStream_t s);
+cudaError_t launch_topk_grouped(const ScoreArgs &a, float alpha, float *out_scores, int32_t *out_docids, cudaStream_t s, int groups);
 cudaError_t launch_score_fused(const ScoreArgs &a, const CUtensorMap *tmap, const ScoreArgs &prev, float alpha, float *out_scores,
                                int32_t *out_docids, cudaStream_t s, int ctas, int groups);
 cudaError_t launch_merge_topk(const float *scores, const int32_t *docids, int G, int B, int k_in, int64_t g_stride, int k,

@@ -54,22 +54,6 @@ __global__ void __launch_bounds__(TKF_THREADS, 10) k_topk_fast(ScoreArgs a, floa
     trace_end(a.dbg, 5);
 }
 
-template <int G>
-__global__ void __launch_bounds__(TKF_THREADS * G, 8 / G) k_topk_fast_grouped(ScoreArgs a, float alpha, float *out_scores, int32_t *out_docids) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    pdl_wait();
-    topk_group_loop<0>(a, alpha, out_scores, out_docids, smem + (size_t)GroupScope<0>::group() * tkg_slice_bytes(a.K));
-    __syncthreads();                                               // every group of this CTA has made its last claim
-    if (threadIdx.x == 0) {
-        __threadfence();
-        if (atomicAdd(&a.counters[CTR_TOPK_DONE], 1) == (int)gridDim.x - 1) {      // last CTA: leave the queue ready for the next launch
-            a.counters[CTR_TOPK_NEXT] = 0;
-            a.counters[CTR_TOPK_DONE] = 0;
-        }
-    }
-    pdl_launch_dependents();
-}
-
 // dynamic shared memory layout: sel[cap] u64 | hist[TK_BINS] u32 | keys[stride] u32 (smem variant) | co[K+1] i32 | cbase[K] i32 | bias[K] f32
 // KEYS: 0 = key array in global scratch, 1 = key array in shared memory, 2 = fast path (k <= 128) without a key array
 // (its mass-tie fallback uses the global scratch)
@@ -138,18 +122,8 @@ cudaError_t launch_topk_store(const ScoreArgs &a, float alpha, float *out_scores
         cudaFuncSetAttribute(k_topk_store<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     }
     const int grid = a.B;      // (a few persistent CTAs per SM walking the queries measured slower in the pipelined step: 62 vs 57 us)
-    const int groups = (int)((a.flags >> 16) & 7u);                // GDR_TOPK_GROUPS (experiment, see k_topk_fast_grouped)
-    if (groups && cap <= 128 && a.gkeys && a.ghist && a.stride <= 65535) {
-        int dev = 0, sms = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const int per_sm = groups >= 4 ? 2 : (groups == 2 ? 4 : 8);          // eight groups per SM in every shape
-        const int ctas = min((a.B + groups - 1) / groups, sms * per_sm);
-        const size_t smem = (size_t)groups * tkg_slice_bytes(a.K);
-        if (groups >= 4) return launch_pdl(k_topk_fast_grouped<4>, dim3(ctas), dim3(TKF_THREADS * 4), smem, s, a, alpha, out_scores, out_docids);
-        if (groups >= 2) return launch_pdl(k_topk_fast_grouped<2>, dim3(ctas), dim3(TKF_THREADS * 2), smem, s, a, alpha, out_scores, out_docids);
-        return launch_pdl(k_topk_fast_grouped<1>, dim3(ctas), dim3(TKF_THREADS), smem, s, a, alpha, out_scores, out_docids);
-    }
+    const int groups = (int)((a.flags >> 16) & 7u);                // GDR_TOPK_GROUPS (experiment, topk_grouped.cu)
+    if (groups && cap <= 128 && a.gkeys && a.ghist && a.stride <= 65535) return launch_topk_grouped(a, alpha, out_scores, out_docids, s, groups);
     if (cap <= 128 && a.gkeys && a.ghist && a.stride <= 65535)
         return launch_pdl(k_topk_fast, dim3(grid), dim3(TKF_THREADS), (size_t)128 * 8 + TK_BINS * 2 + (size_t)(3 * a.K + 1) * 4, s, a, alpha,
                           out_scores, out_docids);

@@ -1,6 +1,7 @@
 // Per-query top-k selection: the device code shared by the stand-alone kernels (topk.cu) and the fused scoring + top-k CTA
 // (score_fused.cu).  See topk.cu for what the kernels are and where they are used.
 #pragma once
+#include <type_traits>
 #include "gdr_common.cuh"
 
 namespace gdr {
@@ -487,7 +488,9 @@ __device__ void topk_fast16(const Src &src, int n, int k, uint32_t *gkeys, uint3
                             TkShared *sh, float *out_s, int32_t *out_d, uint32_t dbg = 0) {
     constexpr int NW = NT / 32;
     constexpr int RANGE = TK_BINS / NW;                            // bins summed by one warp (512 for four warps)
-    const int tid = Scope::tid(), lane = tid & 31, warp = tid >> 5;
+    int tid_;
+    if constexpr (std::is_same<Scope, CtaScope>::value) tid_ = threadIdx.x; else tid_ = Scope::tid();
+    const int tid = tid_, lane = tid & 31, warp = tid >> 5;
     // The caller has STARTED filling co / cbase / bias in shared memory and has not synchronised: the first barrier below
     // covers that fill too, so the score loads (which need only n) are in flight together with the caller's loads.
     if (n <= k) {

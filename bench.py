@@ -768,6 +768,9 @@ def main():
                 "one event-bracketed launch inside a full call", "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "phase_ms": phase, "whole_step_frac": alg_bytes / (step_ms * 1e-3) / 1e9 / peak,
                 "frac_of_nominal_8TBs": achieved / 8000.0}
+    if fused:
+        roofline["note"] = ("the timed step launches k_score_topk_fused (the scoring CTA below plus top-k groups of the previous batch); kernel_ms / "
+                            "achieved are the scoring phase alone (k_score_umma), whole_step_frac is the fused step")
 
     cpu = None
     if not args.no_cpu_baseline:

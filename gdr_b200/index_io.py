@@ -134,3 +134,31 @@ def convert_pickles(doc_embedding_pkl: str, indexmap_pkl: str, out_path: str, dt
     emb, offsets, docid, keys = csr_from_reference(doc_embed, id_mapping)
     write_index(out_path, emb.to(dtype), offsets.numpy(), docid.numpy(), keys)
     return read_header(out_path)
+
+
+def main(argv=None) -> int:
+    """`python -m gdr_b200.index_io convert doc_embedding.pkl indexmap.pkl corpus.gdr [--dtype bf16|f32]` turns the reference's
+    two pickles into the mmap-able index file; `python -m gdr_b200.index_io info corpus.gdr` prints its header.  Host only."""
+    import argparse
+    import json
+    ap = argparse.ArgumentParser(prog="python -m gdr_b200.index_io", description=main.__doc__)
+    sub = ap.add_subparsers(dest="cmd", required=True)
+    c = sub.add_parser("convert", help="reference pickles -> index file")
+    c.add_argument("doc_embedding_pkl")
+    c.add_argument("indexmap_pkl")
+    c.add_argument("out")
+    c.add_argument("--dtype", choices=["bf16", "f32"], default="bf16")
+    i = sub.add_parser("info", help="print the header of an index file")
+    i.add_argument("path")
+    args = ap.parse_args(argv)
+    if args.cmd == "convert":
+        hdr = convert_pickles(args.doc_embedding_pkl, args.indexmap_pkl, args.out, torch.bfloat16 if args.dtype == "bf16" else torch.float32)
+    else:
+        hdr = read_header(args.path)
+    print(json.dumps({k: int(v) for k, v in hdr.items()}))
+    return 0
+
+
+if __name__ == "__main__":
+    import sys
+    sys.exit(main())

@@ -167,6 +167,17 @@ def test_index_file_roundtrip_and_pickle_converter(tmp_path):
     assert m_keys == list(f["id_mapping"].keys()) and torch.equal(torch.from_numpy(np.array(m_emb)), emb)
     with pytest.raises(ValueError):
         read_header(pe)
+    # the command-line converter a maintainer runs once per corpus (`python -m gdr_b200.index_io convert ...` / `info ...`)
+    import json
+    import subprocess
+    import sys
+    cli = str(tmp_path / "cli.gdr")
+    out = subprocess.run([sys.executable, "-m", "gdr_b200.index_io", "convert", pe, pm, cli, "--dtype", "f32"], capture_output=True, text=True, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-1000:]
+    assert json.loads(out.stdout.strip().splitlines()[-1])["n_rows"] == h["n_rows"]
+    assert open(cli, "rb").read() == open(str(tmp_path / "conv.gdr"), "rb").read()
+    out = subprocess.run([sys.executable, "-m", "gdr_b200.index_io", "info", cli], capture_output=True, text=True, cwd=ROOT)
+    assert out.returncode == 0 and json.loads(out.stdout.strip().splitlines()[-1])["n_clusters"] == h["n_clusters"]
 
 
 def test_child_insertion_order_matches_the_dict_order():

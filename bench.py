@@ -150,8 +150,11 @@ def autotune_launch_config(args, local_rank, n_pipe_default):
     if args.workload == "cfg2" and args.path == "auto" and args.schedule == "auto":
         # fused grid on 140 or 132 CTAs: the SMs it leaves are where the inversion's large CTAs (k_scan, k_fill, k_tilemeta) run
         variants += [("fused", "0", n_pipe_default, "fused", 140), ("fused_132", "0", n_pipe_default, "fused", 132)]
-    report, best = {}, None
+    report, best, t_start = {}, None, time.time()
     for name, prio, n_pipe, schedule, fused_ctas in variants:
+        if time.time() - t_start > 210:      # bound on the whole autotune (a hung candidate costs its 120 s timeout)
+            report[name] = {"skipped": "autotune time budget spent", "batches_in_flight": n_pipe}
+            continue
         env = {k_: v_ for k_, v_ in os.environ.items() if k_ not in ("RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE", "GROUP_RANK", "ROLE_RANK",
                                                                      "TORCHELASTIC_RUN_ID", "MASTER_ADDR", "MASTER_PORT")}
         env.update(GDR_LAUNCH_PRIORITIES=prio, LOCAL_RANK=str(local_rank))

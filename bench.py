@@ -142,16 +142,18 @@ def cpu_reference_qps(emb_cpu, offsets, docid, q_cpu, beams_cpu, k, min_seconds,
 def autotune_launch_config(args, local_rank, n_pipe_default):
     """Times the device-resident loop of this workload under a few launch configurations, each in a CHILD process (the library
     reads its launch knobs once per store, and a child that fails or hangs cannot take the bench down), and returns
-    (use_priorities, pipeline, schedule, fused_ctas, report).  A configuration replaces the default only if it is more than 3 % faster; the
+    (use_priorities, pipeline, schedule, fused_ctas, fused_groups, report).  A configuration replaces the default only if it is more than 3 % faster; the
     fused schedule (gdr_score_fused: ONE launch scores batch i and selects the top-k of batch i-1) is eligible only if the
     child found its results identical, bit for bit, to gdr_score_topk's on every batch."""
-    variants = [("default", "0", n_pipe_default, args.schedule, 0), ("priorities", "1", n_pipe_default, args.schedule, 0),
-                ("priorities_deep", "1", n_pipe_default + 3, args.schedule, 0)]
+    variants = [("default", "0", n_pipe_default, args.schedule, 0, 0), ("priorities", "1", n_pipe_default, args.schedule, 0, 0)]
     if args.workload == "cfg2" and args.path == "auto" and args.schedule == "auto":
-        # fused grid on 140 or 132 CTAs: the SMs it leaves are where the inversion's large CTAs (k_scan, k_fill, k_tilemeta) run
-        variants += [("fused", "0", n_pipe_default, "fused", 140), ("fused_132", "0", n_pipe_default, "fused", 132)]
+        # fused grid on 140 or 132 CTAs (the SMs it leaves are where the inversion's large CTAs — k_scan, k_fill, k_tilemeta — run)
+        # with 4 or 5 top-k groups per CTA (more queries in flight against fewer registers per thread)
+        variants += [("fused", "0", n_pipe_default, "fused", 140, 4), ("fused_g5", "0", n_pipe_default, "fused", 140, 5),
+                     ("fused_132_g5", "0", n_pipe_default, "fused", 132, 5)]
+    variants.append(("priorities_deep", "1", n_pipe_default + 3, args.schedule, 0, 0))
     report, best, t_start = {}, None, time.time()
-    for name, prio, n_pipe, schedule, fused_ctas in variants:
+    for name, prio, n_pipe, schedule, fused_ctas, fused_groups in variants:
         if time.time() - t_start > 210:      # bound on the whole autotune (a hung candidate costs its 120 s timeout)
             report[name] = {"skipped": "autotune time budget spent", "batches_in_flight": n_pipe}
             continue
@@ -159,7 +161,7 @@ def autotune_launch_config(args, local_rank, n_pipe_default):
                                                                      "TORCHELASTIC_RUN_ID", "MASTER_ADDR", "MASTER_PORT")}
         env.update(GDR_LAUNCH_PRIORITIES=prio, LOCAL_RANK=str(local_rank))
         if fused_ctas:
-            env["GDR_FUSED_CTAS"] = str(fused_ctas)
+            env.update(GDR_FUSED_CTAS=str(fused_ctas), GDR_FUSED_GROUPS=str(fused_groups))
         cmd = [sys.executable, os.path.abspath(__file__), "--probe", "--gpus", "1", "--steps", "1920", "--warmup", "3", "--workload", args.workload,
                "--path", args.path, "--pipeline", str(n_pipe), "--schedule", schedule, "--replicas", str(args.replicas)]
         us = None
@@ -171,19 +173,19 @@ def autotune_launch_config(args, local_rank, n_pipe_default):
                 us = float(line["us_per_step"])
                 report[name] = {"us_per_step": us, "batches_in_flight": n_pipe}
                 if schedule == "fused":
-                    report[name].update(verified_identical_to_default=True, fused_ctas=fused_ctas)
+                    report[name].update(verified_identical_to_default=True, fused_ctas=fused_ctas, fused_groups=fused_groups)
             else:
                 report[name] = {"failed": (line.get("failed") or out.stderr or out.stdout)[-200:], "batches_in_flight": n_pipe}
         except Exception as e:      # timeout, launch failure, malformed line: the default stays
             report[name] = {"failed": repr(e)[:200], "batches_in_flight": n_pipe}
         if us and (best is None or us < best[0]):
-            best = (us, name, prio == "1", n_pipe, schedule, fused_ctas)
+            best = (us, name, prio == "1", n_pipe, schedule, fused_ctas, fused_groups)
     base = report["default"].get("us_per_step")
     if best is None or base is None or best[1] == "default" or best[0] > 0.97 * base:
         report["chosen"] = "default"
-        return False, n_pipe_default, args.schedule, 0, report
+        return False, n_pipe_default, args.schedule, 0, 0, report
     report["chosen"] = best[1]
-    return best[2], best[3], best[4], best[5], report
+    return best[2], best[3], best[4], best[5], best[6], report
 
 
 def main():
@@ -283,18 +285,19 @@ def main():
         os.environ["GDR_LAUNCH_PRIORITIES"] = "0"
     elif (not args.probe and not sharded and "GDR_LAUNCH_PRIORITIES" not in os.environ and args.pipeline != 1
           and args.schedule != "phases" and not args.no_graph):
-        decision = torch.zeros(4, dtype=torch.int32, device=dev)
+        decision = torch.zeros(5, dtype=torch.int32, device=dev)
         if rank == 0:
-            use_prio, n_best, sched, f_ctas, autotune = autotune_launch_config(args, local_rank, args.pipeline if args.pipeline > 0 else 5)
-            decision = torch.tensor([int(use_prio), n_best, int(sched == "fused"), f_ctas], dtype=torch.int32, device=dev)
+            use_prio, n_best, sched, f_ctas, f_groups, autotune = autotune_launch_config(args, local_rank, args.pipeline if args.pipeline > 0 else 5)
+            decision = torch.tensor([int(use_prio), n_best, int(sched == "fused"), f_ctas, f_groups], dtype=torch.int32, device=dev)
         if world > 1:
             dist.broadcast(decision, src=0)
-        use_prio, n_best, use_fused, f_ctas = (int(x) for x in decision.tolist())
+        use_prio, n_best, use_fused, f_ctas, f_groups = (int(x) for x in decision.tolist())
         os.environ["GDR_LAUNCH_PRIORITIES"] = "1" if use_prio else "0"      # read by the library when a store is created
         args.pipeline = n_best
         if use_fused:
             args.schedule = "fused"
             os.environ["GDR_FUSED_CTAS"] = str(f_ctas)
+            os.environ["GDR_FUSED_GROUPS"] = str(f_groups)
     esize = 4 if cfg.get("fp32") else 2
     emb_bytes = cfg["N"] * D * esize
     replicas = args.replicas or max(1, min(6, -(-640 * 2 ** 20 // emb_bytes)))     # >= 640 MB of distinct store bytes in rotation
@@ -800,7 +803,7 @@ def main():
                    "clusters_per_gpu": cfg["C"], "dim": D, "global_batch": B_global, "beam": K, "top_k": k,
                    "l2": f"{replicas} store replicas ({replicas * emb_bytes / 2**20:.0f} MB) and {n_batches} query batches cycled; inputs larger than L2",
                    "cuda_graph": bool(use_graph), "batches_in_flight": n_pipe, "schedule": ("fused (EXPERIMENT gdr_score_fused: one launch scores batch i and selects the top-k of batch i-1 in the same CTAs; inversion one batch "
-                                "ahead on a second stream; fused grid of " + os.environ.get("GDR_FUSED_CTAS", "140") + " CTAs; 3 scratch sets; results verified bit-identical to gdr_score_topk before timing; e2e and roofline "
+                                "ahead on a second stream; fused grid of " + os.environ.get("GDR_FUSED_CTAS", "140") + " CTAs x " + os.environ.get("GDR_FUSED_GROUPS", "4") + " top-k groups; 3 scratch sets; results verified bit-identical to gdr_score_topk before timing; e2e and roofline "
                                 "legs use the default schedule)") if fused else
                                ("phases (inversion / scoring x3 / top-k x3 streams, events)" if phases else "batches (one stream per batch in flight)"), "scoring_path": args.path,
                    "launch_priorities": os.environ.get("GDR_LAUNCH_PRIORITIES", "0") not in ("", "0"), "launch_autotune": autotune,

@@ -54,7 +54,7 @@ struct gdr_store {
     // what the last gdr_score_topk call on this handle set up (scratch pointers, shapes): input of gdr_score_fused (experiment)
     ScoreArgs last_args;
     bool last_valid = false, last_umma_only = false;
-    int fused_groups = 4;       // env GDR_FUSED_GROUPS: 3 or 4 top-k groups in the fused CTA
+    int fused_groups = 4;       // env GDR_FUSED_GROUPS: 3, 4 or 5 top-k groups in the fused CTA
     long long *dbg = nullptr;   // device timeline scratch for GDR_UMMA_TRACE
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 };
@@ -112,7 +112,7 @@ int gdr_store_create(gdr_store_t **out, const void *emb, int64_t n_docs, int32_t
     if (const char *env = getenv("GDR_UMMA_DEBUG")) s->debug_flags |= (uint32_t)atoi(env) << 27;
     if (const char *env = getenv("GDR_TOPK_DEBUG")) s->debug_flags |= ((uint32_t)atoi(env) & 15u) << 20;   // results are invalid under it
     if (const char *env = getenv("GDR_TOPK_WIDE")) s->topk_wide = *env != 0;
-    if (const char *env = getenv("GDR_FUSED_GROUPS")) s->fused_groups = atoi(env) == 3 ? 3 : 4;
+    if (const char *env = getenv("GDR_FUSED_GROUPS")) s->fused_groups = atoi(env) == 3 ? 3 : (atoi(env) == 5 ? 5 : 4);
     if (const char *env = getenv("GDR_TOPK_GROUPS")) {     // experiment: grouped persistent top-k (k_topk_fast_grouped), 1, 2 or 4 groups per CTA
         const int g = atoi(env);
         if (g > 0) s->debug_flags |= (uint32_t)(g >= 4 ? 4 : (g >= 2 ? 2 : 1)) << 16;

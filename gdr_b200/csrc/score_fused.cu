@@ -18,8 +18,9 @@
 // kept by gdr_score_topk (called with GDR_SKIP_SCORE | GDR_SKIP_TOPK for the inversion) and passed in here.
 //
 // Budget per SM (one CTA): threads 320 + 128 G; shared memory 169 KB + G x 6.3 KB (K = 20); registers 65,536 / threads —
-// G = 4: 72 per thread, G = 3: 88 — against 100 in k_score_umma, so the epilogue warps spill a little until the roles are
-// regrouped into homogeneous warpgroups and rebalanced with setmaxnreg (ROADMAP.md).
+// G = 3: 80 used, G = 4: 72, G = 5 (960 threads, the most a CTA can hold next to the ten scoring warps): 64 — against 100 in
+// k_score_umma; ptxas reports 48-68 bytes of spills in all three, so the uniform allocation is a fair first draft until the
+// roles are regrouped into homogeneous warpgroups and rebalanced with setmaxnreg (ROADMAP.md).
 #include "gdr_common.cuh"
 #include "score_umma.cuh"
 #include "topk_select.cuh"
@@ -61,9 +62,12 @@ cudaError_t launch_score_fused(const ScoreArgs &a, const CUtensorMap *tmap, cons
     if (!((attr_set_mask >> (dev & 63)) & 1ull)) {
         cudaError_t e = cudaFuncSetAttribute(k_score_topk_fused<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FU_MAX_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_score_topk_fused<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FU_MAX_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_score_topk_fused<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, FU_MAX_SMEM);
         if (e != cudaSuccess) return e;
         attr_set_mask |= 1ull << (dev & 63);
     }
+    if (groups == 5)
+        return launch_pdl(k_score_topk_fused<5>, dim3(ctas), dim3(UM_THREADS + 5 * TKF_THREADS), smem, s, *tmap, a, prev, alpha, out_scores, out_docids);
     if (groups == 3)
         return launch_pdl(k_score_topk_fused<3>, dim3(ctas), dim3(UM_THREADS + 3 * TKF_THREADS), smem, s, *tmap, a, prev, alpha, out_scores, out_docids);
     return launch_pdl(k_score_topk_fused<4>, dim3(ctas), dim3(UM_THREADS + 4 * TKF_THREADS), smem, s, *tmap, a, prev, alpha, out_scores, out_docids);

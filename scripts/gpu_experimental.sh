@@ -6,7 +6,7 @@
 # 3. the bench with and without per-launch priorities (the autotune prints both)
 mkdir -p gpurun_out
 timeout 800 python -m pytest tests/test_gpu_zz_experimental.py -q -rxX 2>&1 | tee gpurun_out/experimental_tests.log
-for g in 4 3; do
+for g in 4 5 3; do
     timeout 300 python tools/bench_fused.py --groups $g 2>gpurun_out/bench_fused_g$g.err | tee gpurun_out/bench_fused_g$g.json
 done
 timeout 600 python bench.py --no-cpu-baseline 2>gpurun_out/bench_autotune.err | tee gpurun_out/bench_autotune.json

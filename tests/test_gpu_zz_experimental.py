@@ -29,7 +29,7 @@ def test_grouped_topk_equals_default(groups):
 
 
 @pytest.mark.xfail(strict=False, reason="k_score_topk_fused has not run on a GPU yet (written without GPU access)")
-@pytest.mark.parametrize("groups", ["4"])
+@pytest.mark.parametrize("groups", ["4", "5"])
 def test_fused_score_topk_equals_default(groups):
     """ONE launch scoring batch i and selecting the top-k of batch i-1 (gdr_score_fused, two handles) must return exactly what
     gdr_score_topk returns batch by batch."""

@@ -228,17 +228,19 @@ def test_bench_launch_autotune_decision(monkeypatch):
     import bench
 
     args = argparse.Namespace(workload="cfg2", path="auto", schedule="auto", replicas=0)
-    names = ("default", "priorities", "priorities_deep", "fused", "fused_132")
+    names = ("default", "priorities", "fused", "fused_g5", "fused_132_g5", "priorities_deep")
+    fused_env = {"fused": ("140", "4"), "fused_g5": ("140", "5"), "fused_132_g5": ("132", "5")}
     seen = []
 
     def fake_run(times, fail=(), fused_line=None):
         def run(cmd, env=None, capture_output=None, text=None, timeout=None):
-            name = names[len(seen) % 5]
+            name = names[len(seen) % len(names)]
             seen.append((cmd, env))
             assert "--probe" in cmd and "RANK" not in env and env["LOCAL_RANK"] == "2"
             assert env["GDR_LAUNCH_PRIORITIES"] == ("1" if name.startswith("priorities") else "0")
             assert cmd[cmd.index("--schedule") + 1] == ("fused" if name.startswith("fused") else "auto")
-            assert env.get("GDR_FUSED_CTAS") == {"fused": "140", "fused_132": "132"}.get(name)
+            assert (env.get("GDR_FUSED_CTAS"), env.get("GDR_FUSED_GROUPS")) == fused_env.get(name, (None, None))
+            assert cmd[cmd.index("--pipeline") + 1] == ("8" if name == "priorities_deep" else "5")
             if name in fail:
                 if fail[name] == "timeout":
                     raise subprocess.TimeoutExpired(cmd, timeout)
@@ -249,38 +251,32 @@ def test_bench_launch_autotune_decision(monkeypatch):
             return subprocess.CompletedProcess(cmd, 0, stdout="noise\n" + json.dumps(line) + "\n", stderr="")
         return run
 
+    def tune(times, **kw):
+        assert len(seen) % len(names) == 0
+        monkeypatch.setattr(bench.subprocess, "run", fake_run(times, **kw))
+        return bench.autotune_launch_config(args, 2, 5)
+
     monkeypatch.setenv("RANK", "0")
-    monkeypatch.setattr(bench.subprocess, "run", fake_run({"default": 50.0, "priorities": 40.0, "priorities_deep": 42.0, "fused": 45.0}))
-    assert bench.autotune_launch_config(args, 2, 5)[:4] == (True, 5, "auto", 0)
-    monkeypatch.setattr(bench.subprocess, "run", fake_run({"default": 50.0, "priorities": 42.0, "priorities_deep": 38.0, "fused": 60.0}))
-    use, n_pipe, sched, f_ctas, rep = bench.autotune_launch_config(args, 2, 5)
+    assert tune({"default": 50.0, "priorities": 40.0, "priorities_deep": 42.0, "fused": 45.0})[:5] == (True, 5, "auto", 0, 0)
+    use, n_pipe, sched, f_ctas, f_groups, rep = tune({"default": 50.0, "priorities": 42.0, "priorities_deep": 38.0, "fused": 60.0})
     assert (use, n_pipe, sched, rep["chosen"]) == (True, 8, "auto", "priorities_deep")
-    monkeypatch.setattr(bench.subprocess, "run", fake_run({"default": 50.0, "priorities": 49.0, "priorities_deep": 51.0, "fused": 49.5}))
-    use, n_pipe, sched, f_ctas, rep = bench.autotune_launch_config(args, 2, 5)
+    use, n_pipe, sched, f_ctas, f_groups, rep = tune({"default": 50.0, "priorities": 49.0, "priorities_deep": 51.0, "fused": 49.5})
     assert (use, n_pipe, sched, rep["chosen"]) == (False, 5, "auto", "default") and rep["priorities"]["us_per_step"] == 49.0
-    monkeypatch.setattr(bench.subprocess, "run", fake_run({"default": 50.0, "priorities": 1.0, "priorities_deep": 1.0, "fused": 1.0},
-                                                          fail={"priorities": "rc", "priorities_deep": "timeout", "fused": "rc", "fused_132": "rc"}))
-    use, n_pipe, sched, f_ctas, rep = bench.autotune_launch_config(args, 2, 5)
+    use, n_pipe, sched, f_ctas, f_groups, rep = tune({"default": 50.0}, fail={"priorities": "rc", "priorities_deep": "timeout", "fused": "rc",
+                                                                             "fused_g5": "rc", "fused_132_g5": "timeout"})
     assert (use, n_pipe, sched) == (False, 5, "auto") and all("failed" in rep[n] for n in names[1:])
-    monkeypatch.setattr(bench.subprocess, "run", fake_run({"default": 50.0, "priorities": 30.0, "priorities_deep": 30.0, "fused": 30.0}, fail={"default": "rc"}))
-    assert bench.autotune_launch_config(args, 2, 5)[:3] == (False, 5, "auto")       # no trusted baseline: nothing changes
-    # the fused schedule: chosen when verified and fastest ...
-    monkeypatch.setattr(bench.subprocess, "run", fake_run({"default": 50.0, "priorities": 49.0, "priorities_deep": 50.0, "fused": 38.0}))
-    use, n_pipe, sched, f_ctas, rep = bench.autotune_launch_config(args, 2, 5)
-    assert (use, n_pipe, sched, f_ctas, rep["chosen"]) == (False, 5, "fused", 140, "fused") and rep["fused"]["verified_identical_to_default"]
-    monkeypatch.setattr(bench.subprocess, "run", fake_run({"default": 50.0, "priorities": 49.0, "priorities_deep": 50.0, "fused": 38.0, "fused_132": 36.0}))
-    assert bench.autotune_launch_config(args, 2, 5)[2:4] == ("fused", 132)
+    assert tune({"default": 50.0, "priorities": 30.0, "priorities_deep": 30.0, "fused": 30.0}, fail={"default": "rc"})[:3] == (False, 5, "auto")
+    # the fused schedule: chosen when verified and fastest, with the grid and group count of the winning candidate ...
+    use, n_pipe, sched, f_ctas, f_groups, rep = tune({"default": 50.0, "priorities": 49.0, "priorities_deep": 50.0, "fused": 38.0})
+    assert (use, n_pipe, sched, f_ctas, f_groups, rep["chosen"]) == (False, 5, "fused", 140, 4, "fused") and rep["fused"]["verified_identical_to_default"]
+    assert tune({"default": 50.0, "priorities": 49.0, "fused": 38.0, "fused_g5": 37.0, "fused_132_g5": 36.0})[2:5] == ("fused", 132, 5)
     # ... never when its child reports differing results, or ran another schedule
-    monkeypatch.setattr(bench.subprocess, "run", fake_run({"default": 50.0, "priorities": 49.0, "priorities_deep": 50.0, "fused": 38.0},
-                                                          fused_line={"probe": True, "us_per_step": None, "failed": "fused: batch 3 differs"}))
-    use, n_pipe, sched, f_ctas, rep = bench.autotune_launch_config(args, 2, 5)
+    use, n_pipe, sched, f_ctas, f_groups, rep = tune({"default": 50.0, "priorities": 49.0, "priorities_deep": 50.0},
+                                                     fused_line={"probe": True, "us_per_step": None, "failed": "fused: batch 3 differs"})
     assert sched == "auto" and rep["chosen"] == "default" and "differs" in rep["fused"]["failed"]
-    monkeypatch.setattr(bench.subprocess, "run", fake_run({"default": 50.0, "priorities": 49.0, "priorities_deep": 50.0, "fused": 38.0},
-                                                          fused_line={"probe": True, "us_per_step": 38.0, "schedule": "batches"}))
-    assert bench.autotune_launch_config(args, 2, 5)[2] == "auto"
+    assert tune({"default": 50.0, "priorities": 49.0, "priorities_deep": 50.0}, fused_line={"probe": True, "us_per_step": 38.0, "schedule": "batches"})[2] == "auto"
     # other workloads do not try the fused schedule at all
     seen.clear()
-    names3 = names[:3]
     args3 = argparse.Namespace(workload="cfg3", path="auto", schedule="auto", replicas=0)
 
     def run3(cmd, env=None, capture_output=None, text=None, timeout=None):
@@ -288,4 +284,4 @@ def test_bench_launch_autotune_decision(monkeypatch):
         return subprocess.CompletedProcess(cmd, 0, stdout=json.dumps({"probe": True, "us_per_step": 100.0, "schedule": "batches"}), stderr="")
     monkeypatch.setattr(bench.subprocess, "run", run3)
     bench.autotune_launch_config(args3, 2, 5)
-    assert len(seen) == len(names3) and all("fused" not in c for c in seen)
+    assert len(seen) == 3 and all("fused" not in c for c in seen)

@@ -25,7 +25,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=960)
     ap.add_argument("--pipeline", type=int, default=5)
-    ap.add_argument("--groups", type=int, default=4, choices=[3, 4])
+    ap.add_argument("--groups", type=int, default=4, choices=[3, 4, 5])
     ap.add_argument("--replicas", type=int, default=4)
     ap.add_argument("--ctas", type=int, default=140, help="CTAs of the fused grid (GDR_UMMA_CTAS): fewer than the 148 SMs, because the "
                     "inversion's 1,024-thread k_scan CTA does not fit beside an 832-thread fused CTA and needs SMs of its own; the "

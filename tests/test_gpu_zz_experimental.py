@@ -2,7 +2,7 @@
 child process with a timeout, must reproduce the default variant bit for bit, and is marked xfail(strict=False) — the product
 path does not use them, so a failure here documents the experiment and does not turn the suite red; a pass (XPASS) is the
 first validation step of the round-2 plan.  The file sorts after the other GPU tests on purpose: a variant that hangs costs its
-child's 100 s timeout, and that must not delay the parity suite."""
+child's 75 s timeout (three children in all; scripts/gpu_experimental.sh runs the wider set), and that must not delay the parity suite."""
 import json
 import os
 import subprocess
@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def _run(var, value):
-    out = subprocess.run([sys.executable, os.path.join(HERE, "_experimental_child.py"), var, value], capture_output=True, text=True, timeout=100)
+    out = subprocess.run([sys.executable, os.path.join(HERE, "_experimental_child.py"), var, value], capture_output=True, text=True, timeout=75)
     assert out.returncode == 0, out.stderr[-1500:]
     line = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])
     assert line["ok"], line
@@ -23,13 +23,13 @@ def _run(var, value):
 
 
 @pytest.mark.xfail(strict=False, reason="k_topk_fast_grouped has not run on a GPU yet (written without GPU access)")
-@pytest.mark.parametrize("groups", ["4", "1"])
+@pytest.mark.parametrize("groups", ["4"])
 def test_grouped_topk_equals_default(groups):
     _run("GDR_TOPK_GROUPS", groups)
 
 
 @pytest.mark.xfail(strict=False, reason="k_score_topk_fused has not run on a GPU yet (written without GPU access)")
-@pytest.mark.parametrize("groups", ["4", "5"])
+@pytest.mark.parametrize("groups", ["4"])
 def test_fused_score_topk_equals_default(groups):
     """ONE launch scoring batch i and selecting the top-k of batch i-1 (gdr_score_fused, two handles) must return exactly what
     gdr_score_topk returns batch by batch."""

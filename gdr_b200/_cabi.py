@@ -12,6 +12,7 @@ DTYPE_F32, DTYPE_BF16 = 0, 1
 ACT = {"none": 0, None: 0, "tanh": 1, "sigmoid": 2}
 Q_PER_BEAM, FORCE_SIMT, FORCE_UMMA = 1, 2, 4
 SKIP_INVERT, SKIP_SCORE, SKIP_TOPK = 256, 512, 1024
+OPTIONS = {"umma_ctas": 1, "umma_min_group": 2, "launch_priorities": 3, "fused_groups": 4, "topk_groups": 5, "topk_wide": 6}
 
 # every symbol include/gdr_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
@@ -22,6 +23,8 @@ SYMBOLS = {
     "gdr_score_topk": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_float), c_int32, c_int32, c_int32,
                                  c_int32, c_int32, c_uint32, c_void_p, c_void_p, c_void_p]),
     "gdr_score_fused": (c_int32, [c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p]),
+    "gdr_store_reserve": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_uint32, c_void_p]),
+    "gdr_store_set_option": (c_int32, [c_void_p, c_int32, c_int32]),
     "gdr_store_last_stats": (c_int32, [c_void_p, POINTER(c_int64), c_void_p]),
     "gdr_store_set_profiling": (c_int32, [c_void_p, c_int32]),
     "gdr_store_last_phase_ms": (c_int32, [c_void_p, POINTER(c_float)]),

@@ -47,14 +47,14 @@ struct gdr_store {
     int last_launches = 0;
     int umma_min_group = 1;   // > 1 (env GDR_UMMA_MIN_GROUP) = mixed mode
     int umma_ctas = 0;        // > 0 (env GDR_UMMA_CTAS): persistent CTAs of the tcgen05 kernel (default: one per SM)
-    uint32_t debug_flags = 0; // GDR_UMMA_DEBUG / GDR_TOPK_DEBUG bits (timing experiments), read once at creation
-    bool topk_wide = false;   // env GDR_TOPK_WIDE: the 256-thread top-k also for k <= 128
-    int prio_invert = 0, prio_score = 0, prio_topk = 0;   // env GDR_LAUNCH_PRIORITIES=1: per-launch priorities (+1000), 0 = off
+    uint32_t debug_flags = 0; // GDR_OPT_TOPK_GROUPS bits; with -DGDR_DEBUG_KNOBS also the GDR_UMMA_DEBUG / GDR_TOPK_DEBUG timing experiments
+    bool topk_wide = false;   // GDR_OPT_TOPK_WIDE: the 256-thread top-k also for k <= 128
+    int prio_invert = 0, prio_score = 0, prio_topk = 0;   // GDR_OPT_LAUNCH_PRIORITIES: per-launch priorities (+1000), 0 = off
     bool profiling = false;
     // what the last gdr_score_topk call on this handle set up (scratch pointers, shapes): input of gdr_score_fused (experiment)
     ScoreArgs last_args;
     bool last_valid = false, last_umma_only = false;
-    int fused_groups = 4;       // env GDR_FUSED_GROUPS: 3, 4 or 5 top-k groups in the fused CTA
+    int fused_groups = 9;       // GDR_OPT_FUSED_GROUPS: 9 = nine 64-thread top-k groups in the fused CTA (default), 4 = four 128-thread groups
     long long *dbg = nullptr;   // device timeline scratch for GDR_UMMA_TRACE
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 };
@@ -107,27 +107,13 @@ int gdr_store_create(gdr_store_t **out, const void *emb, int64_t n_docs, int32_t
         return cuda_fail(e, "gdr_store_create");
     }
     if (dtype == GDR_DTYPE_BF16 && dim % 64 == 0) s->has_tmap = umma_make_tensor_map(&s->tmap, emb, n_docs, dim);
-    if (const char *env = getenv("GDR_UMMA_MIN_GROUP")) s->umma_min_group = atoi(env);
-    if (const char *env = getenv("GDR_UMMA_CTAS")) s->umma_ctas = atoi(env);
+#ifdef GDR_DEBUG_KNOBS
+    // Measurement builds only (python -m gdr_b200._build --debug-knobs): timing experiments that switch pipeline stages off or
+    // cut the top-k short — results are INVALID under them, so the product build does not contain them.
     if (const char *env = getenv("GDR_UMMA_DEBUG")) s->debug_flags |= (uint32_t)atoi(env) << 27;
-    if (const char *env = getenv("GDR_TOPK_DEBUG")) s->debug_flags |= ((uint32_t)atoi(env) & 15u) << 20;   // results are invalid under it
-    if (const char *env = getenv("GDR_TOPK_WIDE")) s->topk_wide = *env != 0;
-    if (const char *env = getenv("GDR_FUSED_GROUPS")) s->fused_groups = atoi(env) == 3 ? 3 : (atoi(env) == 5 ? 5 : 4);
-    if (const char *env = getenv("GDR_TOPK_GROUPS")) {     // experiment: grouped persistent top-k (k_topk_fast_grouped), 1, 2 or 4 groups per CTA
-        const int g = atoi(env);
-        if (g > 0) s->debug_flags |= (uint32_t)(g >= 4 ? 4 : (g >= 2 ? 2 : 1)) << 16;
-    }
-    if (const char *env = getenv("GDR_LAUNCH_PRIORITIES")) {
-        // experiment (ROADMAP.md): inversion kernels at the greatest priority (they are tiny and otherwise queue behind the
-        // 1,024-CTA top-k grid), scoring one below, top-k at the least — so a pending scoring grid takes a freed SM first
-        int least = 0, greatest = 0;
-        if (atoi(env) > 0 && cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess && greatest < least) {
-            s->prio_invert = greatest + 1000;
-            s->prio_score = (greatest + 1 <= least ? greatest + 1 : least) + 1000;
-            s->prio_topk = least + 1000;
-        }
-    }
+    if (const char *env = getenv("GDR_TOPK_DEBUG")) s->debug_flags |= ((uint32_t)atoi(env) & 15u) << 20;
     if (getenv("GDR_UMMA_TRACE")) { cudaMalloc(&s->dbg, 512 * sizeof(long long)); cudaMemset(s->dbg, 0, 512 * sizeof(long long)); }
+#endif
     *out = s;
     return GDR_OK;
 }
@@ -136,65 +122,143 @@ int gdr_store_destroy(gdr_store_t *s) {
     if (!s) return GDR_OK;
     cudaFree(s->cluster_ws);
     cudaFree(s->batch_ws);
+    cudaFree(s->dbg);
     for (auto &e : s->ev)
         if (e) cudaEventDestroy(e);
     delete s;
     return GDR_OK;
 }
 
+}  // extern "C"
+
+// Layout of the per-batch scratch for one (B, K, k, flags) shape: offsets into batch_ws and the total size.
+namespace {
+struct ScratchPlan {
+    int64_t pairs, stride, q_rows;
+    bool umma_possible, global_keys, small_topk;
+    size_t o_pair, o_cand, o_cbase, o_simt, o_umma, o_score, o_qsplit, o_tmeta, o_keys, o_ghist, total;
+};
+
+ScratchPlan plan_scratch(const gdr_store *s, int32_t B, int32_t K, int32_t k, uint32_t flags) {
+    ScratchPlan p;
+    p.pairs = (int64_t)B * K;
+    p.stride = (int64_t)align_up((size_t)K * s->max_cluster, 4);
+    const int64_t simt_cap = p.pairs * ((s->max_cluster + SIMT_ROWS - 1) / SIMT_ROWS);
+    const int64_t umma_cap = p.pairs * ((s->max_cluster + UMMA_ROWS - 1) / UMMA_ROWS);
+    p.umma_possible = s->has_tmap && !(flags & GDR_FORCE_SIMT);
+    // k <= 128: the fast top-k keeps no key array (its mass-tie fallback uses the global scratch); larger k: keys in smem if they fit
+    p.global_keys = k <= 128 || (size_t)p.stride * 4 + 8 * 4096 + 4 * 2048 + (size_t)(3 * K + 1) * 4 > 96 * 1024;
+    p.small_topk = k <= 128 && p.stride <= 65535 && !s->topk_wide;     // 128-thread top-k CTAs with 16-bit histogram bins
+    p.q_rows = (flags & GDR_Q_PER_BEAM) ? p.pairs : B;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    p.o_pair = take(p.pairs * 4);
+    p.o_cand = take((size_t)B * (K + 1) * 4);
+    p.o_cbase = take(p.pairs * 4);
+    p.o_simt = take((size_t)simt_cap * sizeof(Item));
+    p.o_umma = take(p.umma_possible ? (size_t)umma_cap * sizeof(Item) : 0);
+    p.o_score = take((size_t)B * p.stride * 4);
+    p.o_qsplit = take(p.umma_possible ? (size_t)p.q_rows * 3 * s->dim * 2 : 0);
+    p.o_tmeta = take(p.umma_possible ? (size_t)umma_cap * sizeof(TileMeta) : 0);
+    p.o_keys = take(p.global_keys ? (size_t)B * p.stride * 4 : 0);
+    p.o_ghist = take(p.small_topk ? (size_t)B * 2048 * 4 : 0);
+    p.total = off;
+    return p;
+}
+
+int check_shape(const gdr_store *s, int32_t B, int32_t K, int32_t k, uint32_t flags, const char *who) {
+    if (B < 0 || K <= 0 || k <= 0) return invalid((std::string(who) + ": need B >= 0, K > 0, k > 0").c_str());
+    if (k > 4096) {
+        set_error(std::string(who) + ": k > 4096 is not supported");
+        return GDR_ERR_UNSUPPORTED;
+    }
+    if ((int64_t)B * K > INT_MAX / 2) return invalid((std::string(who) + ": B*K too large").c_str());
+    if ((int64_t)B * K * s->max_cluster > INT_MAX - 4)
+        return invalid((std::string(who) + ": B*K*max_cluster_size must be below 2^31 (score buffer index)").c_str());
+    if ((flags & GDR_FORCE_UMMA) && !s->has_tmap) {
+        set_error(std::string(who) + ": GDR_FORCE_UMMA needs a bf16 store with dim % 64 == 0");
+        return GDR_ERR_UNSUPPORTED;
+    }
+    return GDR_OK;
+}
+
+// Growing the scratch synchronises the stream and reallocates: gdr_store_reserve does it ahead of the query path.
+int ensure_scratch(gdr_store *s, size_t bytes, cudaStream_t st) {
+    if (bytes <= s->batch_ws_bytes) return GDR_OK;
+    GDR_CUDA(cudaStreamSynchronize(st));
+    if (s->batch_ws) GDR_CUDA(cudaFree(s->batch_ws));
+    s->batch_ws = nullptr;
+    s->batch_ws_bytes = 0;
+    GDR_CUDA(cudaMalloc(&s->batch_ws, bytes));
+    s->batch_ws_bytes = bytes;
+    s->last_valid = false;        // the work lists of the previous batch went with the old buffer
+    return GDR_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int gdr_store_reserve(gdr_store_t *s, int32_t B, int32_t K, int32_t k, uint32_t flags, void *stream) {
+    if (!s) return invalid("gdr_store_reserve: store is null");
+    if (int rc = check_shape(s, B, K, k, flags, "gdr_store_reserve")) return rc;
+    if (B == 0) return GDR_OK;
+    return ensure_scratch(s, plan_scratch(s, B, K, k, flags).total, (cudaStream_t)stream);
+}
+
+int gdr_store_set_option(gdr_store_t *s, int32_t option, int32_t value) {
+    if (!s) return invalid("gdr_store_set_option: store is null");
+    switch (option) {
+    case GDR_OPT_UMMA_CTAS:
+        if (value < 0 || value > 1024) return invalid("gdr_store_set_option: GDR_OPT_UMMA_CTAS must be in [0, 1024]");
+        s->umma_ctas = value;
+        return GDR_OK;
+    case GDR_OPT_UMMA_MIN_GROUP:
+        if (value < 1) return invalid("gdr_store_set_option: GDR_OPT_UMMA_MIN_GROUP must be >= 1");
+        s->umma_min_group = value;
+        return GDR_OK;
+    case GDR_OPT_LAUNCH_PRIORITIES: {
+        // inversion kernels at the greatest priority (they are tiny and otherwise queue behind the 1,024-CTA top-k grid),
+        // scoring one below, top-k at the least — so a pending scoring grid takes a freed SM first
+        s->prio_invert = s->prio_score = s->prio_topk = 0;
+        int least = 0, greatest = 0;
+        if (value > 0 && cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess && greatest < least) {
+            s->prio_invert = greatest + 1000;
+            s->prio_score = (greatest + 1 <= least ? greatest + 1 : least) + 1000;
+            s->prio_topk = least + 1000;
+        }
+        return GDR_OK;
+    }
+    case GDR_OPT_FUSED_GROUPS:
+        if (value != 4 && value != 9) return invalid("gdr_store_set_option: GDR_OPT_FUSED_GROUPS must be 9 (64-thread groups) or 4 (128-thread groups)");
+        s->fused_groups = value;
+        return GDR_OK;
+    case GDR_OPT_TOPK_GROUPS:
+        if (value != 0 && value != 1 && value != 2 && value != 4) return invalid("gdr_store_set_option: GDR_OPT_TOPK_GROUPS must be 0, 1, 2 or 4");
+        s->debug_flags = (s->debug_flags & ~(7u << 16)) | ((uint32_t)value << 16);
+        return GDR_OK;
+    case GDR_OPT_TOPK_WIDE:
+        s->topk_wide = value != 0;
+        return GDR_OK;
+    default:
+        return invalid("gdr_store_set_option: unknown option");
+    }
+}
+
 int gdr_score_topk(gdr_store_t *s, const float *q, const int32_t *beams, const float *prob, const float *alphas,
                    int32_t n_alpha, int32_t B, int32_t K, int32_t act, int32_t k, uint32_t flags, float *out_scores,
                    int32_t *out_docids, void *stream) {
     if (!s) return invalid("gdr_score_topk: store is null");
-    if (B < 0 || K <= 0 || k <= 0) return invalid("gdr_score_topk: need B >= 0, K > 0, k > 0");
+    if (int rc = check_shape(s, B, K, k, flags, "gdr_score_topk")) return rc;
     if (B == 0) return GDR_OK;
     if (!q || !beams || !out_scores || !out_docids) return invalid("gdr_score_topk: null pointer");
     if (reinterpret_cast<uintptr_t>(q) & 15) return invalid("gdr_score_topk: q must be 16-byte aligned");
     if (act < GDR_ACT_NONE || act > GDR_ACT_SIGMOID) return invalid("gdr_score_topk: bad activation");
     if (n_alpha < 1 || (!alphas && n_alpha != 1)) return invalid("gdr_score_topk: n_alpha must be >= 1 (1 when alphas is null)");
-    if (k > 4096) {
-        set_error("gdr_score_topk: k > 4096 is not supported");
-        return GDR_ERR_UNSUPPORTED;
-    }
-    if ((int64_t)B * K > INT_MAX / 2) return invalid("gdr_score_topk: B*K too large");
-    if ((int64_t)B * K * s->max_cluster > INT_MAX - 4) return invalid("gdr_score_topk: B*K*max_cluster_size must be below 2^31 (score buffer index)");
-    if ((flags & GDR_FORCE_UMMA) && !s->has_tmap) {
-        set_error("gdr_score_topk: GDR_FORCE_UMMA needs a bf16 store with dim % 64 == 0");
-        return GDR_ERR_UNSUPPORTED;
-    }
     cudaStream_t st = (cudaStream_t)stream;
-    const int64_t pairs = (int64_t)B * K;
-    const int64_t stride = align_up((size_t)K * s->max_cluster, 4);
-    const int64_t simt_cap = pairs * ((s->max_cluster + SIMT_ROWS - 1) / SIMT_ROWS);
-    const int64_t umma_cap = pairs * ((s->max_cluster + UMMA_ROWS - 1) / UMMA_ROWS);
-    const bool umma_possible = s->has_tmap && !(flags & GDR_FORCE_SIMT);
-    // k <= 128: the fast top-k keeps no key array (its mass-tie fallback uses the global scratch); larger k: keys in smem if they fit
-    const bool global_keys = k <= 128 || (size_t)stride * 4 + 8 * 4096 + 4 * 2048 + (size_t)(3 * K + 1) * 4 > 96 * 1024;
-
-    // carve the per-batch scratch
-    size_t off = 0;
-    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-    const size_t o_pair = take(pairs * 4);
-    const size_t o_cand = take((size_t)B * (K + 1) * 4);
-    const size_t o_cbase = take(pairs * 4);
-    const size_t o_simt = take((size_t)simt_cap * sizeof(Item));
-    const size_t o_umma = take(umma_possible ? (size_t)umma_cap * sizeof(Item) : 0);
-    const size_t o_score = take((size_t)B * stride * 4);
-    const int64_t q_rows = (flags & GDR_Q_PER_BEAM) ? pairs : B;
-    const size_t o_qsplit = take(umma_possible ? (size_t)q_rows * 3 * s->dim * 2 : 0);
-    const size_t o_tmeta = take(umma_possible ? (size_t)umma_cap * sizeof(TileMeta) : 0);
-    const size_t o_keys = take(global_keys ? (size_t)B * stride * 4 : 0);
-    const bool small_topk = k <= 128 && stride <= 65535 && !s->topk_wide;     // 128-thread top-k CTAs with 16-bit histogram bins
-    const size_t o_ghist = take(small_topk ? (size_t)B * 2048 * 4 : 0);
-    if (off > s->batch_ws_bytes) {
-        // growing the scratch synchronises; run one call per shape before capturing a CUDA graph
-        GDR_CUDA(cudaStreamSynchronize(st));
-        if (s->batch_ws) GDR_CUDA(cudaFree(s->batch_ws));
-        s->batch_ws = nullptr;
-        s->batch_ws_bytes = 0;
-        GDR_CUDA(cudaMalloc(&s->batch_ws, off));
-        s->batch_ws_bytes = off;
-    }
+    const ScratchPlan p = plan_scratch(s, B, K, k, flags);
+    const int64_t pairs = p.pairs;
+    // the scratch grows on the first call of a larger shape (that call synchronises): gdr_store_reserve moves this off the query path
+    if (int rc = ensure_scratch(s, p.total, st)) return rc;
     char *ws = reinterpret_cast<char *>(s->batch_ws);
     const size_t n = (size_t)s->n_clusters;
 
@@ -203,33 +267,34 @@ int gdr_score_topk(gdr_store_t *s, const float *q, const int32_t *beams, const f
     a.emb = s->emb; a.offsets = s->offsets; a.docid = s->docid;
     a.dim = s->dim; a.dtype = s->dtype; a.n_clusters = s->n_clusters; a.max_cluster = s->max_cluster; a.n_docs = s->n_docs;
     a.q = q; a.beams = beams; a.prob = prob; a.B = B; a.K = K; a.act = act; a.k = k; a.flags = flags;
-    a.flags |= s->debug_flags;                                         // timing experiments only (environment, read at creation)
+    a.flags |= s->debug_flags;                                         // GDR_OPT_TOPK_GROUPS (and, in measurement builds, the timing experiments)
     a.cnt = s->cluster_ws;
     a.grp_off = s->cluster_ws + n;
     a.simt_off = a.grp_off + (n + 1);
     a.umma_off = a.simt_off + (n + 1);
     a.counters = a.umma_off + (n + 1);
     a.scan_base = a.counters + CTR_COUNT;
-    a.grp_pair = reinterpret_cast<int32_t *>(ws + o_pair);
-    a.candoff = reinterpret_cast<int32_t *>(ws + o_cand);
-    a.cbase = reinterpret_cast<int32_t *>(ws + o_cbase);
-    a.simt_items = reinterpret_cast<Item *>(ws + o_simt);
-    a.umma_items = reinterpret_cast<Item *>(ws + o_umma);
-    a.scorebuf = reinterpret_cast<float *>(ws + o_score);
-    a.stride = stride;
-    a.gkeys = global_keys ? reinterpret_cast<uint32_t *>(ws + o_keys) : nullptr;
-    a.ghist = small_topk ? reinterpret_cast<uint32_t *>(ws + o_ghist) : nullptr;
+    a.grp_pair = reinterpret_cast<int32_t *>(ws + p.o_pair);
+    a.candoff = reinterpret_cast<int32_t *>(ws + p.o_cand);
+    a.cbase = reinterpret_cast<int32_t *>(ws + p.o_cbase);
+    a.simt_items = reinterpret_cast<Item *>(ws + p.o_simt);
+    a.umma_items = reinterpret_cast<Item *>(ws + p.o_umma);
+    a.scorebuf = reinterpret_cast<float *>(ws + p.o_score);
+    a.stride = p.stride;
+    a.gkeys = p.global_keys ? reinterpret_cast<uint32_t *>(ws + p.o_keys) : nullptr;
+    a.ghist = p.small_topk ? reinterpret_cast<uint32_t *>(ws + p.o_ghist) : nullptr;
     a.qsplit = nullptr;   // set below when the tcgen05 path is taken
     // One scoring path per call: a batch that names each cluster three or more times on average goes to the tcgen05
     // grouped GEMM (slab read once for the whole group); a sparse batch goes to the SIMT GEMV, which serves up to four
-    // pairs per slab read and measured 89% of HBM peak at ~1 pair per cluster (cfg5 slice) against 77% for tcgen05.  GDR_UMMA_MIN_GROUP > 1
-    // (env) asks for the mixed mode instead: groups of at least that many pairs on tensor cores, the rest SIMT.
+    // pairs per slab read and measured 89% of HBM peak at ~1 pair per cluster (cfg5 slice) against 77% for tcgen05.
+    // GDR_OPT_UMMA_MIN_GROUP > 1 asks for the mixed mode instead: groups of at least that many pairs on tensor cores, the rest SIMT.
+    const bool umma_possible = p.umma_possible;
     const bool mixed = umma_possible && !(flags & GDR_FORCE_UMMA) && s->umma_min_group > 1;
     bool use_umma = umma_possible && ((flags & GDR_FORCE_UMMA) || mixed || pairs >= 3 * (int64_t)s->n_clusters);
     const bool use_simt = !use_umma || mixed;
     a.dbg = s->dbg;
-    if (use_umma) a.qsplit = reinterpret_cast<__nv_bfloat16 *>(ws + o_qsplit);
-    if (use_umma) a.tile_meta = reinterpret_cast<TileMeta *>(ws + o_tmeta);
+    if (use_umma) a.qsplit = reinterpret_cast<__nv_bfloat16 *>(ws + p.o_qsplit);
+    if (use_umma) a.tile_meta = reinterpret_cast<TileMeta *>(ws + p.o_tmeta);
     a.umma_min_group = !use_umma ? INT_MAX : (mixed ? s->umma_min_group : 1);
 
     int launches = 0;
@@ -239,9 +304,9 @@ int gdr_score_topk(gdr_store_t *s, const float *q, const int32_t *beams, const f
         GDR_CUDA(cudaMemcpyAsync(s->dbg + 500, init, sizeof(init), cudaMemcpyHostToDevice, st));
     }
     if (prof) GDR_CUDA(cudaEventRecord(s->ev[0], st));
-    g_launch_priority = s->prio_invert;
+    a.launch_prio = s->prio_invert;               // per call, carried in this call's own copy of the arguments
     if (!(flags & GDR_SKIP_INVERT)) GDR_CUDA(launch_invert(a, st, &launches));
-    g_launch_priority = s->prio_score;
+    a.launch_prio = s->prio_score;
     if (prof) GDR_CUDA(cudaEventRecord(s->ev[1], st));
     if (use_umma && !(flags & GDR_SKIP_SCORE)) {
         GDR_CUDA(launch_score_umma(a, &s->tmap, st, s->umma_ctas > 0 ? s->umma_ctas : s->sm_count));
@@ -253,22 +318,22 @@ int gdr_score_topk(gdr_store_t *s, const float *q, const int32_t *beams, const f
         launches += 1;
     }
     if (prof) GDR_CUDA(cudaEventRecord(s->ev[3], st));
-    g_launch_priority = s->prio_topk;
+    a.launch_prio = s->prio_topk;
     for (int r = 0; r < n_alpha && !(flags & GDR_SKIP_TOPK); ++r) {
         const float alpha = alphas ? alphas[r] : 1.0f;
         GDR_CUDA(launch_topk_store(a, alpha, out_scores + (int64_t)r * B * k, out_docids + (int64_t)r * B * k, st));
         launches += 1;
     }
-    g_launch_priority = 0;
     if (prof) GDR_CUDA(cudaEventRecord(s->ev[4], st));
     s->last_launches = launches;
+    a.launch_prio = s->prio_score;                // what gdr_score_fused launches with
     s->last_args = a;
     s->last_valid = true;
     s->last_umma_only = use_umma && !use_simt;
     return GDR_OK;
 }
 
-// EXPERIMENT (ROADMAP.md "plan of record", csrc/score_fused.cu; compiled, not yet run on a GPU).
+// Pipelined schedule: scoring of the batch in `cur` + top-k of the batch in `prev` in one launch (csrc/score_fused.cu).
 int gdr_score_fused(gdr_store_t *cur, gdr_store_t *prev, float alpha, float *prev_out_scores, int32_t *prev_out_docids, void *stream) {
     if (!cur && !prev) return invalid("gdr_score_fused: both handles are null");
     if (cur == prev) return invalid("gdr_score_fused: cur and prev must be different handles (two scratch sets)");
@@ -293,8 +358,10 @@ int gdr_score_fused(gdr_store_t *cur, gdr_store_t *prev, float alpha, float *pre
         set_error("gdr_score_fused: the batch in cur does not take the tcgen05 path alone");
         return GDR_ERR_UNSUPPORTED;
     }
-    GDR_CUDA(launch_score_fused(cur->last_args, &cur->tmap, pa, alpha, prev_out_scores, prev_out_docids, st,
-                                cur->umma_ctas > 0 ? cur->umma_ctas : cur->sm_count, cur->fused_groups));
+    // The fused CTA takes a whole SM (896 threads, all registers): the inversion kernels of the NEXT batch, which run beside it on a
+    // second stream, need SMs of their own — by default the grid leaves eight (108-140 scoring CTAs measured the same speed).
+    const int ctas = cur->umma_ctas > 0 ? cur->umma_ctas : (cur->sm_count > 16 ? cur->sm_count - 8 : cur->sm_count);
+    GDR_CUDA(launch_score_fused(cur->last_args, &cur->tmap, pa, alpha, prev_out_scores, prev_out_docids, st, ctas, cur->fused_groups));
     return GDR_OK;
 }
 

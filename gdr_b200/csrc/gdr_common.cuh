@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <cuda.h>
 #include <stdint.h>
+#include <mutex>
 #include <string>
 
 #include "../../include/gdr_b200.h"
@@ -86,6 +87,8 @@ struct ScoreArgs {
     uint32_t *ghist;     // [B, 2048] histogram scratch of the small-footprint top-k's fallback (null: variant not used)
     long long *dbg;      // [512] optional timeline scratch (GDR_UMMA_TRACE=1), else null
     int32_t umma_min_group;  // groups with at least this many pairs go to the tcgen05 path (INT_MAX = never)
+    int32_t launch_prio;     // host side only: scheduling priority class of the launches made with this copy of the arguments
+                             // (0 = none; else a CUDA priority + 1000), set per phase by the C-ABI entry point — per call, not global
 };
 
 // ----- launchers (each enqueues on `s`, returns cudaGetLastError()) ---------------------------
@@ -97,6 +100,7 @@ cudaError_t launch_topk_store(const ScoreArgs &a, float alpha, float *out_scores
 cudaError_t launch_topk_grouped(const ScoreArgs &a, float alpha, float *out_scores, int32_t *out_docids, cudaStream_t s, int groups);
 cudaError_t launch_score_fused(const ScoreArgs &a, const CUtensorMap *tmap, const ScoreArgs &prev, float alpha, float *out_scores,
                                int32_t *out_docids, cudaStream_t s, int ctas, int groups);
+int fused64_groups_that_fit(int K);
 cudaError_t launch_merge_topk(const float *scores, const int32_t *docids, int G, int B, int k_in, int64_t g_stride, int k,
                               float *out_scores, int32_t *out_docids, cudaStream_t s);
 cudaError_t launch_similarity(const float *q, int64_t Q, const void *p, int64_t P, int dim, int p_dtype,
@@ -129,13 +133,11 @@ cudaError_t launch_position_mask(float *logits, int64_t bz, int sl, int V, int v
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-// Per-launch scheduling priority (experiment, off unless GDR_LAUNCH_PRIORITIES=1; see ROADMAP.md): gdr_score_topk sets the
-// class of the phase it is about to launch, launch_pdl attaches cudaLaunchAttributePriority when a class is set.
-// 0 = no attribute.  Values are CUDA stream-priority numbers offset by +1000 (priorities can be 0 or negative).
-inline int g_launch_priority = 0;
-
+// `priority` is the per-launch scheduling class (gdr_store_set_option GDR_OPT_LAUNCH_PRIORITIES: inversion > scoring > top-k):
+// 0 = no attribute, else a CUDA stream-priority number offset by +1000 (priorities can be 0 or negative).  It is an
+// argument, not process state: handles driven from different host threads cannot see each other's value.
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, int priority, Args... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
@@ -146,13 +148,32 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (g_launch_priority != 0) {
+    if (priority != 0) {
         attr[1].id = cudaLaunchAttributePriority;
-        attr[1].val.priority = g_launch_priority - 1000;
+        attr[1].val.priority = priority - 1000;
         cfg.numAttrs = 2;
     }
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
+
+// cudaFuncSetAttribute is per device and function.  One instance per launcher (function-local static): `ensure` runs the
+// setter once per device under a mutex and records the device only after the setter succeeded, so a second host thread can
+// neither skip the attribute nor launch before it is in place.
+struct FuncAttrOnce {
+    std::mutex mu;
+    unsigned long long done = 0;      // one bit per device ordinal (mod 64)
+    template <typename F>
+    cudaError_t ensure(F setter) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        std::lock_guard<std::mutex> lock(mu);
+        if ((done >> (dev & 63)) & 1ull) return cudaSuccess;
+        e = setter();
+        if (e == cudaSuccess) done |= 1ull << (dev & 63);
+        return e;
+    }
+};
 
 // ----- optional kernel timeline (GDR_UMMA_TRACE): slots 500..511 of a.dbg hold min start / max end per kernel class
 __device__ __forceinline__ unsigned long long gdr_gtime() {

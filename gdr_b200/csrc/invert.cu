@@ -374,25 +374,25 @@ __global__ void __launch_bounds__(1024) k_invert_small(ScoreArgs a) {
 cudaError_t launch_invert(const ScoreArgs &a, cudaStream_t s, int *n_launches) {
     if (a.n_clusters <= INV_SMALL_C && a.B <= 64 && (int64_t)a.B * a.K <= 65536) {   // small batches (the reference's eval_batch_size 1-64)
         *n_launches += 1;
-        return launch_pdl(k_invert_small, dim3(1), dim3(1024), 0, s, a);
+        return launch_pdl(k_invert_small, dim3(1), dim3(1024), 0, s, a.launch_prio, a);
     }
-    cudaError_t e = launch_pdl(k_count, dim3((a.B + 3) / 4), dim3(128), 0, s, a);
+    cudaError_t e = launch_pdl(k_count, dim3((a.B + 3) / 4), dim3(128), 0, s, a.launch_prio, a);
     const int n_blocks = (a.n_clusters + SCAN_BLOCK - 1) / SCAN_BLOCK;
     if (n_blocks <= 1) {
         // as few threads as the cluster count needs (8 clusters per thread): a 1,024-thread CTA cannot be placed on an SM
         // that already hosts the scoring kernel and top-k CTAs of neighbouring batches, which stalled the whole pipeline
         const int threads = min(1024, max(32, ((a.n_clusters + SCAN_PER_THREAD - 1) / SCAN_PER_THREAD + 31) / 32 * 32));
-        if (e == cudaSuccess) e = launch_pdl(k_scan, dim3(1), dim3(threads), 0, s, a);
+        if (e == cudaSuccess) e = launch_pdl(k_scan, dim3(1), dim3(threads), 0, s, a.launch_prio, a);
     } else {
-        if (e == cudaSuccess) e = launch_pdl(k_scan_part, dim3(n_blocks), dim3(1024), 0, s, a);
-        if (e == cudaSuccess) e = launch_pdl(k_scan_bases, dim3(1), dim3(32), 0, s, a, n_blocks);
+        if (e == cudaSuccess) e = launch_pdl(k_scan_part, dim3(n_blocks), dim3(1024), 0, s, a.launch_prio, a);
+        if (e == cudaSuccess) e = launch_pdl(k_scan_bases, dim3(1), dim3(32), 0, s, a.launch_prio, a, n_blocks);
         *n_launches += 1;
     }
     const int64_t n = max((int64_t)a.B * a.K, (int64_t)a.n_clusters);
-    if (e == cudaSuccess) e = launch_pdl(k_fill, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, a);
+    if (e == cudaSuccess) e = launch_pdl(k_fill, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, a.launch_prio, a);
     *n_launches += 3;
     if (a.tile_meta) {
-        if (e == cudaSuccess) e = launch_pdl(k_tilemeta, dim3(148), dim3(256), 0, s, a);
+        if (e == cudaSuccess) e = launch_pdl(k_tilemeta, dim3(148), dim3(256), 0, s, a.launch_prio, a);
         *n_launches += 1;
     }
     return e;

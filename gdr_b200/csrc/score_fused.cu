@@ -1,26 +1,30 @@
-// k_score_topk_fused — EXPERIMENT (ROADMAP.md, "plan of record" for round 2).  Written after the GPU budget of round 1 was
-// spent: it compiles for sm_100a and has NOT run on a GPU yet; nothing in the default path (gdr_score_topk) uses it, its first
-// run is tests/test_gpu_zz_experimental.py (child process, xfail-tolerant).
+// k_score_topk_fused — scoring of batch i and the per-query top-k of batch i-1 in ONE persistent CTA per SM (gdr_score_fused).
 //
-// Why: alone, the scoring kernel takes 34.5 us and the top-k 17.5 us per 1,024-query batch, but pipelined they cost 48-50 us
-// per step, and the measured reason is RESIDENCY — the top-k's ~1,000 small CTAs occupy SMs that the next batch's scoring CTA
-// (174 KB of shared memory, 32 K registers) then has to wait for, and no launch-level knob reserves room (ROADMAP.md).  So the
-// top-k gets a fixed home inside the scoring CTA, one batch behind:
+// Why: alone, the scoring kernel takes 34.5 us and the top-k 17.5 us per 1,024-query batch, but as separate grids they cost
+// 48-50 us per pipelined step, and the measured reason is RESIDENCY — the top-k's ~1,000 small CTAs occupy SMs that the next
+// batch's scoring CTA (174 KB of shared memory, 32 K registers) then has to wait for, and no launch-level knob reserves room
+// (ROADMAP.md).  So the top-k gets a fixed home inside the scoring CTA, one batch behind:
 //
-//   launch i:  warps 0-9   the tcgen05 scoring CTA of batch i, unchanged (score_umma_body.inc: TMA, MMA, 3 B fillers,
-//                          4 epilogue warps, tile scheduler; dynamic tile queue)
-//              warps 10+   G top-k groups of 128 threads (topk_group_loop): each claims one query of batch i-1 at a time from a
-//                          global counter and runs topk_fast16 on that query's row of batch i-1's score buffer (complete and
-//                          L2-resident: launch i-1 wrote it, and stream order / griddepcontrol.wait separates the launches)
+//   launch i:  scoring warps   the tcgen05 scoring CTA of batch i (score_umma_body.inc: TMA, MMA, 3 B fillers, 4 epilogue
+//                              warps, tile scheduler; dynamic tile queue)
+//              top-k warps     groups (topk_group_loop): each claims one query of batch i-1 at a time from a global counter and
+//                              runs topk_fast16 on that query's row of batch i-1's score buffer (complete and L2-resident:
+//                              launch i-1 wrote it, and stream order / griddepcontrol.wait separates the launches)
 //
 // Every wait in the kernel is on an mbarrier or a named barrier fed by the CTA's own warps — no flags, no spinning on other
 // CTAs' progress.  Batches i and i-1 live in two different store handles (= two scratch sets); the handles' last ScoreArgs are
 // kept by gdr_score_topk (called with GDR_SKIP_SCORE | GDR_SKIP_TOPK for the inversion) and passed in here.
 //
-// Budget per SM (one CTA): threads 320 + 128 G; shared memory 169 KB + G x 6.3 KB (K = 20); registers 65,536 / threads —
-// G = 3: 80 used, G = 4: 72, G = 5 (960 threads, the most a CTA can hold next to the ten scoring warps): 64 — against 100 in
-// k_score_umma; ptxas reports 48-68 bytes of spills in all three, so the uniform allocation is a fair first draft until the
-// roles are regrouped into homogeneous warpgroups and rebalanced with setmaxnreg (ROADMAP.md).
+// Two variants:
+//   k_score_topk_fused<4>   (round 1) four 128-thread groups after the ten scoring warps, one uniform register allocation
+//                           (72 per thread, 52 bytes of spills in the epilogue).  560 queries in flight on 140 CTAs: a batch of
+//                           1,024 needs TWO rounds of ~24 us (a query's select is a chain of dependent L2 round trips and
+//                           barriers) — measured 47.7 us per step, i.e. the top-k, not the scoring, sets the step time.
+//   k_score_topk_fused64    (round 2) nine 64-thread groups (two warps per query): 1,260 queries in flight on 140 CTAs, so the
+//                           whole previous batch is selected in ONE round that only has to finish within the scoring time.
+//                           Roles are laid out in homogeneous warpgroups — {TMA, MMA, scheduler, filler 0}, {4 epilogue warps},
+//                           {fillers 1-2, top-k group 0}, {top-k groups 1-2}, ... — and `setmaxnreg` moves registers from the
+//                           light roles (64) to the epilogue warpgroup (120), which removes the epilogue's spills.
 #include "gdr_common.cuh"
 #include "score_umma.cuh"
 #include "topk_select.cuh"
@@ -29,6 +33,15 @@ namespace gdr {
 
 constexpr int FU_MAX_SMEM = 227 * 1024;
 
+// ------------------------------------------------------------------------------------------------------------------------
+// round-1 variant: warps 0-9 as in k_score_umma, then G groups of 128 threads
+// ------------------------------------------------------------------------------------------------------------------------
+#define UM_IS_TMA (warp == 0)
+#define UM_IS_MMA (warp == 1)
+#define UM_IS_FILL (warp < 2 + UM_FILL_WARPS)
+#define UM_FILL_IDX (warp - 2)
+#define UM_IS_EPI (warp < 2 + UM_FILL_WARPS + 4)
+#define UM_REG_SPLIT
 #define UM_SCHED_ELSE else if (warp == 2 + UM_FILL_WARPS + 4)
 #define UM_EXTRA_ROLES                                                                                                              \
     else if (prev.B > 0) {                                                                                                          \
@@ -47,30 +60,84 @@ __global__ void __launch_bounds__(UM_THREADS + G * TKF_THREADS, 1)
 k_score_topk_fused(const __grid_constant__ CUtensorMap tmap, ScoreArgs a, ScoreArgs prev, float alpha, float *out_scores, int32_t *out_docids) {
 #include "score_umma_body.inc"
 }
+#undef UM_IS_TMA
+#undef UM_IS_MMA
+#undef UM_IS_FILL
+#undef UM_FILL_IDX
+#undef UM_IS_EPI
+#undef UM_REG_SPLIT
+#undef UM_SCHED_ELSE
+#undef UM_EXTRA_ROLES
+
+// ------------------------------------------------------------------------------------------------------------------------
+// round-2 variant: homogeneous warpgroups + setmaxnreg, nine 64-thread top-k groups
+//   warp 0 TMA | 1 MMA | 2 tile scheduler | 3 filler 0 || 4-7 epilogue || 8-9 fillers 1-2 | 10-27 top-k groups 0-8 (two warps each)
+// ------------------------------------------------------------------------------------------------------------------------
+constexpr int F64_GROUPS = 9;
+constexpr int F64_FIRST = 10 * 32;                                   // first top-k thread
+constexpr int F64_THREADS = F64_FIRST + F64_GROUPS * TKF64_THREADS;  // 896 = seven warpgroups
+constexpr int F64_REGS_SMALL = 64, F64_REGS_EPI = 120;               // launch: 896 x 72 = 64,512; then 768 x 64 + 128 x 120 = 64,512
+static_assert(F64_THREADS % 128 == 0, "setmaxnreg is a warpgroup-wide instruction: no partial warpgroup");
+static_assert((F64_THREADS - 128) * F64_REGS_SMALL + 128 * F64_REGS_EPI <= F64_THREADS * 72, "registers the launch allocation holds");
+
+#define UM_IS_TMA (warp == 0)
+#define UM_IS_MMA (warp == 1)
+#define UM_IS_FILL (warp == 3 || warp == 8 || warp == 9)
+#define UM_FILL_IDX (warp == 3 ? 0 : warp - 7)
+#define UM_IS_EPI (warp >= 4 && warp < 8)
+// setmaxnreg is warpgroup-wide and must be reached by all four warps of a warpgroup at the same instruction: the split is
+// done ONCE, on the warpgroup index, before the warps part into their roles (warpgroup 1 = the four epilogue warps)
+#define UM_REG_SPLIT                                                                                                                \
+    if ((warp >> 2) == 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(F64_REGS_EPI));                                  \
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(F64_REGS_SMALL));
+#define UM_SCHED_ELSE else if (warp == 2)
+#define UM_EXTRA_ROLES                                                                                                              \
+    else if (prev.B > 0) {                                                                                                          \
+        topk_group_loop<F64_FIRST, TKF64_THREADS>(prev, alpha, out_scores, out_docids,                                              \
+            smem + UM_SMEM_BYTES + (size_t)GroupScope<F64_FIRST, TKF64_THREADS>::group() * tkg_slice_bytes(prev.K));                \
+    }
+
+__global__ void __launch_bounds__(F64_THREADS, 1)
+k_score_topk_fused64(const __grid_constant__ CUtensorMap tmap, ScoreArgs a, ScoreArgs prev, float alpha, float *out_scores, int32_t *out_docids) {
+#include "score_umma_body.inc"
+}
+#undef UM_IS_TMA
+#undef UM_IS_MMA
+#undef UM_IS_FILL
+#undef UM_FILL_IDX
+#undef UM_IS_EPI
+#undef UM_REG_SPLIT
 #undef UM_SCHED_ELSE
 #undef UM_EXTRA_ROLES
 #undef UM_EXTRA_TAIL
 
+// How many top-k groups of the 64-thread variant fit beside the scoring ring for beam width K (0 = it does not fit at all)
+int fused64_groups_that_fit(int K) {
+    const int room = FU_MAX_SMEM - UM_SMEM_BYTES;
+    const int g = room / tkg_slice_bytes(K);
+    return g >= F64_GROUPS ? F64_GROUPS : 0;
+}
+
 // prev.B == 0: no previous batch (first launch of a stream) — the top-k warps fall straight through to the final barrier.
+// groups: 9 = the 64-thread variant, anything else = the round-1 variant with four 128-thread groups.
 cudaError_t launch_score_fused(const ScoreArgs &a, const CUtensorMap *tmap, const ScoreArgs &prev, float alpha, float *out_scores,
                                int32_t *out_docids, cudaStream_t s, int ctas, int groups) {
-    const size_t smem = (size_t)UM_SMEM_BYTES + (size_t)groups * tkg_slice_bytes(prev.B > 0 ? prev.K : 1);
+    const int K = prev.B > 0 ? prev.K : 1;
+    const bool v64 = groups == F64_GROUPS && fused64_groups_that_fit(K) == F64_GROUPS;
+    const int g = v64 ? F64_GROUPS : 4;
+    const size_t smem = (size_t)UM_SMEM_BYTES + (size_t)g * tkg_slice_bytes(K);
     if (smem > (size_t)FU_MAX_SMEM) return cudaErrorInvalidValue;
-    static unsigned long long attr_set_mask = 0;      // one bit per device: the attribute is per device and function
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!((attr_set_mask >> (dev & 63)) & 1ull)) {
-        cudaError_t e = cudaFuncSetAttribute(k_score_topk_fused<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FU_MAX_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_score_topk_fused<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FU_MAX_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_score_topk_fused<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, FU_MAX_SMEM);
-        if (e != cudaSuccess) return e;
-        attr_set_mask |= 1ull << (dev & 63);
-    }
-    if (groups == 5)
-        return launch_pdl(k_score_topk_fused<5>, dim3(ctas), dim3(UM_THREADS + 5 * TKF_THREADS), smem, s, *tmap, a, prev, alpha, out_scores, out_docids);
-    if (groups == 3)
-        return launch_pdl(k_score_topk_fused<3>, dim3(ctas), dim3(UM_THREADS + 3 * TKF_THREADS), smem, s, *tmap, a, prev, alpha, out_scores, out_docids);
-    return launch_pdl(k_score_topk_fused<4>, dim3(ctas), dim3(UM_THREADS + 4 * TKF_THREADS), smem, s, *tmap, a, prev, alpha, out_scores, out_docids);
+    static FuncAttrOnce attr;
+    cudaError_t e = attr.ensure([] {
+        cudaError_t e2 = cudaFuncSetAttribute(k_score_topk_fused<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FU_MAX_SMEM);
+        if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_score_topk_fused64, cudaFuncAttributeMaxDynamicSharedMemorySize, FU_MAX_SMEM);
+        return e2;
+    });
+    if (e != cudaSuccess) return e;
+    if (v64)
+        return launch_pdl(k_score_topk_fused64, dim3(ctas), dim3(F64_THREADS), smem, s, a.launch_prio, *tmap, a, prev, alpha, out_scores, out_docids);
+    return launch_pdl(k_score_topk_fused<4>, dim3(ctas), dim3(UM_THREADS + 4 * TKF_THREADS), smem, s, a.launch_prio, *tmap, a, prev, alpha, out_scores,
+                      out_docids);
 }
 
 }  // namespace gdr

@@ -262,9 +262,9 @@ template <typename T> static int cpl_for(int dim) {
 cudaError_t launch_score_simt(const ScoreArgs &a, cudaStream_t s, int sm_count) {
     const int grid = sm_count * 8;   // persistent warps: 8 CTAs x 4 warps per SM, items strided
     if (a.dtype == GDR_DTYPE_BF16) {
-        GDR_DISPATCH_CPL(__nv_bfloat16, cpl_for<__nv_bfloat16>(a.dim), return launch_pdl(k_score_simt<__nv_bfloat16, CPL>, dim3(grid), dim3(128), 0, s, a));
+        GDR_DISPATCH_CPL(__nv_bfloat16, cpl_for<__nv_bfloat16>(a.dim), return launch_pdl(k_score_simt<__nv_bfloat16, CPL>, dim3(grid), dim3(128), 0, s, a.launch_prio, a));
     } else {
-        GDR_DISPATCH_CPL(float, cpl_for<float>(a.dim), return launch_pdl(k_score_simt<float, CPL>, dim3(grid), dim3(128), 0, s, a));
+        GDR_DISPATCH_CPL(float, cpl_for<float>(a.dim), return launch_pdl(k_score_simt<float, CPL>, dim3(grid), dim3(128), 0, s, a.launch_prio, a));
     }
     return cudaGetLastError();
 }

@@ -36,15 +36,27 @@
 
 namespace gdr {
 
+#define UM_IS_TMA (warp == 0)
+#define UM_IS_MMA (warp == 1)
+#define UM_IS_FILL (warp < 2 + UM_FILL_WARPS)
+#define UM_FILL_IDX (warp - 2)
+#define UM_IS_EPI (warp < 2 + UM_FILL_WARPS + 4)
 #define UM_SCHED_ELSE else
 #define UM_EXTRA_ROLES
 #define UM_EXTRA_TAIL
+#define UM_REG_SPLIT
 __global__ void __launch_bounds__(UM_THREADS, 1) k_score_umma(const __grid_constant__ CUtensorMap tmap, ScoreArgs a) {
 #include "score_umma_body.inc"
 }
+#undef UM_IS_TMA
+#undef UM_IS_MMA
+#undef UM_IS_FILL
+#undef UM_FILL_IDX
+#undef UM_IS_EPI
 #undef UM_SCHED_ELSE
 #undef UM_EXTRA_ROLES
 #undef UM_EXTRA_TAIL
+#undef UM_REG_SPLIT
 
 // ---------------------------------------------------------------------------------------------
 // host side
@@ -72,16 +84,10 @@ bool umma_make_tensor_map(CUtensorMap *out, const void *emb, int64_t n_docs, int
 }
 
 cudaError_t launch_score_umma(const ScoreArgs &a, const CUtensorMap *tmap, cudaStream_t s, int sm_count) {
-    static unsigned long long attr_set_mask = 0;      // one bit per device: the attribute is per device and function
-    int dev = 0;
-    cudaGetDevice(&dev);
-    const bool attr_set = (attr_set_mask >> (dev & 63)) & 1ull;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_score_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        attr_set_mask |= 1ull << (dev & 63);
-    }
-    return launch_pdl(k_score_umma, dim3(sm_count), dim3(UM_THREADS), UM_SMEM_BYTES, s, *tmap, a);
+    static FuncAttrOnce attr;
+    cudaError_t e = attr.ensure([] { return cudaFuncSetAttribute(k_score_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM_BYTES); });
+    if (e != cudaSuccess) return e;
+    return launch_pdl(k_score_umma, dim3(sm_count), dim3(UM_THREADS), UM_SMEM_BYTES, s, a.launch_prio, *tmap, a);
 }
 
 }  // namespace gdr

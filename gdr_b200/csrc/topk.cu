@@ -102,36 +102,30 @@ __global__ void __launch_bounds__(TK_THREADS) k_topk_merge(ListSrc src0, int n, 
 
 static int pow2_at_least(int x) { int p = 2; while (p < x) p <<= 1; return p; }
 
-// cudaFuncSetAttribute is per device and function: remember which devices have it (one process may drive several)
-static bool need_attr(unsigned long long &mask) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    const bool need = !((mask >> (dev & 63)) & 1ull);
-    mask |= 1ull << (dev & 63);
-    return need;
-}
-
 cudaError_t launch_topk_store(const ScoreArgs &a, float alpha, float *out_scores, int32_t *out_docids, cudaStream_t s) {
     if (a.B == 0) return cudaSuccess;
     const int cap = pow2_at_least(a.k);
     const size_t fixed = (size_t)cap * 8 + (size_t)TK_BINS * 4 + (size_t)(3 * a.K + 1) * 4;
     const size_t with_keys = fixed + (size_t)a.stride * 4;
-    static unsigned long long attr_mask = 0;
-    if (need_attr(attr_mask)) {
-        cudaFuncSetAttribute(k_topk_store<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-        cudaFuncSetAttribute(k_topk_store<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    }
+    static FuncAttrOnce attr;
+    cudaError_t e = attr.ensure([] {
+        cudaError_t e2 = cudaFuncSetAttribute(k_topk_store<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_topk_store<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        return e2;
+    });
+    if (e != cudaSuccess) return e;
     const int grid = a.B;      // (a few persistent CTAs per SM walking the queries measured slower in the pipelined step: 62 vs 57 us)
-    const int groups = (int)((a.flags >> 16) & 7u);                // GDR_TOPK_GROUPS (experiment, topk_grouped.cu)
+    const int groups = (int)((a.flags >> 16) & 7u);                // GDR_OPT_TOPK_GROUPS (topk_grouped.cu)
+    const int pr = a.launch_prio;
     if (groups && cap <= 128 && a.gkeys && a.ghist && a.stride <= 65535) return launch_topk_grouped(a, alpha, out_scores, out_docids, s, groups);
     if (cap <= 128 && a.gkeys && a.ghist && a.stride <= 65535)
-        return launch_pdl(k_topk_fast, dim3(grid), dim3(TKF_THREADS), (size_t)128 * 8 + TK_BINS * 2 + (size_t)(3 * a.K + 1) * 4, s, a, alpha,
+        return launch_pdl(k_topk_fast, dim3(grid), dim3(TKF_THREADS), (size_t)128 * 8 + TK_BINS * 2 + (size_t)(3 * a.K + 1) * 4, s, pr, a, alpha,
                           out_scores, out_docids);
     if (cap <= 128 && a.gkeys)
-        return launch_pdl(k_topk_store<2>, dim3(grid), dim3(TK_THREADS), fixed, s, a, alpha, cap, out_scores, out_docids);
+        return launch_pdl(k_topk_store<2>, dim3(grid), dim3(TK_THREADS), fixed, s, pr, a, alpha, cap, out_scores, out_docids);
     if (with_keys <= 96 * 1024)
-        return launch_pdl(k_topk_store<1>, dim3(grid), dim3(TK_THREADS), with_keys, s, a, alpha, cap, out_scores, out_docids);
-    return launch_pdl(k_topk_store<0>, dim3(grid), dim3(TK_THREADS), fixed, s, a, alpha, cap, out_scores, out_docids);
+        return launch_pdl(k_topk_store<1>, dim3(grid), dim3(TK_THREADS), with_keys, s, pr, a, alpha, cap, out_scores, out_docids);
+    return launch_pdl(k_topk_store<0>, dim3(grid), dim3(TK_THREADS), fixed, s, pr, a, alpha, cap, out_scores, out_docids);
 }
 
 cudaError_t launch_merge_topk(const float *scores, const int32_t *docids, int G, int B, int k_in, int64_t g_stride, int k,
@@ -141,14 +135,9 @@ cudaError_t launch_merge_topk(const float *scores, const int32_t *docids, int G,
     const int n = G * k_in;
     const size_t smem = (size_t)cap * 8 + TK_BINS * 4 + (size_t)((n + 3) / 4 * 4) * 4;
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
-    static unsigned long long attr_set_mask = 0;      // one bit per device: the attribute is per device and function
-    int dev = 0;
-    cudaGetDevice(&dev);
-    const bool attr_set = (attr_set_mask >> (dev & 63)) & 1ull;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_topk_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set_mask |= 1ull << (dev & 63);
-    }
+    static FuncAttrOnce attr;
+    cudaError_t e = attr.ensure([] { return cudaFuncSetAttribute(k_topk_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
+    if (e != cudaSuccess) return e;
     ListSrc src{scores, docids, g_stride, k_in};
     k_topk_merge<<<B, TK_THREADS, smem, s>>>(src, n, k, cap, out_scores, out_docids);
     return cudaGetLastError();

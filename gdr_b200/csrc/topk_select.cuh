@@ -27,18 +27,19 @@ struct Threshold {
 
 // Who is "the group" that runs one top-k: in the stand-alone kernels it is the whole CTA (CtaScope: threadIdx.x and
 // __syncthreads() — the kernels compile to the SASS they had before the policy existed); GroupScope<FIRST> is one of the
-// 128-thread groups that follow the first FIRST threads of a larger CTA (group g = threads [FIRST + 128 g, FIRST + 128 g + 128),
+// NT-thread groups (128 or 64) that follow the first FIRST threads of a larger CTA (group g = threads [FIRST + NT g, FIRST + NT g + NT),
 // named barrier 1 + g) — the building block of the fused scoring + top-k CTA of ROADMAP.md.  Purely static: no argument is
 // added to any function, so the default instantiation is the code it was.
 struct CtaScope {
     __device__ __forceinline__ static int tid() { return (int)threadIdx.x; }
     __device__ __forceinline__ static void sync() { __syncthreads(); }
 };
-template <int FIRST>
+template <int FIRST, int NT = 128>
 struct GroupScope {
-    __device__ __forceinline__ static int tid() { return ((int)threadIdx.x - FIRST) & 127; }
-    __device__ __forceinline__ static int group() { return ((int)threadIdx.x - FIRST) >> 7; }
-    __device__ __forceinline__ static void sync() { asm volatile("bar.sync %0, 128;" ::"r"(1 + group()) : "memory"); }
+    static_assert(NT == 64 || NT == 128, "group sizes: two or four warps");
+    __device__ __forceinline__ static int tid() { return ((int)threadIdx.x - FIRST) & (NT - 1); }
+    __device__ __forceinline__ static int group() { return ((int)threadIdx.x - FIRST) / NT; }
+    __device__ __forceinline__ static void sync() { asm volatile("bar.sync %0, %1;" ::"r"(1 + group()), "n"(NT) : "memory"); }
 };
 
 // Select the kk largest keys among the active candidates.  key_at(j, key) returns false for
@@ -483,11 +484,20 @@ __device__ __noinline__ void topk_general_cold(const Src &src, int n, int k, int
 // block barriers (latency-bound: ~25 us per query under a saturated memory system), so what matters is how many
 // queries are in flight per SM: eight of these CTAs fit beside the scoring CTA against four of the 256-thread ones.
 // The rare fallbacks (n <= k, mass ties in the boundary bin) run the general select with its histogram in global scratch.
-template <int NT, int R4, typename Src, typename Scope = CtaScope>
+// BITS = width of the first-level digit (11: the 2,048 bins of the stand-alone kernels; 10: 1,024 bins = 2 KB per group for the
+// 64-thread groups of the fused kernel, whose eleven slices must fit beside the scoring ring).  The result does not depend on it.
+template <int NT, int R4, typename Src, typename Scope = CtaScope, int BITS = 11>
 __device__ void topk_fast16(const Src &src, int n, int k, uint32_t *gkeys, uint32_t *ghist, uint64_t *sel, uint32_t *hist_words,
                             TkShared *sh, float *out_s, int32_t *out_d, uint32_t dbg = 0) {
     constexpr int NW = NT / 32;
-    constexpr int RANGE = TK_BINS / NW;                            // bins summed by one warp (512 for four warps)
+    constexpr int NBINS = 1 << BITS;
+    constexpr int SH1 = 32 - BITS;                                 // key >> SH1 = first-level bin
+    constexpr int SH2 = SH1 - 8;                                   // (key >> SH2) & 255 = second-level bin
+    constexpr int RANGE = NBINS / NW;                              // bins summed by one warp (512 for four warps)
+    static_assert(RANGE % 256 == 0, "a warp's range is walked in 256-bin blocks");
+    // 128-bit score loads a thread keeps in flight in the passes that do not hold keys in registers (two-warp groups: every
+    // exposed L2 round trip counts; the 128-thread kernel keeps its one-load loop and its register allocation)
+    constexpr int TK_U = NT == 64 ? 4 : 1;
     int tid_;
     if constexpr (std::is_same<Scope, CtaScope>::value) tid_ = threadIdx.x; else tid_ = Scope::tid();
     const int tid = tid_, lane = tid & 31, warp = tid >> 5;
@@ -499,7 +509,7 @@ __device__ void topk_fast16(const Src &src, int n, int k, uint32_t *gkeys, uint3
         return;
     }
     uint16_t *hist = reinterpret_cast<uint16_t *>(hist_words);     // bin b = half (b & 1) of word b >> 1
-    for (int i = tid; i < TK_BINS / 2; i += NT) hist_words[i] = 0;
+    for (int i = tid; i < NBINS / 2; i += NT) hist_words[i] = 0;
     for (int i = tid; i < 256; i += NT) sh->hist2[i] = 0;
     if (tid == 0) { sh->sel_count = 0; sh->eq2_count = 0; sh->bnd_count = 0; }
     // Up to NT * 4 * R4 candidates (2,560: the reference's beam 20 x ~107-doc clusters) are read ONCE, all loads of a
@@ -523,19 +533,30 @@ __device__ void topk_fast16(const Src &src, int n, int k, uint32_t *gkeys, uint3
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 kreg[r][e] = float_to_ordered(s4[e]);
-                const uint32_t bin = kreg[r][e] >> 21;
+                const uint32_t bin = kreg[r][e] >> SH1;
                 if (j4 + e < n) atomicAdd(&hist_words[bin >> 1], 1u << ((bin & 1u) * 16u));
             }
         }
     } else {
+        // candidates are not kept: both passes read the (L2-resident) scores, TK_U 128-bit loads of a thread in flight together
         Scope::sync();
-        for (int j4 = tid * 4; j4 < n; j4 += NT * 4) {
-            float s4[4];
-            src.score4(j4, n, s4);
+        for (int j0 = 0; j0 < n; j0 += NT * 4 * TK_U) {
+            float4 v[TK_U];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const uint32_t bin = float_to_ordered(s4[e]) >> 21;
-                if (j4 + e < n) atomicAdd(&hist_words[bin >> 1], 1u << ((bin & 1u) * 16u));
+            for (int u = 0; u < TK_U; ++u) {
+                const int j4 = j0 + (u * NT + tid) * 4;
+                v[u] = j4 < n ? src.load4(j4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < TK_U; ++u) {
+                const int j4 = j0 + (u * NT + tid) * 4;
+                float s4[4];
+                if (j4 < n) src.bias4(v[u], j4, n, s4);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const uint32_t bin = float_to_ordered(s4[e]) >> SH1;
+                    if (j4 + e < n) atomicAdd(&hist_words[bin >> 1], 1u << ((bin & 1u) * 16u));
+                }
             }
         }
     }
@@ -583,11 +604,11 @@ __device__ void topk_fast16(const Src &src, int n, int k, uint32_t *gkeys, uint3
     uint64_t *bnd2 = bnd + TK_BND;
     Scope::sync();
     auto classify = [&](uint32_t key, int j) {
-        const int bin = (int)(key >> 21);
+        const int bin = (int)(key >> SH1);
         if (bin > d_bin) sel[atomicAdd(&sh->sel_count, 1)] = ((uint64_t)key << 32) | (uint32_t)j;
         else if (bin == d_bin) {
             bnd[atomicAdd(&sh->bnd_count, 1)] = ((uint64_t)key << 32) | (uint32_t)j;
-            atomicAdd(&sh->hist2[(key >> 13) & 255u], 1u);
+            atomicAdd(&sh->hist2[(key >> SH2) & 255u], 1u);
         }
     };
     if (in_regs) {
@@ -598,7 +619,7 @@ __device__ void topk_fast16(const Src &src, int n, int k, uint32_t *gkeys, uint3
         for (int r = 0; r < R4; ++r) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const int bin = (r * NT + tid) * 4 + e < n ? (int)(kreg[r][e] >> 21) : -1;
+                const int bin = (r * NT + tid) * 4 + e < n ? (int)(kreg[r][e] >> SH1) : -1;
                 c_sel += bin > d_bin;
                 c_bnd += bin == d_bin;
             }
@@ -612,22 +633,32 @@ __device__ void topk_fast16(const Src &src, int n, int k, uint32_t *gkeys, uint3
                 for (int e = 0; e < 4; ++e) {
                     const int j = (r * NT + tid) * 4 + e;
                     const uint32_t key = kreg[r][e];
-                    const int bin = j < n ? (int)(key >> 21) : -1;
+                    const int bin = j < n ? (int)(key >> SH1) : -1;
                     if (bin > d_bin) sel[at_sel++] = ((uint64_t)key << 32) | (uint32_t)j;
                     else if (bin == d_bin) {
                         bnd[at_bnd++] = ((uint64_t)key << 32) | (uint32_t)j;
-                        atomicAdd(&sh->hist2[(key >> 13) & 255u], 1u);
+                        atomicAdd(&sh->hist2[(key >> SH2) & 255u], 1u);
                     }
                 }
             }
         }
     } else {
-        for (int j4 = tid * 4; j4 < n; j4 += NT * 4) {
-            float s4[4];
-            src.score4(j4, n, s4);
+        for (int j0 = 0; j0 < n; j0 += NT * 4 * TK_U) {
+            float4 v[TK_U];
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-                if (j4 + e < n) classify(float_to_ordered(s4[e]), j4 + e);
+            for (int u = 0; u < TK_U; ++u) {
+                const int j4 = j0 + (u * NT + tid) * 4;
+                v[u] = j4 < n ? src.load4(j4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < TK_U; ++u) {
+                const int j4 = j0 + (u * NT + tid) * 4;
+                float s4[4];
+                if (j4 < n) src.bias4(v[u], j4, n, s4);
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (j4 + e < n) classify(float_to_ordered(s4[e]), j4 + e);
+            }
         }
     }
     Scope::sync();
@@ -636,13 +667,13 @@ __device__ void topk_fast16(const Src &src, int n, int k, uint32_t *gkeys, uint3
     // reads (segment search + one global load each) are issued together and overlap the second-level scan, instead of one
     // exposed round trip in front of the final sort.
     auto with_doc = [&](uint64_t e) { return (e & 0xffffffff00000000ull) | (uint32_t)~(uint32_t)src.doc((int)(uint32_t)e); };
-    if (tid < gt) sel[tid] = with_doc(sel[tid]);                   // gt < k <= 128 = NT; slots >= gt are appended below
+    for (int t = tid; t < gt; t += NT) sel[t] = with_doc(sel[t]);  // gt < k <= 128; slots >= gt are appended below
     int d2, gt2, eq2;
     scan_down8(sh->hist2, lane, k - gt, d2, gt2, eq2);
     const int need2 = k - gt - gt2;
     for (int t = tid; t < eq; t += NT) {
         const uint64_t e = with_doc(bnd[t]);
-        const int sub = (int)((e >> 45) & 255u);
+        const int sub = (int)((e >> (32 + SH2)) & 255u);
         if (sub > d2) sel[atomicAdd(&sh->sel_count, 1)] = e;
         else if (sub == d2) bnd2[atomicAdd(&sh->eq2_count, 1)] = e;
     }
@@ -685,20 +716,25 @@ __device__ void topk_fast16(const Src &src, int n, int k, uint32_t *gkeys, uint3
 
 constexpr int TKF_THREADS = 128;
 constexpr int TKF_R4 = 5;            // 128 threads x 5 x 4 = 2,560 candidates held in registers
+constexpr int TKF64_THREADS = 64;    // the fused kernel's groups: two warps per query, no keys in registers, 1,024 first-level bins
+constexpr int TKF64_BITS = 10;
 
-// ---- grouped variant (EXPERIMENT, off unless GDR_TOPK_GROUPS=G is set when the store is created; written after the GPU budget
-// of round 1 was spent: compiled, NOT yet run on a GPU, no parity test yet — ROADMAP.md, "plan of record") ---------------------
-// G independent 128-thread groups per CTA (GroupScope: own named barrier, own shared-memory slice), each claiming one query
-// at a time from a global counter and running the unchanged topk_fast16 on it.  This loop is what the top-k warps of the fused
-// scoring + top-k CTA will execute; stand-alone it is the check that the group-scoped body equals k_topk_fast.
+// ---- grouped variant -----------------------------------------------------------------------------------------------------
+// G independent NT-thread groups per CTA (GroupScope: own named barrier, own shared-memory slice), each claiming one query
+// at a time from a global counter and running topk_fast16 on it.  This loop is what the top-k warps of the fused scoring +
+// top-k CTA execute (score_fused.cu); stand-alone it is k_topk_fast_grouped (topk_grouped.cu), the check that the group-scoped
+// select equals k_topk_fast.  NT = 128: four warps per query, keys of up to 2,560 candidates in registers; NT = 64: two warps
+// per query and no keys in registers (both passes read the L2-resident scores) — half the threads and registers per query in
+// flight, which is what lets one fused CTA hold nine queries at a time.
 // slice: sel[128] u64 | hist[2048] u16 | co[K+1] | cbase[K] | bias[K] | TkShared | next query (int), rounded up to 16 bytes
 __host__ __device__ inline int tkg_slice_bytes(int K) {
     return (128 * 8 + TK_BINS * 2 + (3 * K + 1) * 4 + (int)sizeof(TkShared) + 4 + 15) / 16 * 16;
 }
 
-template <int FIRST>
+template <int FIRST, int NT = TKF_THREADS>
 __device__ void topk_group_loop(const ScoreArgs &a, float alpha, float *out_scores, int32_t *out_docids, unsigned char *slice) {
-    using S = GroupScope<FIRST>;
+    using S = GroupScope<FIRST, NT>;
+    constexpr int R4 = NT == TKF_THREADS ? TKF_R4 : 0;
     const int tid = S::tid();
     uint64_t *sel = reinterpret_cast<uint64_t *>(slice);
     uint32_t *hist_words = reinterpret_cast<uint32_t *>(sel + 128);
@@ -712,7 +748,7 @@ __device__ void topk_group_loop(const ScoreArgs &a, float alpha, float *out_scor
         S::sync();
         const int b = *next;
         if (b >= a.B) break;                                       // group-uniform
-        for (int i = tid; i <= a.K; i += TKF_THREADS) {
+        for (int i = tid; i <= a.K; i += NT) {
             co[i] = a.candoff[(int64_t)b * (a.K + 1) + i];
             if (i < a.K) {
                 cbase[i] = a.cbase[(int64_t)b * a.K + i];
@@ -721,8 +757,8 @@ __device__ void topk_group_loop(const ScoreArgs &a, float alpha, float *out_scor
         }
         const int n = a.candoff[(int64_t)b * (a.K + 1) + a.K];
         StoreSrc src{a.scorebuf + (int64_t)b * a.stride, co, cbase, a.prob ? bias : nullptr, a.docid, a.K};
-        topk_fast16<TKF_THREADS, TKF_R4, StoreSrc, S>(src, n, a.k, a.gkeys + (int64_t)b * a.stride, a.ghist + (int64_t)b * TK_BINS, sel, hist_words,
-                                                      sh, out_scores + (int64_t)b * a.k, out_docids + (int64_t)b * a.k, 0u);
+        topk_fast16<NT, R4, StoreSrc, S>(src, n, a.k, a.gkeys + (int64_t)b * a.stride, a.ghist + (int64_t)b * TK_BINS, sel, hist_words,
+                                         sh, out_scores + (int64_t)b * a.k, out_docids + (int64_t)b * a.k, 0u);
         S::sync();                                                 // the slice (and *next) is free for the next query
     }
 }

@@ -1,0 +1,260 @@
+"""Pipelined fine stage: several independent batches in flight on one GPU.
+
+The reference scores one validation batch at a time (GDR_model/main_models.py:1434-1637).  Batches are independent, so
+this module keeps them in flight; it is the schedule `bench.py` times and the one a serving / validation loop should use:
+
+* `fused` (bf16 store on the tcgen05 path, k <= 128): ONE launch per batch scores batch i and, in the same persistent
+  CTAs, selects the top-k of batch i-1 (`gdr_score_fused`, csrc/score_fused.cu); the pair inversion of batch i+1 runs one
+  batch ahead on a second stream.  Three scratch sets (= three store handles over the same device arrays): launch i scores
+  into set i % 3 and reads set (i-1) % 3, the inversion of batch i+1 fills set (i+1) % 3.
+* `batches` (every other shape): whole `gdr_score_topk` calls round-robin on `depth` streams, one handle each, so the
+  latency-bound inversion and top-k kernels of one batch hide under the HBM-bound scoring kernel of its neighbours.
+
+Contract: `submit()` returns a `Ticket`; the ticket's outputs are complete, in stream order on the stream that calls it, after
+`ticket.wait()` (which needs the NEXT `submit()` or a `flush()` to have been issued: in the fused schedule batch i's top-k
+is part of launch i+1).  Everything is enqueue-only (no host synchronisation) and capturable in a CUDA graph as long as a
+`flush()` is captured last (it joins the internal streams).  Results are bit-identical to `ClusterStore.score_topk`
+(tests/test_gpu_pipeline.py).  There is no CPU path.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+
+from . import _cabi
+from .store import ClusterStore
+
+
+class Ticket:
+    """One submitted batch.  `scores` [B, k] fp32 / `docids` [B, k] int32 are valid after `wait()`."""
+    __slots__ = ("index", "scores", "docids", "event", "keep", "alpha", "host_out", "which")
+
+    def __init__(self, index, scores, docids, alpha, keep):
+        self.index, self.scores, self.docids, self.alpha, self.keep = index, scores, docids, alpha, keep
+        self.event: Optional[torch.cuda.Event] = None      # recorded once the launch that produces the outputs is enqueued
+        self.host_out = None
+
+    def wait(self, stream: Optional[torch.cuda.Stream] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        if self.event is None:
+            raise RuntimeError("this batch's top-k has not been issued yet: submit the next batch or call flush() first")
+        (stream or torch.cuda.current_stream()).wait_event(self.event)
+        return self.scores, self.docids
+
+
+class PipelinedRetriever:
+    def __init__(self, store, schedule: str = "auto", depth: int = 0, fused_ctas: int = 0, fused_groups: int = 0,
+                 launch_priorities: bool = False):
+        """store: the resident ClusterStore — or a list of stores of identical shape (several indexes served by one pipeline;
+        bench.py cycles copies of the corpus so that every step streams embeddings that are not in L2), chosen per batch with
+        `submit(..., which=i)`.  schedule: 'auto' | 'fused' | 'batches'.  depth: batches in flight for the 'batches' schedule
+        (default 5; the fused schedule always uses three scratch sets)."""
+        if schedule not in ("auto", "fused", "batches"):
+            raise ValueError("schedule must be 'auto', 'fused' or 'batches'")
+        self.stores = list(store) if isinstance(store, (list, tuple)) else [store]
+        store = self.stores[0]
+        self.store, self.schedule_request = store, schedule
+        self.depth = depth if depth > 0 else 5
+        self.fused_ctas, self.fused_groups, self.launch_priorities = fused_ctas, fused_groups, launch_priorities
+        self.dev = store.emb.device
+        self._fused_handles: Optional[List[List[ClusterStore]]] = None    # [scratch set][store]
+        self._batch_handles: Optional[List[List[ClusterStore]]] = None    # [stream][store]
+        self._streams: List[torch.cuda.Stream] = []
+        self._s_inv: Optional[torch.cuda.Stream] = None
+        self._n = 0                      # batches submitted so far
+        self._pending: List[Ticket] = []  # tickets whose outputs are not yet enqueued (fused: at most the last one)
+        self._launch_events = {}         # fused: index -> event recorded after launch i (scratch reuse ordering)
+        self._open: List[Ticket] = []    # batches schedule: tickets not yet joined by flush()
+        self.last_schedule = None
+        # host-buffer front end (submit_host): staging slots, one copy stream per direction
+        self._slots: List[dict] = []
+        self._s_h2d: Optional[torch.cuda.Stream] = None
+        self._s_d2h: Optional[torch.cuda.Stream] = None
+        self._host_jobs: List[Tuple[Ticket, dict, object]] = []
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def fused_eligible(self, B: int, K: int, k: int, flags: int = 0) -> bool:
+        """Mirror of gdr_score_fused's requirements (include/gdr_b200.h): the batch takes the tcgen05 path alone and the
+        previous batch's top-k is the small-footprint select."""
+        s = self.store
+        if s.emb.dtype != torch.bfloat16 or s.dim % 64 != 0 or (flags & _cabi.FORCE_SIMT) or (flags & _cabi.Q_PER_BEAM):
+            return False
+        if not ((flags & _cabi.FORCE_UMMA) or B * K >= 3 * s.n_clusters):
+            return False
+        stride = (K * s.max_cluster + 3) // 4 * 4
+        return k <= 128 and stride <= 65535
+
+    def _handles_fused(self) -> List[List[ClusterStore]]:
+        if self._fused_handles is None:
+            self._fused_handles = [[s.clone_handle() for s in self.stores] for _ in range(3)]
+            for h in (h for hs in self._fused_handles for h in hs):
+                if self.fused_ctas:
+                    h.set_option("umma_ctas", self.fused_ctas)
+                if self.fused_groups:
+                    h.set_option("fused_groups", self.fused_groups)
+                if self.launch_priorities:
+                    h.set_option("launch_priorities", 1)
+            self._s_inv = torch.cuda.Stream(device=self.dev)
+        return self._fused_handles
+
+    def _handles_batches(self) -> List[List[ClusterStore]]:
+        if self._batch_handles is None:
+            self._batch_handles = [[s.clone_handle() for s in self.stores] for _ in range(self.depth)]
+            for h in (h for hs in self._batch_handles for h in hs):
+                if self.launch_priorities:
+                    h.set_option("launch_priorities", 1)
+            self._streams = [torch.cuda.Stream(device=self.dev) for _ in range(self.depth)]
+        return self._batch_handles
+
+    def reserve(self, B: int, K: int, k: int, flags: int = 0) -> "PipelinedRetriever":
+        """Allocate every scratch set for this batch shape now (no allocation / synchronisation on the query path later)."""
+        fused = self.schedule_request != "batches" and self.fused_eligible(B, K, k, flags)
+        for hs in (self._handles_fused() if fused else self._handles_batches()):
+            for h in hs:
+                h.reserve(B, K, k, flags)
+        return self
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def submit(self, q: torch.Tensor, beams: torch.Tensor, k: int, prob: Optional[torch.Tensor] = None, alpha: float = 1.0,
+               act: Optional[str] = "none", flags: int = 0, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+               which: int = 0) -> Ticket:
+        """Enqueue one batch (same arguments as ClusterStore.score_topk with a single alpha) against store number `which`.
+        q / beams / prob must not be overwritten until the ticket's outputs are complete (the ticket keeps references)."""
+        B, K = int(beams.shape[0]), int(beams.shape[1])
+        fused = self.schedule_request != "batches" and self.fused_eligible(B, K, k, flags)
+        if self.schedule_request == "fused" and not fused:
+            raise ValueError("this batch shape is not eligible for the fused schedule (see gdr_score_fused in include/gdr_b200.h)")
+        if self.last_schedule is not None and (self.last_schedule == "fused") != fused:
+            self.flush()                                       # the schedule changes with the shape: drain first
+        self.last_schedule = "fused" if fused else "batches"
+        if out is None:
+            out = (torch.empty((B, k), dtype=torch.float32, device=self.dev), torch.empty((B, k), dtype=torch.int32, device=self.dev))
+        t = Ticket(self._n, out[0], out[1], float(alpha), (q, beams, prob))
+        t.which = which
+        cur = torch.cuda.current_stream(self.dev)
+        if fused:
+            self._submit_fused(t, q, beams, k, prob, act, flags, cur)
+        else:
+            self._submit_batch(t, q, beams, k, prob, act, flags, cur)
+        self._n += 1
+        return t
+
+    def _submit_fused(self, t, q, beams, k, prob, act, flags, cur):
+        hs = self._handles_fused()
+        i = t.index
+        h = hs[i % 3][t.which]
+        ev_in = torch.cuda.Event()
+        ev_in.record(cur)                                      # the inputs are ready in stream order here
+        with torch.cuda.stream(self._s_inv):
+            self._s_inv.wait_event(ev_in)
+            if i - 2 in self._launch_events:                   # the batch that last used this scratch set has had its top-k
+                self._s_inv.wait_event(self._launch_events.pop(i - 2))
+            h.invert(q, beams, k, prob=prob, act=act, flags=flags)
+            ev_inv = torch.cuda.Event()
+            ev_inv.record(self._s_inv)
+        cur.wait_event(ev_inv)
+        prev = self._pending.pop() if self._pending else None
+        with torch.cuda.stream(cur):
+            h.score_fused(hs[(i - 1) % 3][prev.which] if prev is not None else None, alpha=prev.alpha if prev is not None else 1.0,
+                          out=(prev.scores, prev.docids) if prev is not None else None)
+            ev = torch.cuda.Event()
+            ev.record(cur)
+        self._launch_events[i] = ev
+        if prev is not None:
+            prev.event, prev.keep = ev, None
+        self._pending.append(t)
+
+    def _submit_batch(self, t, q, beams, k, prob, act, flags, cur):
+        hs = self._handles_batches()
+        i = t.index
+        st = self._streams[i % self.depth]
+        ev_in = torch.cuda.Event()
+        ev_in.record(cur)
+        with torch.cuda.stream(st):
+            st.wait_event(ev_in)
+            hs[i % self.depth][t.which].score_topk(q, beams, k, prob=prob, alphas=[t.alpha], act=act, flags=flags,
+                                          out=(t.scores.view(1, *t.scores.shape), t.docids.view(1, *t.docids.shape)))
+            t.event = torch.cuda.Event()
+            t.event.record(st)
+        self._open.append(t)
+        if len(self._open) > self.depth:                       # bounded bookkeeping; older tickets keep their own events
+            self._open.pop(0)
+
+    # ---- host-buffer front end: what a caller with inputs in (pinned) host memory uses ---------------------------------------
+    def submit_host(self, in_host: torch.Tensor, B: int, K: int, k: int, out_host: torch.Tensor, alpha: float = 1.0,
+                    act: Optional[str] = "none", flags: int = 0, which: int = 0) -> Ticket:
+        """One batch whose inputs live in ONE pinned host buffer `in_host` (uint8: fp32 q [B, D] followed by int32 beams
+        [B, K]) and whose results go to ONE pinned host buffer `out_host` (uint8: fp32 scores [B, k] then int32 docids [B, k]):
+        a single H2D and a single D2H copy per batch, each direction on a copy stream of its own so that batch i+1's upload,
+        batch i's kernels and batch i-1's download overlap.  `ticket.host_out` is the event after which `out_host` is valid."""
+        D = self.store.dim
+        q_bytes, b_bytes, r_bytes = B * D * 4, B * K * 4, B * k * 4
+        if in_host.numel() != q_bytes + b_bytes or out_host.numel() != 2 * r_bytes or in_host.dtype != torch.uint8 or out_host.dtype != torch.uint8:
+            raise ValueError("in_host must hold q then beams, out_host scores then docids, both as uint8 buffers")
+        if self._s_h2d is None:
+            self._s_h2d, self._s_d2h = torch.cuda.Stream(device=self.dev), torch.cuda.Stream(device=self.dev)
+        n_slots = 4 if self.schedule_request != "batches" and self.fused_eligible(B, K, k, flags) else self.depth + 1
+        if len(self._slots) != n_slots or self._slots[0]["in"].numel() != q_bytes + b_bytes or self._slots[0]["out"].numel() != 2 * r_bytes:
+            self.flush()
+            self._slots = [dict(**{"in": torch.empty(q_bytes + b_bytes, dtype=torch.uint8, device=self.dev),
+                                   "out": torch.empty(2 * r_bytes, dtype=torch.uint8, device=self.dev)}, free=None) for _ in range(n_slots)]
+        slot = self._slots[self._n % n_slots]
+        cur = torch.cuda.current_stream(self.dev)
+        with torch.cuda.stream(self._s_h2d):
+            if slot["free"] is not None:
+                self._s_h2d.wait_event(slot["free"])           # the batch that last used this slot has been downloaded
+            else:
+                self._s_h2d.wait_stream(cur)
+            slot["in"].copy_(in_host, non_blocking=True)
+            ev_up = torch.cuda.Event()
+            ev_up.record(self._s_h2d)
+        cur.wait_event(ev_up)
+        q = slot["in"][:q_bytes].view(torch.float32).view(B, D)
+        beams = slot["in"][q_bytes:].view(torch.int32).view(B, K)
+        o_s = slot["out"][:r_bytes].view(torch.float32).view(B, k)
+        o_d = slot["out"][r_bytes:].view(torch.int32).view(B, k)
+        t = self.submit(q, beams, k, alpha=alpha, act=act, flags=flags, out=(o_s, o_d), which=which)
+        self._host_jobs.append((t, slot, out_host))
+        self._drain_host_jobs()
+        return t
+
+    def _drain_host_jobs(self) -> None:
+        """Enqueue the download of every batch whose top-k has been issued."""
+        while self._host_jobs and self._host_jobs[0][0].event is not None:
+            t, slot, out_host = self._host_jobs.pop(0)
+            with torch.cuda.stream(self._s_d2h):
+                self._s_d2h.wait_event(t.event)
+                out_host.copy_(slot["out"], non_blocking=True)
+                t.host_out = torch.cuda.Event()
+                t.host_out.record(self._s_d2h)
+            slot["free"] = t.host_out
+
+    def flush(self) -> None:
+        """Issue what is still outstanding (fused: the last batch's top-k) and join the internal streams into the current one."""
+        cur = torch.cuda.current_stream(self.dev)
+        if self._pending:
+            t = self._pending.pop()
+            hs = self._handles_fused()
+            with torch.cuda.stream(cur):
+                ClusterStore.flush_fused(hs[t.index % 3][t.which], alpha=t.alpha, out=(t.scores, t.docids))
+                t.event = torch.cuda.Event()
+                t.event.record(cur)
+            t.keep = None
+        if self._s_inv is not None:
+            cur.wait_stream(self._s_inv)
+        for st in self._streams:
+            cur.wait_stream(st)
+        self._drain_host_jobs()
+        if self._s_h2d is not None:
+            cur.wait_stream(self._s_h2d)
+            cur.wait_stream(self._s_d2h)
+            for slot in self._slots:
+                slot["free"] = None                            # everything is joined into `cur`: the next upload waits for `cur`
+        self._launch_events.clear()
+        self._open.clear()
+
+    def launches(self) -> int:
+        """Kernels launched per pipelined step (synchronises): inversion kernels + the fused launch, or the whole call."""
+        hs = self._fused_handles if self.last_schedule == "fused" else self._batch_handles
+        n = int(hs[0][0].last_stats()["launches"])
+        return n + 1 if self.last_schedule == "fused" else n

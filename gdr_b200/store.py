@@ -113,8 +113,8 @@ class ClusterStore:
     # ---- the hot path ----------------------------------------------------------------------------
     def score_topk(self, q: torch.Tensor, beams: torch.Tensor, k: int, prob: Optional[torch.Tensor] = None,
                    alphas: Optional[Sequence[float]] = None, act: Optional[str] = "none", per_beam: bool = False,
-                   flags: int = 0, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, stream=None
-                   ) -> Tuple[torch.Tensor, torch.Tensor]:
+                   flags: int = 0, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, stream=None,
+                   _unchecked_out: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
         """Cluster-restricted scoring + top-k for one batch (gdr_score_topk in include/gdr_b200.h).
         q [B, D] fp32 cuda ([B*K, D] with per_beam), beams [B, K] int32 cuda (-1 = absent),
         prob [B, K] fp32 cuda or None, alphas list of floats or None.
@@ -140,6 +140,8 @@ class ClusterStore:
             out_d = torch.empty((n_alpha, B, k), dtype=torch.int32, device=dev)
         else:
             out_s, out_d = out
+            if not _unchecked_out:      # (the inversion-only call passes placeholders: no output is written)
+                _check_out(out_s, out_d, n_alpha * B * int(k), dev)
         if per_beam:
             flags |= _cabi.Q_PER_BEAM
         with torch.cuda.device(dev):
@@ -151,7 +153,25 @@ class ClusterStore:
             return out_s[0], out_d[0]
         return out_s, out_d
 
-    # ---- experiment: fused scoring + top-k, one batch behind (include/gdr_b200.h gdr_score_fused; ROADMAP.md) ----------------
+    # ---- handle options / scratch ---------------------------------------------------------------------------------
+    def set_option(self, name: str, value: int) -> "ClusterStore":
+        """Launch options of this handle (gdr_store_set_option; names in _cabi.OPTIONS).  None changes results."""
+        _cabi.check(_cabi.lib().gdr_store_set_option(self._handle, _cabi.OPTIONS[name], int(value)))
+        return self
+
+    def reserve(self, B: int, K: int, k: int, flags: int = 0, per_beam: bool = False, stream=None) -> "ClusterStore":
+        """Pre-size the scratch for batches of up to this shape: no allocation on the query path afterwards."""
+        with torch.cuda.device(self.emb.device):
+            _cabi.check(_cabi.lib().gdr_store_reserve(self._handle, int(B), int(K), int(k), flags | (_cabi.Q_PER_BEAM if per_beam else 0),
+                                                     _cabi.stream_ptr(stream)))
+        return self
+
+    def clone_handle(self) -> "ClusterStore":
+        """Another handle (= another scratch set) over the SAME device arrays: nothing is copied.  One per batch in flight."""
+        other = ClusterStore(self.emb, torch.as_tensor(self.offsets_host), self.docid, self.keys)
+        return other
+
+    # ---- pipelined schedule: fused scoring + top-k, one batch behind (include/gdr_b200.h gdr_score_fused; pipeline.py drives it) ----
     def invert(self, q: torch.Tensor, beams: torch.Tensor, k: int, prob: Optional[torch.Tensor] = None, act: Optional[str] = "none",
                flags: int = 0, stream=None) -> None:
         """Inversion phase of a batch alone (gdr_score_topk with GDR_SKIP_SCORE | GDR_SKIP_TOPK): leaves the batch's work lists
@@ -160,7 +180,7 @@ class ClusterStore:
             self._fused_dummy = (torch.empty(max(k, 128), dtype=torch.float32, device=self.emb.device),
                                  torch.empty(max(k, 128), dtype=torch.int32, device=self.emb.device))
         self.score_topk(q, beams, k, prob=prob, act=act, flags=flags | _cabi.SKIP_SCORE | _cabi.SKIP_TOPK,
-                        out=self._fused_dummy, stream=stream)
+                        out=self._fused_dummy, stream=stream, _unchecked_out=True)
 
     def score_fused(self, prev: Optional["ClusterStore"], alpha: float = 1.0,
                     out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, stream=None):
@@ -215,12 +235,25 @@ class ClusterStore:
             pass
 
 
+def _check_out(out_s: torch.Tensor, out_d: torch.Tensor, numel: int, dev) -> None:
+    """The kernels write `numel` consecutive elements through raw pointers: refuse anything else before it reaches the C ABI."""
+    if out_s.dtype != torch.float32 or out_d.dtype != torch.int32:
+        raise ValueError("out must be (float32 scores, int32 docids)")
+    if out_s.device != dev or out_d.device != dev:
+        raise ValueError("out tensors must live on the store's device")
+    if not out_s.is_contiguous() or not out_d.is_contiguous():
+        raise ValueError("out tensors must be contiguous")
+    if out_s.numel() != numel or out_d.numel() != numel:
+        raise ValueError(f"out tensors must hold exactly n_alpha * B * k = {numel} elements each, got {out_s.numel()} / {out_d.numel()}")
+
+
 def _score_fused(cur: Optional[ClusterStore], prev: Optional[ClusterStore], alpha, out, stream):
     out_s = out_d = None
     if prev is not None:
         B, k = prev._last_shape
         out_s, out_d = out if out is not None else (torch.empty((B, k), dtype=torch.float32, device=prev.emb.device),
                                                     torch.empty((B, k), dtype=torch.int32, device=prev.emb.device))
+        _check_out(out_s, out_d, B * k, prev.emb.device)
     dev = (cur if cur is not None else prev).emb.device
     with torch.cuda.device(dev):
         _cabi.check(_cabi.lib().gdr_score_fused(

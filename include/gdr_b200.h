@@ -13,8 +13,10 @@
  *
  * Concurrency: a store / trie handle owns ONE set of scratch buffers, so calls on the same handle must be ordered
  * (same stream, or streams ordered with events).  To keep several batches in flight, create one handle per batch in
- * flight over the SAME device arrays (a handle copies nothing: bench.py runs five per GPU).  The scratch grows on the
- * first call of a new shape (that call synchronises the stream): run every shape once before capturing a CUDA graph.
+ * flight over the SAME device arrays (a handle copies nothing: gdr_b200/pipeline.py runs three per GPU).  The scratch grows on
+ * the first call of a larger shape (that call synchronises the stream) unless gdr_store_reserve sized it beforehand.
+ * Handles may be driven from different host threads: there is no mutable process-wide state (launch priorities travel in the
+ * call's own arguments, the one-time per-device kernel attributes are set under a mutex), gdr_last_error is per thread.
  */
 #ifndef GDR_B200_H
 #define GDR_B200_H
@@ -89,20 +91,36 @@ int gdr_score_topk(gdr_store_t *store, const float *q, const int32_t *beams, con
                    const float *alphas, int32_t n_alpha, int32_t B, int32_t K, int32_t act, int32_t k,
                    uint32_t flags, float *out_scores, int32_t *out_docids, void *stream);
 
-/* EXPERIMENT — fused scoring + top-k, one batch behind (ROADMAP.md "plan of record"; csrc/score_fused.cu; compiled for
- * sm_100a but not yet run on a GPU when round 1 ended; gdr_score_topk does not use it).  No reference counterpart: it is a
- * different schedule of main_models.py:1577-1631, not a different result.
+/* Pipelined schedule — scoring of batch i and the top-k of batch i-1 in ONE launch (csrc/score_fused.cu; gdr_b200/pipeline.py
+ * drives it).  No reference counterpart: it is a different schedule of main_models.py:1577-1631, not a different result
+ * (tests/test_gpu_pipeline.py: bit-identical to gdr_score_topk).  Why: as separate grids the top-k CTAs of batch i-1 and the
+ * scoring CTAs of batch i compete for SM residency; fused, the top-k has a fixed home in the scoring CTA.
  * `cur` and `prev` are two handles over the same (or different) embeddings, i.e. two scratch sets.  Protocol per batch i:
- *   gdr_score_topk(h[i % 2], q_i, beams_i, prob_i, NULL, 1, B, K, act, k, GDR_SKIP_SCORE | GDR_SKIP_TOPK, any valid out pointers, stream)
- *                                             -- the inversion of batch i into h[i % 2]'s scratch (the outputs are checked, not written)
- *   gdr_score_fused(h[i % 2], i ? h[(i - 1) % 2] : NULL, alpha, out_scores_{i-1}, out_docids_{i-1}, stream)
+ *   gdr_score_topk(h[i % 3], q_i, beams_i, prob_i, NULL, 1, B, K, act, k, GDR_SKIP_SCORE | GDR_SKIP_TOPK, any valid out pointers, stream_inv)
+ *                                             -- the inversion of batch i into h[i % 3]'s scratch (the outputs are checked, not written);
+ *                                                on a second stream it runs one batch ahead of the fused launches
+ *   gdr_score_fused(h[i % 3], i ? h[(i - 1) % 3] : NULL, alpha, out_scores_{i-1}, out_docids_{i-1}, stream)
  *                                             -- ONE launch: scores batch i and selects the top-k of batch i-1 in the same CTAs
- *   ... and after the last batch n-1:  gdr_score_fused(NULL, h[(n - 1) % 2], alpha, out_scores_{n-1}, out_docids_{n-1}, stream)
+ *   ... and after the last batch n-1:  gdr_score_fused(NULL, h[(n - 1) % 3], alpha, out_scores_{n-1}, out_docids_{n-1}, stream)
  * Requirements: the batch in `cur` takes the tcgen05 path alone (bf16 store, dim % 64 == 0, B*K >= 3 * n_clusters or
  * GDR_FORCE_UMMA); the batch in `prev` has k <= 128 and <= 65,535 candidates per query; prev's q / beams / prob buffers are
- * still alive; one alpha per call (result = score + alpha * prob[b, beam]); outputs DEV [B, k] of the batch in `prev`. */
+ * still alive; one alpha per call (result = score + alpha * prob[b, beam]); outputs DEV [B, k] of the batch in `prev`.
+ * GDR_ERR_UNSUPPORTED otherwise (the caller then runs gdr_score_topk batch by batch). */
 int gdr_score_fused(gdr_store_t *cur, gdr_store_t *prev, float alpha, float *prev_out_scores, int32_t *prev_out_docids,
                     void *stream);
+
+/* Pre-size a handle's scratch for batches of up to (B, K, k) with these flags, so that no allocation (and no stream
+ * synchronisation) happens on the query path and the first call of a shape can already be captured in a CUDA graph. */
+int gdr_store_reserve(gdr_store_t *store, int32_t B, int32_t K, int32_t k, uint32_t flags, void *stream);
+
+/* Launch options of a handle.  None of them changes results (tests/test_gpu_pipeline.py, tests/test_gpu_zz_variants.py). */
+#define GDR_OPT_UMMA_CTAS 1          /* persistent CTAs of the tcgen05 kernels; 0 = default (one per SM; fused launches: SMs - 8) */
+#define GDR_OPT_UMMA_MIN_GROUP 2     /* > 1: mixed mode, groups of at least this many pairs on tensor cores, the rest on the GEMV */
+#define GDR_OPT_LAUNCH_PRIORITIES 3  /* 1: per-launch scheduling priorities, inversion > scoring > top-k */
+#define GDR_OPT_FUSED_GROUPS 4       /* top-k groups in the fused CTA: 9 = nine 64-thread groups (default), 4 = four 128-thread groups */
+#define GDR_OPT_TOPK_GROUPS 5        /* 1, 2, 4: stand-alone top-k as persistent groups walking a query queue; 0 = one CTA per query */
+#define GDR_OPT_TOPK_WIDE 6          /* 1: the 256-thread top-k also for k <= 128 */
+int gdr_store_set_option(gdr_store_t *store, int32_t option, int32_t value);
 
 /* Counters of the most recent gdr_score_topk on this store (device-side work-list sizes):
  * out[0] = (cluster, query-chunk) items scored by the SIMT GEMV path, out[1] = tiles scored by the

@@ -5,7 +5,9 @@ Nothing here is imported by the product package `gdr_b200`; it is used by
 `oracle/make_golden.py` (which generates the committed fixtures under tests/golden/)
 and by the `-m "not gpu"` tests that cross-check the restatement in `oracle/gdr_oracle.py`
 against the live reference when /root/reference is mounted.  /root/reference does not
-exist on the GPU box, so nothing under `-m gpu`, smoke() or bench.py may call this.
+exist on the GPU box: there the same unmodified files are found under baseline/_ref/ (a git-ignored
+copy made by `__graft_entry__.build()` in the dev container, shipped by gpurun like the built .so),
+which is what bench.py's `--impl reference` / `cpu_baseline` legs and tests/test_gpu_integration.py use.
 
 Two loaders, because the reference's two halves need different `transformers`:
   * load_ref_dense()        -> reference GDR_model/dense.py (+ encoder.py) against the
@@ -19,7 +21,17 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("GDR_REFERENCE_ROOT", "/root/reference")
+def _find_ref_root() -> str:
+    """The reference tree: $GDR_REFERENCE_ROOT, the read-only mount of the dev container, or the git-ignored copy that
+    `__graft_entry__.build()` ships to the GPU box as baseline/_ref/ (unmodified files, never committed)."""
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for cand in (os.environ.get("GDR_REFERENCE_ROOT"), "/root/reference", os.path.join(here, "baseline", "_ref")):
+        if cand and os.path.isfile(os.path.join(cand, "GDR_model", "dense.py")):
+            return cand
+    return "/root/reference"
+
+
+REF_ROOT = _find_ref_root()
 REF_MODEL_DIR = os.path.join(REF_ROOT, "GDR_model")
 
 

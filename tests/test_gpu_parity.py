@@ -213,16 +213,47 @@ def test_full_size_cfg2_properties_and_oracle():
     assert torch.equal(s, s2) and torch.equal(d, d2)
 
 
+def test_full_size_cfg1_fp32_store():
+    """BASELINE.json configs[0] at its own shape: 109,739 x 768 fp32 store (what the reference holds, main_models.py:806-814),
+    7,830 queries, beam 10, top-100 — in batches of 1,024 like the bench, oracle on a query slice of the first and the last
+    (ragged) batch, size-independent properties on all of them."""
+    N, C, D, Q, K, k = 109739, 1024, 768, 7830, 10, 100
+    emb, offsets, docid = orc.synth_corpus(N, C, D, seed=1234)
+    q, beams, _ = orc.synth_queries(Q, C, K, D, seed=4322)
+    st = _store(emb, offsets, docid, torch.float32)
+    row_of = torch.empty(N, dtype=torch.int64); row_of[torch.from_numpy(docid)] = torch.arange(N)
+    for lo in range(0, Q, 1024):
+        hi = min(Q, lo + 1024)
+        s, d = st.score_topk(q[lo:hi].cuda(), torch.from_numpy(beams[lo:hi]).cuda(), k)
+        torch.cuda.synchronize()
+        assert torch.all(s[:, :-1] >= s[:, 1:]), "sorted descending"
+        rows = row_of[d.cpu().long()]
+        recomputed = torch.einsum("bkd,bd->bk", emb[rows].double(), q[lo:hi].double())
+        np.testing.assert_allclose(s.cpu().double().numpy(), recomputed.numpy(), rtol=1e-3, atol=1e-3)
+        if lo == 0 or hi == Q:
+            n = min(96, hi - lo)
+            ref_s, ref_d = orc.dense_topk(q[hi - n:hi], emb, offsets, docid, beams[hi - n:hi], k)
+            assert_topk_parity(s[-n:], d[-n:], ref_s, ref_d, f"cfg1 queries {hi - n}..{hi}")
+
+
 def test_cfg3_shape_top1000():
-    """BASELINE.json configs[2] shape: 73,970 x 768, beam 100, top-1000 (C = 1,024 assumed)."""
-    N, C, D, Q, K, k = 73970, 1024, 768, 64, 100, 1000
+    """BASELINE.json configs[2] at full batch: 73,970 x 768, 1,024 queries, beam 100, top-1000 (C = 1,024 assumed, SURVEY.md §8);
+    properties on every query, the oracle on a 48-query slice."""
+    N, C, D, Q, K, k = 73970, 1024, 768, 1024, 100, 1000
     emb, offsets, docid = orc.synth_corpus(N, C, D, seed=77)
     emb = emb.bfloat16().float()
     q, beams, _ = orc.synth_queries(Q, C, K, D, seed=78)
     st = _store(emb, offsets, docid, torch.bfloat16)
     s, d = st.score_topk(q.cuda(), torch.from_numpy(beams).cuda(), k)
-    ref_s, ref_d = orc.dense_topk(q, emb, offsets, docid, beams, k)
-    assert_topk_parity(s, d, ref_s, ref_d, "cfg3")
+    torch.cuda.synchronize()
+    assert torch.all(s[:, :-1] >= s[:, 1:]), "sorted descending"
+    row_of = torch.empty(N, dtype=torch.int64); row_of[torch.from_numpy(docid)] = torch.arange(N)
+    for lo in range(0, Q, 128):                       # recompute every returned score in fp64 (chunked: 1,024 x 1,000 x 768 doubles)
+        rows = row_of[d[lo:lo + 128].cpu().long()]
+        recomputed = torch.einsum("bkd,bd->bk", emb[rows].double(), q[lo:lo + 128].double())
+        np.testing.assert_allclose(s[lo:lo + 128].cpu().double().numpy(), recomputed.numpy(), rtol=1e-3, atol=1e-3)
+    ref_s, ref_d = orc.dense_topk(q[:48], emb, offsets, docid, beams[:48], k)
+    assert_topk_parity(s[:48], d[:48], ref_s, ref_d, "cfg3")
 
 
 def test_compute_similarity_drop_in():

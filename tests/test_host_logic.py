@@ -212,14 +212,18 @@ def test_bench_reference_arm_prints_the_contract_line():
         assert key in line, key
     assert line["impl"] == "reference" and line["unit"] == "queries/s" and line["value"] > 0 and line["steps"] == 2
     assert line["config"]["workload"] == "cfg2" and line["vs_baseline"] is None and line["higher_is_better"] is True
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    # the unmodified reference dense.py when the tree (or its shipped copy baseline/_ref/) is present, else the oracle port
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    sys.path.insert(0, ROOT)
+    import bench
+    assert line["metric"] == bench.METRIC            # ONE metric string for both arms (the driver refuses to divide otherwise)
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
 
 
 def test_bench_launch_autotune_decision(monkeypatch):
-    """bench.py's launch autotune (child processes time the device-resident loop under candidate launch configurations): a
-    candidate replaces the default only when it is > 3 % faster, a failed, hung or garbled child leaves the default, and the
-    fused schedule is eligible only when its child ran it and verified the results."""
+    """bench.py's launch autotune (child processes verify and time the device-resident loop under candidate schedules): a
+    candidate replaces the `batches` default only when it is > 3 % faster, a failed, hung or garbled child leaves the default,
+    and a schedule whose child reports differing results is never chosen."""
     import argparse
     import json
     import subprocess
@@ -228,53 +232,48 @@ def test_bench_launch_autotune_decision(monkeypatch):
     import bench
 
     args = argparse.Namespace(workload="cfg2", path="auto", schedule="auto", replicas=0)
-    names = ("default", "priorities", "fused", "fused_g5", "fused_132_g5", "priorities_deep")
-    fused_env = {"fused": ("140", "4"), "fused_g5": ("140", "5"), "fused_132_g5": ("132", "5")}
+    names = ("batches", "fused64_140", "fused64_132", "fused128x4_140", "batches_priorities")
+    expect = {"fused64_140": ("fused", "9", "140"), "fused64_132": ("fused", "9", "132"), "fused128x4_140": ("fused", "4", "140")}
     seen = []
 
-    def fake_run(times, fail=(), fused_line=None):
+    def fake_run(times, fail=(), bad_line=None):
         def run(cmd, env=None, capture_output=None, text=None, timeout=None):
             name = names[len(seen) % len(names)]
             seen.append((cmd, env))
             assert "--probe" in cmd and "RANK" not in env and env["LOCAL_RANK"] == "2"
-            assert env["GDR_LAUNCH_PRIORITIES"] == ("1" if name.startswith("priorities") else "0")
-            assert cmd[cmd.index("--schedule") + 1] == ("fused" if name.startswith("fused") else "auto")
-            assert (env.get("GDR_FUSED_CTAS"), env.get("GDR_FUSED_GROUPS")) == fused_env.get(name, (None, None))
-            assert cmd[cmd.index("--pipeline") + 1] == ("8" if name == "priorities_deep" else "5")
+            sched = cmd[cmd.index("--schedule") + 1]
+            if name in expect:
+                assert (sched, cmd[cmd.index("--fused-groups") + 1], cmd[cmd.index("--fused-ctas") + 1]) == expect[name]
+            else:
+                assert sched == "batches" and ("--launch-priorities" in cmd) == (name == "batches_priorities")
             if name in fail:
                 if fail[name] == "timeout":
                     raise subprocess.TimeoutExpired(cmd, timeout)
                 return subprocess.CompletedProcess(cmd, 1, stdout="", stderr="CUDA error: invalid value")
-            line = {"probe": True, "us_per_step": times.get(name, 99.0), "schedule": "fused" if name.startswith("fused") else "batches"}
-            if name.startswith("fused") and fused_line is not None:
-                line = fused_line
+            line = {"probe": True, "us_per_step": times.get(name, 99.0), "schedule": sched}
+            if name in expect and bad_line is not None:
+                line = bad_line
             return subprocess.CompletedProcess(cmd, 0, stdout="noise\n" + json.dumps(line) + "\n", stderr="")
         return run
 
     def tune(times, **kw):
         assert len(seen) % len(names) == 0
         monkeypatch.setattr(bench.subprocess, "run", fake_run(times, **kw))
-        return bench.autotune_launch_config(args, 2, 5)
+        return bench.autotune(args, 2)
 
     monkeypatch.setenv("RANK", "0")
-    assert tune({"default": 50.0, "priorities": 40.0, "priorities_deep": 42.0, "fused": 45.0})[:5] == (True, 5, "auto", 0, 0)
-    use, n_pipe, sched, f_ctas, f_groups, rep = tune({"default": 50.0, "priorities": 42.0, "priorities_deep": 38.0, "fused": 60.0})
-    assert (use, n_pipe, sched, rep["chosen"]) == (True, 8, "auto", "priorities_deep")
-    use, n_pipe, sched, f_ctas, f_groups, rep = tune({"default": 50.0, "priorities": 49.0, "priorities_deep": 51.0, "fused": 49.5})
-    assert (use, n_pipe, sched, rep["chosen"]) == (False, 5, "auto", "default") and rep["priorities"]["us_per_step"] == 49.0
-    use, n_pipe, sched, f_ctas, f_groups, rep = tune({"default": 50.0}, fail={"priorities": "rc", "priorities_deep": "timeout", "fused": "rc",
-                                                                             "fused_g5": "rc", "fused_132_g5": "timeout"})
-    assert (use, n_pipe, sched) == (False, 5, "auto") and all("failed" in rep[n] for n in names[1:])
-    assert tune({"default": 50.0, "priorities": 30.0, "priorities_deep": 30.0, "fused": 30.0}, fail={"default": "rc"})[:3] == (False, 5, "auto")
-    # the fused schedule: chosen when verified and fastest, with the grid and group count of the winning candidate ...
-    use, n_pipe, sched, f_ctas, f_groups, rep = tune({"default": 50.0, "priorities": 49.0, "priorities_deep": 50.0, "fused": 38.0})
-    assert (use, n_pipe, sched, f_ctas, f_groups, rep["chosen"]) == (False, 5, "fused", 140, 4, "fused") and rep["fused"]["verified_identical_to_default"]
-    assert tune({"default": 50.0, "priorities": 49.0, "fused": 38.0, "fused_g5": 37.0, "fused_132_g5": 36.0})[2:5] == ("fused", 132, 5)
-    # ... never when its child reports differing results, or ran another schedule
-    use, n_pipe, sched, f_ctas, f_groups, rep = tune({"default": 50.0, "priorities": 49.0, "priorities_deep": 50.0},
-                                                     fused_line={"probe": True, "us_per_step": None, "failed": "fused: batch 3 differs"})
-    assert sched == "auto" and rep["chosen"] == "default" and "differs" in rep["fused"]["failed"]
-    assert tune({"default": 50.0, "priorities": 49.0, "priorities_deep": 50.0}, fused_line={"probe": True, "us_per_step": 38.0, "schedule": "batches"})[2] == "auto"
+    best, rep = tune({"batches": 50.0, "fused64_140": 37.0, "fused64_132": 38.0, "fused128x4_140": 47.0})
+    assert (best["schedule"], best["fused_groups"], best["fused_ctas"], rep["chosen"]) == ("fused", 9, 140, "fused64_140")
+    assert rep["fused64_140"]["verified_identical_to_serial"] and rep["fused128x4_140"]["us_per_step"] == 47.0
+    best, rep = tune({"batches": 50.0, "fused64_140": 49.5, "fused64_132": 52.0, "fused128x4_140": 60.0, "batches_priorities": 49.0})
+    assert best["schedule"] == "batches" and rep["chosen"] == "batches"                      # within 3 %: the default stays
+    best, rep = tune({"batches": 50.0, "batches_priorities": 40.0})
+    assert best.get("launch_priorities") == "on" and rep["chosen"] == "batches_priorities"
+    best, rep = tune({"batches": 50.0}, fail={"fused64_140": "rc", "fused64_132": "timeout", "fused128x4_140": "rc", "batches_priorities": "timeout"})
+    assert best["schedule"] == "batches" and all("failed" in rep[n] for n in names[1:])
+    # a candidate whose child found differing results (or printed no time) is never chosen
+    best, rep = tune({"batches": 50.0}, bad_line={"probe": True, "us_per_step": None, "failed": "RuntimeError: batch 3 differs from gdr_score_topk"})
+    assert best["schedule"] == "batches" and "differs" in rep["fused64_140"]["failed"]
     # other workloads do not try the fused schedule at all
     seen.clear()
     args3 = argparse.Namespace(workload="cfg3", path="auto", schedule="auto", replicas=0)
@@ -283,5 +282,5 @@ def test_bench_launch_autotune_decision(monkeypatch):
         seen.append(cmd)
         return subprocess.CompletedProcess(cmd, 0, stdout=json.dumps({"probe": True, "us_per_step": 100.0, "schedule": "batches"}), stderr="")
     monkeypatch.setattr(bench.subprocess, "run", run3)
-    bench.autotune_launch_config(args3, 2, 5)
-    assert len(seen) == 3 and all("fused" not in c for c in seen)
+    bench.autotune(args3, 2)
+    assert len(seen) == 2 and all("fused" not in c for c in seen)

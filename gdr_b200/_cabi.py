@@ -19,6 +19,11 @@ SYMBOLS = {
     "gdr_abi_version": (c_int32, []),
     "gdr_last_error": (c_char_p, []),
     "gdr_store_create": (c_int32, [POINTER(c_void_p), c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_int32]),
+    "gdr_store_create_shard": (c_int32, [POINTER(c_void_p), c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_int64, c_int32,
+                                          c_int32, c_int32, c_int64]),
+    "gdr_store_p2p_init": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "gdr_store_p2p_attach": (c_int32, [c_void_p, c_void_p]),
+    "gdr_store_p2p_attach_local": (c_int32, [c_void_p, POINTER(c_void_p)]),
     "gdr_store_destroy": (c_int32, [c_void_p]),
     "gdr_score_topk": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_float), c_int32, c_int32, c_int32,
                                  c_int32, c_int32, c_uint32, c_void_p, c_void_p, c_void_p]),

@@ -55,6 +55,16 @@ struct gdr_store {
     ScoreArgs last_args;
     bool last_valid = false, last_umma_only = false;
     int fused_groups = 9;       // GDR_OPT_FUSED_GROUPS: 9 = nine 64-thread top-k groups in the fused CTA (default), 4 = four 128-thread groups
+    // cluster-sharded corpus (gdr_store_create_shard): this handle's emb holds global rows [row_lo, row_lo + n_local) = clusters [c_lo, c_hi)
+    int32_t c_lo = 0, c_hi = 0, row_lo = 0;
+    int64_t n_local = 0;
+    // peer-to-peer candidate exchange (gdr_store_p2p_*): one buffer per handle = [b_own * stride] fp32 scores | [GDR_MAX_RANKS] arrival flags
+    int32_t n_ranks = 1, my_rank = 0, b_own = 0, p2p_K = 0;
+    void *p2p_buf = nullptr;                       // this rank's buffer (cudaMalloc: exportable with cudaIpcGetMemHandle)
+    size_t p2p_score_bytes = 0;
+    void *peer_buf[GDR_MAX_RANKS] = {nullptr};     // every rank's buffer as mapped into this process (own entry = p2p_buf)
+    bool peer_opened[GDR_MAX_RANKS] = {false};     // mapped with cudaIpcOpenMemHandle (to be closed)
+    int32_t *sig_epoch = nullptr;                  // device int: scoring launches of this handle
     long long *dbg = nullptr;   // device timeline scratch for GDR_UMMA_TRACE
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 };
@@ -77,8 +87,27 @@ int gdr_abi_version(void) { return 1; }
 
 const char *gdr_last_error(void) { return g_last_error.c_str(); }
 
+static int store_create_common(gdr_store_t **out, const void *emb, int64_t n_docs, int32_t dim, int32_t dtype, const int32_t *offsets,
+                               int32_t n_clusters, const int32_t *docid, int32_t max_cluster_size, int64_t n_local, int32_t c_lo, int32_t c_hi,
+                               int64_t row_lo);
+
 int gdr_store_create(gdr_store_t **out, const void *emb, int64_t n_docs, int32_t dim, int32_t dtype,
                      const int32_t *offsets, int32_t n_clusters, const int32_t *docid, int32_t max_cluster_size) {
+    return store_create_common(out, emb, n_docs, dim, dtype, offsets, n_clusters, docid, max_cluster_size, n_docs, 0, n_clusters, 0);
+}
+
+int gdr_store_create_shard(gdr_store_t **out, const void *emb_local, int64_t n_local_rows, int32_t dim, int32_t dtype,
+                           const int32_t *offsets_global, int32_t n_clusters_global, const int32_t *docid_global, int64_t n_docs_global,
+                           int32_t max_cluster_size, int32_t c_lo, int32_t c_hi, int64_t row_lo) {
+    if (c_lo < 0 || c_hi < c_lo || c_hi > n_clusters_global) return invalid("gdr_store_create_shard: need 0 <= c_lo <= c_hi <= n_clusters");
+    if (row_lo < 0 || n_local_rows <= 0 || row_lo + n_local_rows > n_docs_global) return invalid("gdr_store_create_shard: local rows outside the corpus");
+    return store_create_common(out, emb_local, n_docs_global, dim, dtype, offsets_global, n_clusters_global, docid_global, max_cluster_size,
+                               n_local_rows, c_lo, c_hi, row_lo);
+}
+
+static int store_create_common(gdr_store_t **out, const void *emb, int64_t n_docs, int32_t dim, int32_t dtype, const int32_t *offsets,
+                               int32_t n_clusters, const int32_t *docid, int32_t max_cluster_size, int64_t n_local, int32_t c_lo, int32_t c_hi,
+                               int64_t row_lo) {
     if (!out) return invalid("gdr_store_create: out is null");
     *out = nullptr;
     if (!emb || !offsets || !docid) return invalid("gdr_store_create: null device pointer");
@@ -96,6 +125,7 @@ int gdr_store_create(gdr_store_t **out, const void *emb, int64_t n_docs, int32_t
     if (!s) return GDR_ERR_NOMEM;
     s->emb = emb; s->n_docs = n_docs; s->dim = dim; s->dtype = dtype;
     s->offsets = offsets; s->n_clusters = n_clusters; s->docid = docid; s->max_cluster = max_cluster_size;
+    s->n_local = n_local; s->c_lo = c_lo; s->c_hi = c_hi; s->row_lo = (int32_t)row_lo;
     cudaError_t e = cudaGetDevice(&s->device);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device);
     const size_t n = (size_t)n_clusters;
@@ -106,7 +136,7 @@ int gdr_store_create(gdr_store_t **out, const void *emb, int64_t n_docs, int32_t
         delete s;
         return cuda_fail(e, "gdr_store_create");
     }
-    if (dtype == GDR_DTYPE_BF16 && dim % 64 == 0) s->has_tmap = umma_make_tensor_map(&s->tmap, emb, n_docs, dim);
+    if (dtype == GDR_DTYPE_BF16 && dim % 64 == 0) s->has_tmap = umma_make_tensor_map(&s->tmap, emb, n_local, dim);   // the rows this handle holds
 #ifdef GDR_DEBUG_KNOBS
     // Measurement builds only (python -m gdr_b200._build --debug-knobs): timing experiments that switch pipeline stages off or
     // cut the top-k short — results are INVALID under them, so the product build does not contain them.
@@ -123,6 +153,10 @@ int gdr_store_destroy(gdr_store_t *s) {
     cudaFree(s->cluster_ws);
     cudaFree(s->batch_ws);
     cudaFree(s->dbg);
+    for (int r = 0; r < GDR_MAX_RANKS; ++r)
+        if (s->peer_opened[r]) cudaIpcCloseMemHandle(s->peer_buf[r]);
+    cudaFree(s->p2p_buf);
+    cudaFree(s->sig_epoch);
     for (auto &e : s->ev)
         if (e) cudaEventDestroy(e);
     delete s;
@@ -157,7 +191,7 @@ ScratchPlan plan_scratch(const gdr_store *s, int32_t B, int32_t K, int32_t k, ui
     p.o_cbase = take(p.pairs * 4);
     p.o_simt = take((size_t)simt_cap * sizeof(Item));
     p.o_umma = take(p.umma_possible ? (size_t)umma_cap * sizeof(Item) : 0);
-    p.o_score = take((size_t)B * p.stride * 4);
+    p.o_score = take(s->n_ranks > 1 ? 0 : (size_t)B * p.stride * 4);       // sharded exchange: the scores live in the p2p buffer
     p.o_qsplit = take(p.umma_possible ? (size_t)p.q_rows * 3 * s->dim * 2 : 0);
     p.o_tmeta = take(p.umma_possible ? (size_t)umma_cap * sizeof(TileMeta) : 0);
     p.o_keys = take(p.global_keys ? (size_t)B * p.stride * 4 : 0);
@@ -203,6 +237,73 @@ int gdr_store_reserve(gdr_store_t *s, int32_t B, int32_t K, int32_t k, uint32_t 
     if (int rc = check_shape(s, B, K, k, flags, "gdr_store_reserve")) return rc;
     if (B == 0) return GDR_OK;
     return ensure_scratch(s, plan_scratch(s, B, K, k, flags).total, (cudaStream_t)stream);
+}
+
+// ---- peer-to-peer candidate exchange of a cluster-sharded corpus (include/gdr_b200.h) --------------------------------------------
+int gdr_store_p2p_init(gdr_store_t *s, int32_t n_ranks, int32_t my_rank, int32_t b_own, int32_t K, void *ipc_handle_out) {
+    if (!s) return invalid("gdr_store_p2p_init: store is null");
+    if (n_ranks < 2 || n_ranks > GDR_MAX_RANKS || my_rank < 0 || my_rank >= n_ranks) return invalid("gdr_store_p2p_init: need 2 <= n_ranks <= 8 and 0 <= my_rank < n_ranks");
+    if (b_own <= 0 || K <= 0) return invalid("gdr_store_p2p_init: need b_own > 0, K > 0");
+    if (s->p2p_buf) return invalid("gdr_store_p2p_init: already initialised");
+    const size_t stride = align_up((size_t)K * s->max_cluster, 4);
+    if ((int64_t)b_own * (int64_t)stride >= (1ll << OFF_OWNER_SHIFT)) return invalid("gdr_store_p2p_init: b_own * K * max_cluster_size must be below 2^28");
+    const size_t score_bytes = align_up((size_t)b_own * stride * 4, 256);
+    GDR_CUDA(cudaMalloc(&s->p2p_buf, score_bytes + 256));
+    GDR_CUDA(cudaMemset(s->p2p_buf, 0, score_bytes + 256));
+    GDR_CUDA(cudaMalloc(&s->sig_epoch, 256));
+    GDR_CUDA(cudaMemset(s->sig_epoch, 0, 256));
+    s->p2p_score_bytes = score_bytes;
+    s->n_ranks = n_ranks; s->my_rank = my_rank; s->b_own = b_own; s->p2p_K = K;
+    s->peer_buf[my_rank] = s->p2p_buf;
+    if (ipc_handle_out) {
+        cudaIpcMemHandle_t h;
+        static_assert(sizeof(h) == GDR_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t is 64 bytes");
+        GDR_CUDA(cudaIpcGetMemHandle(&h, s->p2p_buf));
+        memcpy(ipc_handle_out, &h, sizeof(h));
+    }
+    GDR_CUDA(cudaDeviceSynchronize());
+    s->last_valid = false;
+    return GDR_OK;
+}
+
+int gdr_store_p2p_attach(gdr_store_t *s, const void *all_handles) {
+    if (!s || !all_handles) return invalid("gdr_store_p2p_attach: null argument");
+    if (!s->p2p_buf) return invalid("gdr_store_p2p_attach: call gdr_store_p2p_init first");
+    for (int r = 0; r < s->n_ranks; ++r) {
+        if (r == s->my_rank || s->peer_buf[r]) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, reinterpret_cast<const char *>(all_handles) + (size_t)r * GDR_IPC_HANDLE_BYTES, sizeof(h));
+        void *p = nullptr;
+        GDR_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        s->peer_buf[r] = p;
+        s->peer_opened[r] = true;
+    }
+    return GDR_OK;
+}
+
+int gdr_store_p2p_attach_local(gdr_store_t *s, gdr_store_t *const *peers) {
+    if (!s || !peers) return invalid("gdr_store_p2p_attach_local: null argument");
+    if (!s->p2p_buf) return invalid("gdr_store_p2p_attach_local: call gdr_store_p2p_init first");
+    for (int r = 0; r < s->n_ranks; ++r) {
+        if (r == s->my_rank) continue;
+        const gdr_store *o = peers[r];
+        if (!o || !o->p2p_buf || o->n_ranks != s->n_ranks || o->my_rank != r || o->b_own != s->b_own || o->p2p_K != s->p2p_K ||
+            o->p2p_score_bytes != s->p2p_score_bytes)
+            return invalid("gdr_store_p2p_attach_local: peer handles must be initialised with the same n_ranks / b_own / K and their own rank");
+        int dev_o = o->device, can = 1;
+        if (dev_o != s->device) {
+            GDR_CUDA(cudaDeviceCanAccessPeer(&can, s->device, dev_o));
+            if (!can) {
+                set_error("gdr_store_p2p_attach_local: no peer access between the two devices");
+                return GDR_ERR_UNSUPPORTED;
+            }
+            cudaError_t e = cudaDeviceEnablePeerAccess(dev_o, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_fail(e, "cudaDeviceEnablePeerAccess");
+            cudaGetLastError();
+        }
+        s->peer_buf[r] = o->p2p_buf;
+    }
+    return GDR_OK;
 }
 
 int gdr_store_set_option(gdr_store_t *s, int32_t option, int32_t value) {
@@ -281,6 +382,22 @@ int gdr_score_topk(gdr_store_t *s, const float *q, const int32_t *beams, const f
     a.umma_items = reinterpret_cast<Item *>(ws + p.o_umma);
     a.scorebuf = reinterpret_cast<float *>(ws + p.o_score);
     a.stride = p.stride;
+    a.c_lo = s->c_lo; a.c_hi = s->c_hi; a.row_lo = s->row_lo;
+    a.n_ranks = 1; a.my_rank = 0; a.b_own = B; a.q_base = 0; a.B_top = B;
+    if (s->n_ranks > 1) {
+        // sharded exchange: B is the GLOBAL batch (n_ranks x b_own queries, the same on every rank); this rank selects the top-k of its own
+        // b_own queries out of a score buffer that all ranks fill; outputs are [n_alpha, b_own, k]
+        if (B != s->n_ranks * s->b_own || K != s->p2p_K) return invalid("gdr_score_topk: a p2p handle takes batches of exactly n_ranks * b_own queries with the K given to gdr_store_p2p_init");
+        if ((int64_t)s->b_own * p.stride >= (1ll << OFF_OWNER_SHIFT)) return invalid("gdr_score_topk: b_own * K * max_cluster_size must be below 2^28 on a p2p handle");
+        a.n_ranks = s->n_ranks; a.my_rank = s->my_rank; a.b_own = s->b_own; a.q_base = s->my_rank * s->b_own; a.B_top = s->b_own;
+        a.scorebuf = reinterpret_cast<float *>(s->p2p_buf);
+        for (int r = 0; r < s->n_ranks; ++r) {
+            a.peer_score[r] = reinterpret_cast<float *>(s->peer_buf[r]);
+            a.peer_sig[r] = reinterpret_cast<int32_t *>(reinterpret_cast<char *>(s->peer_buf[r]) + s->p2p_score_bytes);
+        }
+        a.sig_local = a.peer_sig[s->my_rank];
+        a.sig_epoch = s->sig_epoch;
+    }
     a.gkeys = p.global_keys ? reinterpret_cast<uint32_t *>(ws + p.o_keys) : nullptr;
     a.ghist = p.small_topk ? reinterpret_cast<uint32_t *>(ws + p.o_ghist) : nullptr;
     a.qsplit = nullptr;   // set below when the tcgen05 path is taken
@@ -309,11 +426,13 @@ int gdr_score_topk(gdr_store_t *s, const float *q, const int32_t *beams, const f
     a.launch_prio = s->prio_score;
     if (prof) GDR_CUDA(cudaEventRecord(s->ev[1], st));
     if (use_umma && !(flags & GDR_SKIP_SCORE)) {
+        a.signal = use_simt ? 0 : 1;              // (mixed mode: the GEMV kernel is the call's last scoring kernel and signals)
         GDR_CUDA(launch_score_umma(a, &s->tmap, st, s->umma_ctas > 0 ? s->umma_ctas : s->sm_count));
         launches += 1;
     }
     if (prof) GDR_CUDA(cudaEventRecord(s->ev[2], st));
     if (use_simt && !(flags & GDR_SKIP_SCORE)) {
+        a.signal = 1;
         GDR_CUDA(launch_score_simt(a, st, s->sm_count));
         launches += 1;
     }
@@ -321,12 +440,13 @@ int gdr_score_topk(gdr_store_t *s, const float *q, const int32_t *beams, const f
     a.launch_prio = s->prio_topk;
     for (int r = 0; r < n_alpha && !(flags & GDR_SKIP_TOPK); ++r) {
         const float alpha = alphas ? alphas[r] : 1.0f;
-        GDR_CUDA(launch_topk_store(a, alpha, out_scores + (int64_t)r * B * k, out_docids + (int64_t)r * B * k, st));
+        GDR_CUDA(launch_topk_store(a, alpha, out_scores + (int64_t)r * a.B_top * k, out_docids + (int64_t)r * a.B_top * k, st));
         launches += 1;
     }
     if (prof) GDR_CUDA(cudaEventRecord(s->ev[4], st));
     s->last_launches = launches;
     a.launch_prio = s->prio_score;                // what gdr_score_fused launches with
+    a.signal = 1;
     s->last_args = a;
     s->last_valid = true;
     s->last_umma_only = use_umma && !use_simt;

@@ -37,13 +37,15 @@ constexpr int SIMT_QT = 4;       // (query, beam) pairs per SIMT item
 constexpr int UMMA_ROWS = 128;   // rows per tcgen05 tile (UMMA_M)
 constexpr int UMMA_NQ = 32;      // max pairs per tcgen05 tile (UMMA_N)
 constexpr int MAX_DIM = 1024;
+constexpr int GDR_MAX_RANKS = 8;   // GPUs of one NVSwitch domain a sharded corpus may span
+constexpr int OFF_OWNER_SHIFT = 28; // sharded score offsets: owner rank in bits 28-30, offset inside the owner's score buffer below
 
 // counters[] layout (device int32)
 // CTR_TILE_NEXT / CTR_TILE_DONE: the tcgen05 kernel's dynamic tile queue (claimed with atomicAdd; the last CTA to finish
 // resets both, so they are zero between launches)
 // CTR_TOPK_NEXT / CTR_TOPK_DONE: the same protocol for the query queue of the grouped top-k (experiment, GDR_TOPK_GROUPS)
 enum { CTR_N_SIMT = 0, CTR_N_UMMA = 1, CTR_N_TOUCHED = 2, CTR_TILE_NEXT = 3, CTR_TILE_DONE = 4, CTR_TOPK_NEXT = 5, CTR_TOPK_DONE = 6,
-       CTR_COUNT = 8 };
+       CTR_SIMT_DONE = 7, CTR_COUNT = 8 };
 
 // Everything the tcgen05 kernel needs to know about one tile, resolved once per batch by k_tilemeta (work item ->
 // pairs -> candidate offsets: three dependent loads) so that the scoring kernel fetches it with ONE bulk copy.
@@ -87,6 +89,19 @@ struct ScoreArgs {
     uint32_t *ghist;     // [B, 2048] histogram scratch of the small-footprint top-k's fallback (null: variant not used)
     long long *dbg;      // [512] optional timeline scratch (GDR_UMMA_TRACE=1), else null
     int32_t umma_min_group;  // groups with at least this many pairs go to the tcgen05 path (INT_MAX = never)
+    // ---- cluster-sharded corpus (all defaults = one unsharded store: c_lo = 0, c_hi = n_clusters, row_lo = 0, n_ranks = 1)
+    // offsets / docid / n_clusters describe the GLOBAL corpus; emb holds only the rows of the owned clusters [c_lo, c_hi), i.e.
+    // global rows [row_lo, ...).  Every rank inverts the whole global batch, scores the pairs that land in its clusters and
+    // stores each score straight into the score buffer of the query's OWNER (rank b / b_own) over NVLink (peer_score[]); the
+    // owner runs the top-k of its own b_own queries once all ranks have signalled (sig_*).
+    int32_t c_lo, c_hi, row_lo;
+    int32_t n_ranks, my_rank, b_own;   // queries per owner (= B when n_ranks == 1)
+    int32_t q_base, B_top;             // the top-k of this rank covers global queries [q_base, q_base + B_top) (0, B when unsharded)
+    float *peer_score[GDR_MAX_RANKS];  // score buffer [b_own, stride] of each rank (this rank's own entry = scorebuf)
+    int32_t *peer_sig[GDR_MAX_RANKS];  // each rank's arrival flags [n_ranks]: peer_sig[r][my_rank] <- this handle's scoring epoch
+    int32_t *sig_local;                // this rank's arrival flags [n_ranks] (= peer_sig[my_rank])
+    int32_t *sig_epoch;                // [1] device counter: scoring launches of this handle so far
+    int32_t signal;                    // 1 in the copy given to the call's LAST scoring kernel: it signals the owners when it is done
     int32_t launch_prio;     // host side only: scheduling priority class of the launches made with this copy of the arguments
                              // (0 = none; else a CUDA priority + 1000), set per phase by the C-ABI entry point — per call, not global
 };
@@ -186,6 +201,40 @@ __device__ __forceinline__ void trace_start(long long *dbg, int slot) {
 }
 __device__ __forceinline__ void trace_end(long long *dbg, int slot) {
     if (dbg && threadIdx.x == 0) atomicMax(reinterpret_cast<unsigned long long *>(dbg) + 500 + slot, gdr_gtime());
+}
+
+// ----- sharded corpus: where a score goes, when the owner may read it ---------------------------------------------------
+// `off` = index inside a score buffer; with n_ranks > 1 the owner rank sits in bits 28-30 (k_tilemeta / score_dst pack it).
+__device__ __forceinline__ int64_t pack_score_off(const ScoreArgs &a, int b, int64_t within_row) {
+    if (a.n_ranks <= 1) return (int64_t)b * a.stride + within_row;
+    return ((int64_t)(b / a.b_own) << OFF_OWNER_SHIFT) | ((int64_t)(b % a.b_own) * a.stride + within_row);
+}
+__device__ __forceinline__ float *score_ptr(const ScoreArgs &a, int64_t off) {
+    if (a.n_ranks <= 1) return a.scorebuf + off;
+    return a.peer_score[off >> OFF_OWNER_SHIFT] + (off & ((1ll << OFF_OWNER_SHIFT) - 1));
+}
+// Called by ONE thread after the last CTA of a scoring kernel has finished (every CTA fenced at system scope before it
+// counted itself done): bump this handle's scoring epoch and publish it to every owner.
+__device__ __forceinline__ void signal_owners(const ScoreArgs &a) {
+    if (a.n_ranks <= 1 || !a.signal) return;
+    const int e = *a.sig_epoch + 1;
+    *a.sig_epoch = e;
+    __threadfence_system();
+    for (int r = 0; r < a.n_ranks; ++r)
+        asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(a.peer_sig[r] + a.my_rank), "r"(e) : "memory");
+}
+// Called by ONE thread of a top-k CTA / group before the first score is read: every rank's scoring launch of this handle's
+// current epoch has landed in this rank's score buffer.  The local epoch is the expected value: the local scoring launch of
+// the same batch precedes the top-k in stream order, and all ranks step through the handle's batches in the same order.
+__device__ __forceinline__ void wait_for_scorers(const ScoreArgs &a) {
+    if (a.n_ranks <= 1) return;
+    const int expected = *reinterpret_cast<volatile int32_t *>(a.sig_epoch);
+    for (int r = 0; r < a.n_ranks; ++r) {
+        int v;
+        do {
+            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(a.sig_local + r) : "memory");
+        } while (v - expected < 0);
+    }
 }
 
 // ----- small device helpers -----------------------------------------------------------------

@@ -57,7 +57,7 @@ __device__ __forceinline__ void count_query(const ScoreArgs &a, int b, int lane,
             if (c >= 0 && c < a.n_clusters) {
                 row_lo = a.offsets[c];
                 sz = a.offsets[c + 1] - row_lo;
-                atomicAdd(&cnt[c], 1);
+                if (c >= a.c_lo && c < a.c_hi) atomicAdd(&cnt[c], 1);     // sharded corpus: only the owned clusters form groups here
             }
             cb[i] = row_lo;               // the top-k maps a winning candidate back to its store row without touching beams/offsets
         }
@@ -101,7 +101,7 @@ __device__ __forceinline__ void write_items(const ScoreArgs &a, int c, int g0, i
         const int nrows = min(rows_per, size - r);
         for (int s = 0; s < g; s += q_per) {
             Item it;
-            it.row0 = row_lo + r;
+            it.row0 = row_lo + r - a.row_lo;        // row inside this handle's emb (a shard holds global rows [row_lo, ...))
             it.rel0 = r;
             it.nrows_nq = nrows | (min(q_per, g - s) << 16);
             it.slot0 = g0 + s;
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(256) k_fill(ScoreArgs a) {
     // offsets are block-local when the scan ran in several CTAs: add the base of the cluster's 8,192-cluster block
     if (t < n_pairs) {
         const int c = a.beams[t];
-        if (c >= 0 && c < a.n_clusters) {
+        if (c >= a.c_lo && c < a.c_hi && c >= 0 && c < a.n_clusters) {
             const int slot = a.scan_base[4 * (c / SCAN_BLOCK)] + a.grp_off[c] + atomicSub(&a.cnt[c], 1) - 1;
             a.grp_pair[slot] = (int32_t)t;
         }
@@ -287,7 +287,7 @@ __device__ __forceinline__ void write_tile_meta(const ScoreArgs &a, int t, int l
         const int p = a.grp_pair[item.slot0 + lane];
         const int b = p / a.K;
         qrow = (a.flags & GDR_Q_PER_BEAM) ? p : b;
-        off = (int)((int64_t)b * a.stride + a.candoff[p + b] + item.rel0);
+        off = (int)pack_score_off(a, b, a.candoff[p + b] + item.rel0);
     }
     TileMeta *m = a.tile_meta + t;
     if (lane == 0) {
@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(1024) k_invert_small(ScoreArgs a) {
     const int n_pairs = a.B * a.K;
     for (int p = tid; p < n_pairs; p += 1024) {
         const int c = a.beams[p];
-        if (c >= 0 && c < C) a.grp_pair[s_off[c] + atomicSub(&s_cnt[c], 1) - 1] = p;
+        if (c >= a.c_lo && c < a.c_hi && c >= 0 && c < C) a.grp_pair[s_off[c] + atomicSub(&s_cnt[c], 1) - 1] = p;
     }
     // s_cnt is being decremented above; group sizes for the items come from the scan
     for (int c = tid; c < C; c += 1024) {

@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(128) k_score_simt(ScoreArgs a) {
             const int p = a.grp_pair[item.slot0];
             const int b = p / a.K;
             const int qrow[1] = {per_beam ? p : b};
-            float *dst = a.scorebuf + (int64_t)b * a.stride + a.candoff[p + b] + item.rel0;
+            float *dst = score_ptr(a, pack_score_off(a, b, a.candoff[p + b] + item.rel0));
             score_rows<T, CPL, 1, RB1>(rows, a.dim, nrows, a.q, qrow, dst, a.act, lane);
         } else {
             int qrow[SIMT_QT];
@@ -174,9 +174,19 @@ __global__ void __launch_bounds__(128) k_score_simt(ScoreArgs a) {
             if (my_j < nq) {
                 const int p = a.grp_pair[item.slot0 + my_j];
                 const int b = p / a.K;
-                dst = a.scorebuf + (int64_t)b * a.stride + a.candoff[p + b] + item.rel0;
+                dst = score_ptr(a, pack_score_off(a, b, a.candoff[p + b] + item.rel0));
             }
             score_rows<T, CPL, SIMT_QT, RB4>(rows, a.dim, nrows, a.q, qrow, dst, a.act, lane);
+        }
+    }
+    if (a.n_ranks > 1) {              // sharded corpus: the last CTA to finish tells the owners that this rank's scores have landed
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            if (atomicAdd(&a.counters[CTR_SIMT_DONE], 1) == (int)gridDim.x - 1) {
+                a.counters[CTR_SIMT_DONE] = 0;
+                signal_owners(a);
+            }
         }
     }
     pdl_launch_dependents();      // at the end: released at entry, the top-k's CTAs would sit resident for this whole kernel (see k_score_umma)

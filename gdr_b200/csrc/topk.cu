@@ -28,17 +28,22 @@ __global__ void __launch_bounds__(TKF_THREADS, 10) k_topk_fast(ScoreArgs a, floa
     int32_t *co = reinterpret_cast<int32_t *>(hist_words + TK_BINS / 2);
     int32_t *cbase = co + a.K + 1;
     float *bias = reinterpret_cast<float *>(cbase + a.K);
-    const int b = blockIdx.x;
+    const int b = blockIdx.x;                 // row of the score buffer / of the outputs
+    const int bg = b + a.q_base;              // the query's index in the (global) batch: candoff / cbase / prob rows
     pdl_wait();
     trace_start(a.dbg, 4);
+    if (a.n_ranks > 1) {                      // sharded corpus: the other ranks' scores of this batch have landed
+        if (threadIdx.x == 0) wait_for_scorers(a);
+        __syncthreads();
+    }
     for (int i = threadIdx.x; i <= a.K; i += TKF_THREADS) {          // one round trip: k_count left both arrays per query
-        co[i] = a.candoff[(int64_t)b * (a.K + 1) + i];
+        co[i] = a.candoff[(int64_t)bg * (a.K + 1) + i];
         if (i < a.K) {
-            cbase[i] = a.cbase[(int64_t)b * a.K + i];
-            if (a.prob) bias[i] = __fmul_rn(alpha, a.prob[(int64_t)b * a.K + i]);
+            cbase[i] = a.cbase[(int64_t)bg * a.K + i];
+            if (a.prob) bias[i] = __fmul_rn(alpha, a.prob[(int64_t)bg * a.K + i]);
         }
     }
-    const int n = a.candoff[(int64_t)b * (a.K + 1) + a.K];           // every thread reads it itself: no barrier before the score loads
+    const int n = a.candoff[(int64_t)bg * (a.K + 1) + a.K];          // every thread reads it itself: no barrier before the score loads
     const uint32_t dbg = (a.flags >> 20) & 15u;
     if (dbg == 9u) {                          // timing experiment: stay resident ~15 us without doing anything, then stop
         for (int i = 0; i < 150; ++i) __nanosleep(100);
@@ -71,11 +76,13 @@ __global__ void __launch_bounds__(TK_THREADS, 8) k_topk_store(ScoreArgs a, float
     pdl_wait();
     trace_start(a.dbg, 4);
     const int b = blockIdx.x;
+    const int bg = b + a.q_base;
+    if (a.n_ranks > 1 && threadIdx.x == 0) wait_for_scorers(a);      // (the barrier below orders the other threads behind it)
     for (int i = threadIdx.x; i <= a.K; i += TK_THREADS) {
-        co[i] = a.candoff[(int64_t)b * (a.K + 1) + i];
+        co[i] = a.candoff[(int64_t)bg * (a.K + 1) + i];
         if (i < a.K) {
-            cbase[i] = a.cbase[(int64_t)b * a.K + i];
-            if (a.prob) bias[i] = __fmul_rn(alpha, a.prob[(int64_t)b * a.K + i]);
+            cbase[i] = a.cbase[(int64_t)bg * a.K + i];
+            if (a.prob) bias[i] = __fmul_rn(alpha, a.prob[(int64_t)bg * a.K + i]);
         }
     }
     __syncthreads();
@@ -103,7 +110,7 @@ __global__ void __launch_bounds__(TK_THREADS) k_topk_merge(ListSrc src0, int n, 
 static int pow2_at_least(int x) { int p = 2; while (p < x) p <<= 1; return p; }
 
 cudaError_t launch_topk_store(const ScoreArgs &a, float alpha, float *out_scores, int32_t *out_docids, cudaStream_t s) {
-    if (a.B == 0) return cudaSuccess;
+    if (a.B_top == 0) return cudaSuccess;
     const int cap = pow2_at_least(a.k);
     const size_t fixed = (size_t)cap * 8 + (size_t)TK_BINS * 4 + (size_t)(3 * a.K + 1) * 4;
     const size_t with_keys = fixed + (size_t)a.stride * 4;
@@ -114,7 +121,7 @@ cudaError_t launch_topk_store(const ScoreArgs &a, float alpha, float *out_scores
         return e2;
     });
     if (e != cudaSuccess) return e;
-    const int grid = a.B;      // (a few persistent CTAs per SM walking the queries measured slower in the pipelined step: 62 vs 57 us)
+    const int grid = a.B_top;  // (a few persistent CTAs per SM walking the queries measured slower in the pipelined step: 62 vs 57 us)
     const int groups = (int)((a.flags >> 16) & 7u);                // GDR_OPT_TOPK_GROUPS (topk_grouped.cu)
     const int pr = a.launch_prio;
     if (groups && cap <= 128 && a.gkeys && a.ghist && a.stride <= 65535) return launch_topk_grouped(a, alpha, out_scores, out_docids, s, groups);

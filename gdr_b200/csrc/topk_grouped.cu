@@ -30,7 +30,7 @@ cudaError_t launch_topk_grouped(const ScoreArgs &a, float alpha, float *out_scor
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int per_sm = groups >= 4 ? 2 : (groups == 2 ? 4 : 8);          // eight groups per SM in every shape
-    const int ctas = min((a.B + groups - 1) / groups, sms * per_sm);
+    const int ctas = min((a.B_top + groups - 1) / groups, sms * per_sm);
     const size_t smem = (size_t)groups * tkg_slice_bytes(a.K);
     if (groups >= 4) return launch_pdl(k_topk_fast_grouped<4>, dim3(ctas), dim3(TKF_THREADS * 4), smem, s, a.launch_prio, a, alpha, out_scores, out_docids);
     if (groups >= 2) return launch_pdl(k_topk_fast_grouped<2>, dim3(ctas), dim3(TKF_THREADS * 2), smem, s, a.launch_prio, a, alpha, out_scores, out_docids);

@@ -743,19 +743,21 @@ __device__ void topk_group_loop(const ScoreArgs &a, float alpha, float *out_scor
     float *bias = reinterpret_cast<float *>(cbase + a.K);
     TkShared *sh = reinterpret_cast<TkShared *>(bias + a.K);
     volatile int *next = reinterpret_cast<int *>(sh + 1);
+    if (a.n_ranks > 1 && tid == 0) wait_for_scorers(a);            // sharded corpus (the first barrier below orders the group behind it)
     for (;;) {
         if (tid == 0) *next = atomicAdd(&a.counters[CTR_TOPK_NEXT], 1);
         S::sync();
         const int b = *next;
-        if (b >= a.B) break;                                       // group-uniform
+        if (b >= a.B_top) break;                                   // group-uniform
+        const int bg = b + a.q_base;                               // row of candoff / cbase / prob (global batch index)
         for (int i = tid; i <= a.K; i += NT) {
-            co[i] = a.candoff[(int64_t)b * (a.K + 1) + i];
+            co[i] = a.candoff[(int64_t)bg * (a.K + 1) + i];
             if (i < a.K) {
-                cbase[i] = a.cbase[(int64_t)b * a.K + i];
-                if (a.prob) bias[i] = __fmul_rn(alpha, a.prob[(int64_t)b * a.K + i]);
+                cbase[i] = a.cbase[(int64_t)bg * a.K + i];
+                if (a.prob) bias[i] = __fmul_rn(alpha, a.prob[(int64_t)bg * a.K + i]);
             }
         }
-        const int n = a.candoff[(int64_t)b * (a.K + 1) + a.K];
+        const int n = a.candoff[(int64_t)bg * (a.K + 1) + a.K];
         StoreSrc src{a.scorebuf + (int64_t)b * a.stride, co, cbase, a.prob ? bias : nullptr, a.docid, a.K};
         topk_fast16<NT, R4, StoreSrc, S>(src, n, a.k, a.gkeys + (int64_t)b * a.stride, a.ghist + (int64_t)b * TK_BINS, sel, hist_words,
                                          sh, out_scores + (int64_t)b * a.k, out_docids + (int64_t)b * a.k, 0u);

@@ -128,7 +128,8 @@ class PipelinedRetriever:
             self.flush()                                       # the schedule changes with the shape: drain first
         self.last_schedule = "fused" if fused else "batches"
         if out is None:
-            out = (torch.empty((B, k), dtype=torch.float32, device=self.dev), torch.empty((B, k), dtype=torch.int32, device=self.dev))
+            B_out = self.store.p2p[2] if getattr(self.store, "p2p", None) else B
+            out = (torch.empty((B_out, k), dtype=torch.float32, device=self.dev), torch.empty((B_out, k), dtype=torch.int32, device=self.dev))
         t = Ticket(self._n, out[0], out[1], float(alpha), (q, beams, prob))
         t.which = which
         cur = torch.cuda.current_stream(self.dev)

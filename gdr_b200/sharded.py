@@ -38,6 +38,17 @@ def partition_clusters(sizes: Sequence[int], world_size: int) -> np.ndarray:
     return owner
 
 
+def partition_contiguous(sizes: Sequence[int], world_size: int) -> np.ndarray:
+    """Split the cluster sequence into `world_size` CONTIGUOUS ranges balanced by document count (the form the peer-to-peer
+    exchange needs: a shard is one slab of rows).  Returns bounds[world_size + 1]: rank r owns clusters [bounds[r], bounds[r+1])."""
+    sizes = np.asarray(sizes, dtype=np.int64)
+    csum = np.concatenate([[0], np.cumsum(sizes)])
+    targets = csum[-1] * np.arange(1, world_size) / world_size
+    cuts = np.searchsorted(csum, targets, side="left")
+    bounds = np.concatenate([[0], cuts, [sizes.size]]).astype(np.int64)
+    return np.maximum.accumulate(bounds)
+
+
 def global_to_local(owner: np.ndarray, rank: int) -> Tuple[np.ndarray, np.ndarray]:
     """Returns (g2l [C] int32: local cluster index or -1, local_clusters: the global ids this rank owns,
     ascending)."""
@@ -109,3 +120,56 @@ class ShardedRetriever:
         gathered = torch.empty((self.world_size * 2,) + tuple(packed.shape[1:]), dtype=packed.dtype, device=packed.device)
         dist.all_gather_into_tensor(gathered, packed, group=self.group)
         return self._merge(gathered.view((self.world_size,) + tuple(packed.shape)), k)
+
+
+class ShardedPipeline:
+    """The north-star multi-GPU path on a cluster-sharded corpus, pipelined: one process per GPU, `stores` = this rank's shard
+    (`ClusterStore.shard`; a list = several indexes / the bench's L2-defeating copies).  The global batch (world x b_own queries,
+    identical q / beams on every rank, beams with GLOBAL cluster ids) is submitted on every rank; each rank gets the top-k of
+    the b_own queries it owns.
+
+    exchange = "p2p": candidates never become lists — every rank's scoring epilogue stores its scores straight into the owner's
+    score buffer over NVLink and raises a flag; the owner's top-k waits for the flags (include/gdr_b200.h gdr_store_p2p_*).
+    The schedule is PipelinedRetriever's fused one (scoring of batch i + top-k of batch i-1 in one launch) when the shape is
+    eligible, else strictly serial calls — never independent streams: a top-k that spins for a peer must not be able to keep
+    that peer's (or its own) scoring kernel off the SMs.  All ranks must submit the same sequence of batches.
+    exchange = "nccl" is `ShardedRetriever` (local top-k, all-gather of (score, docid) lists, merge): see there."""
+
+    def __init__(self, stores, rank: int, world: int, b_own: int, K: int, k: int, group=None, flags: int = 0,
+                 fused_ctas: int = 0, fused_groups: int = 0, local_peers=None):
+        from .pipeline import PipelinedRetriever
+        self.rank, self.world, self.b_own, self.K, self.k, self.group = rank, world, b_own, K, k, group
+        stores = list(stores) if isinstance(stores, (list, tuple)) else [stores]
+        B = world * b_own
+        self.pr = PipelinedRetriever(stores, schedule="auto", depth=1, fused_ctas=fused_ctas, fused_groups=fused_groups)
+        fused = self.pr.fused_eligible(B, K, k, flags)
+        self.schedule = "fused" if fused else "serial"
+        self.handles = [h for hs in (self.pr._handles_fused() if fused else self.pr._handles_batches()) for h in hs]
+        mine = [h.p2p_init(world, rank, b_own, K) for h in self.handles]
+        if local_peers is not None:             # every rank's ShardedPipeline lives in this process (tests): wired by connect_local
+            self._ipc = None
+        else:
+            gathered: List[Optional[list]] = [None] * world
+            dist.all_gather_object(gathered, mine, group=group)
+            for j, h in enumerate(self.handles):
+                h.p2p_attach([gathered[r][j] for r in range(world)])
+        for h in self.handles:
+            h.reserve(B, K, k, flags)
+
+    @staticmethod
+    def connect_local(pipelines: Sequence["ShardedPipeline"]) -> None:
+        """Wire the exchange buffers of pipelines that live in ONE process (pipelines[r] = rank r)."""
+        for p in pipelines:
+            for j, h in enumerate(p.handles):
+                h.p2p_attach_local([q.handles[j] for q in pipelines])
+
+    def submit(self, q: torch.Tensor, beams: torch.Tensor, prob: Optional[torch.Tensor] = None, alpha: float = 1.0,
+               act: Optional[str] = "none", flags: int = 0, out=None, which: int = 0):
+        """q [world*b_own, D], beams [world*b_own, K] global cluster ids (prob likewise) -> Ticket with [b_own, k] outputs."""
+        if out is None:
+            dev = q.device
+            out = (torch.empty((self.b_own, self.k), dtype=torch.float32, device=dev), torch.empty((self.b_own, self.k), dtype=torch.int32, device=dev))
+        return self.pr.submit(q, beams, self.k, prob=prob, alpha=alpha, act=act, flags=flags, out=out, which=which)
+
+    def flush(self) -> None:
+        self.pr.flush()

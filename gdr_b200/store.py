@@ -71,6 +71,60 @@ class ClusterStore:
                 _cabi.DTYPE_BF16 if emb.dtype == torch.bfloat16 else _cabi.DTYPE_F32,
                 self.offsets.data_ptr(), self.n_clusters, self.docid.data_ptr(), self.max_cluster))
 
+    # ---- one shard of a corpus split across GPUs by cluster (include/gdr_b200.h gdr_store_create_shard) ---------------------------
+    @classmethod
+    def shard(cls, emb_local: torch.Tensor, offsets_global, docid_global: torch.Tensor, c_lo: int, c_hi: int,
+              keys: Optional[Sequence[str]] = None) -> "ClusterStore":
+        """emb_local [n_local, D] cuda: the rows of the GLOBAL clusters [c_lo, c_hi) only; offsets_global [C+1] and docid_global
+        [N] describe the whole corpus and are replicated on every GPU.  Beams given to this store carry global cluster ids."""
+        self = cls.__new__(cls)
+        if not emb_local.is_cuda or emb_local.dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("emb_local must be a float32 / bfloat16 CUDA tensor")
+        off_host = torch.as_tensor(np.asarray(offsets_global)).to("cpu", torch.int64)
+        row_lo, row_hi = int(off_host[c_lo]), int(off_host[c_hi])
+        if row_hi - row_lo != emb_local.shape[0]:
+            raise ValueError(f"emb_local has {emb_local.shape[0]} rows, clusters [{c_lo}, {c_hi}) hold {row_hi - row_lo}")
+        self.emb = emb_local.contiguous()
+        self.offsets_host = off_host.numpy()
+        self.sizes_host = np.diff(self.offsets_host)
+        self.offsets = off_host.to(torch.int32).to(emb_local.device)
+        self.docid = docid_global.detach().to(torch.int32).to(emb_local.device).contiguous()
+        self.n_docs, self.dim = int(off_host[-1]), int(emb_local.shape[1])
+        if self.docid.numel() != self.n_docs:
+            raise ValueError("docid_global must have one entry per document of the whole corpus")
+        self.n_clusters = int(off_host.numel() - 1)
+        self.max_cluster = int(self.sizes_host.max())
+        self.keys = list(keys) if keys is not None else None
+        self.cluster_index = {k: i for i, k in enumerate(self.keys)} if self.keys is not None else {}
+        self.shard_range = (int(c_lo), int(c_hi), row_lo)
+        self._handle = ctypes.c_void_p()
+        with torch.cuda.device(emb_local.device):
+            _cabi.check(_cabi.lib().gdr_store_create_shard(
+                ctypes.byref(self._handle), self.emb.data_ptr(), int(emb_local.shape[0]), self.dim,
+                _cabi.DTYPE_BF16 if emb_local.dtype == torch.bfloat16 else _cabi.DTYPE_F32, self.offsets.data_ptr(), self.n_clusters,
+                self.docid.data_ptr(), self.n_docs, self.max_cluster, int(c_lo), int(c_hi), row_lo))
+        return self
+
+    def p2p_init(self, n_ranks: int, my_rank: int, b_own: int, K: int) -> bytes:
+        """Allocate this handle's peer-to-peer exchange buffer; returns its 64-byte CUDA IPC handle (gdr_store_p2p_init)."""
+        buf = (ctypes.c_ubyte * 64)()
+        with torch.cuda.device(self.emb.device):
+            _cabi.check(_cabi.lib().gdr_store_p2p_init(self._handle, int(n_ranks), int(my_rank), int(b_own), int(K), buf))
+        self.p2p = (int(n_ranks), int(my_rank), int(b_own))
+        return bytes(buf)
+
+    def p2p_attach(self, all_handles: Sequence[bytes]) -> None:
+        """Map every rank's exchange buffer (IPC handles in rank order, one process per GPU)."""
+        blob = b"".join(all_handles)
+        with torch.cuda.device(self.emb.device):
+            _cabi.check(_cabi.lib().gdr_store_p2p_attach(self._handle, ctypes.c_char_p(blob)))
+
+    def p2p_attach_local(self, peers: Sequence["ClusterStore"]) -> None:
+        """The same for handles that live in this process (peers[r] = rank r's handle)."""
+        arr = (ctypes.c_void_p * len(peers))(*[p._handle.value for p in peers])
+        with torch.cuda.device(self.emb.device):
+            _cabi.check(_cabi.lib().gdr_store_p2p_attach_local(self._handle, arr))
+
     # ---- construction from the reference's objects ------------------------------------------
     @classmethod
     def from_reference(cls, doc_embed, id_mapping: Dict[str, List[int]], dtype=torch.bfloat16,
@@ -135,20 +189,21 @@ class ClusterStore:
             prob = prob.contiguous()
         n_alpha = 1 if alphas is None else len(alphas)
         alpha_arr = None if alphas is None else (ctypes.c_float * n_alpha)(*[float(a) for a in alphas])
+        B_out = self.p2p[2] if getattr(self, "p2p", None) else B       # a p2p shard handle returns its own b_own queries of the global batch
         if out is None:
-            out_s = torch.empty((n_alpha, B, k), dtype=torch.float32, device=dev)
-            out_d = torch.empty((n_alpha, B, k), dtype=torch.int32, device=dev)
+            out_s = torch.empty((n_alpha, B_out, k), dtype=torch.float32, device=dev)
+            out_d = torch.empty((n_alpha, B_out, k), dtype=torch.int32, device=dev)
         else:
             out_s, out_d = out
             if not _unchecked_out:      # (the inversion-only call passes placeholders: no output is written)
-                _check_out(out_s, out_d, n_alpha * B * int(k), dev)
+                _check_out(out_s, out_d, n_alpha * B_out * int(k), dev)
         if per_beam:
             flags |= _cabi.Q_PER_BEAM
         with torch.cuda.device(dev):
             _cabi.check(_cabi.lib().gdr_score_topk(
                 self._handle, q.data_ptr(), beams.data_ptr(), None if prob is None else prob.data_ptr(), alpha_arr,
                 n_alpha, B, K, _cabi.ACT[act], int(k), flags, out_s.data_ptr(), out_d.data_ptr(), _cabi.stream_ptr(stream)))
-        self._last_shape = (B, int(k))
+        self._last_shape = (B_out, int(k))
         if alphas is None and out is None:
             return out_s[0], out_d[0]
         return out_s, out_d
@@ -168,8 +223,9 @@ class ClusterStore:
 
     def clone_handle(self) -> "ClusterStore":
         """Another handle (= another scratch set) over the SAME device arrays: nothing is copied.  One per batch in flight."""
-        other = ClusterStore(self.emb, torch.as_tensor(self.offsets_host), self.docid, self.keys)
-        return other
+        if getattr(self, "shard_range", None) is not None:
+            return ClusterStore.shard(self.emb, self.offsets_host, self.docid, self.shard_range[0], self.shard_range[1], self.keys)
+        return ClusterStore(self.emb, torch.as_tensor(self.offsets_host), self.docid, self.keys)
 
     # ---- pipelined schedule: fused scoring + top-k, one batch behind (include/gdr_b200.h gdr_score_fused; pipeline.py drives it) ----
     def invert(self, q: torch.Tensor, beams: torch.Tensor, k: int, prob: Optional[torch.Tensor] = None, act: Optional[str] = "none",

@@ -74,6 +74,36 @@ int gdr_store_create(gdr_store_t **out, const void *emb, int64_t n_docs, int32_t
                      int32_t max_cluster_size);
 int gdr_store_destroy(gdr_store_t *store);
 
+/* ---- cluster-sharded corpus (new design; the reference keeps a full replica per rank, main_models.py:806-814) ----
+ * One handle per GPU over a corpus whose clusters are split across GPUs by contiguous ranges of a GLOBAL cluster numbering:
+ *   emb_local       DEV [n_local_rows, dim]: the rows of clusters c_lo .. c_hi-1 only (global rows row_lo .. row_lo+n_local_rows-1)
+ *   offsets_global  DEV int32 [n_clusters_global + 1], docid_global DEV int32 [n_docs_global]: the WHOLE corpus' CSR metadata,
+ *                   replicated on every GPU (4 bytes per document)
+ * gdr_score_topk on such a handle takes beams with GLOBAL cluster ids and scores only the beams that land in [c_lo, c_hi).
+ * Alone it is useful only together with the peer-to-peer exchange below (candidate segments of clusters other ranks own
+ * are not written by this rank). */
+int gdr_store_create_shard(gdr_store_t **out, const void *emb_local, int64_t n_local_rows, int32_t dim, int32_t dtype,
+                           const int32_t *offsets_global, int32_t n_clusters_global, const int32_t *docid_global,
+                           int64_t n_docs_global, int32_t max_cluster_size, int32_t c_lo, int32_t c_hi, int64_t row_lo);
+
+/* Peer-to-peer candidate exchange between the n_ranks handles (one per GPU of an NVLink / NVSwitch domain) that hold the shards
+ * of one corpus.  The global batch is n_ranks * b_own queries, the same q / beams on every rank; rank r OWNS queries
+ * r*b_own .. (r+1)*b_own-1.  Every rank inverts the whole batch and scores the beams of its clusters; its scoring kernel
+ * stores each score straight into the OWNER's score buffer over NVLink (the exchange is fused into the scoring epilogue — no
+ * collective, no candidate lists), then publishes an arrival flag to every owner; the owner's top-k (stand-alone, or the
+ * top-k groups of the next fused launch) waits for the n_ranks flags and selects exactly as on one GPU.  On such a handle
+ * gdr_score_topk / gdr_score_fused take B = n_ranks * b_own and write outputs [n_alpha, b_own, k] for the rank's own queries.
+ * All ranks must issue the same sequence of batches on corresponding handles.
+ *   gdr_store_p2p_init    allocates this handle's buffer (b_own * align4(K * max_cluster_size) scores + flags) and returns its
+ *                         CUDA IPC handle (HOST, GDR_IPC_HANDLE_BYTES bytes; may be NULL for same-process use)
+ *   gdr_store_p2p_attach  all_handles HOST [n_ranks][GDR_IPC_HANDLE_BYTES], rank order (one process per GPU: exchange them with
+ *                         any host-side all-gather, e.g. torch.distributed); maps every peer's buffer
+ *   gdr_store_p2p_attach_local  the same for handles that live in ONE process (peers[r] = rank r's handle; tests, single-process multi-GPU) */
+#define GDR_IPC_HANDLE_BYTES 64
+int gdr_store_p2p_init(gdr_store_t *store, int32_t n_ranks, int32_t my_rank, int32_t b_own, int32_t K, void *ipc_handle_out);
+int gdr_store_p2p_attach(gdr_store_t *store, const void *all_handles);
+int gdr_store_p2p_attach_local(gdr_store_t *store, gdr_store_t *const *peers);
+
 /* ---- fine stage: cluster-restricted scoring + top-k ---------------------------------------
  * Replaces main_models.py:1441-1462 (gather), :1577-1594 (score), :1596-1624 (rerank bias),
  * :1625 (topk) and :1628-1631 (index -> doc index) for one batch; with act = NONE, prob = NULL

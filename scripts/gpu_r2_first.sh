@@ -2,8 +2,8 @@
 # Round 2, GPU call 1: parity suite (pipeline / fused variants first), smoke, the bench with its autotune, launch list + ncu of the fused kernel.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.max.sm --format=csv,noheader > gpurun_out/gpu.txt
-timeout 420 python -m pytest tests/test_gpu_pipeline.py -q -x --timeout 120 > gpurun_out/r02_pytest_pipeline.log 2>&1; tail -4 gpurun_out/r02_pytest_pipeline.log
-timeout 900 python -m pytest tests -m gpu -q --timeout 300 --deselect tests/test_gpu_pipeline.py > gpurun_out/r02_pytest_gpu.log 2>&1; tail -6 gpurun_out/r02_pytest_gpu.log
+timeout 600 python -m pytest tests/test_gpu_pipeline.py tests/test_gpu_sharded_p2p.py -q --timeout 150 > gpurun_out/r02_pytest_pipeline.log 2>&1; tail -15 gpurun_out/r02_pytest_pipeline.log
+timeout 900 python -m pytest tests -m gpu -q --timeout 300 --deselect tests/test_gpu_pipeline.py --deselect tests/test_gpu_sharded_p2p.py > gpurun_out/r02_pytest_gpu.log 2>&1; tail -6 gpurun_out/r02_pytest_gpu.log
 timeout 200 python __graft_entry__.py smoke > gpurun_out/r02_smoke.log 2>&1; tail -2 gpurun_out/r02_smoke.log
 timeout 500 python bench.py > gpurun_out/r02_bench_default.json 2> gpurun_out/r02_bench_default.err; tail -c 1500 gpurun_out/r02_bench_default.err; python - <<'PY'
 import json

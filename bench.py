@@ -280,9 +280,9 @@ def autotune(args, local_rank):
     default (`batches`) stays if nothing beats it by > 3 %.  All timings / failures are reported in config.launch_autotune."""
     cands = [("batches", dict(schedule="batches", pipeline=5))]
     if args.workload == "cfg2" and args.path == "auto":
-        cands += [("fused64_140", dict(schedule="fused", fused_groups=9, fused_ctas=140)),
-                  ("fused64_132", dict(schedule="fused", fused_groups=9, fused_ctas=132)),
-                  ("fused128x4_140", dict(schedule="fused", fused_groups=4, fused_ctas=140))]
+        cands += [("fused_140", dict(schedule="fused", fused_groups=5, fused_ctas=140)),
+                  ("fused_132", dict(schedule="fused", fused_groups=5, fused_ctas=132)),
+                  ("fused64_140", dict(schedule="fused", fused_groups=9, fused_ctas=140))]
     cands.append(("batches_priorities", dict(schedule="batches", pipeline=5, launch_priorities="on")))
     report, best, t_start = {}, None, time.time()
     for name, opt in cands:
@@ -597,7 +597,7 @@ def main():
     emb_touched = int(stores[0].sizes_host[torch.unique(beams0[beams0 >= 0]).cpu().numpy()].sum()) * D * esize
     alg_bytes = emb_touched + B * D * 4 + B * k * 8
     simt = int(stats["umma_tiles"]) == 0
-    kname = ("k_score_topk_fused64" if (opt["fused_groups"] or 9) == 9 else "k_score_topk_fused<4>") if schedule == "fused" else ("k_score_simt" if simt else "k_score_umma")
+    kname = ("k_score_topk_fused64" if opt["fused_groups"] == 9 else "k_score_topk_fused") if schedule == "fused" else ("k_score_simt" if simt else "k_score_umma")
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -633,7 +633,7 @@ def main():
                "sample": f"{done} queries of the {args.workload} workload in {dt:.1f} s: {what}; torch {torch.__version__} CPU with {os.cpu_count()} threads"}
 
     sched_txt = {"fused": f"fused (gdr_score_fused via PipelinedRetriever: one launch scores batch i and selects the top-k of batch i-1 in the same CTAs; "
-                          f"inversion one batch ahead on a second stream; 3 scratch sets; grid of {opt['fused_ctas'] or 140} CTAs x {opt['fused_groups'] or 9} top-k groups)",
+                          f"inversion one batch ahead on a second stream; 3 scratch sets; grid of {opt['fused_ctas'] or 140} CTAs x {opt['fused_groups'] or 5} top-k groups)",
                  "batches": f"batches (PipelinedRetriever: whole gdr_score_topk calls round-robin on {n_pipe} streams)"}[schedule]
     line = {
         "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world,

@@ -54,7 +54,7 @@ struct gdr_store {
     // what the last gdr_score_topk call on this handle set up (scratch pointers, shapes): input of gdr_score_fused (experiment)
     ScoreArgs last_args;
     bool last_valid = false, last_umma_only = false;
-    int fused_groups = 9;       // GDR_OPT_FUSED_GROUPS: 9 = nine 64-thread top-k groups in the fused CTA (default), 4 = four 128-thread groups
+    int fused_groups = 5;       // GDR_OPT_FUSED_GROUPS: 5 = five 128-thread top-k groups running the lean select (default), 9 = nine 64-thread groups
     // cluster-sharded corpus (gdr_store_create_shard): this handle's emb holds global rows [row_lo, row_lo + n_local) = clusters [c_lo, c_hi)
     int32_t c_lo = 0, c_hi = 0, row_lo = 0;
     int64_t n_local = 0;
@@ -330,7 +330,7 @@ int gdr_store_set_option(gdr_store_t *s, int32_t option, int32_t value) {
         return GDR_OK;
     }
     case GDR_OPT_FUSED_GROUPS:
-        if (value != 4 && value != 9) return invalid("gdr_store_set_option: GDR_OPT_FUSED_GROUPS must be 9 (64-thread groups) or 4 (128-thread groups)");
+        if (value != 5 && value != 9) return invalid("gdr_store_set_option: GDR_OPT_FUSED_GROUPS must be 5 (128-thread groups) or 9 (64-thread groups)");
         s->fused_groups = value;
         return GDR_OK;
     case GDR_OPT_TOPK_GROUPS:
@@ -478,7 +478,7 @@ int gdr_score_fused(gdr_store_t *cur, gdr_store_t *prev, float alpha, float *pre
         set_error("gdr_score_fused: the batch in cur does not take the tcgen05 path alone");
         return GDR_ERR_UNSUPPORTED;
     }
-    // The fused CTA takes a whole SM (896 threads, all registers): the inversion kernels of the NEXT batch, which run beside it on a
+    // The fused CTA takes a whole SM (1,024 threads, all registers): the inversion kernels of the NEXT batch, which run beside it on a
     // second stream, need SMs of their own — by default the grid leaves eight (108-140 scoring CTAs measured the same speed).
     const int ctas = cur->umma_ctas > 0 ? cur->umma_ctas : (cur->sm_count > 16 ? cur->sm_count - 8 : cur->sm_count);
     GDR_CUDA(launch_score_fused(cur->last_args, &cur->tmap, pa, alpha, prev_out_scores, prev_out_docids, st, ctas, cur->fused_groups));

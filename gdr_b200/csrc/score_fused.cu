@@ -34,19 +34,36 @@ namespace gdr {
 constexpr int FU_MAX_SMEM = 227 * 1024;
 
 // ------------------------------------------------------------------------------------------------------------------------
-// round-1 variant: warps 0-9 as in k_score_umma, then G groups of 128 threads
+// variant A (default): five 128-thread top-k groups running the lean select (topk_lean128), homogeneous warpgroups + setmaxnreg
+//   warp 0 TMA | 1 MMA | 2 tile scheduler | 3 filler 0 || 4-7 epilogue || 8-9 fillers 1-2 | 10-11 idle || 12-31 top-k groups 0-4
+//   1,024 threads = the launch holds 64 registers per thread; the two light scoring warpgroups drop to 48, the epilogue rises to
+//   96, the five top-k warpgroups keep their 64
 // ------------------------------------------------------------------------------------------------------------------------
-#define UM_IS_TMA (warp == 0)
-#define UM_IS_MMA (warp == 1)
-#define UM_IS_FILL (warp < 2 + UM_FILL_WARPS)
-#define UM_FILL_IDX (warp - 2)
-#define UM_IS_EPI (warp < 2 + UM_FILL_WARPS + 4)
-#define UM_REG_SPLIT
-#define UM_SCHED_ELSE else if (warp == 2 + UM_FILL_WARPS + 4)
-#define UM_EXTRA_ROLES                                                                                                              \
-    else if (prev.B > 0) {                                                                                                          \
-        topk_group_loop<UM_THREADS>(prev, alpha, out_scores, out_docids,                                                            \
-                                    smem + UM_SMEM_BYTES + (size_t)GroupScope<UM_THREADS>::group() * tkg_slice_bytes(prev.K));      \
+constexpr int F128_GROUPS = 5;
+constexpr int F128_FIRST = 12 * 32;                                   // first top-k thread
+constexpr int F128_THREADS = F128_FIRST + F128_GROUPS * TKF_THREADS;  // 1,024 = eight warpgroups
+constexpr int F128_REGS_LIGHT = 48, F128_REGS_TOPK = 64, F128_REGS_EPI = 96;    // warpgroups 0 and 2 | 3-7 | 1
+static_assert(F128_THREADS == 1024, "eight whole warpgroups");
+static_assert(2 * 128 * F128_REGS_LIGHT + F128_GROUPS * 128 * F128_REGS_TOPK + 128 * F128_REGS_EPI <= 65536, "register file");
+
+#define UM_FILL_IDX (warp == 3 ? 0 : warp - 7)
+// setmaxnreg is warpgroup-wide: it sits at the head of each WARPGROUP's branch (all four warps of a warpgroup reach the same
+// instruction), and the roles of a warpgroup are dispatched inside that branch, so that ptxas sizes each role's registers by it
+#define UM_DISPATCH                                                                                                                 \
+    if ((warp >> 2) == 1) {                                                                                                         \
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(F128_REGS_EPI));                                                   \
+        role_epi();                                                                                                                 \
+    } else if ((warp >> 2) >= 3) {                                                                                                  \
+        /* the top-k warpgroups keep the launch allocation (F128_REGS_TOPK = 64) */                                                 \
+        if (prev.B > 0)                                                                                                             \
+            topk_group_loop<F128_FIRST, TKF_THREADS>(prev, alpha, out_scores, out_docids,                                           \
+                smem + UM_SMEM_BYTES + (size_t)GroupScope<F128_FIRST, TKF_THREADS>::group() * tkg_slice_bytes(prev.K));             \
+    } else {                                                                                                                        \
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(F128_REGS_LIGHT));                                                 \
+        if (warp == 0) role_tma();                                                                                                  \
+        else if (warp == 1) role_mma();                                                                                             \
+        else if (warp == 2) role_sched();                                                                                           \
+        else if (warp == 3 || warp == 8 || warp == 9) role_fill();                                                                  \
     }
 // after the CTA-wide barrier every group of this CTA has made its last claim: the last CTA leaves the query queue ready
 #define UM_EXTRA_TAIL                                                                                                               \
@@ -55,22 +72,33 @@ constexpr int FU_MAX_SMEM = 227 * 1024;
         prev.counters[CTR_TOPK_DONE] = 0;                                                                                           \
     }
 
-template <int G>
-__global__ void __launch_bounds__(UM_THREADS + G * TKF_THREADS, 1)
+#define UM_SCORE_PTR(o) (a.scorebuf + (o))
+#define UM_P2P_FENCE
+#define UM_P2P_SIGNAL
+__global__ void __launch_bounds__(F128_THREADS, 1)
 k_score_topk_fused(const __grid_constant__ CUtensorMap tmap, ScoreArgs a, ScoreArgs prev, float alpha, float *out_scores, int32_t *out_docids) {
 #include "score_umma_body.inc"
 }
-#undef UM_IS_TMA
-#undef UM_IS_MMA
-#undef UM_IS_FILL
+#undef UM_SCORE_PTR
+#undef UM_P2P_FENCE
+#undef UM_P2P_SIGNAL
+// ... and for one shard of a cluster-sharded corpus (scores into the owners' buffers over NVLink, arrival flags; the top-k groups
+// wait for every rank's flag before they read the previous batch's scores: topk_group_loop)
+#define UM_SCORE_PTR(o) score_ptr(a, (o))
+#define UM_P2P_FENCE __threadfence_system();
+#define UM_P2P_SIGNAL signal_owners(a);
+__global__ void __launch_bounds__(F128_THREADS, 1)
+k_score_topk_fused_p2p(const __grid_constant__ CUtensorMap tmap, ScoreArgs a, ScoreArgs prev, float alpha, float *out_scores, int32_t *out_docids) {
+#include "score_umma_body.inc"
+}
+#undef UM_SCORE_PTR
+#undef UM_P2P_FENCE
+#undef UM_P2P_SIGNAL
 #undef UM_FILL_IDX
-#undef UM_IS_EPI
-#undef UM_REG_SPLIT
-#undef UM_SCHED_ELSE
-#undef UM_EXTRA_ROLES
+#undef UM_DISPATCH
 
 // ------------------------------------------------------------------------------------------------------------------------
-// round-2 variant: homogeneous warpgroups + setmaxnreg, nine 64-thread top-k groups
+// variant B: nine 64-thread top-k groups (two warps per query, no keys in registers)
 //   warp 0 TMA | 1 MMA | 2 tile scheduler | 3 filler 0 || 4-7 epilogue || 8-9 fillers 1-2 | 10-27 top-k groups 0-8 (two warps each)
 // ------------------------------------------------------------------------------------------------------------------------
 constexpr int F64_GROUPS = 9;
@@ -80,35 +108,46 @@ constexpr int F64_REGS_SMALL = 64, F64_REGS_EPI = 120;               // launch: 
 static_assert(F64_THREADS % 128 == 0, "setmaxnreg is a warpgroup-wide instruction: no partial warpgroup");
 static_assert((F64_THREADS - 128) * F64_REGS_SMALL + 128 * F64_REGS_EPI <= F64_THREADS * 72, "registers the launch allocation holds");
 
-#define UM_IS_TMA (warp == 0)
-#define UM_IS_MMA (warp == 1)
-#define UM_IS_FILL (warp == 3 || warp == 8 || warp == 9)
 #define UM_FILL_IDX (warp == 3 ? 0 : warp - 7)
-#define UM_IS_EPI (warp >= 4 && warp < 8)
-// setmaxnreg is warpgroup-wide and must be reached by all four warps of a warpgroup at the same instruction: the split is
-// done ONCE, on the warpgroup index, before the warps part into their roles (warpgroup 1 = the four epilogue warps)
-#define UM_REG_SPLIT                                                                                                                \
-    if ((warp >> 2) == 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(F64_REGS_EPI));                                  \
-    else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(F64_REGS_SMALL));
-#define UM_SCHED_ELSE else if (warp == 2)
-#define UM_EXTRA_ROLES                                                                                                              \
-    else if (prev.B > 0) {                                                                                                          \
-        topk_group_loop<F64_FIRST, TKF64_THREADS>(prev, alpha, out_scores, out_docids,                                              \
-            smem + UM_SMEM_BYTES + (size_t)GroupScope<F64_FIRST, TKF64_THREADS>::group() * tkg_slice_bytes(prev.K));                \
+// warpgroup 0 = {TMA, MMA, scheduler, filler 0}, 1 = epilogue, 2 = {fillers 1-2, top-k group 0}, 3-6 = top-k groups 1-8
+#define UM_DISPATCH                                                                                                                 \
+    if ((warp >> 2) == 1) {                                                                                                         \
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(F64_REGS_EPI));                                                    \
+        role_epi();                                                                                                                 \
+    } else {                                                                                                                        \
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(F64_REGS_SMALL));                                                  \
+        if (warp == 0) role_tma();                                                                                                  \
+        else if (warp == 1) role_mma();                                                                                             \
+        else if (warp == 2) role_sched();                                                                                           \
+        else if (warp == 3 || warp == 8 || warp == 9) role_fill();                                                                  \
+        else if (prev.B > 0)                                                                                                        \
+            topk_group_loop<F64_FIRST, TKF64_THREADS>(prev, alpha, out_scores, out_docids,                                          \
+                smem + UM_SMEM_BYTES + (size_t)GroupScope<F64_FIRST, TKF64_THREADS>::group() * tkg_slice_bytes(prev.K));            \
     }
-
+#define UM_SCORE_PTR(o) (a.scorebuf + (o))
+#define UM_P2P_FENCE
+#define UM_P2P_SIGNAL
 __global__ void __launch_bounds__(F64_THREADS, 1)
 k_score_topk_fused64(const __grid_constant__ CUtensorMap tmap, ScoreArgs a, ScoreArgs prev, float alpha, float *out_scores, int32_t *out_docids) {
 #include "score_umma_body.inc"
 }
-#undef UM_IS_TMA
-#undef UM_IS_MMA
-#undef UM_IS_FILL
+#undef UM_SCORE_PTR
+#undef UM_P2P_FENCE
+#undef UM_P2P_SIGNAL
+// ... and for one shard of a cluster-sharded corpus (scores into the owners' buffers over NVLink, arrival flags; the top-k groups
+// wait for every rank's flag before they read the previous batch's scores: topk_group_loop)
+#define UM_SCORE_PTR(o) score_ptr(a, (o))
+#define UM_P2P_FENCE __threadfence_system();
+#define UM_P2P_SIGNAL signal_owners(a);
+__global__ void __launch_bounds__(F64_THREADS, 1)
+k_score_topk_fused64_p2p(const __grid_constant__ CUtensorMap tmap, ScoreArgs a, ScoreArgs prev, float alpha, float *out_scores, int32_t *out_docids) {
+#include "score_umma_body.inc"
+}
+#undef UM_SCORE_PTR
+#undef UM_P2P_FENCE
+#undef UM_P2P_SIGNAL
 #undef UM_FILL_IDX
-#undef UM_IS_EPI
-#undef UM_REG_SPLIT
-#undef UM_SCHED_ELSE
-#undef UM_EXTRA_ROLES
+#undef UM_DISPATCH
 #undef UM_EXTRA_TAIL
 
 // How many top-k groups of the 64-thread variant fit beside the scoring ring for beam width K (0 = it does not fit at all)
@@ -119,25 +158,26 @@ int fused64_groups_that_fit(int K) {
 }
 
 // prev.B == 0: no previous batch (first launch of a stream) — the top-k warps fall straight through to the final barrier.
-// groups: 9 = the 64-thread variant, anything else = the round-1 variant with four 128-thread groups.
+// groups: 9 = variant B (nine 64-thread groups), anything else = variant A (five 128-thread groups, the default).
 cudaError_t launch_score_fused(const ScoreArgs &a, const CUtensorMap *tmap, const ScoreArgs &prev, float alpha, float *out_scores,
                                int32_t *out_docids, cudaStream_t s, int ctas, int groups) {
     const int K = prev.B > 0 ? prev.K : 1;
+    const bool p2p = a.n_ranks > 1;       // a shard of a cluster-sharded corpus
     const bool v64 = groups == F64_GROUPS && fused64_groups_that_fit(K) == F64_GROUPS;
-    const int g = v64 ? F64_GROUPS : 4;
+    const int g = v64 ? F64_GROUPS : F128_GROUPS;
     const size_t smem = (size_t)UM_SMEM_BYTES + (size_t)g * tkg_slice_bytes(K);
     if (smem > (size_t)FU_MAX_SMEM) return cudaErrorInvalidValue;
     static FuncAttrOnce attr;
     cudaError_t e = attr.ensure([] {
-        cudaError_t e2 = cudaFuncSetAttribute(k_score_topk_fused<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FU_MAX_SMEM);
+        cudaError_t e2 = cudaFuncSetAttribute(k_score_topk_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, FU_MAX_SMEM);
+        if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_score_topk_fused_p2p, cudaFuncAttributeMaxDynamicSharedMemorySize, FU_MAX_SMEM);
         if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_score_topk_fused64, cudaFuncAttributeMaxDynamicSharedMemorySize, FU_MAX_SMEM);
+        if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_score_topk_fused64_p2p, cudaFuncAttributeMaxDynamicSharedMemorySize, FU_MAX_SMEM);
         return e2;
     });
     if (e != cudaSuccess) return e;
-    if (v64)
-        return launch_pdl(k_score_topk_fused64, dim3(ctas), dim3(F64_THREADS), smem, s, a.launch_prio, *tmap, a, prev, alpha, out_scores, out_docids);
-    return launch_pdl(k_score_topk_fused<4>, dim3(ctas), dim3(UM_THREADS + 4 * TKF_THREADS), smem, s, a.launch_prio, *tmap, a, prev, alpha, out_scores,
-                      out_docids);
+    auto kernel = v64 ? (p2p ? k_score_topk_fused64_p2p : k_score_topk_fused64) : (p2p ? k_score_topk_fused_p2p : k_score_topk_fused);
+    return launch_pdl(kernel, dim3(ctas), dim3(v64 ? F64_THREADS : F128_THREADS), smem, s, a.launch_prio, *tmap, a, prev, alpha, out_scores, out_docids);
 }
 
 }  // namespace gdr

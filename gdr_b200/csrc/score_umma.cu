@@ -36,27 +36,37 @@
 
 namespace gdr {
 
-#define UM_IS_TMA (warp == 0)
-#define UM_IS_MMA (warp == 1)
-#define UM_IS_FILL (warp < 2 + UM_FILL_WARPS)
 #define UM_FILL_IDX (warp - 2)
-#define UM_IS_EPI (warp < 2 + UM_FILL_WARPS + 4)
-#define UM_SCHED_ELSE else
-#define UM_EXTRA_ROLES
+#define UM_DISPATCH                                       \
+    if (warp == 0) role_tma();                            \
+    else if (warp == 1) role_mma();                       \
+    else if (warp < 2 + UM_FILL_WARPS) role_fill();       \
+    else if (warp < 2 + UM_FILL_WARPS + 4) role_epi();    \
+    else role_sched();
 #define UM_EXTRA_TAIL
-#define UM_REG_SPLIT
+#define UM_SCORE_PTR(o) (a.scorebuf + (o))
+#define UM_P2P_FENCE
+#define UM_P2P_SIGNAL
 __global__ void __launch_bounds__(UM_THREADS, 1) k_score_umma(const __grid_constant__ CUtensorMap tmap, ScoreArgs a) {
 #include "score_umma_body.inc"
 }
-#undef UM_IS_TMA
-#undef UM_IS_MMA
-#undef UM_IS_FILL
+#undef UM_SCORE_PTR
+#undef UM_P2P_FENCE
+#undef UM_P2P_SIGNAL
+// the same CTA for one shard of a cluster-sharded corpus: scores go straight into the score buffer of the query's owner (a peer
+// GPU's memory over NVLink), the last CTA raises this rank's arrival flag on every owner (gdr_common.cuh, include/gdr_b200.h)
+#define UM_SCORE_PTR(o) score_ptr(a, (o))
+#define UM_P2P_FENCE __threadfence_system();
+#define UM_P2P_SIGNAL signal_owners(a);
+__global__ void __launch_bounds__(UM_THREADS, 1) k_score_umma_p2p(const __grid_constant__ CUtensorMap tmap, ScoreArgs a) {
+#include "score_umma_body.inc"
+}
+#undef UM_SCORE_PTR
+#undef UM_P2P_FENCE
+#undef UM_P2P_SIGNAL
 #undef UM_FILL_IDX
-#undef UM_IS_EPI
-#undef UM_SCHED_ELSE
-#undef UM_EXTRA_ROLES
+#undef UM_DISPATCH
 #undef UM_EXTRA_TAIL
-#undef UM_REG_SPLIT
 
 // ---------------------------------------------------------------------------------------------
 // host side
@@ -85,8 +95,13 @@ bool umma_make_tensor_map(CUtensorMap *out, const void *emb, int64_t n_docs, int
 
 cudaError_t launch_score_umma(const ScoreArgs &a, const CUtensorMap *tmap, cudaStream_t s, int sm_count) {
     static FuncAttrOnce attr;
-    cudaError_t e = attr.ensure([] { return cudaFuncSetAttribute(k_score_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM_BYTES); });
+    cudaError_t e = attr.ensure([] {
+        cudaError_t e2 = cudaFuncSetAttribute(k_score_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM_BYTES);
+        if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_score_umma_p2p, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM_BYTES);
+        return e2;
+    });
     if (e != cudaSuccess) return e;
+    if (a.n_ranks > 1) return launch_pdl(k_score_umma_p2p, dim3(sm_count), dim3(UM_THREADS), UM_SMEM_BYTES, s, a.launch_prio, *tmap, a);
     return launch_pdl(k_score_umma, dim3(sm_count), dim3(UM_THREADS), UM_SMEM_BYTES, s, a.launch_prio, *tmap, a);
 }
 

@@ -20,7 +20,8 @@
 namespace gdr {
 
 // dynamic shared memory: sel[128] u64 | hist[2048] u16 | co[K+1] | cbase[K] | bias[K]
-__global__ void __launch_bounds__(TKF_THREADS, 10) k_topk_fast(ScoreArgs a, float alpha, float *out_scores, int32_t *out_docids) {
+// (eight CTAs per SM = 64 registers: 1,024 queries on 148 SMs are seven CTAs per SM)
+__global__ void __launch_bounds__(TKF_THREADS, 8) k_topk_fast(ScoreArgs a, float alpha, float *out_scores, int32_t *out_docids) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ TkShared sh;
     uint64_t *sel = reinterpret_cast<uint64_t *>(smem);
@@ -51,8 +52,19 @@ __global__ void __launch_bounds__(TKF_THREADS, 10) k_topk_fast(ScoreArgs a, floa
     }
     if (dbg & 1u) return;                     // stop after the prologue
     StoreSrc src{a.scorebuf + (int64_t)b * a.stride, co, cbase, a.prob ? bias : nullptr, a.docid, a.K};
-    topk_fast16<TKF_THREADS, TKF_R4>(src, n, a.k, a.gkeys + (int64_t)b * a.stride, a.ghist + (int64_t)b * TK_BINS, sel, hist_words, &sh,
-                             out_scores + (int64_t)b * a.k, out_docids + (int64_t)b * a.k, dbg);
+#ifdef GDR_DEBUG_KNOBS
+    if (dbg) {                                // measurement builds: the phase-by-phase cut-offs live in topk_fast16
+        topk_fast16<TKF_THREADS, TKF_R4>(src, n, a.k, a.gkeys + (int64_t)b * a.stride, a.ghist + (int64_t)b * TK_BINS, sel, hist_words, &sh,
+                                         out_scores + (int64_t)b * a.k, out_docids + (int64_t)b * a.k, dbg);
+        return;
+    }
+#endif
+    if (topk_lean_eligible<StoreSrc, CtaScope>(n, a.k))                  // the reference's regime: k <= 128 out of <= 2,560 candidates
+        topk_lean128<StoreSrc>(src, n, a.k, a.gkeys + (int64_t)b * a.stride, a.ghist + (int64_t)b * TK_BINS, sel, hist_words, &sh,
+                               out_scores + (int64_t)b * a.k, out_docids + (int64_t)b * a.k);
+    else                                                                 // more candidates (streamed twice), n <= k: out of line
+        topk_fast16_cold<TKF_THREADS, TKF_R4, StoreSrc, CtaScope>(src, n, a.k, a.gkeys + (int64_t)b * a.stride, a.ghist + (int64_t)b * TK_BINS, sel,
+                                                                  hist_words, &sh, out_scores + (int64_t)b * a.k, out_docids + (int64_t)b * a.k);
     // dependents (the next batch's k_count on this stream) are released at the end: released at entry, their CTAs would hold
     // registers and thread slots beside this kernel for its whole duration (see k_score_umma)
     pdl_launch_dependents();

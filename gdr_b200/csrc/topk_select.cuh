@@ -477,6 +477,223 @@ __device__ __noinline__ void topk_general_cold(const Src &src, int n, int k, int
     topk_general<NT, Src, Scope>(src, n, k, cap, keys, sel, hist, sh, out_s, out_d);
 }
 
+constexpr int TKF_THREADS = 128;
+constexpr int TKF_R4 = 5;            // 128 threads x 5 x 4 = 2,560 candidates held in registers
+// topk_fast16 as the COLD path of kernels whose hot path is the lean select: out of line, so that its registers and spills do not
+// shape the hot code
+template <int NT, int R4, typename Src, typename Scope>
+__device__ __noinline__ void topk_fast16_cold(const Src &src, int n, int k, uint32_t *gkeys, uint32_t *ghist, uint64_t *sel, uint32_t *hist_words,
+                                              TkShared *sh, float *out_s, int32_t *out_d);
+constexpr int TKF64_THREADS = 64;    // the fused kernel's groups: two warps per query, no keys in registers, 1,024 first-level bins
+constexpr int TKF64_BITS = 10;
+
+// ---- lean select (round 2) -----------------------------------------------------------------------------------------------
+// The same result as topk_fast16 for the reference's regime (k <= 128, k < n <= 2,560 candidates, 128 threads) with half the
+// instructions and a third of the dependent chain (ncu per-line profile of k_topk_fast, profiles/r02_topk_lines.txt: 8,000 warp
+// instructions per query, 1,450 of them the final sort on ONE warp, 2,500 the two classify loops, 800 the threshold walk):
+//   * 1,024 first-level bins of 32 bits (10 key bits): one shift and one RED per candidate, the threshold is found by ONE
+//     block-wide top-down scan (thread t owns bins [1024 - 8(t+1), 1024 - 8t)): two barriers, no 2,048-bin walk
+//   * candidates are classified from the keys in registers with predicated code only (count, two atomics per thread, store)
+//   * the second-level histogram is built from the boundary list (<= 256 entries), not inside the classify loop
+//   * the k survivors are sorted by ALL FOUR warps: each warp sorts its 32 entries with a shuffle bitonic network (15 stages,
+//     one entry per lane), the four sorted runs are merged by rank — every thread finds its entry's position in the other three
+//     runs with a 5-step binary search — and written straight to the output row
+// Everything else (order-preserving keys, (key desc, docid asc) ties, fallbacks for n <= k, mass ties, n > 2,560) is shared
+// with / delegated to topk_fast16, so the two produce identical bits (tests/test_gpu_pipeline.py, tests/test_gpu_parity.py).
+constexpr int TKL_BITS = 10, TKL_BINS = 1 << TKL_BITS, TKL_SH1 = 32 - TKL_BITS, TKL_SH2 = TKL_SH1 - 8;
+static_assert(TKL_BINS * 4 == TK_BINS * 2, "the lean select's 1,024 32-bit bins live in the 4 KB of the 2,048 16-bit bins");
+
+__device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int m) {
+    const uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, m), hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), m);
+    return ((uint64_t)hi << 32) | lo;
+}
+
+template <typename Src, typename Scope>
+__device__ __forceinline__ bool topk_lean_eligible(int n, int k) { return n > k && n <= TKF_THREADS * 4 * TKF_R4 && k <= 128; }
+
+template <typename Src, typename Scope = CtaScope>
+__device__ void topk_lean128(const Src &src, int n, int k, uint32_t *gkeys, uint32_t *ghist, uint64_t *sel, uint32_t *hist,
+                             TkShared *sh, float *out_s, int32_t *out_d) {
+    constexpr int NT = TKF_THREADS, R4 = TKF_R4;
+    int tid_;
+    if constexpr (std::is_same<Scope, CtaScope>::value) tid_ = threadIdx.x; else tid_ = Scope::tid();
+    const int tid = tid_, lane = tid & 31, warp = tid >> 5;
+    // (the caller has STARTED filling co / cbase / bias in shared memory and has not synchronised: the first barrier covers it)
+    {
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        reinterpret_cast<uint4 *>(hist)[tid] = z;                  // 1,024 words = 256 x 16 bytes
+        reinterpret_cast<uint4 *>(hist)[tid + NT] = z;
+        sh->hist2[tid] = 0u;
+        sh->hist2[tid + NT] = 0u;
+        if (tid == 0) { sh->sel_count = 0; sh->eq2_count = 0; sh->bnd_count = 0; }
+    }
+    float4 v[R4];
+#pragma unroll
+    for (int r = 0; r < R4; ++r) {
+        const int j4 = (r * NT + tid) * 4;
+        v[r] = j4 < n ? src.load4(j4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    Scope::sync();                                                 // bins are zero, the caller's segment tables are in place
+    uint32_t key[R4][4];
+#pragma unroll
+    for (int r = 0; r < R4; ++r) {
+        const int j4 = (r * NT + tid) * 4;
+        float s4[4] = {v[r].x, v[r].y, v[r].z, v[r].w};
+        if (j4 < n) src.bias4(v[r], j4, n, s4);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            key[r][e] = float_to_ordered(s4[e]);
+            if (j4 + e < n) atomicAdd(&hist[key[r][e] >> TKL_SH1], 1u);
+        }
+    }
+    Scope::sync();
+    // ---- threshold: the bin where the count accumulated from the top reaches k
+    {
+        const uint4 *h4 = reinterpret_cast<const uint4 *>(hist + TKL_BINS - 8 * (tid + 1));
+        const uint4 lo4 = h4[0], hi4 = h4[1];                      // bins ascending: lo4.x is the thread's LOWEST bin
+        const int local = (int)(lo4.x + lo4.y + lo4.z + lo4.w + hi4.x + hi4.y + hi4.z + hi4.w);
+        int incl = local;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) sh->warp_tot[warp] = incl;
+        Scope::sync();
+        int before = 0;
+#pragma unroll
+        for (int w = 0; w < NT / 32 - 1; ++w) before += w < warp ? sh->warp_tot[w] : 0;
+        incl += before;
+        const int excl = incl - local;                             // candidates in bins above this thread's eight
+        if (excl < k && k <= incl) {
+            const uint32_t b8[8] = {hi4.w, hi4.z, hi4.y, hi4.x, lo4.w, lo4.z, lo4.y, lo4.x};      // top-down
+            int running = excl, found = 0, fg = 0, fe = 0;
+            bool done = false;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int hcnt = (int)b8[i];
+                if (!done && running + hcnt >= k) { found = TKL_BINS - 8 * tid - 1 - i; fg = running; fe = hcnt; done = true; }
+                running += hcnt;
+            }
+            sh->found_bin = found; sh->found_gt = fg; sh->found_eq = fe;
+        }
+        Scope::sync();
+    }
+    const int d_bin = sh->found_bin, gt = sh->found_gt, eq = sh->found_eq;
+    if (eq > TK_BND) {                        // mass ties in the boundary bin: the general select (uniform decision)
+        Scope::sync();
+        topk_general_cold<NT, Src, Scope>(src, n, k, 128, gkeys, sel, ghist, sh, out_s, out_d);
+        return;
+    }
+    // ---- classify from the registers: sel[0, gt) <- keys above the boundary bin, bnd[0, eq) <- keys inside it (bnd aliases the bins:
+    // nobody reads them after the barrier above)
+    uint64_t *bnd = reinterpret_cast<uint64_t *>(hist);            // 2 x TK_BND x 8 B = the 4 KB of the bins
+    uint64_t *bnd2 = bnd + TK_BND;
+    {
+        int c_sel = 0, c_bnd = 0;
+#pragma unroll
+        for (int r = 0; r < R4; ++r) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const bool valid = (r * NT + tid) * 4 + e < n;
+                const int bin = (int)(key[r][e] >> TKL_SH1);
+                c_sel += (valid && bin > d_bin) ? 1 : 0;
+                c_bnd += (valid && bin == d_bin) ? 1 : 0;
+            }
+        }
+        int at_sel = c_sel ? atomicAdd(&sh->sel_count, c_sel) : 0;
+        int at_bnd = c_bnd ? atomicAdd(&sh->bnd_count, c_bnd) : 0;
+        if (c_sel | c_bnd) {
+#pragma unroll
+            for (int r = 0; r < R4; ++r) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int j = (r * NT + tid) * 4 + e;
+                    const int bin = j < n ? (int)(key[r][e] >> TKL_SH1) : -1;
+                    const uint64_t ent = ((uint64_t)key[r][e] << 32) | (uint32_t)j;
+                    if (bin > d_bin) sel[at_sel++] = ent;
+                    else if (bin == d_bin) bnd[at_bnd++] = ent;
+                }
+            }
+        }
+    }
+    Scope::sync();
+    // ---- second level: the next 8 key bits of the boundary list; every listed candidate becomes (key, ~docid) on the way (the docid
+    // reads — segment search + one global load each — are issued together, one or two per thread)
+    auto with_doc = [&](uint64_t e) { return (e & 0xffffffff00000000ull) | (uint32_t)~(uint32_t)src.doc((int)(uint32_t)e); };
+    for (int t = tid; t < eq; t += NT) atomicAdd(&sh->hist2[(uint32_t)(bnd[t] >> (32 + TKL_SH2)) & 255u], 1u);
+    if (tid < gt) sel[tid] = with_doc(sel[tid]);                   // gt < k <= 128 = NT; slots >= gt are appended below
+    uint64_t mine_b[TK_BND / NT];
+#pragma unroll
+    for (int u = 0; u < TK_BND / NT; ++u) mine_b[u] = tid + u * NT < eq ? with_doc(bnd[tid + u * NT]) : 0ull;
+    Scope::sync();
+    int d2, gt2, eq2;
+    scan_down8(sh->hist2, lane, k - gt, d2, gt2, eq2);
+    const int need2 = k - gt - gt2;                                // 1 <= need2 <= eq2
+#pragma unroll
+    for (int u = 0; u < TK_BND / NT; ++u) {
+        if (tid + u * NT < eq) {
+            const int sub = (int)((uint32_t)(mine_b[u] >> (32 + TKL_SH2)) & 255u);
+            if (sub > d2) sel[atomicAdd(&sh->sel_count, 1)] = mine_b[u];
+            else if (sub == d2) bnd2[atomicAdd(&sh->eq2_count, 1)] = mine_b[u];
+        }
+    }
+    Scope::sync();
+    if (need2 == eq2) {
+        for (int t = tid; t < eq2; t += NT) sel[gt + gt2 + t] = bnd2[t];
+    } else {
+        // still tied after 18 key bits: order by (key desc, docid asc); identical (key, docid) pairs by list position
+        for (int t = tid; t < eq2; t += NT) {
+            const uint64_t mine = bnd2[t];
+            int rank = 0;
+            for (int u = 0; u < eq2; ++u) {
+                const uint64_t o = bnd2[u];
+                rank += (o > mine) || (o == mine && u < t);
+            }
+            if (rank < need2) sel[gt + gt2 + rank] = mine;
+        }
+    }
+    Scope::sync();
+    // ---- sort: every warp sorts 32 entries (shuffle bitonic network, descending, one entry per lane), then the four runs are merged by rank
+    uint64_t x = tid < k ? sel[tid] : 0ull;
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            const uint64_t other = shfl_xor_u64(x, stride);
+            const bool desc = (lane & size) == 0;                  // size == 32: every lane
+            const bool lower = (lane & stride) == 0;
+            const uint64_t mx = x > other ? x : other, mn = x > other ? other : x;
+            x = (lower == desc) ? mx : mn;
+        }
+    }
+    Scope::sync();                                                 // everyone holds its entry: sel can be overwritten
+    sel[tid] = x;
+    Scope::sync();
+    int rank = lane;
+#pragma unroll
+    for (int w = 0; w < NT / 32; ++w) {
+        if (w == warp) continue;
+        const uint64_t *run = sel + w * 32;                        // descending
+        int lo = 0, hi = 32;                                       // number of entries of `run` that come before x
+#pragma unroll
+        for (int it = 0; it < 6; ++it) {
+            if (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                const uint64_t y = run[mid];
+                const bool before = (y > x) || (y == x && w < warp);
+                lo = before ? mid + 1 : lo;
+                hi = before ? hi : mid;
+            }
+        }
+        rank += lo;
+    }
+    if (rank < k) {
+        out_s[rank] = ordered_to_float((uint32_t)(x >> 32));
+        out_d[rank] = (int32_t)(~(uint32_t)x);
+    }
+}
+
 // ---- fast path, small-footprint variant --------------------------------------------------------------------------
 // Same algorithm as topk_body<false> for CTAs of NT = 128 threads with 16-bit histogram bins (n <= 65,535): 6.4 KB of
 // shared memory and 4 K registers per query.  A batch's top-k overlaps the NEXT batch's scoring kernel, whose CTA leaves
@@ -714,10 +931,12 @@ __device__ void topk_fast16(const Src &src, int n, int k, uint32_t *gkeys, uint3
     }
 }
 
-constexpr int TKF_THREADS = 128;
-constexpr int TKF_R4 = 5;            // 128 threads x 5 x 4 = 2,560 candidates held in registers
-constexpr int TKF64_THREADS = 64;    // the fused kernel's groups: two warps per query, no keys in registers, 1,024 first-level bins
-constexpr int TKF64_BITS = 10;
+
+template <int NT, int R4, typename Src, typename Scope>
+__device__ __noinline__ void topk_fast16_cold(const Src &src, int n, int k, uint32_t *gkeys, uint32_t *ghist, uint64_t *sel, uint32_t *hist_words,
+                                              TkShared *sh, float *out_s, int32_t *out_d) {
+    topk_fast16<NT, R4, Src, Scope>(src, n, k, gkeys, ghist, sel, hist_words, sh, out_s, out_d, 0u);
+}
 
 // ---- grouped variant -----------------------------------------------------------------------------------------------------
 // G independent NT-thread groups per CTA (GroupScope: own named barrier, own shared-memory slice), each claiming one query
@@ -759,8 +978,20 @@ __device__ void topk_group_loop(const ScoreArgs &a, float alpha, float *out_scor
         }
         const int n = a.candoff[(int64_t)bg * (a.K + 1) + a.K];
         StoreSrc src{a.scorebuf + (int64_t)b * a.stride, co, cbase, a.prob ? bias : nullptr, a.docid, a.K};
-        topk_fast16<NT, R4, StoreSrc, S>(src, n, a.k, a.gkeys + (int64_t)b * a.stride, a.ghist + (int64_t)b * TK_BINS, sel, hist_words,
-                                         sh, out_scores + (int64_t)b * a.k, out_docids + (int64_t)b * a.k, 0u);
+        bool lean = false;
+        if constexpr (NT == TKF_THREADS) lean = topk_lean_eligible<StoreSrc, S>(n, a.k);
+        if constexpr (NT == TKF_THREADS) {
+            if (lean) topk_lean128<StoreSrc, S>(src, n, a.k, a.gkeys + (int64_t)b * a.stride, a.ghist + (int64_t)b * TK_BINS, sel, hist_words, sh,
+                                                out_scores + (int64_t)b * a.k, out_docids + (int64_t)b * a.k);
+        }
+        if (!lean) {
+            if constexpr (NT == TKF_THREADS)
+                topk_fast16_cold<NT, R4, StoreSrc, S>(src, n, a.k, a.gkeys + (int64_t)b * a.stride, a.ghist + (int64_t)b * TK_BINS, sel, hist_words,
+                                                      sh, out_scores + (int64_t)b * a.k, out_docids + (int64_t)b * a.k);
+            else
+                topk_fast16<NT, R4, StoreSrc, S>(src, n, a.k, a.gkeys + (int64_t)b * a.stride, a.ghist + (int64_t)b * TK_BINS, sel, hist_words,
+                                                 sh, out_scores + (int64_t)b * a.k, out_docids + (int64_t)b * a.k, 0u);
+        }
         S::sync();                                                 // the slice (and *next) is free for the next query
     }
 }

@@ -11,8 +11,8 @@ this module keeps them in flight; it is the schedule `bench.py` times and the on
   latency-bound inversion and top-k kernels of one batch hide under the HBM-bound scoring kernel of its neighbours.
 
 Contract: `submit()` returns a `Ticket`; the ticket's outputs are complete, in stream order on the stream that calls it, after
-`ticket.wait()` (which needs the NEXT `submit()` or a `flush()` to have been issued: in the fused schedule batch i's top-k
-is part of launch i+1).  Everything is enqueue-only (no host synchronisation) and capturable in a CUDA graph as long as a
+`ticket.wait()` (which needs two further `submit()`s or a `flush()` to have been issued: in the fused schedule `submit(i)`
+enqueues the inversion of batch i and the launch that scores batch i-1 and selects batch i-2).  Everything is enqueue-only (no host synchronisation) and capturable in a CUDA graph as long as a
 `flush()` is captured last (it joins the internal streams).  Results are bit-identical to `ClusterStore.score_topk`
 (tests/test_gpu_pipeline.py).  There is no CPU path.
 """
@@ -28,7 +28,7 @@ from .store import ClusterStore
 
 class Ticket:
     """One submitted batch.  `scores` [B, k] fp32 / `docids` [B, k] int32 are valid after `wait()`."""
-    __slots__ = ("index", "scores", "docids", "event", "keep", "alpha", "host_out", "which")
+    __slots__ = ("index", "scores", "docids", "event", "keep", "alpha", "host_out", "which", "ev_inv")
 
     def __init__(self, index, scores, docids, alpha, keep):
         self.index, self.scores, self.docids, self.alpha, self.keep = index, scores, docids, alpha, keep
@@ -62,7 +62,8 @@ class PipelinedRetriever:
         self._streams: List[torch.cuda.Stream] = []
         self._s_inv: Optional[torch.cuda.Stream] = None
         self._n = 0                      # batches submitted so far
-        self._pending: List[Ticket] = []  # tickets whose outputs are not yet enqueued (fused: at most the last one)
+        self._inverted: Optional[Ticket] = None   # fused: inverted, its scoring launch not yet issued
+        self._scored: Optional[Ticket] = None     # fused: scored, its top-k (part of the next launch) not yet issued
         self._launch_events = {}         # fused: index -> event recorded after launch i (scratch reuse ordering)
         self._open: List[Ticket] = []    # batches schedule: tickets not yet joined by flush()
         self.last_schedule = None
@@ -141,6 +142,8 @@ class PipelinedRetriever:
         return t
 
     def _submit_fused(self, t, q, beams, k, prob, act, flags, cur):
+        """Batch i: its inversion goes to the side stream NOW; the fused launch that scores batch i-1 (and selects batch i-2) is
+        enqueued right behind it, so the inversion of batch i runs beside the scoring of batch i-1 — one batch ahead."""
         hs = self._handles_fused()
         i = t.index
         h = hs[i % 3][t.which]
@@ -151,19 +154,27 @@ class PipelinedRetriever:
             if i - 2 in self._launch_events:                   # the batch that last used this scratch set has had its top-k
                 self._s_inv.wait_event(self._launch_events.pop(i - 2))
             h.invert(q, beams, k, prob=prob, act=act, flags=flags)
-            ev_inv = torch.cuda.Event()
-            ev_inv.record(self._s_inv)
-        cur.wait_event(ev_inv)
-        prev = self._pending.pop() if self._pending else None
+            t.ev_inv = torch.cuda.Event()
+            t.ev_inv.record(self._s_inv)
+        if self._inverted is not None:
+            self._launch_fused(self._inverted, cur)
+        self._inverted = t
+
+    def _launch_fused(self, t, cur):
+        """ONE launch: score batch `t` (inverted earlier) and select the top-k of the batch scored by the previous launch."""
+        hs = self._handles_fused()
+        prev = self._scored
+        cur.wait_event(t.ev_inv)
         with torch.cuda.stream(cur):
-            h.score_fused(hs[(i - 1) % 3][prev.which] if prev is not None else None, alpha=prev.alpha if prev is not None else 1.0,
-                          out=(prev.scores, prev.docids) if prev is not None else None)
+            hs[t.index % 3][t.which].score_fused(hs[prev.index % 3][prev.which] if prev is not None else None,
+                                                 alpha=prev.alpha if prev is not None else 1.0,
+                                                 out=(prev.scores, prev.docids) if prev is not None else None)
             ev = torch.cuda.Event()
             ev.record(cur)
-        self._launch_events[i] = ev
+        self._launch_events[t.index] = ev
         if prev is not None:
             prev.event, prev.keep = ev, None
-        self._pending.append(t)
+        self._scored = t
 
     def _submit_batch(self, t, q, beams, k, prob, act, flags, cur):
         hs = self._handles_batches()
@@ -194,7 +205,7 @@ class PipelinedRetriever:
             raise ValueError("in_host must hold q then beams, out_host scores then docids, both as uint8 buffers")
         if self._s_h2d is None:
             self._s_h2d, self._s_d2h = torch.cuda.Stream(device=self.dev), torch.cuda.Stream(device=self.dev)
-        n_slots = 4 if self.schedule_request != "batches" and self.fused_eligible(B, K, k, flags) else self.depth + 1
+        n_slots = 5 if self.schedule_request != "batches" and self.fused_eligible(B, K, k, flags) else self.depth + 1
         if len(self._slots) != n_slots or self._slots[0]["in"].numel() != q_bytes + b_bytes or self._slots[0]["out"].numel() != 2 * r_bytes:
             self.flush()
             self._slots = [dict(**{"in": torch.empty(q_bytes + b_bytes, dtype=torch.uint8, device=self.dev),
@@ -233,8 +244,11 @@ class PipelinedRetriever:
     def flush(self) -> None:
         """Issue what is still outstanding (fused: the last batch's top-k) and join the internal streams into the current one."""
         cur = torch.cuda.current_stream(self.dev)
-        if self._pending:
-            t = self._pending.pop()
+        if self._inverted is not None:
+            self._launch_fused(self._inverted, cur)
+            self._inverted = None
+        if self._scored is not None:
+            t, self._scored = self._scored, None
             hs = self._handles_fused()
             with torch.cuda.stream(cur):
                 ClusterStore.flush_fused(hs[t.index % 3][t.which], alpha=t.alpha, out=(t.scores, t.docids))

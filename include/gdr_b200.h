@@ -147,7 +147,7 @@ int gdr_store_reserve(gdr_store_t *store, int32_t B, int32_t K, int32_t k, uint3
 #define GDR_OPT_UMMA_CTAS 1          /* persistent CTAs of the tcgen05 kernels; 0 = default (one per SM; fused launches: SMs - 8) */
 #define GDR_OPT_UMMA_MIN_GROUP 2     /* > 1: mixed mode, groups of at least this many pairs on tensor cores, the rest on the GEMV */
 #define GDR_OPT_LAUNCH_PRIORITIES 3  /* 1: per-launch scheduling priorities, inversion > scoring > top-k */
-#define GDR_OPT_FUSED_GROUPS 4       /* top-k groups in the fused CTA: 9 = nine 64-thread groups (default), 4 = four 128-thread groups */
+#define GDR_OPT_FUSED_GROUPS 4       /* top-k groups in the fused CTA: 5 = five 128-thread groups, lean select (default); 9 = nine 64-thread groups */
 #define GDR_OPT_TOPK_GROUPS 5        /* 1, 2, 4: stand-alone top-k as persistent groups walking a query queue; 0 = one CTA per query */
 #define GDR_OPT_TOPK_WIDE 6          /* 1: the 256-thread top-k also for k <= 128 */
 int gdr_store_set_option(gdr_store_t *store, int32_t option, int32_t value);

@@ -21,14 +21,14 @@ def _run(mode, value):
     return line
 
 
-@pytest.mark.parametrize("groups", ["9", "4"])
+@pytest.mark.parametrize("groups", ["5", "9"])
 def test_fused_score_topk_equals_default(groups):
     """ONE launch scoring batch i and selecting the top-k of batch i-1 (gdr_score_fused, two handles; prob + tanh + alpha) must
-    return exactly what gdr_score_topk returns batch by batch — nine 64-thread groups (default) and four 128-thread groups."""
+    return exactly what gdr_score_topk returns batch by batch — five 128-thread groups running the lean select (default) and nine 64-thread groups."""
     _run("FUSED", groups)
 
 
-@pytest.mark.parametrize("schedule,groups", [("auto", "9"), ("batches", "9")])
+@pytest.mark.parametrize("schedule,groups", [("auto", "5"), ("auto", "9"), ("batches", "5")])
 def test_pipelined_retriever_equals_default(schedule, groups):
     """gdr_b200.PipelinedRetriever: eager, replayed from a CUDA graph, and through pinned host buffers."""
     _run("PIPELINE_" + schedule.upper(), groups)

@@ -232,8 +232,8 @@ def test_bench_launch_autotune_decision(monkeypatch):
     import bench
 
     args = argparse.Namespace(workload="cfg2", path="auto", schedule="auto", replicas=0)
-    names = ("batches", "fused64_140", "fused64_132", "fused128x4_140", "batches_priorities")
-    expect = {"fused64_140": ("fused", "9", "140"), "fused64_132": ("fused", "9", "132"), "fused128x4_140": ("fused", "4", "140")}
+    names = ("batches", "fused_140", "fused_132", "fused64_140", "batches_priorities")
+    expect = {"fused_140": ("fused", "5", "140"), "fused_132": ("fused", "5", "132"), "fused64_140": ("fused", "9", "140")}
     seen = []
 
     def fake_run(times, fail=(), bad_line=None):
@@ -262,18 +262,18 @@ def test_bench_launch_autotune_decision(monkeypatch):
         return bench.autotune(args, 2)
 
     monkeypatch.setenv("RANK", "0")
-    best, rep = tune({"batches": 50.0, "fused64_140": 37.0, "fused64_132": 38.0, "fused128x4_140": 47.0})
-    assert (best["schedule"], best["fused_groups"], best["fused_ctas"], rep["chosen"]) == ("fused", 9, 140, "fused64_140")
-    assert rep["fused64_140"]["verified_identical_to_serial"] and rep["fused128x4_140"]["us_per_step"] == 47.0
-    best, rep = tune({"batches": 50.0, "fused64_140": 49.5, "fused64_132": 52.0, "fused128x4_140": 60.0, "batches_priorities": 49.0})
+    best, rep = tune({"batches": 50.0, "fused_140": 37.0, "fused_132": 38.0, "fused64_140": 47.0})
+    assert (best["schedule"], best["fused_groups"], best["fused_ctas"], rep["chosen"]) == ("fused", 5, 140, "fused_140")
+    assert rep["fused_140"]["verified_identical_to_serial"] and rep["fused64_140"]["us_per_step"] == 47.0
+    best, rep = tune({"batches": 50.0, "fused_140": 49.5, "fused_132": 52.0, "fused64_140": 60.0, "batches_priorities": 49.0})
     assert best["schedule"] == "batches" and rep["chosen"] == "batches"                      # within 3 %: the default stays
     best, rep = tune({"batches": 50.0, "batches_priorities": 40.0})
     assert best.get("launch_priorities") == "on" and rep["chosen"] == "batches_priorities"
-    best, rep = tune({"batches": 50.0}, fail={"fused64_140": "rc", "fused64_132": "timeout", "fused128x4_140": "rc", "batches_priorities": "timeout"})
+    best, rep = tune({"batches": 50.0}, fail={"fused_140": "rc", "fused_132": "timeout", "fused64_140": "rc", "batches_priorities": "timeout"})
     assert best["schedule"] == "batches" and all("failed" in rep[n] for n in names[1:])
     # a candidate whose child found differing results (or printed no time) is never chosen
     best, rep = tune({"batches": 50.0}, bad_line={"probe": True, "us_per_step": None, "failed": "RuntimeError: batch 3 differs from gdr_score_topk"})
-    assert best["schedule"] == "batches" and "differs" in rep["fused64_140"]["failed"]
+    assert best["schedule"] == "batches" and "differs" in rep["fused_140"]["failed"]
     # other workloads do not try the fused schedule at all
     seen.clear()
     args3 = argparse.Namespace(workload="cfg3", path="auto", schedule="auto", replicas=0)

@@ -239,8 +239,8 @@ __device__ __forceinline__ void wait_for_scorers(const ScoreArgs &a) {
 
 // ----- small device helpers -----------------------------------------------------------------
 __device__ __forceinline__ uint32_t float_to_ordered(float f) {
-    uint32_t u = __float_as_uint(f);
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    const uint32_t u = __float_as_uint(f);
+    return u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u);      // negative: ~u, else u | sign bit — two instructions
 }
 __device__ __forceinline__ float ordered_to_float(uint32_t k) {
     uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;

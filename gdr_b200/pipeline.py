@@ -241,12 +241,19 @@ class PipelinedRetriever:
                 t.host_out.record(self._s_d2h)
             slot["free"] = t.host_out
 
-    def flush(self) -> None:
-        """Issue what is still outstanding (fused: the last batch's top-k) and join the internal streams into the current one."""
-        cur = torch.cuda.current_stream(self.dev)
+    def flush_scoring(self) -> None:
+        """First half of `flush()`: issue the scoring launch that is still outstanding.  Only callers that drive SEVERAL pipelines
+        from one host thread on one stream need it separately (the one-process tests of the peer-to-peer exchange: every rank's last
+        scoring launch must be enqueued before any rank's final top-k, which waits for all of them)."""
         if self._inverted is not None:
-            self._launch_fused(self._inverted, cur)
+            self._launch_fused(self._inverted, torch.cuda.current_stream(self.dev))
             self._inverted = None
+
+    def flush(self) -> None:
+        """Issue what is still outstanding (fused: the last scoring launch and the last batch's top-k) and join the internal streams
+        into the current one."""
+        cur = torch.cuda.current_stream(self.dev)
+        self.flush_scoring()
         if self._scored is not None:
             t, self._scored = self._scored, None
             hs = self._handles_fused()

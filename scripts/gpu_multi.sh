@@ -1,12 +1,29 @@
 #!/bin/bash
+# multi-GPU call:  gpurun --gpus N -- 'bash scripts/gpu_multi.sh N'
 N=${1:-2}
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests -m gpu -q -x --timeout 280 2>&1 | tail -3
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus $N --steps 480 --warmup 5 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err
-tail -1 gpurun_out/bench_n$N.json | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); print('N=$N replica: value %.3fM q/s ms/step %.4f e2e %.3fM %s' % (d['value']/1e6, d['ms_per_step'], d['e2e']['value']/1e6, d['config']['parallelism']))" || tail -5 gpurun_out/bench_n$N.err
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus $N --workload cfg5s --steps 20 --warmup 3 > gpurun_out/bench_cfg5s_n$N.json 2> gpurun_out/bench_cfg5s_n$N.err
-tail -1 gpurun_out/bench_cfg5s_n$N.json | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); r=d['roofline']; print('N=$N cfg5s sharded: value %.3fM q/s ms/step %.4f e2e %.3fM phases %s frac %.3f cpu %s' % (d['value']/1e6, d['ms_per_step'], d['e2e']['value']/1e6, {k: round(v*1000,1) for k,v in r['phase_ms'].items()}, r['frac'], d['cpu_baseline']['value'] if d['cpu_baseline'] else None))" || tail -5 gpurun_out/bench_cfg5s_n$N.err
+nvidia-smi topo -m > gpurun_out/r02_topo_n$N.txt 2>&1
+timeout 600 python -m pytest tests/test_gpu_sharded_p2p.py tests/test_gpu_sharded.py -q --timeout 300 > gpurun_out/r02_pytest_multi_n$N.log 2>&1; tail -12 gpurun_out/r02_pytest_multi_n$N.log
+show() { python - "$1" <<'PY'
+import json, sys
+try:
+    d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1]); c = d['config']
+    e = d.get('e2e') or {}
+    print(sys.argv[1], 'value %.2fM q/s  us/step %.2f  e2e %s  exchange %s schedule %s graph %s step_frac %.3f' % (d['value'] / 1e6, d['ms_per_step'] * 1e3,
+          ('%.2fM' % (e['value'] / 1e6)) if e else None, c.get('exchange'), str(c.get('schedule'))[:12], c.get('cuda_graph'), d['roofline']['whole_step_frac']))
+    print('   checks', c.get('results_verified'), 'notes', c.get('notes'), 'e2e copies', e.get('copies'), 'e2e graph', e.get('cuda_graph'))
+except Exception as ex:
+    print(sys.argv[1], 'unreadable', ex)
+PY
+}
+run() { # name, extra args
+  name=$1; shift
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --no-cpu-baseline "$@" \
+      > gpurun_out/r02_bench_n${N}_$name.json 2> gpurun_out/r02_bench_n${N}_$name.err
+  tail -c 600 gpurun_out/r02_bench_n${N}_$name.err | grep -v "^$" | tail -4; show gpurun_out/r02_bench_n${N}_$name.json
+}
+run p2p --exchange auto
+if [ -z "$SHORT" ]; then
+run nccl --exchange nccl
+run replica --mode replica --no-autotune --schedule batches
+fi

@@ -82,7 +82,9 @@ def fused(world):
         for qd, bd, pd in batches:             # lock step: every rank submits batch i before anyone submits batch i+1
             for r, p in enumerate(pipes):
                 tickets[r].append(p.submit(qd, bd, prob=pd, alpha=0.5, act="tanh"))
-        for p in pipes:
+        for p in pipes:                        # one host thread drives every rank: all last scoring launches first ...
+            p.pr.flush_scoring()
+        for p in pipes:                        # ... then the final top-k of each (it waits for every rank's scores)
             p.flush()
         torch.cuda.synchronize()
         for r in range(world):

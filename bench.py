@@ -368,7 +368,13 @@ def main():
     sharded = world > 1 and args.mode != "replica"
     if sharded:
         import bench_sharded
-        return bench_sharded.run(args, cfg, rank, world, local_rank, dev)
+        try:
+            return bench_sharded.run(args, cfg, rank, world, local_rank, dev)
+        except BaseException:          # a rank that fails must not leave the others waiting in a collective until the launcher's timeout
+            import traceback
+            traceback.print_exc()
+            sys.stderr.flush()
+            os._exit(1)
 
     B = cfg["B"]
     flags = {"auto": 0, "simt": 2, "umma": 4}[args.path]

@@ -7,7 +7,7 @@ rank owns the results of its B queries.  Per step and rank: invert the global ba
 clusters, deliver the candidates to the owners, select the owners' top-k.
 
 exchange `p2p` (default): the scoring epilogue stores every score straight into the owner's score buffer over NVLink and the
-owner's top-k waits for per-rank arrival flags (gdr_b200.sharded.ShardedPipeline; fused schedule).  exchange `nccl`: local top-k of
+owner's top-k waits for per-rank arrival flags (gdr_b200.sharded.ShardedPipeline; five batches in flight).  exchange `nccl`: local top-k of
 all N x B queries, NCCL all-gather of packed (score, docid) lists, merge (gdr_b200.sharded.ShardedRetriever) — the fallback when
 peer mapping is unavailable, and the cross-check.  Before anything is timed, the sharded result of every rank is compared bit for
 bit with a plain single-GPU call on the gathered corpus (when the gathered corpus fits: cfg1-3), and p2p with nccl.
@@ -39,6 +39,18 @@ def run(args, cfg, rank, world, local_rank, dev):
         dist.barrier()
         torch.cuda.synchronize()
 
+    def finish():
+        """Leave without tearing down NCCL communicators / IPC mappings that CUDA graphs still reference (that teardown hung for the whole
+        launcher timeout): every rank has reported, a last barrier, then a hard exit."""
+        try:
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            import sys
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
+
     # ---- the corpus: rank r generates shard r; the CSR metadata (cluster sizes, docids) is gathered and replicated
     emb_l, offsets_l, order_l = bench.synth_shard(cfg, 1234 + 1000 * rank, dev)
     sizes_l = torch.diff(offsets_l).to(torch.int32).to(dev)
@@ -61,7 +73,8 @@ def run(args, cfg, rank, world, local_rank, dev):
     sp = None
     if args.exchange in ("auto", "p2p"):
         try:
-            sp = ShardedPipeline(shards, rank, world, B, K, k, flags=flags, fused_ctas=args.fused_ctas, fused_groups=args.fused_groups)
+            sp = ShardedPipeline(shards, rank, world, B, K, k, flags=flags, schedule="fused" if args.schedule == "fused" else "auto",
+                                 depth=args.pipeline or 5, fused_ctas=args.fused_ctas, fused_groups=args.fused_groups)
         except Exception as e:             # e.g. no peer access between the GPUs of this box
             notes["p2p_setup_failed"] = f"{type(e).__name__}: {e}"[:300]
             sp = None
@@ -129,7 +142,7 @@ def run(args, cfg, rank, world, local_rank, dev):
 
     run_steps(max(args.warmup, 2 * n_batches))
     barrier()
-    period = math.lcm(replicas, n_batches, 3)
+    period = math.lcm(replicas, n_batches, 3, args.pipeline or 5)
     period *= max(2, -(-80 // period))
     if args.steps < period:
         period = max(1, args.steps)
@@ -318,8 +331,7 @@ def run(args, cfg, rank, world, local_rank, dev):
         e2e = None
 
     if rank != 0:
-        dist.destroy_process_group()
-        return
+        finish()
 
     peak, peak_src = bench.peaks()
     beams0 = batches[0][1]
@@ -329,7 +341,7 @@ def run(args, cfg, rank, world, local_rank, dev):
     stats = shards[0].last_stats() if sp is None else sp.handles[0].last_stats()
     launches = (sp.pr.launches() if sp is not None else int(local_store.last_stats()["launches"]) + 2)
     roofline = {"bound": "hbm", "achieved": alg_bytes / (step_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg_bytes / (step_ms * 1e-3) / 1e9 / peak,
-                "traffic": None, "kernel": ("k_score_topk_fused64" if sp is not None and sp.schedule == "fused" else "scoring kernel") + " (per-rank step; the whole step is the unit here)",
+                "traffic": None, "kernel": ("k_score_topk_fused_p2p" if sp is not None and sp.schedule == "fused" else ("k_score_umma_p2p" if sp is not None else "scoring kernel")) + " (per-rank step; the whole step is the unit here)",
                 "kernel_ms": step_ms, "kernel_ms_method": "the timed region / steps (max over ranks)", "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "whole_step_frac": alg_bytes / (step_ms * 1e-3) / 1e9 / peak,
                 "note": "per rank; replicated queries count as algorithmic bytes (every rank reads all N x B queries once)"}
@@ -351,8 +363,8 @@ def run(args, cfg, rank, world, local_rank, dev):
         "clocks": clocks, "gpu_launches": int(launches) * steps * world, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
         "path": {"simt_items": int(stats["simt_items"]), "umma_tiles": int(stats["umma_tiles"]), "clusters_touched": int(stats["clusters_touched"])},
     }
-    print(json.dumps(line))
-    dist.destroy_process_group()
+    print(json.dumps(line), flush=True)
+    finish()
 
 
 def capture(fn, n):

@@ -438,6 +438,11 @@ int gdr_score_topk(gdr_store_t *s, const float *q, const int32_t *beams, const f
     }
     if (prof) GDR_CUDA(cudaEventRecord(s->ev[3], st));
     a.launch_prio = s->prio_topk;
+    a.wait_in_topk = 0;
+    if (a.n_ranks > 1 && !(flags & GDR_SKIP_TOPK)) {      // sharded corpus: one warp waits for every rank's scores, then the top-k grid runs
+        GDR_CUDA(launch_wait_scorers(a, st));
+        launches += 1;
+    }
     for (int r = 0; r < n_alpha && !(flags & GDR_SKIP_TOPK); ++r) {
         const float alpha = alphas ? alphas[r] : 1.0f;
         GDR_CUDA(launch_topk_store(a, alpha, out_scores + (int64_t)r * a.B_top * k, out_docids + (int64_t)r * a.B_top * k, st));
@@ -447,6 +452,7 @@ int gdr_score_topk(gdr_store_t *s, const float *q, const int32_t *beams, const f
     s->last_launches = launches;
     a.launch_prio = s->prio_score;                // what gdr_score_fused launches with
     a.signal = 1;
+    a.wait_in_topk = 1;                           // ... and its top-k groups wait for the arrival flags themselves
     s->last_args = a;
     s->last_valid = true;
     s->last_umma_only = use_umma && !use_simt;
@@ -470,6 +476,10 @@ int gdr_score_fused(gdr_store_t *cur, gdr_store_t *prev, float alpha, float *pre
         }
     }
     if (!cur) {                                                    // flush: the last batch's top-k alone
+        if (pa.n_ranks > 1) {
+            pa.wait_in_topk = 0;
+            GDR_CUDA(launch_wait_scorers(pa, st));
+        }
         GDR_CUDA(launch_topk_store(pa, alpha, prev_out_scores, prev_out_docids, st));
         return GDR_OK;
     }

@@ -102,6 +102,8 @@ struct ScoreArgs {
     int32_t *sig_local;                // this rank's arrival flags [n_ranks] (= peer_sig[my_rank])
     int32_t *sig_epoch;                // [1] device counter: scoring launches of this handle so far
     int32_t signal;                    // 1 in the copy given to the call's LAST scoring kernel: it signals the owners when it is done
+    int32_t wait_in_topk;              // 1: the top-k kernel itself waits for the arrival flags (fused launches); 0: a one-warp k_wait_scorers
+                                       // launched in front of it did (stand-alone top-k: a grid of spinning CTAs could keep a scoring kernel off the SMs)
     int32_t launch_prio;     // host side only: scheduling priority class of the launches made with this copy of the arguments
                              // (0 = none; else a CUDA priority + 1000), set per phase by the C-ABI entry point — per call, not global
 };
@@ -112,6 +114,7 @@ cudaError_t launch_score_simt(const ScoreArgs &a, cudaStream_t s, int sm_count);
 cudaError_t launch_score_umma(const ScoreArgs &a, const CUtensorMap *tmap, cudaStream_t s, int sm_count);
 cudaError_t launch_topk_store(const ScoreArgs &a, float alpha, float *out_scores, int32_t *out_docids,
                               cudaStream_t s);
+cudaError_t launch_wait_scorers(const ScoreArgs &a, cudaStream_t s);
 cudaError_t launch_topk_grouped(const ScoreArgs &a, float alpha, float *out_scores, int32_t *out_docids, cudaStream_t s, int groups);
 cudaError_t launch_score_fused(const ScoreArgs &a, const CUtensorMap *tmap, const ScoreArgs &prev, float alpha, float *out_scores,
                                int32_t *out_docids, cudaStream_t s, int ctas, int groups);
@@ -226,8 +229,8 @@ __device__ __forceinline__ void signal_owners(const ScoreArgs &a) {
 // Called by ONE thread of a top-k CTA / group before the first score is read: every rank's scoring launch of this handle's
 // current epoch has landed in this rank's score buffer.  The local epoch is the expected value: the local scoring launch of
 // the same batch precedes the top-k in stream order, and all ranks step through the handle's batches in the same order.
-__device__ __forceinline__ void wait_for_scorers(const ScoreArgs &a) {
-    if (a.n_ranks <= 1) return;
+__device__ __forceinline__ void wait_for_scorers(const ScoreArgs &a, bool in_topk = true) {
+    if (a.n_ranks <= 1 || (in_topk && !a.wait_in_topk)) return;
     const int expected = *reinterpret_cast<volatile int32_t *>(a.sig_epoch);
     for (int r = 0; r < a.n_ranks; ++r) {
         int v;

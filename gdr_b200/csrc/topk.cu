@@ -119,6 +119,20 @@ __global__ void __launch_bounds__(TK_THREADS) k_topk_merge(ListSrc src0, int n, 
     topk_body<TK_THREADS, true>(src, n, k, cap, keys, sel, hist, &sh, out_scores + (int64_t)b * k, out_docids + (int64_t)b * k);
 }
 
+// Sharded corpus, stand-alone top-k: ONE warp waits for every rank's arrival flag; the top-k grid behind it (same stream) then starts
+// with all scores in place.  The wait is not done by the top-k CTAs themselves: with several batches in flight a grid of ~1,000 spinning
+// CTAs could occupy the SMs that the scoring kernel another rank is waiting for needs — a cross-GPU deadlock; one spinning warp cannot.
+__global__ void __launch_bounds__(32) k_wait_scorers(ScoreArgs a) {
+    pdl_wait();
+    if (threadIdx.x == 0) wait_for_scorers(a, false);
+    __syncwarp();
+    __threadfence_system();
+}
+
+cudaError_t launch_wait_scorers(const ScoreArgs &a, cudaStream_t s) {
+    return launch_pdl(k_wait_scorers, dim3(1), dim3(32), 0, s, a.launch_prio, a);
+}
+
 static int pow2_at_least(int x) { int p = 2; while (p < x) p <<= 1; return p; }
 
 cudaError_t launch_topk_store(const ScoreArgs &a, float alpha, float *out_scores, int32_t *out_docids, cudaStream_t s) {

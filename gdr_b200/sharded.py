@@ -130,20 +130,26 @@ class ShardedPipeline:
 
     exchange = "p2p": candidates never become lists — every rank's scoring epilogue stores its scores straight into the owner's
     score buffer over NVLink and raises a flag; the owner's top-k waits for the flags (include/gdr_b200.h gdr_store_p2p_*).
-    The schedule is PipelinedRetriever's fused one (scoring of batch i + top-k of batch i-1 in one launch) when the shape is
-    eligible, else strictly serial calls — never independent streams: a top-k that spins for a peer must not be able to keep
-    that peer's (or its own) scoring kernel off the SMs.  All ranks must submit the same sequence of batches.
+    Several batches are in flight (PipelinedRetriever's schedules, one exchange buffer per handle); whatever waits for a peer is
+    built so that it cannot keep a scoring kernel off the SMs: one spinning warp in front of the stand-alone top-k, or the top-k
+    groups inside the scoring CTA of the fused launch.  All ranks must submit the same sequence of batches.
     exchange = "nccl" is `ShardedRetriever` (local top-k, all-gather of (score, docid) lists, merge): see there."""
 
     def __init__(self, stores, rank: int, world: int, b_own: int, K: int, k: int, group=None, flags: int = 0,
-                 fused_ctas: int = 0, fused_groups: int = 0, local_peers=None):
+                 schedule: str = "auto", depth: int = 5, fused_ctas: int = 0, fused_groups: int = 0, local_peers=None):
+        """schedule: 'batches' = whole calls round-robin on `depth` streams (each handle has its own exchange buffer; the stand-alone
+        top-k is preceded by a one-warp wait kernel, so nothing that spins can keep a scoring kernel off the SMs), 'fused' = scoring of
+        batch i + top-k of batch i-1 in one launch (the top-k groups wait for the flags inside the scoring CTA), 'auto' = batches."""
         from .pipeline import PipelinedRetriever
         self.rank, self.world, self.b_own, self.K, self.k, self.group = rank, world, b_own, K, k, group
         stores = list(stores) if isinstance(stores, (list, tuple)) else [stores]
         B = world * b_own
-        self.pr = PipelinedRetriever(stores, schedule="auto", depth=1, fused_ctas=fused_ctas, fused_groups=fused_groups)
-        fused = self.pr.fused_eligible(B, K, k, flags)
-        self.schedule = "fused" if fused else "serial"
+        want_fused = schedule == "fused"
+        self.pr = PipelinedRetriever(stores, schedule="fused" if want_fused else "batches", depth=depth, fused_ctas=fused_ctas, fused_groups=fused_groups)
+        fused = want_fused and self.pr.fused_eligible(B, K, k, flags)
+        if want_fused and not fused:
+            raise ValueError("this batch shape is not eligible for the fused schedule")
+        self.schedule = "fused" if fused else f"batches x{depth}"
         self.handles = [h for hs in (self.pr._handles_fused() if fused else self.pr._handles_batches()) for h in hs]
         mine = [h.p2p_init(world, rank, b_own, K) for h in self.handles]
         if local_peers is not None:             # every rank's ShardedPipeline lives in this process (tests): wired by connect_local

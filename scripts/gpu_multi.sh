@@ -18,7 +18,7 @@ PY
 }
 run() { # name, extra args
   name=$1; shift
-  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --no-cpu-baseline "$@" \
+  timeout ${BENCH_TIMEOUT:-300} python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --no-cpu-baseline "$@" \
       > gpurun_out/r02_bench_n${N}_$name.json 2> gpurun_out/r02_bench_n${N}_$name.err
   tail -c 600 gpurun_out/r02_bench_n${N}_$name.err | grep -v "^$" | tail -4; show gpurun_out/r02_bench_n${N}_$name.json
 }

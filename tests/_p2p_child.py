@@ -59,14 +59,14 @@ def serial(world, path):
     print(json.dumps({"variant": f"p2p serial world={world} {path}", "identical": ok, "ok": all(ok)}))
 
 
-def fused(world):
-    """ShardedPipeline (fused schedule) per simulated rank, the ranks' launches interleaved on one stream."""
+def fused(world, schedule="fused"):
+    """ShardedPipeline per simulated rank (fused schedule: the ranks' launches interleaved on one stream; batches: five streams per rank)."""
     N, C, D, K, k, b_own = 30000, 160, 768, 20, 100, 128
     emb, offsets, docid = orc.synth_corpus(N, C, D, seed=81)
     emb = emb.bfloat16().float()
     full = ClusterStore.from_csr(emb, offsets, docid, dtype=torch.bfloat16)
     st = shards(emb, offsets, docid, world, torch.bfloat16)
-    pipes = [ShardedPipeline(st[r], r, world, b_own, K, k, local_peers=True) for r in range(world)]
+    pipes = [ShardedPipeline(st[r], r, world, b_own, K, k, schedule=schedule, depth=3, local_peers=True) for r in range(world)]
     ShardedPipeline.connect_local(pipes)
     B = world * b_own
     batches, refs = [], []
@@ -90,14 +90,14 @@ def fused(world):
         for r in range(world):
             sl = slice(r * b_own, (r + 1) * b_own)
             ok += [bool(torch.equal(t.scores, ref[0][sl]) and torch.equal(t.docids, ref[1][sl])) for t, ref in zip(tickets[r], refs)]
-    print(json.dumps({"variant": f"p2p fused world={world}", "schedule": pipes[0].schedule, "identical": ok,
-                      "ok": all(ok) and pipes[0].schedule == "fused"}))
+    print(json.dumps({"variant": f"p2p {schedule} world={world}", "schedule": pipes[0].schedule, "identical": ok,
+                      "ok": all(ok) and pipes[0].schedule.startswith(schedule)}))
 
 
 if __name__ == "__main__":
     torch.cuda.set_device(0)
     mode, world = sys.argv[1], int(sys.argv[2])
-    if mode == "fused":
-        fused(world)
+    if mode in ("fused", "batches"):
+        fused(world, mode)
     else:
         serial(world, mode)

@@ -31,9 +31,9 @@ def test_p2p_exchange_one_process(mode, world):
     _run(mode, world)
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_p2p_fused_pipeline_one_process(world):
-    _run("fused", world)
+@pytest.mark.parametrize("schedule,world", [("fused", 2), ("fused", 4), ("batches", 3)])
+def test_p2p_pipeline_one_process(schedule, world):
+    _run(schedule, world)
 
 
 def _free_port():
@@ -62,7 +62,7 @@ def _worker(rank, world, port, out_dir):
         lo, hi = int(offsets[bounds[rank]]), int(offsets[bounds[rank + 1]])
         shard = ClusterStore.shard(emb[lo:hi].bfloat16().cuda(), offsets, torch.from_numpy(docid).cuda(), int(bounds[rank]), int(bounds[rank + 1]))
         full = ClusterStore.from_csr(emb, offsets, docid, dtype=torch.bfloat16)
-        sp = ShardedPipeline(shard, rank, world, b_own, K, k)
+        sp = ShardedPipeline(shard, rank, world, b_own, K, k, schedule=os.environ.get("GDR_TEST_SHARDED_SCHEDULE", "auto"))
         tickets, refs = [], []
         for i in range(6):
             q, beams, beam_scores = orc.synth_queries(world * b_own, C, K, D, seed=20 + i)
@@ -75,7 +75,6 @@ def _worker(rank, world, port, out_dir):
         sl = slice(rank * b_own, (rank + 1) * b_own)
         for t, (rs, rd) in zip(tickets, refs):
             assert torch.equal(t.docids, rd[sl]) and torch.equal(t.scores, rs[sl]), "p2p-sharded result differs from the single-GPU result"
-        assert sp.schedule == "fused"
         dist.barrier()
         open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     finally:

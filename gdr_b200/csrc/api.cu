@@ -24,7 +24,6 @@ static int invalid(const char *msg) {
     return GDR_ERR_INVALID;
 }
 
-bool umma_make_tensor_map(CUtensorMap *out, const void *emb, int64_t n_docs, int dim);   // score_umma.cu
 
 }  // namespace gdr
 
@@ -578,6 +577,13 @@ int gdr_similarity(const float *q, int64_t Q, const void *p, int64_t P, int32_t 
     int dev = 0, sms = 148;
     GDR_CUDA(cudaGetDevice(&dev));
     GDR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    // bf16 passages with dim % 64 == 0 and enough work to fill tiles: the tcgen05 grouped GEMM (similarity.cu); everything else: the GEMV
+    if (p_dtype == GDR_DTYPE_BF16 && dim % 64 == 0 && P >= 64 && Q >= 8) {
+        const cudaError_t e = launch_similarity_umma(q, Q, p, P, dim, out, (cudaStream_t)stream, sms);
+        if (e == cudaSuccess) return GDR_OK;
+        if (e != cudaErrorNotSupported) return cuda_fail(e, "gdr_similarity (tensor-core path)");
+        cudaGetLastError();
+    }
     GDR_CUDA(launch_similarity(q, Q, p, P, dim, p_dtype, out, (cudaStream_t)stream, sms));
     return GDR_OK;
 }

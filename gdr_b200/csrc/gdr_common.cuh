@@ -123,6 +123,9 @@ cudaError_t launch_merge_topk(const float *scores, const int32_t *docids, int G,
                               float *out_scores, int32_t *out_docids, cudaStream_t s);
 cudaError_t launch_similarity(const float *q, int64_t Q, const void *p, int64_t P, int dim, int p_dtype,
                               float *out, cudaStream_t s, int sm_count);
+// tensor-core form for bf16 passages with dim % 64 == 0 (similarity.cu): returns cudaErrorNotSupported when it does not apply
+cudaError_t launch_similarity_umma(const float *q, int64_t Q, const void *p, int64_t P, int dim, float *out, cudaStream_t s, int sm_count);
+bool umma_make_tensor_map(CUtensorMap *out, const void *emb, int64_t n_docs, int dim);
 cudaError_t launch_centroids(const void *emb, int dtype, const int32_t *offsets, int n_clusters, int dim, float *out, cudaStream_t s);
 cudaError_t launch_tree_mask(const int32_t *first_child, const int32_t *child_tok, const int32_t *child_node,
                              const int64_t *input_ids, int64_t ids_stride, int R, int cur_len, float *scores,
@@ -241,6 +244,14 @@ __device__ __forceinline__ void wait_for_scorers(const ScoreArgs &a, bool in_top
 }
 
 // ----- small device helpers -----------------------------------------------------------------
+// fp32 -> (hi, mid, lo) bf16 with x == hi + mid + lo exactly (8 + 8 + 8 mantissa bits)
+__device__ __forceinline__ void split3(float x, __nv_bfloat16 &hi, __nv_bfloat16 &mid, __nv_bfloat16 &lo) {
+    hi = __float2bfloat16_rn(x);
+    const float r1 = x - __bfloat162float(hi);
+    mid = __float2bfloat16_rn(r1);
+    lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+}
+
 __device__ __forceinline__ uint32_t float_to_ordered(float f) {
     const uint32_t u = __float_as_uint(f);
     return u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u);      // negative: ~u, else u | sign bit — two instructions

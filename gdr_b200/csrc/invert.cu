@@ -12,14 +12,6 @@
 
 namespace gdr {
 
-// fp32 -> (hi, mid, lo) bf16 with x == hi + mid + lo exactly (8 + 8 + 8 mantissa bits)
-__device__ __forceinline__ void split3(float x, __nv_bfloat16 &hi, __nv_bfloat16 &mid, __nv_bfloat16 &lo) {
-    hi = __float2bfloat16_rn(x);
-    const float r1 = x - __bfloat162float(hi);
-    mid = __float2bfloat16_rn(r1);
-    lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
-}
-
 // One warp: rows [row0, row0 + nrows) of q -> a.qsplit[row][term][dim] (the B operand of the tcgen05 path)
 __device__ __forceinline__ void split_rows(const ScoreArgs &a, int64_t row0, int nrows, int lane) {
     for (int r = 0; r < nrows; ++r) {

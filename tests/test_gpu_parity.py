@@ -259,7 +259,9 @@ def test_cfg3_shape_top1000():
 def test_compute_similarity_drop_in():
     from gdr_b200 import DenseModel
     g = torch.Generator().manual_seed(5)
-    for Q, P, D, dt in ((7, 33, 96, torch.float32), (130, 1000, 768, torch.float32), (64, 513, 768, torch.bfloat16)):
+    # fp32 / small shapes: the GEMV; bf16 passages with dim % 64 == 0: the tcgen05 grouped GEMM (ragged query chunk, ragged last row tile)
+    for Q, P, D, dt in ((7, 33, 96, torch.float32), (130, 1000, 768, torch.float32), (64, 513, 768, torch.bfloat16),
+                        (1000, 3001, 768, torch.bfloat16), (33, 200, 128, torch.bfloat16), (8, 64, 64, torch.bfloat16)):
         q = torch.randn(Q, D, generator=g)
         p = (torch.randn(P, D, generator=g) * D ** -0.5).to(dt)
         out = DenseModel().compute_similarity(q.cuda(), p.cuda())

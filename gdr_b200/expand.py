@@ -22,16 +22,27 @@ def assign_to_clusters(centroids: torch.Tensor, docs: torch.Tensor) -> Tuple[tor
     C = centroids.shape[0]
     dev = centroids.device
     store = ClusterStore(centroids.contiguous(), torch.tensor([0, C]), torch.arange(C))
-    beams = torch.zeros((docs.shape[0], 1), dtype=torch.int32, device=dev)
-    s, d = store.score_topk(docs.to(dev, torch.float32), beams, 1)
-    return d[:, 0].long(), s[:, 0]
+    docs = docs.to(dev, torch.float32)
+    # The call's scratch holds M x C scores (and as many keys): documents go in chunks that keep it within ~256 MB and the
+    # score-buffer index below 2^31 — the reference's per-document loop (main_models.py:283-290) has no limit on M either.
+    chunk = max(1, min(docs.shape[0], (64 << 20) // max(C, 1)))
+    idx = torch.empty(docs.shape[0], dtype=torch.int64, device=dev)
+    val = torch.empty(docs.shape[0], dtype=torch.float32, device=dev)
+    for lo in range(0, docs.shape[0], chunk):
+        part = docs[lo:lo + chunk].contiguous()
+        beams = torch.zeros((part.shape[0], 1), dtype=torch.int32, device=dev)
+        s, d = store.score_topk(part, beams, 1)
+        idx[lo:lo + chunk], val[lo:lo + chunk] = d[:, 0].long(), s[:, 0]
+    return idx, val
 
 
 def tree_embedding_insert(store: ClusterStore, id_mapping: Dict[str, List[int]], insert_doc, docnum: int
                           ) -> Dict[str, List[int]]:
     """reference main_models.py:268-295 on top of a ClusterStore built from (doc_embed, id_mapping): documents
     `insert_doc[docnum:]` are appended to the `id_mapping` list of their nearest leaf cluster (centroids from the
-    store).  Returns `id_mapping` (modified in place; each list de-duplicated like the reference's list(set(...)),
+    store: an fp32 store reproduces the reference's fp32 means bit for bit; a bf16 store averages the ROUNDED embeddings, so a
+    document whose two best clusters are within bf16 rounding of each other can land in the other one — build the store with
+    dtype=torch.float32 for index expansion when that matters).  Returns `id_mapping` (modified in place; each list de-duplicated like the reference's list(set(...)),
     here keeping first-seen order)."""
     if store.keys is None:
         raise ValueError("the store must carry its cluster keys")

@@ -116,7 +116,14 @@ class DeviceTrie:
         """Fused log_softmax -> tree mask -> + beam score -> view [B, K*V] -> topk(2K) of the reference's beam search
         (generation_utils_previous.py:694, 714-729, 757-771) with one read of the logits.
         next_token_logits [B*K, V] fp32, input_ids [B*K, cur_len] int64, beam_scores [B*K] fp32 (all CUDA).
-        Returns (next_scores [B, 2K] fp32, next_tokens [B, 2K] int64 = beam * V + token; -inf / -1 past the survivors)."""
+        Returns (next_scores [B, 2K] fp32, next_tokens [B, 2K] int64 = beam * V + token).  When fewer than 2K entries survive the
+        mask (routine at the leaf level, where every beam only allows EOS) the tail has score -inf and — like the in-row indices
+        `torch.topk` returns for the reference's -inf entries — a VALID flat index (beam 0, token `eos_token_id`), so the
+        Hugging Face bookkeeping that follows (`beam_id = idx // V`, `token_id = idx % V`, generation_utils_previous.py:783-834)
+        never indexes outside its own batch element.
+        The fused step stands in for `postprocess_next_token_scores` (:696-708) only when its options are at their no-op defaults
+        (repetition_penalty 1.0, no_repeat_ngram_size 0, bad_words_ids None, min_length 0), which is how the reference calls
+        `generate` (main_models.py:1380-1397); pass non-default options through the unfused path (`TreeMask.__call__`)."""
         if not (next_token_logits.is_cuda and input_ids.is_cuda and beam_scores.is_cuda):
             raise ValueError("beam_step runs on the device (no CPU fallback)")
         if next_token_logits.dtype != torch.float32 or input_ids.dtype != torch.int64 or next_token_logits.stride(1) != 1:
@@ -134,7 +141,8 @@ class DeviceTrie:
                 self._handle, next_token_logits.data_ptr(), next_token_logits.stride(0) if R > 1 else V, ids.data_ptr(),
                 ids.stride(0) if R > 1 else ids.shape[1], bs.data_ptr(), B, num_beams, ids.shape[1], V, int(eos_token_id),
                 out_s.data_ptr(), out_t.data_ptr(), _cabi.stream_ptr(stream)))
-        return out_s, out_t.long()
+        out_t = out_t.long()
+        return out_s, torch.where(out_t < 0, torch.full_like(out_t, int(eos_token_id)), out_t)
 
     def close(self):
         if getattr(self, "_handle", None) is not None and self._handle.value:

@@ -114,12 +114,14 @@ def test_position_mask_golden():
 
 def _check_beam_step(got_s, got_t, ref_s, ref_t, what):
     """values within 1e-5; tokens equal wherever the reference value is finite and not within 1e-5 of a neighbour;
-    past the survivors ours is (-inf, -1) (the reference's topk returns -inf with unspecified indices there)."""
+    past the survivors ours is (-inf, a valid in-row index: beam 0, EOS) — the reference's topk returns -inf with unspecified
+    (but in-row) indices there, and the Hugging Face bookkeeping derives beam / token ids from them."""
     got_s, got_t = got_s.cpu().numpy(), got_t.cpu().numpy()
     finite = np.isfinite(ref_s)
     assert np.array_equal(np.isfinite(got_s), finite), what
     np.testing.assert_allclose(got_s[finite], ref_s[finite], rtol=1e-5, atol=1e-5, err_msg=what)
-    assert np.all(got_t[~finite] == -1), what
+    assert np.all(got_t[~finite] == 1), what          # flat index 0 * V + eos (= 1)
+    assert got_t.min() >= 0, what
     for b in range(ref_s.shape[0]):
         for i in np.nonzero(finite[b] & (got_t[b] != ref_t[b]))[0]:
             js = np.nonzero(ref_t[b] == got_t[b, i])[0]

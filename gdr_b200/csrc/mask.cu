@@ -13,6 +13,8 @@
 // strict mode reads everything and computes s + (-inf) so NaN / +inf inputs propagate exactly as in
 // the reference.  Allowed entries are always read and rewritten as s + 0.0f (so -0.0 becomes
 // +0.0, as `scores += mask` does).
+#include <type_traits>
+
 #include "gdr_common.cuh"
 
 namespace gdr {
@@ -215,6 +217,9 @@ cudaError_t launch_beam_rows(const int32_t *first_child, const int32_t *child_to
 template <int VEC>
 __global__ void __launch_bounds__(256) k_position_mask(float *__restrict__ logits, int64_t n_rows, int sl, int V,
                                                        int v_out, int last_eos_only) {
+    using Vec = typename std::conditional<VEC == 4, float4, typename std::conditional<VEC == 2, float2, float>::type>::type;
+    constexpr int U = 8;                                    // vector loads a lane has in flight before its first store (the row is
+                                                            // modified in place: without the explicit batch every load waits for the store before it)
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -223,29 +228,26 @@ __global__ void __launch_bounds__(256) k_position_mask(float *__restrict__ logit
         const int t = (int)(row % sl);
         const bool digits = !(last_eos_only && t == sl - 1);
         const int lo = digits ? t * v_out + 2 : V, hi = digits ? t * v_out + v_out + 2 : V;      // kept range [lo, hi), plus token 1
-        float *base = logits + row * V;
+        Vec *p = reinterpret_cast<Vec *>(logits + row * V);
         auto fix = [&](float x, int v) { return __fadd_rn(x, (v == 1 || (v >= lo && v < hi)) ? 0.0f : -1e9f); };
-        if constexpr (VEC == 4) {
-            float4 *p = reinterpret_cast<float4 *>(base);
-#pragma unroll 4
-            for (int i = lane; i < nv; i += 32) {
-                float4 x = __ldcs(p + i);
-                const int v = i * 4;
-                x.x = fix(x.x, v); x.y = fix(x.y, v + 1); x.z = fix(x.z, v + 2); x.w = fix(x.w, v + 3);
-                __stcs(p + i, x);
+        for (int i0 = 0; i0 < nv; i0 += 32 * U) {
+            Vec x[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + u * 32 + lane;
+                if (i < nv) x[u] = __ldcs(p + i);
             }
-        } else if constexpr (VEC == 2) {
-            float2 *p = reinterpret_cast<float2 *>(base);
-#pragma unroll 4
-            for (int i = lane; i < nv; i += 32) {
-                float2 x = __ldcs(p + i);
-                const int v = i * 2;
-                x.x = fix(x.x, v); x.y = fix(x.y, v + 1);
-                __stcs(p + i, x);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + u * 32 + lane;
+                if (i < nv) {
+                    const int v = i * VEC;
+                    if constexpr (VEC == 4) { x[u].x = fix(x[u].x, v); x[u].y = fix(x[u].y, v + 1); x[u].z = fix(x[u].z, v + 2); x[u].w = fix(x[u].w, v + 3); }
+                    else if constexpr (VEC == 2) { x[u].x = fix(x[u].x, v); x[u].y = fix(x[u].y, v + 1); }
+                    else x[u] = fix(x[u], v);
+                    __stcs(p + i, x[u]);
+                }
             }
-        } else {
-#pragma unroll 4
-            for (int v = lane; v < V; v += 32) __stcs(base + v, fix(__ldcs(base + v), v));
         }
     }
 }

@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(TKF_THREADS, 8) k_topk_fast(ScoreArgs a, float
 // KEYS: 0 = key array in global scratch, 1 = key array in shared memory, 2 = fast path (k <= 128) without a key array
 // (its mass-tie fallback uses the global scratch)
 template <int KEYS>
-__global__ void __launch_bounds__(TK_THREADS, 8) k_topk_store(ScoreArgs a, float alpha, int cap, float *out_scores,
+__global__ void __launch_bounds__(TK_THREADS, 4) k_topk_store(ScoreArgs a, float alpha, int cap, float *out_scores,
                                                               int32_t *out_docids) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ TkShared sh;

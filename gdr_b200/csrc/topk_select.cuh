@@ -330,11 +330,219 @@ __device__ __forceinline__ void warp_bitonic128_desc(uint64_t (&v)[4], int lane)
 // STORE_KEYS = false: the keys are not kept between the two passes (pass 2 re-reads the L2-resident scores), which cuts
 // the CTA's shared memory from ~20 KB to ~9 KB so that more of these CTAs co-reside with the scoring kernel of the next
 // batch on every SM; `keys` then points to global scratch used only by the general fallback.
+__device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int m) {
+    const uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, m), hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), m);
+    return ((uint64_t)hi << 32) | lo;
+}
+
+// ---- large k (128 < k <= 1,024: the reference's default beam = top-k = 100 ... 1,000 regime, BASELINE.json configs[2]) ----------------
+// The general select above makes three histogram passes over ALL n keys and sorts with a shared-memory bitonic network of 55
+// barrier-separated stages (measured 170 us per 1,024-query batch at k = 1,000).  Here: ONE pass over the keys (2,048-bin histogram
+// of the top 11 bits), one pass that classifies them against the boundary bin — keys above it are selected, keys inside it go to a
+// boundary list that aliases the histogram — then the list alone is cut by its next 8 bits and, if still tied, ranked on
+// (key desc, docid asc).  The k survivors are sorted by a BLOCKED bitonic network: every thread holds EPT = cap / 256 entries in
+// registers; strides below EPT are register swaps, strides inside a warp are shuffles, only the strides that cross warps (three
+// sizes, six stages at cap = 1,024) go through shared memory.  Falls back to the general select when a list would overflow.
+template <int EPT, typename Scope>
+__device__ __forceinline__ void blocked_bitonic_desc(uint64_t *sel, int tid) {
+    constexpr int NT = 256, CAP = NT * EPT;
+    const int lane = tid & 31;
+    uint64_t v[EPT];
+#pragma unroll
+    for (int r = 0; r < EPT; ++r) v[r] = sel[tid * EPT + r];
+#pragma unroll 1
+    for (int size = 2; size <= CAP; size <<= 1) {
+#pragma unroll 1
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride >= 32 * EPT) {                              // partner in another warp: through shared memory
+                Scope::sync();
+#pragma unroll
+                for (int r = 0; r < EPT; ++r) sel[tid * EPT + r] = v[r];
+                Scope::sync();
+#pragma unroll
+                for (int r = 0; r < EPT; ++r) {
+                    const int e = tid * EPT + r;
+                    const uint64_t o = sel[e ^ stride];
+                    const bool keep_max = (((e & stride) == 0) == ((e & size) == 0));
+                    v[r] = keep_max ? (v[r] > o ? v[r] : o) : (v[r] > o ? o : v[r]);
+                }
+            } else if (stride >= EPT) {                            // partner in another lane of this warp
+                const int lm = stride / EPT;
+#pragma unroll
+                for (int r = 0; r < EPT; ++r) {
+                    const int e = tid * EPT + r;
+                    const uint64_t o = shfl_xor_u64(v[r], lm);
+                    const bool keep_max = (((e & stride) == 0) == ((e & size) == 0));
+                    v[r] = keep_max ? (v[r] > o ? v[r] : o) : (v[r] > o ? o : v[r]);
+                }
+            } else {                                               // both entries in this thread's registers (compile-time indices)
+                auto cx = [&](int a, int b) {
+                    const bool desc = ((tid * EPT + a) & size) == 0;
+                    const uint64_t mx = v[a] > v[b] ? v[a] : v[b], mn = v[a] > v[b] ? v[b] : v[a];
+                    v[a] = desc ? mx : mn;
+                    v[b] = desc ? mn : mx;
+                };
+                if constexpr (EPT == 4) {
+                    if (stride == 2) { cx(0, 2); cx(1, 3); }
+                    else { cx(0, 1); cx(2, 3); }
+                } else if constexpr (EPT == 2) {
+                    cx(0, 1);
+                }
+            }
+        }
+    }
+    Scope::sync();
+#pragma unroll
+    for (int r = 0; r < EPT; ++r) sel[tid * EPT + r] = v[r];
+    Scope::sync();
+    (void)lane;
+}
+
+// returns false (nothing written) when a list would overflow: the caller then runs the general select
+template <int NT, typename Src, typename Scope = CtaScope>
+__device__ bool topk_big(const Src &src, int n, int k, int cap, uint32_t *keys, uint64_t *sel, uint32_t *hist, TkShared *sh,
+                         float *out_s, int32_t *out_d) {
+    static_assert(NT == 256, "eight warps: 8 bins per thread in the threshold scan, cap / 256 entries per thread in the sort");
+    const int tid = Scope::tid(), lane = tid & 31, warp = tid >> 5;
+    constexpr int BND_CAP = TK_BINS * 4 / 8;                       // the boundary list aliases the 8 KB histogram: 1,024 entries
+    for (int i = tid; i < TK_BINS; i += NT) hist[i] = 0;
+    sh->hist2[tid] = 0;
+    if (tid == 0) { sh->sel_count = 0; sh->eq2_count = 0; sh->bnd_count = 0; }
+    Scope::sync();
+    for (int j4 = tid * 4; j4 < n; j4 += NT * 4) {                 // keys[] is padded to a multiple of 4
+        float s4[4];
+        src.score4(j4, n, s4);
+        uint32_t k4[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            k4[e] = float_to_ordered(s4[e]);
+            if (j4 + e < n) atomicAdd(&hist[k4[e] >> 21], 1u);
+        }
+        *reinterpret_cast<uint4 *>(keys + j4) = make_uint4(k4[0], k4[1], k4[2], k4[3]);
+    }
+    Scope::sync();
+    {   // threshold: thread t owns bins [2048 - 8(t+1), 2048 - 8t), counted from the top
+        const uint4 *h4 = reinterpret_cast<const uint4 *>(hist + TK_BINS - 8 * (tid + 1));
+        const uint4 lo4 = h4[0], hi4 = h4[1];
+        const int local = (int)(lo4.x + lo4.y + lo4.z + lo4.w + hi4.x + hi4.y + hi4.z + hi4.w);
+        int incl = local;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) sh->warp_tot[warp] = incl;
+        Scope::sync();
+        int before = 0;
+#pragma unroll
+        for (int w = 0; w < NT / 32 - 1; ++w) before += w < warp ? sh->warp_tot[w] : 0;
+        incl += before;
+        const int excl = incl - local;
+        if (excl < k && k <= incl) {
+            const uint32_t b8[8] = {hi4.w, hi4.z, hi4.y, hi4.x, lo4.w, lo4.z, lo4.y, lo4.x};      // top-down
+            int running = excl, found = 0, fg = 0, fe = 0;
+            bool done = false;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int hcnt = (int)b8[i];
+                if (!done && running + hcnt >= k) { found = TK_BINS - 8 * tid - 1 - i; fg = running; fe = hcnt; done = true; }
+                running += hcnt;
+            }
+            sh->found_bin = found; sh->found_gt = fg; sh->found_eq = fe;
+        }
+        Scope::sync();
+    }
+    const int d_bin = sh->found_bin, gt = sh->found_gt, eq = sh->found_eq;
+    if (eq > BND_CAP) return false;                                // uniform
+    uint64_t *bnd = reinterpret_cast<uint64_t *>(hist);
+    for (int j4 = tid * 4; j4 < n; j4 += NT * 4) {
+        const uint4 kv = *reinterpret_cast<const uint4 *>(keys + j4);
+        const uint32_t k4[4] = {kv.x, kv.y, kv.z, kv.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (j4 + e < n) {
+                const int bin = (int)(k4[e] >> 21);
+                if (bin > d_bin) sel[atomicAdd(&sh->sel_count, 1)] = ((uint64_t)k4[e] << 32) | (uint32_t)(j4 + e);
+                else if (bin == d_bin) bnd[atomicAdd(&sh->bnd_count, 1)] = ((uint64_t)k4[e] << 32) | (uint32_t)(j4 + e);
+            }
+        }
+    }
+    Scope::sync();
+    // the boundary list: the next 8 key bits, then (rarely) a rank count on (key desc, docid asc)
+    for (int t = tid; t < eq; t += NT) atomicAdd(&sh->hist2[(uint32_t)(bnd[t] >> 45) & 255u], 1u);
+    Scope::sync();
+    int d2, gt2, eq2;
+    scan_down8(sh->hist2, lane, k - gt, d2, gt2, eq2);
+    const int need2 = k - gt - gt2;                                // 1 <= need2 <= eq2
+    if (need2 < eq2 && eq2 > 512) return false;                    // a long exact tie: the general select's docid radix pass (uniform)
+    auto with_doc = [&](uint64_t e) { return (e & 0xffffffff00000000ull) | (uint32_t)~(uint32_t)src.doc((int)(uint32_t)e); };
+    // entries above the second-level bin join sel; the tied ones are compacted to the FRONT of a second list.  That list lives in the
+    // upper half of sel's capacity when it fits there (k <= cap), else right behind the boundary list: keep it simple — it reuses
+    // bnd in place through a per-thread staging register (at most BND_CAP / NT = 4 entries per thread).
+    uint64_t mine[BND_CAP / NT];
+    int n_mine = 0;
+#pragma unroll
+    for (int u = 0; u < BND_CAP / NT; ++u) {
+        const int t = tid + u * NT;
+        mine[u] = 0ull;
+        if (t < eq) {
+            const uint64_t e = bnd[t];
+            const int sub = (int)((uint32_t)(e >> 45) & 255u);
+            if (sub > d2) sel[atomicAdd(&sh->sel_count, 1)] = e;
+            else if (sub == d2) { mine[u] = e; n_mine |= 1 << u; }
+        }
+    }
+    Scope::sync();                                                 // everyone has read its entries of bnd: it can be overwritten
+    uint64_t *bnd2 = bnd;
+#pragma unroll
+    for (int u = 0; u < BND_CAP / NT; ++u)
+        if (n_mine & (1 << u)) bnd2[atomicAdd(&sh->eq2_count, 1)] = need2 < eq2 ? with_doc(mine[u]) : mine[u];
+    Scope::sync();
+    if (need2 == eq2) {
+        for (int t = tid; t < eq2; t += NT) sel[gt + gt2 + t] = bnd2[t];
+    } else {
+        for (int t = tid; t < eq2; t += NT) {                      // entries carry ~docid: (key desc, docid asc), identical pairs by list position
+            const uint64_t me = bnd2[t];
+            int rank = 0;
+            for (int u = 0; u < eq2; ++u) {
+                const uint64_t o = bnd2[u];
+                rank += (o > me) || (o == me && u < t);
+            }
+            if (rank < need2) sel[gt + gt2 + rank] = me;
+        }
+    }
+    Scope::sync();
+    // (key, candidate index) -> (key, ~docid) for the entries that do not carry the docid yet, zero padding up to cap
+    const bool tied = need2 < eq2;
+    for (int i = tid; i < cap; i += NT) {
+        uint64_t e = 0ull;
+        if (i < k) {
+            e = sel[i];
+            if (!(tied && i >= gt + gt2)) e = with_doc(e);
+        }
+        sel[i] = e;
+    }
+    Scope::sync();
+    if (cap == 1024) blocked_bitonic_desc<4, Scope>(sel, tid);
+    else if (cap == 512) blocked_bitonic_desc<2, Scope>(sel, tid);
+    else blocked_bitonic_desc<1, Scope>(sel, tid);
+    for (int r = tid; r < k; r += NT) {
+        const uint64_t v = sel[r];
+        out_s[r] = ordered_to_float((uint32_t)(v >> 32));
+        out_d[r] = (int32_t)(~(uint32_t)v);
+    }
+    return true;
+}
+
 template <int NT, bool STORE_KEYS, typename Src>
 __device__ void topk_body(const Src &src, int n, int k, int cap, uint32_t *keys, uint64_t *sel, uint32_t *hist,
                           TkShared *sh, float *out_s, int32_t *out_d) {
     static_assert(NT == 256, "the bin ranges below assume eight warps");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (n > k && cap > 128 && cap <= 1024 && STORE_KEYS) {         // large k: one-pass select + blocked bitonic sort
+        if (topk_big<NT, Src>(src, n, k, cap, keys, sel, hist, sh, out_s, out_d)) return;
+        __syncthreads();                                           // (a list would overflow: the general select, from scratch)
+    }
     if (n <= k || cap > 128) {     // few candidates (take all) or large k: general path
         topk_general<NT>(src, n, k, cap, keys, sel, hist, sh, out_s, out_d);
         return;
@@ -502,11 +710,6 @@ constexpr int TKF64_BITS = 10;
 // with / delegated to topk_fast16, so the two produce identical bits (tests/test_gpu_pipeline.py, tests/test_gpu_parity.py).
 constexpr int TKL_BITS = 10, TKL_BINS = 1 << TKL_BITS, TKL_SH1 = 32 - TKL_BITS, TKL_SH2 = TKL_SH1 - 8;
 static_assert(TKL_BINS * 4 == TK_BINS * 2, "the lean select's 1,024 32-bit bins live in the 4 KB of the 2,048 16-bit bins");
-
-__device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int m) {
-    const uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, m), hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), m);
-    return ((uint64_t)hi << 32) | lo;
-}
 
 template <typename Src, typename Scope>
 __device__ __forceinline__ bool topk_lean_eligible(int n, int k) { return n > k && n <= TKF_THREADS * 4 * TKF_R4 && k <= 128; }

@@ -26,7 +26,7 @@ import bench
 
 def run(args, cfg, rank, world, local_rank, dev):
     from gdr_b200 import ClusterStore
-    from gdr_b200.sharded import ShardedPipeline, ShardedRetriever
+    from gdr_b200.sharded import PeerAllGather, ShardedPipeline, ShardedRetriever
 
     k, K, D, B, C, N = cfg["k"], cfg["K"], cfg["D"], cfg["B"], cfg["C"], cfg["N"]
     flags = {"auto": 0, "simt": 2, "umma": 4}[args.path]
@@ -199,10 +199,24 @@ def run(args, cfg, rank, world, local_rank, dev):
         h[q_bytes:].view(torch.int32).view(B, K).copy_(bb[own].cpu())
         in_host.append(h)
         out_host.append(torch.empty(2 * r_bytes, dtype=torch.uint8).pin_memory())
-    n_slots = 4
-    slots = [dict(own=torch.empty(q_bytes + b_bytes, dtype=torch.uint8, device=dev), gq=torch.empty((B_g, D), dtype=torch.float32, device=dev),
-                  gb=torch.empty((B_g, K), dtype=torch.int32, device=dev), out=torch.empty(2 * r_bytes, dtype=torch.uint8, device=dev), free=None)
-             for _ in range(n_slots)]
+    n_slots = 6
+    # the global batch is assembled on every rank by the copy engines over NVLink (PeerAllGather); NCCL all-gather only if that cannot be set up
+    pag = None
+    if sp is not None:
+        try:
+            pag = PeerAllGather(rank, world, [(B, D, torch.float32), (B, K, torch.int32)], n_slots, dev)
+        except Exception as e:
+            notes["peer_all_gather_failed"] = f"{type(e).__name__}: {e}"[:200]
+            pag = None
+    okp = torch.tensor([int(pag is not None)], device=dev)
+    dist.all_reduce(okp, op=dist.ReduceOp.MIN)
+    if not int(okp.item()):
+        pag = None
+    slots = [dict(own=torch.empty(q_bytes + b_bytes, dtype=torch.uint8, device=dev),
+                  gq=pag.gathered(i_, 0) if pag is not None else torch.empty((B_g, D), dtype=torch.float32, device=dev),
+                  gb=pag.gathered(i_, 1) if pag is not None else torch.empty((B_g, K), dtype=torch.int32, device=dev),
+                  out=torch.empty(2 * r_bytes, dtype=torch.uint8, device=dev), free=None)
+             for i_ in range(n_slots)]
     s_h2d, s_comm, s_d2h = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
 
     def run_e2e(n):
@@ -236,8 +250,11 @@ def run(args, cfg, rank, world, local_rank, dev):
                 ev_up.record(s_h2d)
             with torch.cuda.stream(s_comm):
                 s_comm.wait_event(ev_up)
-                dist.all_gather_into_tensor(sl["gq"], sl["own"][:q_bytes].view(torch.float32).view(B, D))
-                dist.all_gather_into_tensor(sl["gb"], sl["own"][q_bytes:].view(torch.int32).view(B, K))
+                if pag is not None:
+                    pag.all_gather(i % n_slots, sl["own"])
+                else:
+                    dist.all_gather_into_tensor(sl["gq"], sl["own"][:q_bytes].view(torch.float32).view(B, D))
+                    dist.all_gather_into_tensor(sl["gb"], sl["own"][q_bytes:].view(torch.int32).view(B, K))
                 ev_g = torch.cuda.Event()
                 ev_g.record(s_comm)
             cur.wait_event(ev_g)
@@ -318,7 +335,8 @@ def run(args, cfg, rank, world, local_rank, dev):
         e2e = {"value": e2e_steps * B_g / (e2e_ms * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": q_bytes + b_bytes, "d2h_bytes_per_step": 2 * r_bytes,
                "steps": e2e_steps, "segments_ms_per_step": [round(x / e2e_steps, 5) for x in segs], "estimator": "median of 5 timed segments, max over ranks",
                "cuda_graph": e2e_graph is not None, "copies": pcie,
-               "pipeline": f"per rank and step: one H2D copy of the rank's own {B} queries + beams, NCCL all-gather of q ({B_g * D * 4} B) and beams over NVLink, "
+               "all_gather": "copy engines over NVLink + arrival flags (gdr_b200.sharded.PeerAllGather)" if pag is not None else "NCCL all_gather_into_tensor",
+               "pipeline": f"per rank and step: one H2D copy of the rank's own {B} queries + beams, all-gather of q ({B_g * D * 4} B) and beams over NVLink, "
                            f"the sharded pipeline, one D2H copy of the rank's {B} results; copy / collective / compute on separate streams, {n_slots} slots"}
     except Exception as e:
         notes["e2e_failed"] = f"{type(e).__name__}: {e}"[:300]

@@ -24,6 +24,13 @@ SYMBOLS = {
     "gdr_store_p2p_init": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "gdr_store_p2p_attach": (c_int32, [c_void_p, c_void_p]),
     "gdr_store_p2p_attach_local": (c_int32, [c_void_p, POINTER(c_void_p)]),
+    "gdr_xchg_bytes": (c_int64, [c_int32, c_int32, POINTER(c_int64), c_int32]),
+    "gdr_xchg_create": (c_int32, [POINTER(c_void_p), c_void_p, c_int32, c_int32, c_int32, POINTER(c_int64), c_int32, c_void_p]),
+    "gdr_xchg_attach": (c_int32, [c_void_p, c_void_p]),
+    "gdr_xchg_attach_local": (c_int32, [c_void_p, POINTER(c_void_p)]),
+    "gdr_xchg_all_gather": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p]),
+    "gdr_xchg_part_offset": (c_int64, [c_void_p, c_int32, c_int32]),
+    "gdr_xchg_destroy": (c_int32, [c_void_p]),
     "gdr_store_destroy": (c_int32, [c_void_p]),
     "gdr_score_topk": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_float), c_int32, c_int32, c_int32,
                                  c_int32, c_int32, c_uint32, c_void_p, c_void_p, c_void_p]),

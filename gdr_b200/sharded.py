@@ -179,3 +179,66 @@ class ShardedPipeline:
 
     def flush(self) -> None:
         self.pr.flush()
+
+
+class PeerAllGather:
+    """All-gather of a batch's per-rank inputs (queries, beams) over NVLink by the copy engines (include/gdr_b200.h gdr_xchg_*,
+    csrc/xchg.cu): every rank copies its parts into slot `slot` of every rank's buffer, raises an arrival flag, and one warp waits
+    for the peers' flags — no collective kernel that would compete with the persistent scoring CTAs for SMs.
+    parts: [(rows_per_rank, cols, dtype), ...]; `gathered(slot, p)` is the [world * rows, cols] tensor the consumers read."""
+
+    def __init__(self, rank: int, world: int, parts, n_slots: int, device, group=None, local: bool = False):
+        import ctypes
+        from . import _cabi
+        self.rank, self.world, self.parts, self.n_slots = rank, world, list(parts), n_slots
+        self.part_bytes = [int(r) * int(c) * torch.empty((), dtype=dt).element_size() for r, c, dt in self.parts]
+        arr = (ctypes.c_int64 * len(self.parts))(*self.part_bytes)
+        total = int(_cabi.lib().gdr_xchg_bytes(world, n_slots, arr, len(self.parts)))
+        if total <= 0:
+            raise ValueError("every part must be a positive multiple of 16 bytes (at most 4 parts, 8 ranks)")
+        self.buf = torch.zeros(total, dtype=torch.uint8, device=device)
+        self._handle = ctypes.c_void_p()
+        blob = (ctypes.c_ubyte * 72)()
+        with torch.cuda.device(device):
+            _cabi.check(_cabi.lib().gdr_xchg_create(ctypes.byref(self._handle), self.buf.data_ptr(), world, rank, n_slots, arr, len(self.parts), blob))
+        self.own_bytes = sum(self.part_bytes)
+        if not local and world > 1:
+            gathered: List[Optional[bytes]] = [None] * world
+            dist.all_gather_object(gathered, bytes(blob), group=group)
+            with torch.cuda.device(device):
+                _cabi.check(_cabi.lib().gdr_xchg_attach(self._handle, ctypes.c_char_p(b"".join(gathered))))
+
+    @staticmethod
+    def connect_local(objs: Sequence["PeerAllGather"]) -> None:
+        import ctypes
+        from . import _cabi
+        arr = (ctypes.c_void_p * len(objs))(*[o._handle.value for o in objs])
+        for o in objs:
+            _cabi.check(_cabi.lib().gdr_xchg_attach_local(o._handle, arr))
+
+    def gathered(self, slot: int, part: int) -> torch.Tensor:
+        from . import _cabi
+        rows, cols, dt = self.parts[part]
+        off = int(_cabi.lib().gdr_xchg_part_offset(self._handle, slot, part))
+        return self.buf[off:off + self.world * self.part_bytes[part]].view(dt).view(self.world * rows, cols)
+
+    def all_gather(self, slot: int, own: torch.Tensor, stream=None) -> None:
+        """own: this rank's parts back to back (uint8 [own_bytes], device).  Enqueue-only; work enqueued afterwards on the same
+        stream sees the complete slot."""
+        from . import _cabi
+        if own.dtype != torch.uint8 or own.numel() != self.own_bytes or not own.is_cuda or not own.is_contiguous():
+            raise ValueError(f"own must be a contiguous CUDA uint8 tensor of {self.own_bytes} bytes")
+        with torch.cuda.device(self.buf.device):
+            _cabi.check(_cabi.lib().gdr_xchg_all_gather(self._handle, int(slot), own.data_ptr(), _cabi.stream_ptr(stream)))
+
+    def close(self):
+        from . import _cabi
+        if getattr(self, "_handle", None) is not None and self._handle.value:
+            _cabi.lib().gdr_xchg_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -104,6 +104,29 @@ int gdr_store_p2p_init(gdr_store_t *store, int32_t n_ranks, int32_t my_rank, int
 int gdr_store_p2p_attach(gdr_store_t *store, const void *all_handles);
 int gdr_store_p2p_attach_local(gdr_store_t *store, gdr_store_t *const *peers);
 
+/* Peer-to-peer all-gather of a batch's inputs (csrc/xchg.cu): in the sharded fine stage every rank needs the queries and beams of
+ * the whole global batch every step; the transfer is done by the copy engines into buffers mapped with CUDA IPC and one warp
+ * handles the arrival flags — no collective kernel competes with the persistent scoring CTAs for SMs.
+ *   gdr_xchg_bytes        size of the buffer the caller must provide (DEV, 256-byte aligned, e.g. a torch uint8 tensor): n_slots
+ *                         slot regions (part after part, each part [n_ranks x part_bytes[p]] in rank order), flags, epochs
+ *   gdr_xchg_create       blob_out HOST [GDR_XCHG_BLOB_BYTES]: the buffer's CUDA IPC handle + its offset inside the allocation
+ *   gdr_xchg_attach       all_blobs HOST [n_ranks][GDR_XCHG_BLOB_BYTES] in rank order (exchanged by any host-side all-gather);
+ *                         gdr_xchg_attach_local: the same for objects living in one process
+ *   gdr_xchg_all_gather   own DEV = this rank's parts back to back; copies them into slot `slot` of EVERY rank's buffer, raises this
+ *                         rank's arrival flag on every rank and waits (one warp, stream-ordered) for all ranks' flags: work enqueued
+ *                         on `stream` afterwards sees the complete slot.  All ranks must call it for the same slots in the same order.
+ *   gdr_xchg_part_offset  byte offset of part `part` of slot `slot` inside the buffer */
+#define GDR_XCHG_BLOB_BYTES 72
+typedef struct gdr_xchg gdr_xchg_t;
+int64_t gdr_xchg_bytes(int32_t n_ranks, int32_t n_slots, const int64_t *part_bytes, int32_t n_parts);
+int gdr_xchg_create(gdr_xchg_t **out, void *buffer, int32_t n_ranks, int32_t my_rank, int32_t n_slots, const int64_t *part_bytes,
+                    int32_t n_parts, void *blob_out);
+int gdr_xchg_attach(gdr_xchg_t *x, const void *all_blobs);
+int gdr_xchg_attach_local(gdr_xchg_t *x, gdr_xchg_t *const *peers);
+int gdr_xchg_all_gather(gdr_xchg_t *x, int32_t slot, const void *own, void *stream);
+int64_t gdr_xchg_part_offset(gdr_xchg_t *x, int32_t slot, int32_t part);
+int gdr_xchg_destroy(gdr_xchg_t *x);
+
 /* ---- fine stage: cluster-restricted scoring + top-k ---------------------------------------
  * Replaces main_models.py:1441-1462 (gather), :1577-1594 (score), :1596-1624 (rerank bias),
  * :1625 (topk) and :1628-1631 (index -> doc index) for one batch; with act = NONE, prob = NULL

@@ -94,10 +94,40 @@ def fused(world, schedule="fused"):
                       "ok": all(ok) and pipes[0].schedule.startswith(schedule)}))
 
 
+def gather(world):
+    """PeerAllGather with every rank in this process: one stream per simulated rank (each rank's wait kernel needs the others' copies)."""
+    from gdr_b200.sharded import PeerAllGather
+    B, D, K, S = 96, 64, 12, 3
+    objs = [PeerAllGather(r, world, [(B, D, torch.float32), (B, K, torch.int32)], S, torch.device("cuda", 0), local=True) for r in range(world)]
+    PeerAllGather.connect_local(objs)
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    ok = []
+    for it in range(2 * S + 1):                # slots are reused, epochs advance
+        g = torch.Generator().manual_seed(100 + it)
+        q = torch.randn(world * B, D, generator=g)
+        b = torch.randint(0, 1000, (world * B, K), generator=g, dtype=torch.int32)
+        owns = []
+        for r in range(world):
+            own = torch.empty(objs[r].own_bytes, dtype=torch.uint8, device="cuda")
+            own[:B * D * 4].view(torch.float32).view(B, D).copy_(q[r * B:(r + 1) * B])
+            own[B * D * 4:].view(torch.int32).view(B, K).copy_(b[r * B:(r + 1) * B])
+            owns.append(own)
+        torch.cuda.synchronize()
+        for r in range(world):
+            with torch.cuda.stream(streams[r]):
+                objs[r].all_gather(it % S, owns[r])
+        torch.cuda.synchronize()
+        for r in range(world):
+            ok.append(bool(torch.equal(objs[r].gathered(it % S, 0).cpu(), q) and torch.equal(objs[r].gathered(it % S, 1).cpu(), b)))
+    print(json.dumps({"variant": f"peer all-gather world={world}", "identical": ok, "ok": all(ok)}))
+
+
 if __name__ == "__main__":
     torch.cuda.set_device(0)
     mode, world = sys.argv[1], int(sys.argv[2])
-    if mode in ("fused", "batches"):
+    if mode == "gather":
+        gather(world)
+    elif mode in ("fused", "batches"):
         fused(world, mode)
     else:
         serial(world, mode)

@@ -36,6 +36,10 @@ def test_p2p_pipeline_one_process(schedule, world):
     _run(schedule, world)
 
 
+def test_peer_all_gather_one_process():
+    _run("gather", 3)
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -72,6 +76,20 @@ def _worker(rank, world, port, out_dir):
             refs.append((s[0], d[0]))
         sp.flush()
         torch.cuda.synchronize()
+        # the inputs' all-gather over NVLink by the copy engines (PeerAllGather): every rank ends up with the rank-order concatenation
+        from gdr_b200.sharded import PeerAllGather
+        pag = PeerAllGather(rank, world, [(b_own, D, torch.float32), (b_own, K, torch.int32)], 2, torch.device("cuda", rank))
+        for it in range(5):
+            g = torch.Generator().manual_seed(500 + it)
+            gq = torch.randn(world * b_own, D, generator=g)
+            gb = torch.randint(0, C, (world * b_own, K), generator=g, dtype=torch.int32)
+            own = torch.empty(pag.own_bytes, dtype=torch.uint8, device="cuda")
+            own[:b_own * D * 4].view(torch.float32).view(b_own, D).copy_(gq[rank * b_own:(rank + 1) * b_own])
+            own[b_own * D * 4:].view(torch.int32).view(b_own, K).copy_(gb[rank * b_own:(rank + 1) * b_own])
+            pag.all_gather(it % 2, own)
+            torch.cuda.synchronize()
+            assert torch.equal(pag.gathered(it % 2, 0).cpu(), gq) and torch.equal(pag.gathered(it % 2, 1).cpu(), gb), "peer all-gather differs"
+            dist.barrier()                 # (a slot is refilled only after every rank has consumed it)
         sl = slice(rank * b_own, (rank + 1) * b_own)
         for t, (rs, rd) in zip(tickets, refs):
             assert torch.equal(t.docids, rd[sl]) and torch.equal(t.scores, rs[sl]), "p2p-sharded result differs from the single-GPU result"

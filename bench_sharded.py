@@ -90,14 +90,19 @@ def run(args, cfg, rank, world, local_rank, dev):
     local_store = ClusterStore(emb_l, offsets_l, docid_l)
     retr = ShardedRetriever(local_store, g2l)
 
-    def nccl_step(i):
+    # (the cross-check against the p2p path must score with the SAME kernel family: the shard handle decides by the global pair density,
+    # the local view would decide by its own — bf16 x 3-term tcgen05 and the fp32 GEMV differ in accumulation order, i.e. in the last bits)
+    shard_umma = (not cfg.get("fp32")) and D % 64 == 0 and (args.path == "umma" or (args.path == "auto" and B_g * K >= 3 * C_g))
+    nccl_flags = flags or (4 if shard_umma else 2)
+
+    def nccl_step(i, f=0):
         q, beams = batches[i % n_batches]
-        return retr.score_topk(q, beams, k)
+        return retr.score_topk(q, beams, k, flags=f)
 
     # ---- results first
     checks = {}
     q0, b0 = batches[0]
-    ns, nd = nccl_step(0)
+    ns, nd = nccl_step(0, nccl_flags)
     if sp is not None:
         t0 = sp.submit(q0, b0, flags=flags, which=0)
         t1 = sp.submit(batches[1][0], batches[1][1], flags=flags, which=1 % replicas)

@@ -84,8 +84,8 @@ class ShardedRetriever:
         self._merge = merge if merge is not None else self._cuda_merge
 
     # ---- CUDA implementations ---------------------------------------------------------------------
-    def _cuda_local_topk(self, q, local_beams, k, prob, alphas, act):
-        return self.store.score_topk(q, local_beams, k, prob=prob, alphas=alphas if alphas is not None else [1.0], act=act)
+    def _cuda_local_topk(self, q, local_beams, k, prob, alphas, act, flags=0):
+        return self.store.score_topk(q, local_beams, k, prob=prob, alphas=alphas if alphas is not None else [1.0], act=act, flags=flags)
 
     @staticmethod
     def _cuda_merge(gathered: torch.Tensor, k: int):
@@ -108,10 +108,13 @@ class ShardedRetriever:
         return torch.where(idx >= 0, loc, torch.full_like(loc, -1)).to(torch.int32)
 
     def score_topk(self, q: torch.Tensor, beams: torch.Tensor, k: int, prob: Optional[torch.Tensor] = None,
-                   alpha: Optional[float] = None, act: str = "none") -> Tuple[torch.Tensor, torch.Tensor]:
+                   alpha: Optional[float] = None, act: str = "none", flags: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
         """q [B, D] and beams [B, K] (GLOBAL cluster ids) are replicated on every rank.
-        Returns the merged (scores [B, k], docids [B, k]) on every rank."""
-        s, d = self._local_topk(q, self.localize(beams), k, prob, None if alpha is None else [alpha], act)
+        Returns the merged (scores [B, k], docids [B, k]) on every rank.  `flags` (GDR_FORCE_SIMT / GDR_FORCE_UMMA) go to the local call."""
+        if flags:
+            s, d = self._local_topk(q, self.localize(beams), k, prob, None if alpha is None else [alpha], act, flags)
+        else:
+            s, d = self._local_topk(q, self.localize(beams), k, prob, None if alpha is None else [alpha], act)
         s, d = s[0], d[0]
         if self.world_size == 1:
             return s, d

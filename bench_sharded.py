@@ -35,6 +35,13 @@ def run(args, cfg, rank, world, local_rank, dev):
     replicas = args.replicas or max(1, min(6, -(-640 * 2 ** 20 // emb_bytes)))
     B_g, C_g = B * world, C * world
 
+    trace = bool(os.environ.get("GDR_BENCH_TRACE"))
+
+    def mark(what):
+        if trace:
+            torch.cuda.synchronize()
+            print(f"[rank {rank}] {what}", file=__import__("sys").stderr, flush=True)
+
     def barrier():
         dist.barrier()
         torch.cuda.synchronize()
@@ -99,15 +106,18 @@ def run(args, cfg, rank, world, local_rank, dev):
         q, beams = batches[i % n_batches]
         return retr.score_topk(q, beams, k, flags=f)
 
+    mark('stores and pipelines built')
     # ---- results first
     checks = {}
     q0, b0 = batches[0]
     ns, nd = nccl_step(0, nccl_flags)
+    mark('nccl cross-check call done')
     if sp is not None:
         t0 = sp.submit(q0, b0, flags=flags, which=0)
         t1 = sp.submit(batches[1][0], batches[1][1], flags=flags, which=1 % replicas)
         sp.flush()
         torch.cuda.synchronize()
+        mark('p2p first batches done')
         same = bool(torch.equal(t0.scores, ns[own]) and torch.equal(t0.docids, nd[own]))
         checks["p2p_equals_nccl"] = same
         flag = torch.tensor([int(same)], device=dev)
@@ -147,6 +157,7 @@ def run(args, cfg, rank, world, local_rank, dev):
 
     run_steps(max(args.warmup, 2 * n_batches))
     barrier()
+    mark('warm-up steps done')
     period = math.lcm(replicas, n_batches, 3, args.pipeline or 5)
     period *= max(2, -(-80 // period))
     if args.steps < period:
@@ -187,6 +198,7 @@ def run(args, cfg, rank, world, local_rank, dev):
     e1.record()
     barrier()
     t_wall1 = time.time()
+    mark('timed region done')
     t = torch.tensor([e0.elapsed_time(e1)], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
@@ -284,6 +296,7 @@ def run(args, cfg, rank, world, local_rank, dev):
     try:
         run_e2e(2 * n_batches)
         barrier()
+        mark('e2e warm-up done')
         e2e_period = math.lcm(period, n_slots)
         e2e_graph = None
         if use_graph:

@@ -167,7 +167,9 @@ def run(args, cfg, rank, world, local_rank, dev):
     if use_graph:
         try:
             graph = capture(run_steps, period)
+            mark('graph captured')
             graph.replay()
+            mark('graph replayed once')
             rem = args.steps % period
             if rem:
                 graph_rem = capture(run_steps, rem)
@@ -302,7 +304,9 @@ def run(args, cfg, rank, world, local_rank, dev):
         if use_graph:
             try:
                 e2e_graph = capture(run_e2e, e2e_period)
+                mark('e2e graph captured')
                 e2e_graph.replay()
+                mark('e2e graph replayed once')
             except Exception as e:
                 notes["e2e_graph_capture_failed"] = f"{type(e).__name__}: {e}"[:200]
                 e2e_graph = None

@@ -424,6 +424,10 @@ int gdr_score_topk(gdr_store_t *s, const float *q, const int32_t *beams, const f
     if (!(flags & GDR_SKIP_INVERT)) GDR_CUDA(launch_invert(a, st, &launches));
     a.launch_prio = s->prio_score;
     if (prof) GDR_CUDA(cudaEventRecord(s->ev[1], st));
+    if (a.n_ranks > 1 && !(flags & GDR_SKIP_SCORE)) {     // sharded corpus: every owner's top-k of this handle's previous batch has read its scores
+        GDR_CUDA(launch_wait_consumed(a, st));
+        launches += 1;
+    }
     if (use_umma && !(flags & GDR_SKIP_SCORE)) {
         a.signal = use_simt ? 0 : 1;              // (mixed mode: the GEMV kernel is the call's last scoring kernel and signals)
         GDR_CUDA(launch_score_umma(a, &s->tmap, st, s->umma_ctas > 0 ? s->umma_ctas : s->sm_count));
@@ -445,6 +449,10 @@ int gdr_score_topk(gdr_store_t *s, const float *q, const int32_t *beams, const f
     for (int r = 0; r < n_alpha && !(flags & GDR_SKIP_TOPK); ++r) {
         const float alpha = alphas ? alphas[r] : 1.0f;
         GDR_CUDA(launch_topk_store(a, alpha, out_scores + (int64_t)r * a.B_top * k, out_docids + (int64_t)r * a.B_top * k, st));
+        launches += 1;
+    }
+    if (a.n_ranks > 1 && !(flags & GDR_SKIP_TOPK)) {      // ... and tell every rank that this batch's scores have been read here
+        GDR_CUDA(launch_signal_consumed(a, st));
         launches += 1;
     }
     if (prof) GDR_CUDA(cudaEventRecord(s->ev[4], st));
@@ -480,6 +488,7 @@ int gdr_score_fused(gdr_store_t *cur, gdr_store_t *prev, float alpha, float *pre
             GDR_CUDA(launch_wait_scorers(pa, st));
         }
         GDR_CUDA(launch_topk_store(pa, alpha, prev_out_scores, prev_out_docids, st));
+        if (pa.n_ranks > 1) GDR_CUDA(launch_signal_consumed(pa, st));
         return GDR_OK;
     }
     if (!cur->last_valid) return invalid("gdr_score_fused: cur has no inversion (call gdr_score_topk with GDR_SKIP_SCORE | GDR_SKIP_TOPK first)");

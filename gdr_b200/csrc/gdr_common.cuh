@@ -99,7 +99,8 @@ struct ScoreArgs {
     int32_t q_base, B_top;             // the top-k of this rank covers global queries [q_base, q_base + B_top) (0, B when unsharded)
     float *peer_score[GDR_MAX_RANKS];  // score buffer [b_own, stride] of each rank (this rank's own entry = scorebuf)
     int32_t *peer_sig[GDR_MAX_RANKS];  // each rank's arrival flags [n_ranks]: peer_sig[r][my_rank] <- this handle's scoring epoch
-    int32_t *sig_local;                // this rank's arrival flags [n_ranks] (= peer_sig[my_rank])
+    int32_t *sig_local;                // this rank's arrival flags [n_ranks] (= peer_sig[my_rank]); the CONSUMED flags follow GDR_MAX_RANKS ints later:
+                                       // peer_sig[r][GDR_MAX_RANKS + my_rank] <- "this rank's top-k of epoch e has read its score buffer"
     int32_t *sig_epoch;                // [1] device counter: scoring launches of this handle so far
     int32_t signal;                    // 1 in the copy given to the call's LAST scoring kernel: it signals the owners when it is done
     int32_t wait_in_topk;              // 1: the top-k kernel itself waits for the arrival flags (fused launches); 0: a one-warp k_wait_scorers
@@ -115,6 +116,8 @@ cudaError_t launch_score_umma(const ScoreArgs &a, const CUtensorMap *tmap, cudaS
 cudaError_t launch_topk_store(const ScoreArgs &a, float alpha, float *out_scores, int32_t *out_docids,
                               cudaStream_t s);
 cudaError_t launch_wait_scorers(const ScoreArgs &a, cudaStream_t s);
+cudaError_t launch_wait_consumed(const ScoreArgs &a, cudaStream_t s);
+cudaError_t launch_signal_consumed(const ScoreArgs &a, cudaStream_t s);
 cudaError_t launch_topk_grouped(const ScoreArgs &a, float alpha, float *out_scores, int32_t *out_docids, cudaStream_t s, int groups);
 cudaError_t launch_score_fused(const ScoreArgs &a, const CUtensorMap *tmap, const ScoreArgs &prev, float alpha, float *out_scores,
                                int32_t *out_docids, cudaStream_t s, int ctas, int groups);
@@ -239,6 +242,26 @@ __device__ __forceinline__ void wait_for_scorers(const ScoreArgs &a, bool in_top
         int v;
         do {
             asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(a.sig_local + r) : "memory");
+        } while (v - expected < 0);
+    }
+}
+
+// The reverse handshake: "this rank's top-k has read epoch e of this handle's score buffer" (flags GDR_MAX_RANKS ints behind the arrival
+// flags).  A scoring launch into a handle waits for every owner's flag of the handle's previous epoch before it overwrites their buffers.
+__device__ __forceinline__ void signal_consumed(const ScoreArgs &a) {
+    if (a.n_ranks <= 1) return;
+    const int e = *reinterpret_cast<volatile int32_t *>(a.sig_epoch);
+    __threadfence_system();
+    for (int r = 0; r < a.n_ranks; ++r)
+        asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(a.peer_sig[r] + GDR_MAX_RANKS + a.my_rank), "r"(e) : "memory");
+}
+__device__ __forceinline__ void wait_consumed(const ScoreArgs &a) {
+    if (a.n_ranks <= 1) return;
+    const int expected = *reinterpret_cast<volatile int32_t *>(a.sig_epoch);      // the epoch of this handle's PREVIOUS scoring launch
+    for (int r = 0; r < a.n_ranks; ++r) {
+        int v;
+        do {
+            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(a.sig_local + GDR_MAX_RANKS + r) : "memory");
         } while (v - expected < 0);
     }
 }

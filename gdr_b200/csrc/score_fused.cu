@@ -75,6 +75,7 @@ static_assert(2 * 128 * F128_REGS_LIGHT + F128_GROUPS * 128 * F128_REGS_TOPK + 1
 #define UM_SCORE_PTR(o) (a.scorebuf + (o))
 #define UM_P2P_FENCE
 #define UM_P2P_SIGNAL
+#define UM_P2P_WAIT_CONSUMED
 __global__ void __launch_bounds__(F128_THREADS, 1)
 k_score_topk_fused(const __grid_constant__ CUtensorMap tmap, ScoreArgs a, ScoreArgs prev, float alpha, float *out_scores, int32_t *out_docids) {
 #include "score_umma_body.inc"
@@ -82,11 +83,13 @@ k_score_topk_fused(const __grid_constant__ CUtensorMap tmap, ScoreArgs a, ScoreA
 #undef UM_SCORE_PTR
 #undef UM_P2P_FENCE
 #undef UM_P2P_SIGNAL
+#undef UM_P2P_WAIT_CONSUMED
 // ... and for one shard of a cluster-sharded corpus (scores into the owners' buffers over NVLink, arrival flags; the top-k groups
 // wait for every rank's flag before they read the previous batch's scores: topk_group_loop)
 #define UM_SCORE_PTR(o) score_ptr(a, (o))
 #define UM_P2P_FENCE __threadfence_system();
-#define UM_P2P_SIGNAL signal_owners(a);
+#define UM_P2P_SIGNAL { signal_owners(a); if (prev.B > 0) signal_consumed(prev); }
+#define UM_P2P_WAIT_CONSUMED { if (lane == 0) wait_consumed(a); __syncwarp(); }
 __global__ void __launch_bounds__(F128_THREADS, 1)
 k_score_topk_fused_p2p(const __grid_constant__ CUtensorMap tmap, ScoreArgs a, ScoreArgs prev, float alpha, float *out_scores, int32_t *out_docids) {
 #include "score_umma_body.inc"
@@ -94,6 +97,7 @@ k_score_topk_fused_p2p(const __grid_constant__ CUtensorMap tmap, ScoreArgs a, Sc
 #undef UM_SCORE_PTR
 #undef UM_P2P_FENCE
 #undef UM_P2P_SIGNAL
+#undef UM_P2P_WAIT_CONSUMED
 #undef UM_FILL_IDX
 #undef UM_DISPATCH
 
@@ -127,6 +131,7 @@ static_assert((F64_THREADS - 128) * F64_REGS_SMALL + 128 * F64_REGS_EPI <= F64_T
 #define UM_SCORE_PTR(o) (a.scorebuf + (o))
 #define UM_P2P_FENCE
 #define UM_P2P_SIGNAL
+#define UM_P2P_WAIT_CONSUMED
 __global__ void __launch_bounds__(F64_THREADS, 1)
 k_score_topk_fused64(const __grid_constant__ CUtensorMap tmap, ScoreArgs a, ScoreArgs prev, float alpha, float *out_scores, int32_t *out_docids) {
 #include "score_umma_body.inc"
@@ -134,11 +139,13 @@ k_score_topk_fused64(const __grid_constant__ CUtensorMap tmap, ScoreArgs a, Scor
 #undef UM_SCORE_PTR
 #undef UM_P2P_FENCE
 #undef UM_P2P_SIGNAL
+#undef UM_P2P_WAIT_CONSUMED
 // ... and for one shard of a cluster-sharded corpus (scores into the owners' buffers over NVLink, arrival flags; the top-k groups
 // wait for every rank's flag before they read the previous batch's scores: topk_group_loop)
 #define UM_SCORE_PTR(o) score_ptr(a, (o))
 #define UM_P2P_FENCE __threadfence_system();
-#define UM_P2P_SIGNAL signal_owners(a);
+#define UM_P2P_SIGNAL { signal_owners(a); if (prev.B > 0) signal_consumed(prev); }
+#define UM_P2P_WAIT_CONSUMED { if (lane == 0) wait_consumed(a); __syncwarp(); }
 __global__ void __launch_bounds__(F64_THREADS, 1)
 k_score_topk_fused64_p2p(const __grid_constant__ CUtensorMap tmap, ScoreArgs a, ScoreArgs prev, float alpha, float *out_scores, int32_t *out_docids) {
 #include "score_umma_body.inc"
@@ -146,6 +153,7 @@ k_score_topk_fused64_p2p(const __grid_constant__ CUtensorMap tmap, ScoreArgs a, 
 #undef UM_SCORE_PTR
 #undef UM_P2P_FENCE
 #undef UM_P2P_SIGNAL
+#undef UM_P2P_WAIT_CONSUMED
 #undef UM_FILL_IDX
 #undef UM_DISPATCH
 #undef UM_EXTRA_TAIL

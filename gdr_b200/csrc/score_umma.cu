@@ -47,23 +47,27 @@ namespace gdr {
 #define UM_SCORE_PTR(o) (a.scorebuf + (o))
 #define UM_P2P_FENCE
 #define UM_P2P_SIGNAL
+#define UM_P2P_WAIT_CONSUMED
 __global__ void __launch_bounds__(UM_THREADS, 1) k_score_umma(const __grid_constant__ CUtensorMap tmap, ScoreArgs a) {
 #include "score_umma_body.inc"
 }
 #undef UM_SCORE_PTR
 #undef UM_P2P_FENCE
 #undef UM_P2P_SIGNAL
+#undef UM_P2P_WAIT_CONSUMED
 // the same CTA for one shard of a cluster-sharded corpus: scores go straight into the score buffer of the query's owner (a peer
 // GPU's memory over NVLink), the last CTA raises this rank's arrival flag on every owner (gdr_common.cuh, include/gdr_b200.h)
 #define UM_SCORE_PTR(o) score_ptr(a, (o))
 #define UM_P2P_FENCE __threadfence_system();
 #define UM_P2P_SIGNAL signal_owners(a);
+#define UM_P2P_WAIT_CONSUMED     /* the one-warp k_wait_consumed launched in front of this kernel did */
 __global__ void __launch_bounds__(UM_THREADS, 1) k_score_umma_p2p(const __grid_constant__ CUtensorMap tmap, ScoreArgs a) {
 #include "score_umma_body.inc"
 }
 #undef UM_SCORE_PTR
 #undef UM_P2P_FENCE
 #undef UM_P2P_SIGNAL
+#undef UM_P2P_WAIT_CONSUMED
 #undef UM_FILL_IDX
 #undef UM_DISPATCH
 #undef UM_EXTRA_TAIL

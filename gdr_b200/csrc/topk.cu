@@ -129,6 +129,25 @@ __global__ void __launch_bounds__(32) k_wait_scorers(ScoreArgs a) {
     __threadfence_system();
 }
 
+// The other direction of the handshake (stand-alone schedule, several batches in flight): a rank may overwrite an owner's score buffer with
+// the NEXT batch of this handle only after the owner's top-k of the previous batch has read it.  k_signal_consumed runs behind the top-k
+// launches of a call and tells every rank "epoch e of this handle is consumed here"; k_wait_consumed runs in front of the scoring kernel of
+// the handle's next call and waits for every owner's flag.  (The fused launches need neither: a launch raises its arrival flags only after
+// its own top-k groups are done, and the next launch's groups wait for those flags — DESIGN.md §3.10.)
+__global__ void __launch_bounds__(32) k_signal_consumed(ScoreArgs a) {
+    pdl_wait();
+    if (threadIdx.x == 0) signal_consumed(a);
+}
+
+__global__ void __launch_bounds__(32) k_wait_consumed(ScoreArgs a) {
+    pdl_wait();
+    if (threadIdx.x == 0) wait_consumed(a);
+    __syncwarp();
+}
+
+cudaError_t launch_signal_consumed(const ScoreArgs &a, cudaStream_t s) { return launch_pdl(k_signal_consumed, dim3(1), dim3(32), 0, s, a.launch_prio, a); }
+cudaError_t launch_wait_consumed(const ScoreArgs &a, cudaStream_t s) { return launch_pdl(k_wait_consumed, dim3(1), dim3(32), 0, s, a.launch_prio, a); }
+
 cudaError_t launch_wait_scorers(const ScoreArgs &a, cudaStream_t s) {
     return launch_pdl(k_wait_scorers, dim3(1), dim3(32), 0, s, a.launch_prio, a);
 }

@@ -32,6 +32,10 @@ import sys
 import threading
 import time
 
+# The pipelines keep a dozen streams busy and, on a sharded corpus, some one-warp kernels spin until a peer GPU's kernel has run: with the
+# default of 8 hardware work queues two streams can share a queue and a spinning kernel could sit in front of the work it waits for.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import numpy as np
 import torch
 

@@ -6,6 +6,10 @@ import json
 import os
 import sys
 
+# every simulated rank drives several streams and some of their kernels SPIN for a peer's kernel: with the default of 8 hardware work
+# queues two such streams can share a queue, and the spinning kernel then blocks the very kernel it waits for
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import numpy as np
 import torch
 

@@ -20,7 +20,7 @@ ROOT = os.path.dirname(HERE)
 
 
 def _run(mode, world):
-    out = subprocess.run([sys.executable, os.path.join(HERE, "_p2p_child.py"), mode, str(world)], capture_output=True, text=True, timeout=120)
+    out = subprocess.run([sys.executable, os.path.join(HERE, "_p2p_child.py"), mode, str(world)], capture_output=True, text=True, timeout=75)
     assert out.returncode == 0, out.stderr[-1500:]
     line = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])
     assert line["ok"], line

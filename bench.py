@@ -607,7 +607,8 @@ def main():
     emb_touched = int(stores[0].sizes_host[torch.unique(beams0[beams0 >= 0]).cpu().numpy()].sum()) * D * esize
     alg_bytes = emb_touched + B * D * 4 + B * k * 8
     simt = int(stats["umma_tiles"]) == 0
-    kname = ("k_score_topk_fused64" if opt["fused_groups"] == 9 else "k_score_topk_fused") if schedule == "fused" else ("k_score_simt" if simt else "k_score_umma")
+    kname = ("k_score_topk_fused64" if opt["fused_groups"] == 9 else "k_score_topk_fused") if schedule == "fused" else (
+        "k_score_simt" if simt else ("k_score_tile_f32" if cfg.get("fp32") else "k_score_umma"))
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -616,13 +617,13 @@ def main():
         if t and t["kernel"] == kname:
             traffic = t["dram_read_bytes"] + t["dram_write_bytes"]       # one ncu --set full capture of this workload (profiles/)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": kname + {"k_score_simt": " (GEMV)", "k_score_umma": " (tcgen05 grouped GEMM)"}.get(
+                "kernel": kname + {"k_score_simt": " (GEMV)", "k_score_umma": " (tcgen05 grouped GEMM)", "k_score_tile_f32": " (shared-memory-tiled fp32, fma.rn.f32x2)"}.get(
                     kname, " (tcgen05 grouped GEMM of batch i + per-query top-k of batch i-1 in one persistent CTA per SM)"),
                 "kernel_ms": kernel_ms,
                 "kernel_ms_method": f"median of 5 replays of a CUDA graph of {n_rep} back-to-back launches of this kernel over alternating store "
                                     "replicas, between two CUDA events",
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                "scoring_alone": {"kernel": "k_score_simt" if simt else "k_score_umma", "kernel_ms": scoring_ms,
+                "scoring_alone": {"kernel": "k_score_simt" if simt else ("k_score_tile_f32" if cfg.get("fp32") else "k_score_umma"), "kernel_ms": scoring_ms,
                                   "frac": alg_bytes / (scoring_ms * 1e-3) / 1e9 / peak},
                 "whole_step_frac": alg_bytes / (step_ms * 1e-3) / 1e9 / peak, "frac_of_nominal_8TBs": achieved / 8000.0}
 
@@ -650,7 +651,7 @@ def main():
         "steps": steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32" if cfg.get("fp32") else "bf16", "data": "synthetic",
         "config": {"workload": args.workload + ("" if world == 1 else f" x{world} replicas, queries sharded"),
-                   "precision": "fp32 embeddings x fp32 queries, fp32 FMA" if cfg.get("fp32") else "bf16 embeddings x fp32 queries (exact 3-term bf16 split), fp32 accumulate",
+                   "precision": "fp32 embeddings x fp32 queries, fp32 FMA accumulate" if cfg.get("fp32") else "bf16 embeddings x fp32 queries (exact 3-term bf16 split), fp32 accumulate",
                    "docs_per_gpu": cfg["N"], "clusters_per_gpu": cfg["C"], "dim": D, "global_batch": B * world, "beam": K, "top_k": k,
                    "l2": f"{replicas} store replicas ({replicas * emb_bytes / 2**20:.0f} MB) and {n_batches} query batches cycled; inputs larger than L2",
                    "cuda_graph": bool(use_graph), "api": "gdr_b200.PipelinedRetriever.submit / submit_host", "schedule": sched_txt,

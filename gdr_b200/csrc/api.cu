@@ -168,7 +168,7 @@ int gdr_store_destroy(gdr_store_t *s) {
 namespace {
 struct ScratchPlan {
     int64_t pairs, stride, q_rows;
-    bool umma_possible, global_keys, small_topk;
+    bool umma_possible, tile_possible, global_keys, small_topk;
     size_t o_pair, o_cand, o_cbase, o_simt, o_umma, o_score, o_qsplit, o_tmeta, o_keys, o_ghist, total;
 };
 
@@ -179,6 +179,8 @@ ScratchPlan plan_scratch(const gdr_store *s, int32_t B, int32_t K, int32_t k, ui
     const int64_t simt_cap = p.pairs * ((s->max_cluster + SIMT_ROWS - 1) / SIMT_ROWS);
     const int64_t umma_cap = p.pairs * ((s->max_cluster + UMMA_ROWS - 1) / UMMA_ROWS);
     p.umma_possible = s->has_tmap && !(flags & GDR_FORCE_SIMT);
+    // fp32 stores with dense groups: the shared-memory-tiled fp32 kernel (score_tile_f32.cu) walks the same tile records as the tcgen05 path
+    p.tile_possible = s->dtype == GDR_DTYPE_F32 && s->dim % 32 == 0 && !(flags & GDR_FORCE_SIMT);
     // k <= 128: the fast top-k keeps no key array (its mass-tie fallback uses the global scratch); larger k: keys in smem if they fit
     p.global_keys = k <= 128 || (size_t)p.stride * 4 + 8 * 4096 + 4 * 2048 + (size_t)(3 * K + 1) * 4 > 96 * 1024;
     p.small_topk = k <= 128 && p.stride <= 65535 && !s->topk_wide;     // 128-thread top-k CTAs with 16-bit histogram bins
@@ -189,10 +191,10 @@ ScratchPlan plan_scratch(const gdr_store *s, int32_t B, int32_t K, int32_t k, ui
     p.o_cand = take((size_t)B * (K + 1) * 4);
     p.o_cbase = take(p.pairs * 4);
     p.o_simt = take((size_t)simt_cap * sizeof(Item));
-    p.o_umma = take(p.umma_possible ? (size_t)umma_cap * sizeof(Item) : 0);
+    p.o_umma = take(p.umma_possible || p.tile_possible ? (size_t)umma_cap * sizeof(Item) : 0);
     p.o_score = take(s->n_ranks > 1 ? 0 : (size_t)B * p.stride * 4);       // sharded exchange: the scores live in the p2p buffer
     p.o_qsplit = take(p.umma_possible ? (size_t)p.q_rows * 3 * s->dim * 2 : 0);
-    p.o_tmeta = take(p.umma_possible ? (size_t)umma_cap * sizeof(TileMeta) : 0);
+    p.o_tmeta = take(p.umma_possible || p.tile_possible ? (size_t)umma_cap * sizeof(TileMeta) : 0);
     p.o_keys = take(p.global_keys ? (size_t)B * p.stride * 4 : 0);
     p.o_ghist = take(p.small_topk ? (size_t)B * 2048 * 4 : 0);
     p.total = off;
@@ -407,11 +409,12 @@ int gdr_score_topk(gdr_store_t *s, const float *q, const int32_t *beams, const f
     const bool umma_possible = p.umma_possible;
     const bool mixed = umma_possible && !(flags & GDR_FORCE_UMMA) && s->umma_min_group > 1;
     bool use_umma = umma_possible && ((flags & GDR_FORCE_UMMA) || mixed || pairs >= 3 * (int64_t)s->n_clusters);
-    const bool use_simt = !use_umma || mixed;
+    const bool use_tile = p.tile_possible && pairs >= 3 * (int64_t)s->n_clusters;       // fp32 store, dense groups: tiled fp32 kernel, same tile queue
+    const bool use_simt = (!use_umma && !use_tile) || mixed;
     a.dbg = s->dbg;
     if (use_umma) a.qsplit = reinterpret_cast<__nv_bfloat16 *>(ws + p.o_qsplit);
-    if (use_umma) a.tile_meta = reinterpret_cast<TileMeta *>(ws + p.o_tmeta);
-    a.umma_min_group = !use_umma ? INT_MAX : (mixed ? s->umma_min_group : 1);
+    if (use_umma || use_tile) a.tile_meta = reinterpret_cast<TileMeta *>(ws + p.o_tmeta);
+    a.umma_min_group = (!use_umma && !use_tile) ? INT_MAX : (mixed ? s->umma_min_group : 1);
 
     int launches = 0;
     const bool prof = s->profiling;
@@ -431,6 +434,11 @@ int gdr_score_topk(gdr_store_t *s, const float *q, const int32_t *beams, const f
     if (use_umma && !(flags & GDR_SKIP_SCORE)) {
         a.signal = use_simt ? 0 : 1;              // (mixed mode: the GEMV kernel is the call's last scoring kernel and signals)
         GDR_CUDA(launch_score_umma(a, &s->tmap, st, s->umma_ctas > 0 ? s->umma_ctas : s->sm_count));
+        launches += 1;
+    }
+    if (use_tile && !(flags & GDR_SKIP_SCORE)) {
+        a.signal = 1;
+        GDR_CUDA(launch_score_tile_f32(a, st, s->sm_count));
         launches += 1;
     }
     if (prof) GDR_CUDA(cudaEventRecord(s->ev[2], st));

@@ -76,6 +76,9 @@ CASES = [
     (40000, 256, 64, 96, 24, 100, 0.0, torch.bfloat16, 0),            # ~3,700 candidates per query: top-100 streams the scores twice (more than fit in registers)
     (30000, 300, 64, 40, 16, 64, 1.2, torch.bfloat16, 0),            # K x largest cluster > 65,535: 256-thread top-k with 32-bit histogram bins
     (3000, 200, 64, 500, 3, 10, 0.0, torch.bfloat16, FLAG_UMMA),      # fewer tiles than CTAs in the tile queue, one-K-block tiles
+    (20000, 128, 768, 256, 20, 100, 0.0, torch.float32, 0),          # fp32 store, dense groups (~40 pairs per cluster): the tiled fp32 kernel, chunked groups
+    (9000, 96, 96, 200, 8, 64, 1.2, torch.float32, 0),               # ... Zipf-skewed clusters (multi-tile slabs), three K chunks
+    (9000, 96, 96, 200, 8, 64, 0.0, torch.float32, FLAG_SIMT),       # ... and the same store forced onto the GEMV
 ]
 
 

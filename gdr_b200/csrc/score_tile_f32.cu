@@ -5,12 +5,15 @@
 // per lane (3 warps per scheduler): 0.32 of the HBM roofline at cfg1, latency-bound.  Why not tcgen05: an fp32 embedding would have to be split
 // on the fly into tf32 / bf16 terms in shared memory (4x the shared-memory traffic of the tile) — not built.  This kernel keeps fp32 end to
 // end: a tile = 128 rows of one cluster x up to 32 (query, beam) pairs (the SAME TileMeta records and tile queue as the tcgen05 path), K in
-// chunks of 32 floats brought in by cp.async (five stages: four chunks in flight), every WARP owns four pairs and every lane one to four rows (few pairs: the rows are split over the warps too), and the inner product runs
+// chunks of 32 floats brought in by cp.async (three stages), every WARP owns four pairs and every lane four rows, and the inner product runs
 // on `fma.rn.f32x2` (two fp32 FMAs per instruction and lane — the only way to the FP32 pipe's full rate on sm_100): the even and the odd k of
 // a (row, pair) accumulate in the two halves of one 64-bit register and are added at the end.  Warps whose four pairs do not exist in the
-// tile (groups of ~10 pairs: five of eight) only help with the loads.  HBM-bound by design: algorithmic bytes per tile = rows x dim x 4.
-#include <type_traits>
-
+// tile (groups of ~10 pairs: five of eight) only help with the loads.  Algorithmic bytes per tile = rows x dim x 4.
+// Measured at cfg1 (B200): 113 us per launch = 0.46 of the HBM roofline (the GEMV: 164 us = 0.32).  It is not HBM-bound yet: per SM the
+// three pipes cost about the same — HBM 52 us, packed FMAs ~30 us, shared-memory reads ~42 us (8 LDS.128 per 32 FFMA2 and warp) — and the
+// barrier-separated chunk loop overlaps them poorly.  Tried without gain: five stages / four chunks in flight (the loop is not latency-
+// bound), rows split over all eight warps for tiles with few pairs (fewer FMAs per LDS: more shared-memory traffic).  The next step is
+// the tcgen05 kernel's structure — a producer warp, mbarriers instead of block barriers — or a tensor-core path with an on-the-fly split.
 #include "gdr_common.cuh"
 
 namespace gdr {
@@ -18,7 +21,7 @@ namespace gdr {
 constexpr int TF_ROWS = UMMA_ROWS;          // 128
 constexpr int TF_NQ = UMMA_NQ;              // 32
 constexpr int TF_KC = 32;                   // floats per K chunk
-constexpr int TF_STAGES = 5;                // four chunks (80 KB per CTA, two CTAs per SM) in flight ahead of the one being multiplied
+constexpr int TF_STAGES = 3;
 constexpr int TF_THREADS = 256;
 constexpr int TF_ASTRIDE = TF_KC + 4;       // padded row (144 B): lanes l, l+1, ... of a quarter-warp hit distinct 16-byte bank groups
 constexpr int TF_A_FLOATS = TF_ROWS * TF_ASTRIDE;
@@ -69,70 +72,53 @@ __global__ void __launch_bounds__(TF_THREADS, 2) k_score_tile_f32(ScoreArgs a) {
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
-        // Work split inside the CTA: a warp owns a group of four pairs; with few groups the rows are split too, so that all eight warps
-        // multiply — S = 4 row quarters for <= 8 pairs (one row per lane), 2 halves for <= 16 pairs (two rows per lane), else 1 (four rows).
-        const int n_grp = (nq + 3) >> 2;
-        const int S = n_grp <= 2 ? 4 : (n_grp <= 4 ? 2 : 1);
-        const int grp = warp % (8 / S), part = warp / (8 / S);     // pair group, row part
-        const bool active = grp < n_grp;                           // (warp-uniform)
-        auto tile = [&](auto RT) {
-            constexpr int R = decltype(RT)::value;                 // rows per lane: 4 / S
-            uint64_t acc[R][4];
+        uint64_t acc[4][4];
 #pragma unroll
-            for (int r = 0; r < R; ++r)
+        for (int r = 0; r < 4; ++r)
 #pragma unroll
-                for (int p = 0; p < 4; ++p) acc[r][p] = 0ull;
-            const int rbase = part * (32 * R) + lane;              // this lane's rows: rbase + 32 r
-#pragma unroll 1
-            for (int i = 0; i < TF_STAGES - 1 && i < nkc; ++i) issue(i);
-#pragma unroll 1
-            for (int kc = 0; kc < nkc; ++kc) {
-                // chunk kc is the oldest group in flight: at most min(TF_STAGES - 2, nkc - 1 - kc) younger ones may stay pending
-                const int younger = min(TF_STAGES - 2, nkc - 1 - kc);
-                if (younger >= 3) asm volatile("cp.async.wait_group 3;" ::: "memory");
-                else if (younger == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
-                else if (younger == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
-                else asm volatile("cp.async.wait_group 0;" ::: "memory");
-                __syncthreads();                                   // chunk kc has landed for everyone; the stage of chunk kc-1 is free
-                if (kc + TF_STAGES - 1 < nkc) issue(kc + TF_STAGES - 1);
-                if (active) {
-                    const float *sA = stage0 + (kc % TF_STAGES) * TF_STAGE_FLOATS, *sB = sA + TF_A_FLOATS + grp * 4 * TF_KC;
-#pragma unroll
-                    for (int k4 = 0; k4 < TF_KC / 4; ++k4) {
-                        ulonglong2 av[R], bv[4];
-#pragma unroll
-                        for (int r = 0; r < R; ++r) av[r] = *reinterpret_cast<const ulonglong2 *>(sA + (rbase + 32 * r) * TF_ASTRIDE + k4 * 4);
-#pragma unroll
-                        for (int p = 0; p < 4; ++p) bv[p] = *reinterpret_cast<const ulonglong2 *>(sB + p * TF_KC + k4 * 4);
-#pragma unroll
-                        for (int r = 0; r < R; ++r)
-#pragma unroll
-                            for (int p = 0; p < 4; ++p) {
-                                ffma2(acc[r][p], av[r].x, bv[p].x);
-                                ffma2(acc[r][p], av[r].y, bv[p].y);
-                            }
-                    }
-                }
-            }
+            for (int p = 0; p < 4; ++p) acc[r][p] = 0ull;
+        const bool active = warp * 4 < nq;                         // this warp's four pairs exist (warp-uniform)
+        issue(0);
+        if (nkc > 1) issue(1);
+        for (int kc = 0; kc < nkc; ++kc) {
+            if (kc + 1 < nkc) asm volatile("cp.async.wait_group 1;" ::: "memory");
+            else asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();                                       // chunk kc has landed for everyone; chunk kc-1's stage is free
+            if (kc + 2 < nkc) issue(kc + 2);
             if (active) {
+                const float *sA = stage0 + (kc % TF_STAGES) * TF_STAGE_FLOATS, *sB = sA + TF_A_FLOATS + warp * 4 * TF_KC;
 #pragma unroll
-                for (int p = 0; p < 4; ++p) {
-                    const int j = grp * 4 + p;
-                    if (j < nq) {
-                        float *dst = score_ptr(a, (int64_t)meta->off[j]);
+                for (int k4 = 0; k4 < TF_KC / 4; ++k4) {
+                    ulonglong2 av[4], bv[4];
 #pragma unroll
-                        for (int r = 0; r < R; ++r) {
-                            const int row = rbase + 32 * r;
-                            const float s = __uint_as_float((uint32_t)acc[r][p]) + __uint_as_float((uint32_t)(acc[r][p] >> 32));
-                            if (row < nrows) dst[row] = apply_act(s, a.act);
+                    for (int r = 0; r < 4; ++r) av[r] = *reinterpret_cast<const ulonglong2 *>(sA + (lane + 32 * r) * TF_ASTRIDE + k4 * 4);
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) bv[p] = *reinterpret_cast<const ulonglong2 *>(sB + p * TF_KC + k4 * 4);
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) {
+                            ffma2(acc[r][p], av[r].x, bv[p].x);
+                            ffma2(acc[r][p], av[r].y, bv[p].y);
                         }
+                }
+            }
+        }
+        if (active) {
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const int j = warp * 4 + p;
+                if (j < nq) {
+                    float *dst = score_ptr(a, (int64_t)meta->off[j]);
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const int row = lane + 32 * r;
+                        const float s = __uint_as_float((uint32_t)acc[r][p]) + __uint_as_float((uint32_t)(acc[r][p] >> 32));
+                        if (row < nrows) dst[row] = apply_act(s, a.act);
                     }
                 }
             }
-        };
-        if (S == 4) tile(std::integral_constant<int, 1>{});
-        else if (S == 2) tile(std::integral_constant<int, 2>{});
-        else tile(std::integral_constant<int, 4>{});
+        }
     }
     // (rows of a short tile that were not loaded hold stale shared memory: their products are computed and never stored)
     __syncthreads();

@@ -13,6 +13,10 @@ SOURCES = ["api.cu", "invert.cu", "score_simt.cu", "score_umma.cu", "score_tile_
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+# Developer builds only: `python -m gdr_b200._build --debug-knobs` compiles the stage-skipping timing experiments in
+# (GDR_UMMA_DEBUG / GDR_TOPK_DEBUG environment masks; they invalidate results, so the product library does not contain them).
+if "--debug-knobs" in sys.argv or os.environ.get("GDR_BUILD_DEBUG_KNOBS") == "1":
+    FLAGS.append("-DGDR_DEBUG_KNOBS")
 
 
 def _digest() -> str:

@@ -613,9 +613,10 @@ def main():
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.isfile(tpath) and args.path == "auto":
-        t = json.load(open(tpath)).get(args.workload)
-        if t and t["kernel"] == kname:
-            traffic = t["dram_read_bytes"] + t["dram_write_bytes"]       # one ncu --set full capture of this workload (profiles/)
+        entries = json.load(open(tpath)).get(args.workload) or []
+        for t in (entries if isinstance(entries, list) else [entries]):
+            if t["kernel"] == kname:
+                traffic = t["dram_read_bytes"] + t["dram_write_bytes"]   # one ncu --set full capture of this workload (profiles/)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "kernel": kname + {"k_score_simt": " (GEMV)", "k_score_umma": " (tcgen05 grouped GEMM)", "k_score_tile_f32": " (shared-memory-tiled fp32, fma.rn.f32x2)"}.get(
                     kname, " (tcgen05 grouped GEMM of batch i + per-query top-k of batch i-1 in one persistent CTA per SM)"),

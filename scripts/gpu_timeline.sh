@@ -1,4 +1,6 @@
 #!/bin/bash
+# the timeline / stage masks exist only in developer builds of the library
+export GDR_BUILD_DEBUG_KNOBS=1; python -m gdr_b200._build > /dev/null
 GDR_UMMA_TRACE=1 timeout 200 python - <<'PY' 2>&1 | grep timeline | python -c "
 import sys
 rows=[list(map(int,l.split()[1:])) for l in sys.stdin if l.startswith('[timeline]')]

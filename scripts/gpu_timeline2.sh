@@ -1,4 +1,6 @@
 #!/bin/bash
+# the timeline / stage masks exist only in developer builds of the library
+export GDR_BUILD_DEBUG_KNOBS=1; python -m gdr_b200._build > /dev/null
 GDR_UMMA_TRACE=${TRACE:-} timeout 200 python - "$@" <<'PY' 2>&1 | grep -v "umma trace" | python -u -c "
 import sys
 rows=[]

@@ -1,4 +1,6 @@
 #!/bin/bash
+# the timeline / stage masks exist only in developer builds of the library
+export GDR_BUILD_DEBUG_KNOBS=1; python -m gdr_b200._build > /dev/null
 for v in $@; do
 echo "== dbg=$v"
 GDR_UMMA_TRACE=1 GDR_UMMA_DEBUG=$v timeout 100 python - <<'PY' 2>&1 | grep "umma trace" | tail -1 | cut -c1-1500

@@ -239,7 +239,7 @@ def probe_main(args, cfg, dev):
     batches = synth_batches(cfg, 8, cfg["C"], B, 4321, dev)
     flags = {"auto": 0, "simt": 2, "umma": 4}[args.path]
     pr = PipelinedRetriever(stores, schedule=args.schedule, depth=args.pipeline, fused_ctas=args.fused_ctas, fused_groups=args.fused_groups,
-                            launch_priorities=args.launch_priorities == "on").reserve(B, cfg["K"], k, flags)
+                            launch_priorities=args.launch_priorities == "on", small_sms=args.small_sms, big_streams=args.big_streams).reserve(B, cfg["K"], k, flags)
     R, nb = len(stores), len(batches)
 
     def run(n, keep=None):
@@ -259,22 +259,36 @@ def probe_main(args, cfg, dev):
                 raise RuntimeError(f"batch {i} differs from gdr_score_topk")
         period = math.lcm(R, nb, 3, args.pipeline or 5)
         period *= max(1, -(-80 // period))
-        g = capture(run, period)
-        g.replay()
-        torch.cuda.synchronize()
+        g, graph_error = None, None
+        if not args.no_graph:
+            try:
+                g = capture(run, period)
+                g.replay()
+                torch.cuda.synchronize()
+            except Exception as e:              # (reported; the caller treats a candidate that cannot be captured as failed)
+                g, graph_error = None, f"{type(e).__name__}: {e}"[:300]
+                torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = []
         for _ in range(3):
             e0.record()
             for _ in range(max(1, args.steps // period)):
-                g.replay()
+                g.replay() if g is not None else run(period)
             e1.record()
             torch.cuda.synchronize()
             reps.append(e0.elapsed_time(e1) * 1e3 / (max(1, args.steps // period) * period))
+        if graph_error is not None:
+            raise RuntimeError(f"CUDA graph capture failed ({graph_error}); launched from the host the step takes {sorted(reps)[1]:.2f} us")
+        if pr.last_schedule != args.schedule and args.schedule != "auto":
+            raise RuntimeError(f"asked for schedule '{args.schedule}', the pipeline ran '{pr.last_schedule}'")
+        extra = {"sms": [pr.partition.sms_big, pr.partition.sms_small]} if pr.partition is not None else {}
         print(json.dumps({"probe": True, "us_per_step": sorted(reps)[1], "reps_us_per_step": reps, "schedule": pr.last_schedule,
-                          "verified_identical_to_serial": True}))
+                          "verified_identical_to_serial": True, **extra}))
     except Exception as e:
         print(json.dumps({"probe": True, "us_per_step": None, "failed": f"{type(e).__name__}: {e}"[:300]}))
+
+
+SCHEDULES = ["batches", "fused", "partitioned"]
 
 
 def autotune(args, local_rank):
@@ -288,6 +302,10 @@ def autotune(args, local_rank):
                   ("fused_132", dict(schedule="fused", fused_groups=5, fused_ctas=132)),
                   ("fused64_140", dict(schedule="fused", fused_groups=9, fused_ctas=140))]
     cands.append(("batches_priorities", dict(schedule="batches", pipeline=5, launch_priorities="on")))
+    if args.workload == "cfg2" and args.path == "auto":     # SM partition (green contexts): inversion + top-k on 56 / 64 / 72 SMs, scoring on the rest
+        cands += [("partitioned_64", dict(schedule="partitioned", pipeline=5, small_sms=64)),
+                  ("partitioned_56", dict(schedule="partitioned", pipeline=5, small_sms=56)),
+                  ("partitioned_72", dict(schedule="partitioned", pipeline=5, small_sms=72))]
     report, best, t_start = {}, None, time.time()
     for name, opt in cands:
         if time.time() - t_start > 240:
@@ -306,6 +324,8 @@ def autotune(args, local_rank):
             line = json.loads(lines[-1]) if out.returncode == 0 and lines else {}
             if line.get("us_per_step"):
                 report[name] = {"us_per_step": round(line["us_per_step"], 3), "schedule": line.get("schedule"), "verified_identical_to_serial": True}
+                if line.get("sms"):
+                    report[name]["sms_scoring_and_topk"] = line["sms"]
                 if best is None or line["us_per_step"] < best[0]:
                     best = (line["us_per_step"], name, opt)
             else:
@@ -337,7 +357,9 @@ def main():
                          "nccl = local top-k, NCCL all-gather of (score, docid) lists, merge; auto = p2p if it sets up and verifies, else nccl")
     ap.add_argument("--path", default="auto", choices=["auto", "simt", "umma"], help="force a scoring path")
     ap.add_argument("--pipeline", type=int, default=0, help="batches in flight of the `batches` schedule (0 = 5; 1 = strictly serial)")
-    ap.add_argument("--schedule", default="auto", choices=["auto", "batches", "fused"],
+    ap.add_argument("--small-sms", type=int, default=64, help="`partitioned` schedule: SMs of the inversion + top-k side")
+    ap.add_argument("--big-streams", type=int, default=2, help="`partitioned` schedule: streams of the scoring side")
+    ap.add_argument("--schedule", default="auto", choices=["auto", "batches", "fused", "partitioned"],
                     help="PipelinedRetriever schedule; auto = launch autotune (N = 1) / the pipeline's own choice")
     ap.add_argument("--fused-ctas", type=int, default=0)
     ap.add_argument("--fused-groups", type=int, default=0)
@@ -390,17 +412,18 @@ def main():
     # ---- schedule: measured, not assumed
     tune_report = None
     opt = dict(schedule=args.schedule, pipeline=args.pipeline, fused_ctas=args.fused_ctas, fused_groups=args.fused_groups,
-               launch_priorities=args.launch_priorities)
+               launch_priorities=args.launch_priorities, small_sms=args.small_sms)
     if args.schedule == "auto" and not args.no_autotune and not args.no_graph and args.pipeline != 1:
-        decision = torch.zeros(5, dtype=torch.int32, device=dev)
+        decision = torch.zeros(6, dtype=torch.int32, device=dev)
         if rank == 0:
             best, tune_report = autotune(args, local_rank)
-            decision = torch.tensor([int(best.get("schedule") == "fused"), best.get("pipeline", 0), best.get("fused_ctas", 0),
-                                     best.get("fused_groups", 0), int(best.get("launch_priorities") == "on")], dtype=torch.int32, device=dev)
+            decision = torch.tensor([SCHEDULES.index(best.get("schedule")), best.get("pipeline", 0), best.get("fused_ctas", 0),
+                                     best.get("fused_groups", 0), int(best.get("launch_priorities") == "on"), best.get("small_sms", 64)],
+                                    dtype=torch.int32, device=dev)
         if world > 1:
             dist.broadcast(decision, src=0)
-        f, p_, fc, fg, lp = (int(x) for x in decision.tolist())
-        opt = dict(schedule="fused" if f else "batches", pipeline=p_, fused_ctas=fc, fused_groups=fg, launch_priorities="on" if lp else "off")
+        f, p_, fc, fg, lp, ssm = (int(x) for x in decision.tolist())
+        opt = dict(schedule=SCHEDULES[f], pipeline=p_, fused_ctas=fc, fused_groups=fg, launch_priorities="on" if lp else "off", small_sms=ssm)
     n_pipe = opt["pipeline"] if opt["pipeline"] > 0 else 5
 
     stores = []
@@ -410,7 +433,8 @@ def main():
     n_batches = 8
     batches = synth_batches(cfg, n_batches, cfg["C"], B, 4321 + (0 if world == 1 else rank), dev)
     pr = PipelinedRetriever(stores, schedule=opt["schedule"] if opt["schedule"] != "auto" else "auto", depth=n_pipe, fused_ctas=opt["fused_ctas"],
-                            fused_groups=opt["fused_groups"], launch_priorities=opt["launch_priorities"] == "on").reserve(B, K, k, flags)
+                            fused_groups=opt["fused_groups"], launch_priorities=opt["launch_priorities"] == "on", small_sms=opt["small_sms"],
+                            big_streams=args.big_streams).reserve(B, K, k, flags)
 
     def barrier():
         if world > 1:
@@ -489,6 +513,9 @@ def main():
                 h.set_option("umma_ctas", opt["fused_ctas"])
             if opt["fused_groups"]:
                 h.set_option("fused_groups", opt["fused_groups"])
+    if schedule == "partitioned":                 # the kernel as the step runs it: CTAs = the scoring side's SMs, on a stream of that side
+        for h in (h for hs in h_k for h in hs):
+            h.set_option("umma_ctas", pr.partition.sms_big)
     dummy = (torch.empty((1, B, k), dtype=torch.float32, device=dev), torch.empty((1, B, k), dtype=torch.int32, device=dev))
     for s_ in range(2):
         for r in range(replicas):
@@ -499,6 +526,13 @@ def main():
     out2 = (dummy[0][0], dummy[1][0])
 
     def kernel_only(n):
+        if schedule == "partitioned":
+            cur_, big_ = torch.cuda.current_stream(), pr.partition.big[0]
+            big_.wait_stream(cur_)
+            with torch.cuda.stream(big_):
+                scoring_alone(n)
+            cur_.wait_stream(big_)
+            return
         for i in range(n):
             r, s_ = i % replicas, i % 2
             if schedule == "fused":
@@ -646,6 +680,9 @@ def main():
 
     sched_txt = {"fused": f"fused (gdr_score_fused via PipelinedRetriever: one launch scores batch i and selects the top-k of batch i-1 in the same CTAs; "
                           f"inversion one batch ahead on a second stream; 3 scratch sets; grid of {opt['fused_ctas'] or 140} CTAs x {opt['fused_groups'] or 5} top-k groups)",
+                 "partitioned": f"partitioned (PipelinedRetriever: SM partition by CUDA green contexts - inversion and top-k of every batch on {n_pipe} streams of a "
+                                f"{pr.partition.sms_small if pr.partition else 0}-SM set, scoring kernels on {args.big_streams} streams of the other "
+                                f"{pr.partition.sms_big if pr.partition else 0} SMs; {n_pipe} batches in flight)",
                  "batches": f"batches (PipelinedRetriever: whole gdr_score_topk calls round-robin on {n_pipe} streams)"}[schedule]
     line = {
         "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world,

@@ -9,7 +9,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB_DIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIB_DIR, "libgdr_b200.so")
-SOURCES = ["api.cu", "invert.cu", "score_simt.cu", "score_umma.cu", "score_tile_f32.cu", "similarity.cu", "score_fused.cu", "topk.cu", "topk_grouped.cu", "mask.cu", "tree.cu", "contrastive.cu", "xchg.cu"]
+SOURCES = ["api.cu", "invert.cu", "score_simt.cu", "score_umma.cu", "score_tile_f32.cu", "similarity.cu", "score_fused.cu", "topk.cu", "topk_grouped.cu", "mask.cu", "tree.cu", "contrastive.cu", "xchg.cu", "partition.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]

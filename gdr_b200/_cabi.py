@@ -31,6 +31,10 @@ SYMBOLS = {
     "gdr_xchg_all_gather": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p]),
     "gdr_xchg_part_offset": (c_int64, [c_void_p, c_int32, c_int32]),
     "gdr_xchg_destroy": (c_int32, [c_void_p]),
+    "gdr_partition_create": (c_int32, [POINTER(c_void_p), c_int32, c_int32, c_int32]),
+    "gdr_partition_sms": (c_int32, [c_void_p, POINTER(c_int32)]),
+    "gdr_partition_stream": (c_void_p, [c_void_p, c_int32, c_int32]),
+    "gdr_partition_destroy": (c_int32, [c_void_p]),
     "gdr_store_destroy": (c_int32, [c_void_p]),
     "gdr_score_topk": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_float), c_int32, c_int32, c_int32,
                                  c_int32, c_int32, c_uint32, c_void_p, c_void_p, c_void_p]),

@@ -44,6 +44,7 @@ struct gdr_store {
     bool has_tmap = false;
     CUtensorMap tmap;
     int last_launches = 0;
+    int phase_launches[3] = {0, 0, 0};             // inversion, scoring, top-k kernels of the handle's current batch (phases may come in separate calls)
     int umma_min_group = 1;   // > 1 (env GDR_UMMA_MIN_GROUP) = mixed mode
     int umma_ctas = 0;        // > 0 (env GDR_UMMA_CTAS): persistent CTAs of the tcgen05 kernel (default: one per SM)
     uint32_t debug_flags = 0; // GDR_OPT_TOPK_GROUPS bits; with -DGDR_DEBUG_KNOBS also the GDR_UMMA_DEBUG / GDR_TOPK_DEBUG timing experiments
@@ -425,6 +426,7 @@ int gdr_score_topk(gdr_store_t *s, const float *q, const int32_t *beams, const f
     if (prof) GDR_CUDA(cudaEventRecord(s->ev[0], st));
     a.launch_prio = s->prio_invert;               // per call, carried in this call's own copy of the arguments
     if (!(flags & GDR_SKIP_INVERT)) GDR_CUDA(launch_invert(a, st, &launches));
+    const int l_inv = launches;
     a.launch_prio = s->prio_score;
     if (prof) GDR_CUDA(cudaEventRecord(s->ev[1], st));
     if (a.n_ranks > 1 && !(flags & GDR_SKIP_SCORE)) {     // sharded corpus: every owner's top-k of this handle's previous batch has read its scores
@@ -448,6 +450,7 @@ int gdr_score_topk(gdr_store_t *s, const float *q, const int32_t *beams, const f
         launches += 1;
     }
     if (prof) GDR_CUDA(cudaEventRecord(s->ev[3], st));
+    const int l_score = launches - l_inv;
     a.launch_prio = s->prio_topk;
     a.wait_in_topk = 0;
     if (a.n_ranks > 1 && !(flags & GDR_SKIP_TOPK)) {      // sharded corpus: one warp waits for every rank's scores, then the top-k grid runs
@@ -464,7 +467,14 @@ int gdr_score_topk(gdr_store_t *s, const float *q, const int32_t *beams, const f
         launches += 1;
     }
     if (prof) GDR_CUDA(cudaEventRecord(s->ev[4], st));
-    s->last_launches = launches;
+    if (!(flags & GDR_SKIP_INVERT)) s->phase_launches[0] = l_inv;
+    if (!(flags & GDR_SKIP_SCORE)) s->phase_launches[1] = l_score;
+    if (!(flags & GDR_SKIP_TOPK)) s->phase_launches[2] = launches - l_inv - l_score;
+    if (!(flags & GDR_SKIP_INVERT)) {             // a new batch enters the handle: phases not issued yet count as zero
+        if (flags & GDR_SKIP_SCORE) s->phase_launches[1] = 0;
+        if (flags & GDR_SKIP_TOPK) s->phase_launches[2] = 0;
+    }
+    s->last_launches = s->phase_launches[0] + s->phase_launches[1] + s->phase_launches[2];
     a.launch_prio = s->prio_score;                // what gdr_score_fused launches with
     a.signal = 1;
     a.wait_in_topk = 1;                           // ... and its top-k groups wait for the arrival flags themselves

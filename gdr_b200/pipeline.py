@@ -9,6 +9,9 @@ this module keeps them in flight; it is the schedule `bench.py` times and the on
   into set i % 3 and reads set (i-1) % 3, the inversion of batch i+1 fills set (i+1) % 3.
 * `batches` (every other shape): whole `gdr_score_topk` calls round-robin on `depth` streams, one handle each, so the
   latency-bound inversion and top-k kernels of one batch hide under the HBM-bound scoring kernel of its neighbours.
+* `partitioned` (opt-in; tcgen05 shapes): the SMs are split into two disjoint sets (CUDA green contexts, `SmPartition`): the
+  inversion and the top-k of every batch run on streams of the small set, the scoring kernels on streams of the big set, so the
+  two sides do not compete for residency on the same SMs.  Same handles / scratch sets as `batches`.
 
 Contract: `submit()` returns a `Ticket`; the ticket's outputs are complete, in stream order on the stream that calls it, after
 `ticket.wait()` (which needs two further `submit()`s or a `flush()` to have been issued: in the fused schedule `submit(i)`
@@ -42,20 +45,56 @@ class Ticket:
         return self.scores, self.docids
 
 
+class SmPartition:
+    """Two disjoint SM sets of one device with streams of their own (include/gdr_b200.h gdr_partition_*; csrc/partition.cu).
+    `big` / `small` are lists of torch streams (torch.cuda.ExternalStream over the library's green-context streams)."""
+
+    def __init__(self, device, small_sms: int, n_big: int = 2, n_small: int = 5):
+        import ctypes
+        self._handle = None
+        self.device = torch.device(device)
+        h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _cabi.check(_cabi.lib().gdr_partition_create(ctypes.byref(h), int(small_sms), int(n_big), int(n_small)))
+        self._handle = h
+        sms = (ctypes.c_int32 * 2)()
+        _cabi.check(_cabi.lib().gdr_partition_sms(h, sms))
+        self.sms_big, self.sms_small = int(sms[0]), int(sms[1])
+        self.big = [torch.cuda.ExternalStream(int(_cabi.lib().gdr_partition_stream(h, 0, i)), device=self.device) for i in range(n_big)]
+        self.small = [torch.cuda.ExternalStream(int(_cabi.lib().gdr_partition_stream(h, 1, i)), device=self.device) for i in range(n_small)]
+
+    def close(self) -> None:
+        if self._handle is not None:
+            with torch.cuda.device(self.device):
+                torch.cuda.synchronize()
+                _cabi.lib().gdr_partition_destroy(self._handle)
+            self._handle, self.big, self.small = None, [], []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class PipelinedRetriever:
     def __init__(self, store, schedule: str = "auto", depth: int = 0, fused_ctas: int = 0, fused_groups: int = 0,
-                 launch_priorities: bool = False):
+                 launch_priorities: bool = False, small_sms: int = 64, big_streams: int = 2):
         """store: the resident ClusterStore — or a list of stores of identical shape (several indexes served by one pipeline;
         bench.py cycles copies of the corpus so that every step streams embeddings that are not in L2), chosen per batch with
-        `submit(..., which=i)`.  schedule: 'auto' | 'fused' | 'batches'.  depth: batches in flight for the 'batches' schedule
-        (default 5; the fused schedule always uses three scratch sets)."""
-        if schedule not in ("auto", "fused", "batches"):
-            raise ValueError("schedule must be 'auto', 'fused' or 'batches'")
+        `submit(..., which=i)`.  schedule: 'auto' (= fused where eligible, else batches) | 'fused' | 'batches' | 'partitioned'
+        (SM partition: `small_sms` SMs for inversion + top-k, the rest for scoring on `big_streams` streams; falls back to 'batches'
+        for shapes that do not take the tcgen05 path).  depth: batches in flight for 'batches' / 'partitioned' (default 5; the fused
+        schedule always uses three scratch sets)."""
+        if schedule not in ("auto", "fused", "batches", "partitioned"):
+            raise ValueError("schedule must be 'auto', 'fused', 'batches' or 'partitioned'")
         self.stores = list(store) if isinstance(store, (list, tuple)) else [store]
         store = self.stores[0]
         self.store, self.schedule_request = store, schedule
         self.depth = depth if depth > 0 else 5
         self.fused_ctas, self.fused_groups, self.launch_priorities = fused_ctas, fused_groups, launch_priorities
+        self.small_sms, self.big_streams = small_sms, big_streams
+        self.partition: Optional[SmPartition] = None     # 'partitioned' schedule: created on first use
         self.dev = store.emb.device
         self._fused_handles: Optional[List[List[ClusterStore]]] = None    # [scratch set][store]
         self._batch_handles: Optional[List[List[ClusterStore]]] = None    # [stream][store]
@@ -85,6 +124,21 @@ class PipelinedRetriever:
         stride = (K * s.max_cluster + 3) // 4 * 4
         return k <= 128 and stride <= 65535
 
+    def partition_eligible(self, B: int, K: int, flags: int = 0) -> bool:
+        """The batch takes the tcgen05 path alone (one scoring kernel whose persistent CTAs can be sized to the big SM set)."""
+        s = self.store
+        if s.emb.dtype != torch.bfloat16 or s.dim % 64 != 0 or (flags & _cabi.FORCE_SIMT) or getattr(s, "p2p", None):
+            return False
+        return bool((flags & _cabi.FORCE_UMMA) or B * K >= 3 * s.n_clusters)
+
+    def _handles_partitioned(self) -> List[List[ClusterStore]]:
+        hs = self._handles_batches()
+        if self.partition is None:
+            self.partition = SmPartition(self.dev, self.small_sms, self.big_streams, self.depth)
+            for h in (h for row in hs for h in row):
+                h.set_option("umma_ctas", self.partition.sms_big)
+        return hs
+
     def _handles_fused(self) -> List[List[ClusterStore]]:
         if self._fused_handles is None:
             self._fused_handles = [[s.clone_handle() for s in self.stores] for _ in range(3)]
@@ -109,7 +163,7 @@ class PipelinedRetriever:
 
     def reserve(self, B: int, K: int, k: int, flags: int = 0) -> "PipelinedRetriever":
         """Allocate every scratch set for this batch shape now (no allocation / synchronisation on the query path later)."""
-        fused = self.schedule_request != "batches" and self.fused_eligible(B, K, k, flags)
+        fused = self.schedule_request in ("auto", "fused") and self.fused_eligible(B, K, k, flags)
         for hs in (self._handles_fused() if fused else self._handles_batches()):
             for h in hs:
                 h.reserve(B, K, k, flags)
@@ -122,12 +176,13 @@ class PipelinedRetriever:
         """Enqueue one batch (same arguments as ClusterStore.score_topk with a single alpha) against store number `which`.
         q / beams / prob must not be overwritten until the ticket's outputs are complete (the ticket keeps references)."""
         B, K = int(beams.shape[0]), int(beams.shape[1])
-        fused = self.schedule_request != "batches" and self.fused_eligible(B, K, k, flags)
+        fused = self.schedule_request in ("auto", "fused") and self.fused_eligible(B, K, k, flags)
         if self.schedule_request == "fused" and not fused:
             raise ValueError("this batch shape is not eligible for the fused schedule (see gdr_score_fused in include/gdr_b200.h)")
-        if self.last_schedule is not None and (self.last_schedule == "fused") != fused:
+        sched = "fused" if fused else ("partitioned" if self.schedule_request == "partitioned" and self.partition_eligible(B, K, flags) else "batches")
+        if self.last_schedule is not None and self.last_schedule != sched:
             self.flush()                                       # the schedule changes with the shape: drain first
-        self.last_schedule = "fused" if fused else "batches"
+        self.last_schedule = sched
         if out is None:
             B_out = self.store.p2p[2] if getattr(self.store, "p2p", None) else B
             out = (torch.empty((B_out, k), dtype=torch.float32, device=self.dev), torch.empty((B_out, k), dtype=torch.int32, device=self.dev))
@@ -136,6 +191,8 @@ class PipelinedRetriever:
         cur = torch.cuda.current_stream(self.dev)
         if fused:
             self._submit_fused(t, q, beams, k, prob, act, flags, cur)
+        elif sched == "partitioned":
+            self._submit_partitioned(t, q, beams, k, prob, act, flags, cur)
         else:
             self._submit_batch(t, q, beams, k, prob, act, flags, cur)
         self._n += 1
@@ -192,6 +249,37 @@ class PipelinedRetriever:
         if len(self._open) > self.depth:                       # bounded bookkeeping; older tickets keep their own events
             self._open.pop(0)
 
+    def _submit_partitioned(self, t, q, beams, k, prob, act, flags, cur):
+        """The three phases of batch i as three calls on the same handle: inversion and top-k on small-set stream i % depth, scoring
+        on big-set stream i % big_streams; events carry the order.  The handle's next batch (i + depth) starts on the same small-set
+        stream, i.e. behind this batch's top-k, so a scratch set is never written while it is read."""
+        hs = self._handles_partitioned()
+        part, i = self.partition, t.index
+        h = hs[i % self.depth][t.which]
+        ss, bs = part.small[i % self.depth], part.big[i % len(part.big)]
+        ev_in = torch.cuda.Event()
+        ev_in.record(cur)
+        with torch.cuda.stream(ss):
+            ss.wait_event(ev_in)
+            h.invert(q, beams, k, prob=prob, act=act, flags=flags)
+            ev_inv = torch.cuda.Event()
+            ev_inv.record(ss)
+        with torch.cuda.stream(bs):
+            bs.wait_event(ev_inv)
+            h.score_topk(q, beams, k, prob=prob, alphas=[t.alpha], act=act, flags=flags | _cabi.SKIP_INVERT | _cabi.SKIP_TOPK,
+                         out=h._fused_dummy, _unchecked_out=True)
+            ev_sc = torch.cuda.Event()
+            ev_sc.record(bs)
+        with torch.cuda.stream(ss):
+            ss.wait_event(ev_sc)
+            h.score_topk(q, beams, k, prob=prob, alphas=[t.alpha], act=act, flags=flags | _cabi.SKIP_INVERT | _cabi.SKIP_SCORE,
+                         out=(t.scores.view(1, *t.scores.shape), t.docids.view(1, *t.docids.shape)))
+            t.event = torch.cuda.Event()
+            t.event.record(ss)
+        self._open.append(t)
+        if len(self._open) > self.depth:
+            self._open.pop(0)
+
     # ---- host-buffer front end: what a caller with inputs in (pinned) host memory uses ---------------------------------------
     def submit_host(self, in_host: torch.Tensor, B: int, K: int, k: int, out_host: torch.Tensor, alpha: float = 1.0,
                     act: Optional[str] = "none", flags: int = 0, which: int = 0) -> Ticket:
@@ -205,7 +293,7 @@ class PipelinedRetriever:
             raise ValueError("in_host must hold q then beams, out_host scores then docids, both as uint8 buffers")
         if self._s_h2d is None:
             self._s_h2d, self._s_d2h = torch.cuda.Stream(device=self.dev), torch.cuda.Stream(device=self.dev)
-        n_slots = 5 if self.schedule_request != "batches" and self.fused_eligible(B, K, k, flags) else self.depth + 1
+        n_slots = 5 if self.schedule_request in ("auto", "fused") and self.fused_eligible(B, K, k, flags) else self.depth + 1
         if len(self._slots) != n_slots or self._slots[0]["in"].numel() != q_bytes + b_bytes or self._slots[0]["out"].numel() != 2 * r_bytes:
             self.flush()
             self._slots = [dict(**{"in": torch.empty(q_bytes + b_bytes, dtype=torch.uint8, device=self.dev),
@@ -266,6 +354,9 @@ class PipelinedRetriever:
             cur.wait_stream(self._s_inv)
         for st in self._streams:
             cur.wait_stream(st)
+        if self.partition is not None:
+            for st in self.partition.small + self.partition.big:
+                cur.wait_stream(st)
         self._drain_host_jobs()
         if self._s_h2d is not None:
             cur.wait_stream(self._s_h2d)

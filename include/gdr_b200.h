@@ -166,7 +166,7 @@ int gdr_score_fused(gdr_store_t *cur, gdr_store_t *prev, float alpha, float *pre
  * synchronisation) happens on the query path and the first call of a shape can already be captured in a CUDA graph. */
 int gdr_store_reserve(gdr_store_t *store, int32_t B, int32_t K, int32_t k, uint32_t flags, void *stream);
 
-/* Launch options of a handle.  None of them changes results (tests/test_gpu_pipeline.py, tests/test_gpu_zz_variants.py). */
+/* Launch options of a handle.  None of them changes results (tests/test_gpu_pipeline.py). */
 #define GDR_OPT_UMMA_CTAS 1          /* persistent CTAs of the tcgen05 kernels; 0 = default (one per SM; fused launches: SMs - 8) */
 #define GDR_OPT_UMMA_MIN_GROUP 2     /* > 1: mixed mode, groups of at least this many pairs on tensor cores, the rest on the GEMV */
 #define GDR_OPT_LAUNCH_PRIORITIES 3  /* 1: per-launch scheduling priorities, inversion > scoring > top-k */
@@ -175,9 +175,23 @@ int gdr_store_reserve(gdr_store_t *store, int32_t B, int32_t K, int32_t k, uint3
 #define GDR_OPT_TOPK_WIDE 6          /* 1: the 256-thread top-k also for k <= 128 */
 int gdr_store_set_option(gdr_store_t *store, int32_t option, int32_t value);
 
+/* ---- SM partition for the pipelined schedule (csrc/partition.cu) -------------------------------------------------------------
+ * Splits the SMs of the CURRENT device into two disjoint sets behind CUDA green contexts (driver 12.4+) and creates streams in
+ * each: `small_sms` SMs (rounded up by the driver to its granularity, 8 on sm_90+) for the latency-bound inversion and top-k
+ * kernels, the rest for the HBM-bound scoring kernel — so that the two sides stop competing for residency (the reference runs one
+ * batch at a time on one stream, main_models.py:1434-1637, and has no counterpart).  The streams are ordinary CUDA streams of the
+ * primary context's address space: pass them as the `stream` argument of gdr_score_topk with GDR_SKIP_* flags to issue a batch's
+ * phases on either side (events order them; gdr_b200/pipeline.py, schedule "partitioned"), and set GDR_OPT_UMMA_CTAS of the
+ * handles to the big side's SM count.  Never changes results.  GDR_ERR_UNSUPPORTED when the driver has no green contexts. */
+typedef struct gdr_partition gdr_partition_t;
+int gdr_partition_create(gdr_partition_t **out, int32_t small_sms, int32_t n_streams_big, int32_t n_streams_small);
+int gdr_partition_sms(const gdr_partition_t *partition, int32_t out[2]);               /* out[0] = SMs of the big side, out[1] = small side */
+void *gdr_partition_stream(gdr_partition_t *partition, int32_t small, int32_t index);  /* cudaStream_t, NULL when out of range */
+int gdr_partition_destroy(gdr_partition_t *partition);                                 /* after all work on its streams has completed */
+
 /* Counters of the most recent gdr_score_topk on this store (device-side work-list sizes):
  * out[0] = (cluster, query-chunk) items scored by the SIMT GEMV path, out[1] = tiles scored by the
- * tcgen05 grouped-GEMM path, out[2] = kernels launched by that call, out[3] = clusters touched.
+ * tcgen05 grouped-GEMM path, out[2] = kernels launched for that batch (summed over the calls that issued its phases), out[3] = clusters touched.
  * Synchronises `stream`. */
 int gdr_store_last_stats(gdr_store_t *store, int64_t out[4], void *stream);
 

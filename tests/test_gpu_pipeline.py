@@ -34,6 +34,14 @@ def test_pipelined_retriever_equals_default(schedule, groups):
     _run("PIPELINE_" + schedule.upper(), groups)
 
 
+def test_partitioned_schedule_equals_default():
+    """SM partition (CUDA green contexts; gdr_partition_*, PipelinedRetriever(schedule="partitioned")): inversion and top-k on one SM
+    set, scoring on the other — eager, replayed from a CUDA graph, and through pinned host buffers."""
+    line = _run("PIPELINE_PARTITIONED", "5")
+    if line.get("skipped"):
+        pytest.skip(line["skipped"])
+
+
 @pytest.mark.parametrize("groups", ["4", "1"])
 def test_grouped_topk_equals_default(groups):
     _run("topk_groups", groups)

@@ -232,8 +232,9 @@ def test_bench_launch_autotune_decision(monkeypatch):
     import bench
 
     args = argparse.Namespace(workload="cfg2", path="auto", schedule="auto", replicas=0)
-    names = ("batches", "fused_140", "fused_132", "fused64_140", "batches_priorities")
+    names = ("batches", "fused_140", "fused_132", "fused64_140", "batches_priorities", "partitioned_64", "partitioned_56", "partitioned_72")
     expect = {"fused_140": ("fused", "5", "140"), "fused_132": ("fused", "5", "132"), "fused64_140": ("fused", "9", "140")}
+    expect_part = {"partitioned_64": "64", "partitioned_56": "56", "partitioned_72": "72"}
     seen = []
 
     def fake_run(times, fail=(), bad_line=None):
@@ -244,6 +245,8 @@ def test_bench_launch_autotune_decision(monkeypatch):
             sched = cmd[cmd.index("--schedule") + 1]
             if name in expect:
                 assert (sched, cmd[cmd.index("--fused-groups") + 1], cmd[cmd.index("--fused-ctas") + 1]) == expect[name]
+            elif name in expect_part:
+                assert (sched, cmd[cmd.index("--small-sms") + 1]) == ("partitioned", expect_part[name])
             else:
                 assert sched == "batches" and ("--launch-priorities" in cmd) == (name == "batches_priorities")
             if name in fail:
@@ -251,7 +254,7 @@ def test_bench_launch_autotune_decision(monkeypatch):
                     raise subprocess.TimeoutExpired(cmd, timeout)
                 return subprocess.CompletedProcess(cmd, 1, stdout="", stderr="CUDA error: invalid value")
             line = {"probe": True, "us_per_step": times.get(name, 99.0), "schedule": sched}
-            if name in expect and bad_line is not None:
+            if (name in expect or name in expect_part) and bad_line is not None:
                 line = bad_line
             return subprocess.CompletedProcess(cmd, 0, stdout="noise\n" + json.dumps(line) + "\n", stderr="")
         return run
@@ -269,7 +272,10 @@ def test_bench_launch_autotune_decision(monkeypatch):
     assert best["schedule"] == "batches" and rep["chosen"] == "batches"                      # within 3 %: the default stays
     best, rep = tune({"batches": 50.0, "batches_priorities": 40.0})
     assert best.get("launch_priorities") == "on" and rep["chosen"] == "batches_priorities"
-    best, rep = tune({"batches": 50.0}, fail={"fused_140": "rc", "fused_132": "timeout", "fused64_140": "rc", "batches_priorities": "timeout"})
+    best, rep = tune({"batches": 50.0, "partitioned_56": 39.0, "partitioned_64": 41.0})
+    assert (best["schedule"], best["small_sms"], rep["chosen"]) == ("partitioned", 56, "partitioned_56")
+    best, rep = tune({"batches": 50.0}, fail={"fused_140": "rc", "fused_132": "timeout", "fused64_140": "rc", "batches_priorities": "timeout",
+                                             "partitioned_64": "rc", "partitioned_56": "rc", "partitioned_72": "timeout"})
     assert best["schedule"] == "batches" and all("failed" in rep[n] for n in names[1:])
     # a candidate whose child found differing results (or printed no time) is never chosen
     best, rep = tune({"batches": 50.0}, bad_line={"probe": True, "us_per_step": None, "failed": "RuntimeError: batch 3 differs from gdr_score_topk"})

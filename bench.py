@@ -261,13 +261,24 @@ def probe_main(args, cfg, dev):
         period *= max(1, -(-80 // period))
         g, graph_error = None, None
         if not args.no_graph:
+            inner = []
+
+            def run_guarded(n):
+                try:
+                    run(n)
+                except Exception as e_:         # the error that invalidates a capture is raised here; capture_end would mask it
+                    inner.append(f"{type(e_).__name__}: {e_}"[:200])
+                    raise
             try:
-                g = capture(run, period)
+                g = capture(run_guarded, period)
                 g.replay()
                 torch.cuda.synchronize()
             except Exception as e:              # (reported; the caller treats a candidate that cannot be captured as failed)
-                g, graph_error = None, f"{type(e).__name__}: {e}"[:300]
-                torch.cuda.synchronize()
+                g, graph_error = None, (inner[0] if inner else f"{type(e).__name__}: {e}")[:200]
+                try:
+                    torch.cuda.synchronize()
+                except Exception:
+                    pass
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = []
         for _ in range(3):
@@ -278,7 +289,7 @@ def probe_main(args, cfg, dev):
             torch.cuda.synchronize()
             reps.append(e0.elapsed_time(e1) * 1e3 / (max(1, args.steps // period) * period))
         if graph_error is not None:
-            raise RuntimeError(f"CUDA graph capture failed ({graph_error}); launched from the host the step takes {sorted(reps)[1]:.2f} us")
+            raise RuntimeError(f"host-launched step {sorted(reps)[1]:.2f} us; CUDA graph capture failed: {graph_error}")
         if pr.last_schedule != args.schedule and args.schedule != "auto":
             raise RuntimeError(f"asked for schedule '{args.schedule}', the pipeline ran '{pr.last_schedule}'")
         extra = {"sms": [pr.partition.sms_big, pr.partition.sms_small]} if pr.partition is not None else {}

@@ -105,6 +105,8 @@ class PipelinedRetriever:
         self._scored: Optional[Ticket] = None     # fused: scored, its top-k (part of the next launch) not yet issued
         self._launch_events = {}         # fused: index -> event recorded after launch i (scratch reuse ordering)
         self._open: List[Ticket] = []    # batches schedule: tickets not yet joined by flush()
+        self._dirty = {}                 # internal streams that have work since the last flush() (only those are joined: a stream that took
+                                         # no part in a CUDA graph capture must not be waited for inside it)
         self.last_schedule = None
         # host-buffer front end (submit_host): staging slots, one copy stream per direction
         self._slots: List[dict] = []
@@ -206,6 +208,7 @@ class PipelinedRetriever:
         h = hs[i % 3][t.which]
         ev_in = torch.cuda.Event()
         ev_in.record(cur)                                      # the inputs are ready in stream order here
+        self._dirty[id(self._s_inv)] = self._s_inv
         with torch.cuda.stream(self._s_inv):
             self._s_inv.wait_event(ev_in)
             if i - 2 in self._launch_events:                   # the batch that last used this scratch set has had its top-k
@@ -237,6 +240,7 @@ class PipelinedRetriever:
         hs = self._handles_batches()
         i = t.index
         st = self._streams[i % self.depth]
+        self._dirty[id(st)] = st
         ev_in = torch.cuda.Event()
         ev_in.record(cur)
         with torch.cuda.stream(st):
@@ -257,6 +261,7 @@ class PipelinedRetriever:
         part, i = self.partition, t.index
         h = hs[i % self.depth][t.which]
         ss, bs = part.small[i % self.depth], part.big[i % len(part.big)]
+        self._dirty[id(ss)], self._dirty[id(bs)] = ss, bs
         ev_in = torch.cuda.Event()
         ev_in.record(cur)
         with torch.cuda.stream(ss):
@@ -299,6 +304,7 @@ class PipelinedRetriever:
             self._slots = [dict(**{"in": torch.empty(q_bytes + b_bytes, dtype=torch.uint8, device=self.dev),
                                    "out": torch.empty(2 * r_bytes, dtype=torch.uint8, device=self.dev)}, free=None) for _ in range(n_slots)]
         slot = self._slots[self._n % n_slots]
+        self._dirty[id(self._s_h2d)], self._dirty[id(self._s_d2h)] = self._s_h2d, self._s_d2h
         cur = torch.cuda.current_stream(self.dev)
         with torch.cuda.stream(self._s_h2d):
             if slot["free"] is not None:
@@ -350,17 +356,12 @@ class PipelinedRetriever:
                 t.event = torch.cuda.Event()
                 t.event.record(cur)
             t.keep = None
-        if self._s_inv is not None:
-            cur.wait_stream(self._s_inv)
-        for st in self._streams:
-            cur.wait_stream(st)
-        if self.partition is not None:
-            for st in self.partition.small + self.partition.big:
-                cur.wait_stream(st)
         self._drain_host_jobs()
-        if self._s_h2d is not None:
-            cur.wait_stream(self._s_h2d)
-            cur.wait_stream(self._s_d2h)
+        host = self._s_h2d is not None and id(self._s_h2d) in self._dirty
+        for st in self._dirty.values():
+            cur.wait_stream(st)
+        self._dirty.clear()
+        if host:
             for slot in self._slots:
                 slot["free"] = None                            # everything is joined into `cur`: the next upload waits for `cur`
         self._launch_events.clear()

@@ -232,9 +232,9 @@ def test_bench_launch_autotune_decision(monkeypatch):
     import bench
 
     args = argparse.Namespace(workload="cfg2", path="auto", schedule="auto", replicas=0)
-    names = ("batches", "fused_140", "fused_132", "fused64_140", "batches_priorities", "partitioned_64", "partitioned_56", "partitioned_72")
+    names = ("batches", "fused_140", "fused_132", "fused64_140", "batches_priorities", "partitioned_48", "partitioned_56")
     expect = {"fused_140": ("fused", "5", "140"), "fused_132": ("fused", "5", "132"), "fused64_140": ("fused", "9", "140")}
-    expect_part = {"partitioned_64": "64", "partitioned_56": "56", "partitioned_72": "72"}
+    expect_part = {"partitioned_48": "48", "partitioned_56": "56"}
     seen = []
 
     def fake_run(times, fail=(), bad_line=None):
@@ -272,10 +272,10 @@ def test_bench_launch_autotune_decision(monkeypatch):
     assert best["schedule"] == "batches" and rep["chosen"] == "batches"                      # within 3 %: the default stays
     best, rep = tune({"batches": 50.0, "batches_priorities": 40.0})
     assert best.get("launch_priorities") == "on" and rep["chosen"] == "batches_priorities"
-    best, rep = tune({"batches": 50.0, "partitioned_56": 39.0, "partitioned_64": 41.0})
+    best, rep = tune({"batches": 50.0, "partitioned_56": 39.0, "partitioned_48": 41.0})
     assert (best["schedule"], best["small_sms"], rep["chosen"]) == ("partitioned", 56, "partitioned_56")
     best, rep = tune({"batches": 50.0}, fail={"fused_140": "rc", "fused_132": "timeout", "fused64_140": "rc", "batches_priorities": "timeout",
-                                             "partitioned_64": "rc", "partitioned_56": "rc", "partitioned_72": "timeout"})
+                                             "partitioned_48": "rc", "partitioned_56": "timeout"})
     assert best["schedule"] == "batches" and all("failed" in rep[n] for n in names[1:])
     # a candidate whose child found differing results (or printed no time) is never chosen
     best, rep = tune({"batches": 50.0}, bad_line={"probe": True, "us_per_step": None, "failed": "RuntimeError: batch 3 differs from gdr_score_topk"})

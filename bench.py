@@ -239,7 +239,8 @@ def probe_main(args, cfg, dev):
     batches = synth_batches(cfg, 8, cfg["C"], B, 4321, dev)
     flags = {"auto": 0, "simt": 2, "umma": 4}[args.path]
     pr = PipelinedRetriever(stores, schedule=args.schedule, depth=args.pipeline, fused_ctas=args.fused_ctas, fused_groups=args.fused_groups,
-                            launch_priorities=args.launch_priorities == "on", small_sms=args.small_sms, big_streams=args.big_streams).reserve(B, cfg["K"], k, flags)
+                            launch_priorities=args.launch_priorities == "on", small_sms=args.small_sms, big_streams=args.big_streams,
+                            scoring_ctas_per_sm=args.ctas_per_sm).reserve(B, cfg["K"], k, flags)
     R, nb = len(stores), len(batches)
 
     def run(n, keep=None):
@@ -310,12 +311,15 @@ def autotune(args, local_rank):
     cands = [("batches", dict(schedule="batches", pipeline=5))]
     if args.workload == "cfg2" and args.path == "auto":
         cands += [("fused_140", dict(schedule="fused", fused_groups=5, fused_ctas=140)),
-                  ("fused_132", dict(schedule="fused", fused_groups=5, fused_ctas=132)),
                   ("fused64_140", dict(schedule="fused", fused_groups=9, fused_ctas=140))]
     cands.append(("batches_priorities", dict(schedule="batches", pipeline=5, launch_priorities="on")))
-    if args.workload == "cfg2" and args.path == "auto":     # SM partition (green contexts): inversion + top-k on 48 / 56 SMs, scoring on the rest
-        cands += [("partitioned_48", dict(schedule="partitioned", pipeline=5, small_sms=48)),     # (measured: 40 -> 52.3, 48 -> 48.4, 56 -> 50.6,
-                  ("partitioned_56", dict(schedule="partitioned", pipeline=5, small_sms=56))]     #  64 -> 52.7, 72 -> 55.1 us per step)
+    if args.workload == "cfg2" and args.path == "auto":     # SM partition (green contexts): inversion + top-k on a small SM set, scoring on the rest
+        # measured, us per step: one 6-stage scoring CTA per SM: 40 SMs -> 52.3, 48 -> 48.4, 56 -> 50.6, 64 -> 52.7, 72 -> 55.1;
+        # two 4-stage scoring CTAs per SM (k_score_umma_x2): 48 -> 45.7, 56 -> 44.3, 64 -> 45.6, 72 -> 47.5
+        cands += [("partitioned_56x2", dict(schedule="partitioned", pipeline=5, small_sms=56, ctas_per_sm=2)),
+                  ("partitioned_48x2", dict(schedule="partitioned", pipeline=5, small_sms=48, ctas_per_sm=2)),
+                  ("partitioned_64x2", dict(schedule="partitioned", pipeline=5, small_sms=64, ctas_per_sm=2)),
+                  ("partitioned_48", dict(schedule="partitioned", pipeline=5, small_sms=48, ctas_per_sm=1))]
     report, best, t_start = {}, None, time.time()
     for name, opt in cands:
         if time.time() - t_start > 240:
@@ -367,8 +371,9 @@ def main():
                          "nccl = local top-k, NCCL all-gather of (score, docid) lists, merge; auto = p2p if it sets up and verifies, else nccl")
     ap.add_argument("--path", default="auto", choices=["auto", "simt", "umma"], help="force a scoring path")
     ap.add_argument("--pipeline", type=int, default=0, help="batches in flight of the `batches` schedule (0 = 5; 1 = strictly serial)")
-    ap.add_argument("--small-sms", type=int, default=64, help="`partitioned` schedule: SMs of the inversion + top-k side")
+    ap.add_argument("--small-sms", type=int, default=56, help="`partitioned` schedule: SMs of the inversion + top-k side")
     ap.add_argument("--big-streams", type=int, default=2, help="`partitioned` schedule: streams of the scoring side")
+    ap.add_argument("--ctas-per-sm", type=int, default=0, help="persistent tcgen05 scoring CTAs per SM (0 = the schedule's default: 2 for `partitioned`, else 1)")
     ap.add_argument("--schedule", default="auto", choices=["auto", "batches", "fused", "partitioned"],
                     help="PipelinedRetriever schedule; auto = launch autotune (N = 1) / the pipeline's own choice")
     ap.add_argument("--fused-ctas", type=int, default=0)
@@ -422,18 +427,18 @@ def main():
     # ---- schedule: measured, not assumed
     tune_report = None
     opt = dict(schedule=args.schedule, pipeline=args.pipeline, fused_ctas=args.fused_ctas, fused_groups=args.fused_groups,
-               launch_priorities=args.launch_priorities, small_sms=args.small_sms)
+               launch_priorities=args.launch_priorities, small_sms=args.small_sms, ctas_per_sm=args.ctas_per_sm)
     if args.schedule == "auto" and not args.no_autotune and not args.no_graph and args.pipeline != 1:
-        decision = torch.zeros(6, dtype=torch.int32, device=dev)
+        decision = torch.zeros(7, dtype=torch.int32, device=dev)
         if rank == 0:
             best, tune_report = autotune(args, local_rank)
             decision = torch.tensor([SCHEDULES.index(best.get("schedule")), best.get("pipeline", 0), best.get("fused_ctas", 0),
-                                     best.get("fused_groups", 0), int(best.get("launch_priorities") == "on"), best.get("small_sms", 64)],
+                                     best.get("fused_groups", 0), int(best.get("launch_priorities") == "on"), best.get("small_sms", 56), best.get("ctas_per_sm", 0)],
                                     dtype=torch.int32, device=dev)
         if world > 1:
             dist.broadcast(decision, src=0)
-        f, p_, fc, fg, lp, ssm = (int(x) for x in decision.tolist())
-        opt = dict(schedule=SCHEDULES[f], pipeline=p_, fused_ctas=fc, fused_groups=fg, launch_priorities="on" if lp else "off", small_sms=ssm)
+        f, p_, fc, fg, lp, ssm, cps = (int(x) for x in decision.tolist())
+        opt = dict(schedule=SCHEDULES[f], pipeline=p_, fused_ctas=fc, fused_groups=fg, launch_priorities="on" if lp else "off", small_sms=ssm, ctas_per_sm=cps)
     n_pipe = opt["pipeline"] if opt["pipeline"] > 0 else 5
 
     stores = []
@@ -444,7 +449,7 @@ def main():
     batches = synth_batches(cfg, n_batches, cfg["C"], B, 4321 + (0 if world == 1 else rank), dev)
     pr = PipelinedRetriever(stores, schedule=opt["schedule"] if opt["schedule"] != "auto" else "auto", depth=n_pipe, fused_ctas=opt["fused_ctas"],
                             fused_groups=opt["fused_groups"], launch_priorities=opt["launch_priorities"] == "on", small_sms=opt["small_sms"],
-                            big_streams=args.big_streams).reserve(B, K, k, flags)
+                            big_streams=args.big_streams, scoring_ctas_per_sm=opt["ctas_per_sm"]).reserve(B, K, k, flags)
 
     def barrier():
         if world > 1:
@@ -526,7 +531,8 @@ def main():
     h_alone = h_k
     if schedule == "partitioned":                 # the kernel as the step runs it: CTAs = the scoring side's SMs, on a stream of that side
         for h in (h for hs in h_k for h in hs):
-            h.set_option("umma_ctas", pr.partition.sms_big)
+            h.set_option("umma_ctas_per_sm", pr.scoring_ctas_per_sm)
+            h.set_option("umma_ctas", pr.scoring_ctas_per_sm * pr.partition.sms_big)
         h_alone = [[s.clone_handle() for s in stores] for _ in range(2)]          # ... and on the whole device for comparison
     dummy = (torch.empty((1, B, k), dtype=torch.float32, device=dev), torch.empty((1, B, k), dtype=torch.int32, device=dev))
     for s_ in range(2):
@@ -657,7 +663,8 @@ def main():
     alg_bytes = emb_touched + B * D * 4 + B * k * 8
     simt = int(stats["umma_tiles"]) == 0
     kname = ("k_score_topk_fused64" if opt["fused_groups"] == 9 else "k_score_topk_fused") if schedule == "fused" else (
-        "k_score_simt" if simt else ("k_score_tile_f32" if cfg.get("fp32") else "k_score_umma"))
+        "k_score_simt" if simt else ("k_score_tile_f32" if cfg.get("fp32") else (
+            "k_score_umma_x2" if schedule == "partitioned" and pr.scoring_ctas_per_sm == 2 else "k_score_umma")))
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -667,7 +674,7 @@ def main():
             if t["kernel"] == kname:
                 traffic = t["dram_read_bytes"] + t["dram_write_bytes"]   # one ncu --set full capture of this workload (profiles/)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": kname + {"k_score_simt": " (GEMV)", "k_score_umma": " (tcgen05 grouped GEMM)", "k_score_tile_f32": " (shared-memory-tiled fp32, fma.rn.f32x2)"}.get(
+                "kernel": kname + {"k_score_simt": " (GEMV)", "k_score_umma": " (tcgen05 grouped GEMM)", "k_score_umma_x2": " (tcgen05 grouped GEMM, 4-stage ring, two CTAs per SM)", "k_score_tile_f32": " (shared-memory-tiled fp32, fma.rn.f32x2)"}.get(
                     kname, " (tcgen05 grouped GEMM of batch i + per-query top-k of batch i-1 in one persistent CTA per SM)") + (
                     f", as the timed step runs it: confined to the scoring side's {pr.partition.sms_big} of {pr.partition.sms_big + pr.partition.sms_small} SMs "
                     "(the other SMs run the top-k and inversion kernels of the neighbouring batches); `scoring_alone` is the same kernel on the whole device"
@@ -699,8 +706,8 @@ def main():
     sched_txt = {"fused": f"fused (gdr_score_fused via PipelinedRetriever: one launch scores batch i and selects the top-k of batch i-1 in the same CTAs; "
                           f"inversion one batch ahead on a second stream; 3 scratch sets; grid of {opt['fused_ctas'] or 140} CTAs x {opt['fused_groups'] or 5} top-k groups)",
                  "partitioned": f"partitioned (PipelinedRetriever: SM partition by CUDA green contexts - inversion and top-k of every batch on {n_pipe} streams of a "
-                                f"{pr.partition.sms_small if pr.partition else 0}-SM set, scoring kernels on {args.big_streams} streams of the other "
-                                f"{pr.partition.sms_big if pr.partition else 0} SMs; {n_pipe} batches in flight)",
+                                f"{pr.partition.sms_small if pr.partition else 0}-SM set, scoring kernels ({pr.scoring_ctas_per_sm} persistent CTA(s) per SM) on {args.big_streams} streams of the "
+                                f"other {pr.partition.sms_big if pr.partition else 0} SMs; {n_pipe} batches in flight)",
                  "batches": f"batches (PipelinedRetriever: whole gdr_score_topk calls round-robin on {n_pipe} streams)"}[schedule]
     line = {
         "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world,

@@ -9,12 +9,14 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB_DIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIB_DIR, "libgdr_b200.so")
-SOURCES = ["api.cu", "invert.cu", "score_simt.cu", "score_umma.cu", "score_tile_f32.cu", "similarity.cu", "score_fused.cu", "topk.cu", "topk_grouped.cu", "mask.cu", "tree.cu", "contrastive.cu", "xchg.cu", "partition.cu"]
+SOURCES = ["api.cu", "invert.cu", "score_simt.cu", "score_umma.cu", "score_umma_x2.cu", "score_tile_f32.cu", "similarity.cu", "score_fused.cu", "topk.cu", "topk_grouped.cu", "mask.cu", "tree.cu", "contrastive.cu", "xchg.cu", "partition.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 # Developer builds only: `python -m gdr_b200._build --debug-knobs` compiles the stage-skipping timing experiments in
 # (GDR_UMMA_DEBUG / GDR_TOPK_DEBUG environment masks; they invalidate results, so the product library does not contain them).
+if os.environ.get("GDR_BUILD_UM_STAGES"):        # ring depth of the tcgen05 scoring CTA (default 6; the fused kernels need 6)
+    FLAGS.append("-DGDR_UM_STAGES=" + str(int(os.environ["GDR_BUILD_UM_STAGES"])))
 if "--debug-knobs" in sys.argv or os.environ.get("GDR_BUILD_DEBUG_KNOBS") == "1":
     FLAGS.append("-DGDR_DEBUG_KNOBS")
 

@@ -12,7 +12,7 @@ DTYPE_F32, DTYPE_BF16 = 0, 1
 ACT = {"none": 0, None: 0, "tanh": 1, "sigmoid": 2}
 Q_PER_BEAM, FORCE_SIMT, FORCE_UMMA = 1, 2, 4
 SKIP_INVERT, SKIP_SCORE, SKIP_TOPK = 256, 512, 1024
-OPTIONS = {"umma_ctas": 1, "umma_min_group": 2, "launch_priorities": 3, "fused_groups": 4, "topk_groups": 5, "topk_wide": 6}
+OPTIONS = {"umma_ctas": 1, "umma_min_group": 2, "launch_priorities": 3, "fused_groups": 4, "topk_groups": 5, "topk_wide": 6, "umma_ctas_per_sm": 7}
 
 # every symbol include/gdr_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {

@@ -46,6 +46,7 @@ struct gdr_store {
     int last_launches = 0;
     int phase_launches[3] = {0, 0, 0};             // inversion, scoring, top-k kernels of the handle's current batch (phases may come in separate calls)
     int umma_min_group = 1;   // > 1 (env GDR_UMMA_MIN_GROUP) = mixed mode
+    int umma_ctas_per_sm = 1; // GDR_OPT_UMMA_CTAS_PER_SM: 2 = the 4-stage kernel, two scoring CTAs per SM (score_umma_x2.cu)
     int umma_ctas = 0;        // > 0 (env GDR_UMMA_CTAS): persistent CTAs of the tcgen05 kernel (default: one per SM)
     uint32_t debug_flags = 0; // GDR_OPT_TOPK_GROUPS bits; with -DGDR_DEBUG_KNOBS also the GDR_UMMA_DEBUG / GDR_TOPK_DEBUG timing experiments
     bool topk_wide = false;   // GDR_OPT_TOPK_WIDE: the 256-thread top-k also for k <= 128
@@ -315,6 +316,10 @@ int gdr_store_set_option(gdr_store_t *s, int32_t option, int32_t value) {
         if (value < 0 || value > 1024) return invalid("gdr_store_set_option: GDR_OPT_UMMA_CTAS must be in [0, 1024]");
         s->umma_ctas = value;
         return GDR_OK;
+    case GDR_OPT_UMMA_CTAS_PER_SM:
+        if (value != 1 && value != 2) return invalid("gdr_store_set_option: GDR_OPT_UMMA_CTAS_PER_SM must be 1 or 2");
+        s->umma_ctas_per_sm = value;
+        return GDR_OK;
     case GDR_OPT_UMMA_MIN_GROUP:
         if (value < 1) return invalid("gdr_store_set_option: GDR_OPT_UMMA_MIN_GROUP must be >= 1");
         s->umma_min_group = value;
@@ -435,7 +440,10 @@ int gdr_score_topk(gdr_store_t *s, const float *q, const int32_t *beams, const f
     }
     if (use_umma && !(flags & GDR_SKIP_SCORE)) {
         a.signal = use_simt ? 0 : 1;              // (mixed mode: the GEMV kernel is the call's last scoring kernel and signals)
-        GDR_CUDA(launch_score_umma(a, &s->tmap, st, s->umma_ctas > 0 ? s->umma_ctas : s->sm_count));
+        if (s->umma_ctas_per_sm == 2 && a.n_ranks == 1)
+            GDR_CUDA(launch_score_umma_x2(a, &s->tmap, st, s->umma_ctas > 0 ? s->umma_ctas : 2 * s->sm_count));
+        else
+            GDR_CUDA(launch_score_umma(a, &s->tmap, st, s->umma_ctas > 0 ? s->umma_ctas : s->sm_count));
         launches += 1;
     }
     if (use_tile && !(flags & GDR_SKIP_SCORE)) {

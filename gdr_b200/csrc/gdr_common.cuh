@@ -113,6 +113,7 @@ struct ScoreArgs {
 cudaError_t launch_invert(const ScoreArgs &a, cudaStream_t s, int *n_launches);
 cudaError_t launch_score_simt(const ScoreArgs &a, cudaStream_t s, int sm_count);
 cudaError_t launch_score_umma(const ScoreArgs &a, const CUtensorMap *tmap, cudaStream_t s, int sm_count);
+cudaError_t launch_score_umma_x2(const ScoreArgs &a, const CUtensorMap *tmap, cudaStream_t s, int ctas);   // 4-stage ring, two CTAs per SM
 cudaError_t launch_score_tile_f32(const ScoreArgs &a, cudaStream_t s, int sm_count);
 cudaError_t launch_topk_store(const ScoreArgs &a, float alpha, float *out_scores, int32_t *out_docids,
                               cudaStream_t s);

@@ -6,11 +6,15 @@
 namespace gdr {
 
 constexpr int UM_BLOCK_K = 64;                 // bf16 elements per K block = one 128-byte swizzle atom
-constexpr int UM_SA = 6;                       // ONE ring of 6 stages, each = A tile (TMA) + B tile (cp.async): one full and one empty
-constexpr int UM_SB = 6;                       // barrier per stage, so the MMA warp pays one wait + one commit per K block.  Every stage
+#ifndef GDR_UM_STAGES
+#define GDR_UM_STAGES 6                        // score_umma_x2.cu defines 4 (two CTAs per SM); GDR_BUILD_UM_STAGES=8 in developer builds
+#endif
+constexpr int UM_SA = GDR_UM_STAGES;           // ONE ring of 6 stages, each = A tile (TMA) + B tile (cp.async): one full and one empty
+constexpr int UM_SB = GDR_UM_STAGES;           // barrier per stage, so the MMA warp pays one wait + one commit per K block.  Every stage
                                                // is owned by exactly one filler warp, which keeps each waiter at most one mbarrier phase
                                                // ahead (parity waits stay unambiguous).  6 x 28 KB = 168 KB leaves ~58 KB of the SM for
-                                               // co-resident top-k / inversion CTAs of neighbouring batches (8 stages: same speed alone).
+                                               // co-resident top-k / inversion CTAs of neighbouring batches (8 stages: same speed alone; confined to 100 / 92 / 84 SMs by
+                                               // the partitioned schedule, 8 stages gain 1 us of a 48 - 53 us step: the CTA is not bound by bytes in flight).
 constexpr int UM_FILL_WARPS = UM_SB / 2;       // each filler warp owns two stages (one cp.async group in flight per stage)
 constexpr int UM_A_BYTES = UMMA_ROWS * 128;    // 16 KB
 constexpr int UM_BT_BYTES = UMMA_NQ * 128;     // 4 KB per query term
@@ -22,7 +26,7 @@ constexpr int UM_RING_BYTES = UM_SA * UM_A_BYTES + UM_SB * UM_B_BYTES;   // 168 
 static_assert(UM_SA == UM_SB, "A and B share one ring");
 constexpr int UM_MD = 2;                       // tile-metadata ring depth = how far ahead of its slowest role a CTA claims tiles
 constexpr int UM_META_CONSUMERS = 2 + UM_FILL_WARPS + 4;    // TMA, MMA, fillers, epilogue warps
-constexpr int UM_BAR_BYTES = 512;
+constexpr int UM_BAR_BYTES = GDR_UM_STAGES <= 4 ? 272 : 512;          // mbarriers (8 bytes each) from 0, the TMEM base slot at 256
 constexpr int UM_SMEM_BYTES = UM_RING_BYTES + UM_BAR_BYTES + UM_MD * (int)sizeof(TileMeta);
 static_assert(UM_SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static_assert(sizeof(TileMeta) % 16 == 0 && UM_BAR_BYTES % 16 == 0 && UM_RING_BYTES % 16 == 0, "bulk-copy alignment of the metadata ring");

@@ -79,12 +79,13 @@ class SmPartition:
 
 class PipelinedRetriever:
     def __init__(self, store, schedule: str = "auto", depth: int = 0, fused_ctas: int = 0, fused_groups: int = 0,
-                 launch_priorities: bool = False, small_sms: int = 64, big_streams: int = 2):
+                 launch_priorities: bool = False, small_sms: int = 56, big_streams: int = 2, scoring_ctas_per_sm: int = 0):
         """store: the resident ClusterStore — or a list of stores of identical shape (several indexes served by one pipeline;
         bench.py cycles copies of the corpus so that every step streams embeddings that are not in L2), chosen per batch with
         `submit(..., which=i)`.  schedule: 'auto' (= fused where eligible, else batches) | 'fused' | 'batches' | 'partitioned'
-        (SM partition: `small_sms` SMs for inversion + top-k, the rest for scoring on `big_streams` streams; falls back to 'batches'
-        for shapes that do not take the tcgen05 path).  depth: batches in flight for 'batches' / 'partitioned' (default 5; the fused
+        (SM partition: `small_sms` SMs for inversion + top-k, the rest for scoring on `big_streams` streams, with
+        `scoring_ctas_per_sm` = 2 persistent scoring CTAs per SM by default — the 4-stage kernel of csrc/score_umma_x2.cu; falls back to
+        'batches' for shapes that do not take the tcgen05 path).  depth: batches in flight for 'batches' / 'partitioned' (default 5; the fused
         schedule always uses three scratch sets)."""
         if schedule not in ("auto", "fused", "batches", "partitioned"):
             raise ValueError("schedule must be 'auto', 'fused', 'batches' or 'partitioned'")
@@ -94,6 +95,7 @@ class PipelinedRetriever:
         self.depth = depth if depth > 0 else 5
         self.fused_ctas, self.fused_groups, self.launch_priorities = fused_ctas, fused_groups, launch_priorities
         self.small_sms, self.big_streams = small_sms, big_streams
+        self.scoring_ctas_per_sm = int(scoring_ctas_per_sm) if scoring_ctas_per_sm else (2 if schedule == "partitioned" else 1)
         self.partition: Optional[SmPartition] = None     # 'partitioned' schedule: created on first use
         self.dev = store.emb.device
         self._fused_handles: Optional[List[List[ClusterStore]]] = None    # [scratch set][store]
@@ -138,7 +140,8 @@ class PipelinedRetriever:
         if self.partition is None:
             self.partition = SmPartition(self.dev, self.small_sms, self.big_streams, self.depth)
             for h in (h for row in hs for h in row):
-                h.set_option("umma_ctas", self.partition.sms_big)
+                h.set_option("umma_ctas_per_sm", self.scoring_ctas_per_sm)
+                h.set_option("umma_ctas", self.scoring_ctas_per_sm * self.partition.sms_big)
         return hs
 
     def _handles_fused(self) -> List[List[ClusterStore]]:
@@ -160,6 +163,9 @@ class PipelinedRetriever:
             for h in (h for hs in self._batch_handles for h in hs):
                 if self.launch_priorities:
                     h.set_option("launch_priorities", 1)
+                if self.scoring_ctas_per_sm > 1:
+                    h.set_option("umma_ctas_per_sm", self.scoring_ctas_per_sm)
+                    h.set_option("umma_ctas", self.scoring_ctas_per_sm * torch.cuda.get_device_properties(self.dev).multi_processor_count)
             self._streams = [torch.cuda.Stream(device=self.dev) for _ in range(self.depth)]
         return self._batch_handles
 

@@ -173,6 +173,8 @@ int gdr_store_reserve(gdr_store_t *store, int32_t B, int32_t K, int32_t k, uint3
 #define GDR_OPT_FUSED_GROUPS 4       /* top-k groups in the fused CTA: 5 = five 128-thread groups, lean select (default); 9 = nine 64-thread groups */
 #define GDR_OPT_TOPK_GROUPS 5        /* 1, 2, 4: stand-alone top-k as persistent groups walking a query queue; 0 = one CTA per query */
 #define GDR_OPT_TOPK_WIDE 6          /* 1: the 256-thread top-k also for k <= 128 */
+#define GDR_OPT_UMMA_CTAS_PER_SM 7   /* 2: tcgen05 scoring kernel with a 4-stage ring, two CTAs per SM (default grid 2 x SMs; set GDR_OPT_UMMA_CTAS
+                                      * to 2 x the SMs of an SM partition); for gdr_score_topk on unsharded handles, ignored elsewhere */
 int gdr_store_set_option(gdr_store_t *store, int32_t option, int32_t value);
 
 /* ---- SM partition for the pipelined schedule (csrc/partition.cu) -------------------------------------------------------------

@@ -17,13 +17,17 @@ PY
 timeout 900 python -m pytest tests -m gpu -q --timeout 300 > gpurun_out/r02_pytest_gpu_final.log 2>&1; tail -8 gpurun_out/r02_pytest_gpu_final.log
 timeout 200 python __graft_entry__.py smoke > gpurun_out/r02_smoke.log 2>&1; tail -2 gpurun_out/r02_smoke.log
 timeout 500 python bench.py > gpurun_out/r02_bench_default.json 2> gpurun_out/r02_bench_default.err; tail -c 600 gpurun_out/r02_bench_default.err; show gpurun_out/r02_bench_default.json
+if [ -n "$ALL" ]; then
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r02_bench_reference.json 2> gpurun_out/r02_bench_reference.err; show gpurun_out/r02_bench_reference.json
 timeout 300 python bench.py --workload cfg1 --steps 960 --warmup 5 --no-cpu-baseline --no-autotune --schedule batches > gpurun_out/r02_bench_cfg1.json 2> gpurun_out/r02_bench_cfg1.err; show gpurun_out/r02_bench_cfg1.json
+fi
 NCU="ncu --clock-control none --cache-control none"
 timeout 200 $NCU --metrics gpu__time_duration.sum -s 70 -c 70 --csv --log-file gpurun_out/r02_launches_cfg2_partitioned.csv \
-    python bench.py --steps 24 --warmup 3 --no-cpu-baseline --no-graph --no-autotune --schedule partitioned --small-sms 48 > /dev/null 2> gpurun_out/r02_ncu_launches.err
-timeout 300 $NCU --set full --import-source on -k regex:"k_score_umma|k_topk_fast" -s 8 -c 2 -o gpurun_out/r02_cfg2_partitioned \
-    python bench.py --steps 16 --warmup 3 --no-cpu-baseline --no-graph --no-autotune --schedule partitioned --small-sms 48 > /dev/null 2> gpurun_out/r02_ncu_full.err
+    python bench.py --steps 24 --warmup 3 --no-cpu-baseline --no-graph --no-autotune --schedule partitioned --small-sms 56 --ctas-per-sm 2 > /dev/null 2> gpurun_out/r02_ncu_launches.err
+timeout 300 $NCU --set full --import-source on -k regex:"k_score_umma_x2|k_topk_fast" -s 8 -c 2 -o gpurun_out/r02_cfg2_partitioned_x2 \
+    python bench.py --steps 16 --warmup 3 --no-cpu-baseline --no-graph --no-autotune --schedule partitioned --small-sms 56 --ctas-per-sm 2 > /dev/null 2> gpurun_out/r02_ncu_full.err
+if [ -n "$ALL" ]; then
 timeout 200 $NCU --set full --import-source on -k regex:"k_score_tile_f32" -s 4 -c 1 -o gpurun_out/r02_cfg1_tile_f32 \
     python bench.py --workload cfg1 --steps 16 --warmup 3 --no-cpu-baseline --no-graph --no-autotune --schedule batches --pipeline 1 > /dev/null 2> gpurun_out/r02_ncu_full_cfg1.err
+fi
 ls -la gpurun_out/*.ncu-rep | tail -4; tail -3 gpurun_out/r02_ncu_full.err

@@ -60,7 +60,10 @@ def pipeline(schedule, groups):
     for i, (q, b, p) in enumerate(batches):
         s, d = stores[i % 2].score_topk(q, b, k, prob=p, alphas=[0.5], act="tanh")
         refs.append((s[0].clone(), d[0].clone()))
-    pr = PipelinedRetriever(stores, schedule=schedule, fused_groups=int(groups)).reserve(256, K, k)
+    if schedule == "partitioned":             # (`groups` = persistent scoring CTAs per SM here: 1 = k_score_umma, 2 = k_score_umma_x2)
+        pr = PipelinedRetriever(stores, schedule=schedule, scoring_ctas_per_sm=int(groups)).reserve(256, K, k)
+    else:
+        pr = PipelinedRetriever(stores, schedule=schedule, fused_groups=int(groups)).reserve(256, K, k)
     checks = {}
 
     def run():

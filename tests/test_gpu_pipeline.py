@@ -34,10 +34,12 @@ def test_pipelined_retriever_equals_default(schedule, groups):
     _run("PIPELINE_" + schedule.upper(), groups)
 
 
-def test_partitioned_schedule_equals_default():
+@pytest.mark.parametrize("ctas_per_sm", ["2", "1"])
+def test_partitioned_schedule_equals_default(ctas_per_sm):
     """SM partition (CUDA green contexts; gdr_partition_*, PipelinedRetriever(schedule="partitioned")): inversion and top-k on one SM
-    set, scoring on the other — eager, replayed from a CUDA graph, and through pinned host buffers."""
-    line = _run("PIPELINE_PARTITIONED", "5")
+    set, scoring on the other with two 4-stage CTAs per SM (k_score_umma_x2) or one 6-stage CTA — eager, replayed from a CUDA graph,
+    and through pinned host buffers."""
+    line = _run("PIPELINE_PARTITIONED", ctas_per_sm)
     if line.get("skipped"):
         pytest.skip(line["skipped"])
 
@@ -45,6 +47,11 @@ def test_partitioned_schedule_equals_default():
 @pytest.mark.parametrize("groups", ["4", "1"])
 def test_grouped_topk_equals_default(groups):
     _run("topk_groups", groups)
+
+
+def test_two_scoring_ctas_per_sm_equal_default():
+    """GDR_OPT_UMMA_CTAS_PER_SM = 2 (k_score_umma_x2: 4-stage ring, two CTAs per SM) on the whole device: same bits as the default kernel."""
+    _run("umma_ctas_per_sm", "2")
 
 
 def test_launch_priorities_do_not_change_results():

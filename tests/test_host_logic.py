@@ -232,9 +232,9 @@ def test_bench_launch_autotune_decision(monkeypatch):
     import bench
 
     args = argparse.Namespace(workload="cfg2", path="auto", schedule="auto", replicas=0)
-    names = ("batches", "fused_140", "fused_132", "fused64_140", "batches_priorities", "partitioned_48", "partitioned_56")
-    expect = {"fused_140": ("fused", "5", "140"), "fused_132": ("fused", "5", "132"), "fused64_140": ("fused", "9", "140")}
-    expect_part = {"partitioned_48": "48", "partitioned_56": "56"}
+    names = ("batches", "fused_140", "fused64_140", "batches_priorities", "partitioned_56x2", "partitioned_48x2", "partitioned_64x2", "partitioned_48")
+    expect = {"fused_140": ("fused", "5", "140"), "fused64_140": ("fused", "9", "140")}
+    expect_part = {"partitioned_56x2": ("56", "2"), "partitioned_48x2": ("48", "2"), "partitioned_64x2": ("64", "2"), "partitioned_48": ("48", "1")}
     seen = []
 
     def fake_run(times, fail=(), bad_line=None):
@@ -246,7 +246,7 @@ def test_bench_launch_autotune_decision(monkeypatch):
             if name in expect:
                 assert (sched, cmd[cmd.index("--fused-groups") + 1], cmd[cmd.index("--fused-ctas") + 1]) == expect[name]
             elif name in expect_part:
-                assert (sched, cmd[cmd.index("--small-sms") + 1]) == ("partitioned", expect_part[name])
+                assert (sched, cmd[cmd.index("--small-sms") + 1], cmd[cmd.index("--ctas-per-sm") + 1]) == ("partitioned",) + expect_part[name]
             else:
                 assert sched == "batches" and ("--launch-priorities" in cmd) == (name == "batches_priorities")
             if name in fail:
@@ -265,17 +265,17 @@ def test_bench_launch_autotune_decision(monkeypatch):
         return bench.autotune(args, 2)
 
     monkeypatch.setenv("RANK", "0")
-    best, rep = tune({"batches": 50.0, "fused_140": 37.0, "fused_132": 38.0, "fused64_140": 47.0})
+    best, rep = tune({"batches": 50.0, "fused_140": 37.0, "fused64_140": 47.0})
     assert (best["schedule"], best["fused_groups"], best["fused_ctas"], rep["chosen"]) == ("fused", 5, 140, "fused_140")
     assert rep["fused_140"]["verified_identical_to_serial"] and rep["fused64_140"]["us_per_step"] == 47.0
-    best, rep = tune({"batches": 50.0, "fused_140": 49.5, "fused_132": 52.0, "fused64_140": 60.0, "batches_priorities": 49.0})
+    best, rep = tune({"batches": 50.0, "fused_140": 49.5, "fused64_140": 60.0, "batches_priorities": 49.0})
     assert best["schedule"] == "batches" and rep["chosen"] == "batches"                      # within 3 %: the default stays
     best, rep = tune({"batches": 50.0, "batches_priorities": 40.0})
     assert best.get("launch_priorities") == "on" and rep["chosen"] == "batches_priorities"
-    best, rep = tune({"batches": 50.0, "partitioned_56": 39.0, "partitioned_48": 41.0})
-    assert (best["schedule"], best["small_sms"], rep["chosen"]) == ("partitioned", 56, "partitioned_56")
-    best, rep = tune({"batches": 50.0}, fail={"fused_140": "rc", "fused_132": "timeout", "fused64_140": "rc", "batches_priorities": "timeout",
-                                             "partitioned_48": "rc", "partitioned_56": "timeout"})
+    best, rep = tune({"batches": 50.0, "partitioned_56x2": 39.0, "partitioned_48": 41.0})
+    assert (best["schedule"], best["small_sms"], best["ctas_per_sm"], rep["chosen"]) == ("partitioned", 56, 2, "partitioned_56x2")
+    best, rep = tune({"batches": 50.0}, fail={"fused_140": "rc", "fused64_140": "timeout", "batches_priorities": "timeout",
+                                             "partitioned_56x2": "rc", "partitioned_48x2": "timeout", "partitioned_64x2": "rc", "partitioned_48": "rc"})
     assert best["schedule"] == "batches" and all("failed" in rep[n] for n in names[1:])
     # a candidate whose child found differing results (or printed no time) is never chosen
     best, rep = tune({"batches": 50.0}, bad_line={"probe": True, "us_per_step": None, "failed": "RuntimeError: batch 3 differs from gdr_score_topk"})

@@ -598,19 +598,7 @@ def main():
         in_host.append(h)
         out_host.append(torch.empty(2 * r_bytes, dtype=torch.uint8).pin_memory())
 
-    def run_e2e(n):
-        for i in range(n):
-            pr.submit_host(in_host[i % n_batches], B, K, k, out_host[i % n_batches], flags=flags, which=i % replicas)
-        pr.flush()
-
-    run_e2e(2 * n_batches)
-    barrier()
-    e2e_period = math.lcm(period, 4)
-    e2e_graph = capture(run_e2e, e2e_period) if use_graph else None
-    if e2e_graph is not None:
-        e2e_graph.replay()
-        barrier()
-    e2e_steps = max(e2e_period, (min(steps, 1920) // e2e_period) * e2e_period)
+    e2e_steps_box = []
     pcie = {}
     d_in = torch.empty(q_bytes + b_bytes, dtype=torch.uint8, device=dev)
     d_out = torch.empty(2 * r_bytes, dtype=torch.uint8, device=dev)
@@ -625,30 +613,61 @@ def main():
         torch.cuda.synchronize()
         pcie[name + "_us_per_step"] = e0.elapsed_time(e1) * 1000 / 50
         pcie[name + "_GBps"] = nbytes * 50 / (e0.elapsed_time(e1) * 1e-3) / 1e9
-    e2e_segments = []
-    for _ in range(7):            # PCIe on a shared host is noisy: seven timed segments, the median is reported
-        e0.record()
-        if e2e_graph is not None:
-            for _ in range(e2e_steps // e2e_period):
-                e2e_graph.replay()
-        else:
-            run_e2e(e2e_steps)
-        e1.record()
+
+    def measure_e2e(pr_x):
+        """Median-of-7 time of e2e_steps host-buffer steps through `pr_x`, results checked against the serial call."""
+        def run_e2e(n):
+            for i in range(n):
+                pr_x.submit_host(in_host[i % n_batches], B, K, k, out_host[i % n_batches], flags=flags, which=i % replicas)
+            pr_x.flush()
+
+        for o in out_host:
+            o.zero_()
+        run_e2e(2 * n_batches)
         barrier()
-        e2e_segments.append(e0.elapsed_time(e1))
-    e2e_ms = sorted(e2e_segments)[len(e2e_segments) // 2]
-    # the host buffers must hold what a plain serial call returns for the same batch
-    for i in range(n_batches):
-        j = max(x for x in range(e2e_period) if x % n_batches == i)          # the last step of a replay that wrote out_host[i]
-        cs, cd = stores[j % replicas].score_topk(batches[i][0], batches[i][1], k, flags=flags)
-        torch.cuda.synchronize()
-        if not (torch.equal(out_host[i][:r_bytes].view(torch.float32).view(B, k), cs.cpu()) and
-                torch.equal(out_host[i][r_bytes:].view(torch.int32).view(B, k), cd.cpu())):
-            raise RuntimeError("end-to-end pipeline result differs from the serial call")
-    if world > 1:
-        t = torch.tensor([e2e_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+        e2e_period = math.lcm(period, 4)
+        e2e_graph = capture(run_e2e, e2e_period) if use_graph else None
+        if e2e_graph is not None:
+            e2e_graph.replay()
+            barrier()
+        e2e_steps = max(e2e_period, (min(steps, 1920) // e2e_period) * e2e_period)
+        e2e_steps_box.append(e2e_steps)
+        segments = []
+        for _ in range(7):            # PCIe on a shared host is noisy: seven timed segments, the median is reported
+            e0.record()
+            if e2e_graph is not None:
+                for _ in range(e2e_steps // e2e_period):
+                    e2e_graph.replay()
+            else:
+                run_e2e(e2e_steps)
+            e1.record()
+            barrier()
+            segments.append(e0.elapsed_time(e1))
+        ms_ = sorted(segments)[len(segments) // 2]
+        # the host buffers must hold what a plain serial call returns for the same batch
+        for i in range(n_batches):
+            j = max(x for x in range(e2e_period) if x % n_batches == i)          # the last step of a replay that wrote out_host[i]
+            cs, cd = stores[j % replicas].score_topk(batches[i][0], batches[i][1], k, flags=flags)
+            torch.cuda.synchronize()
+            if not (torch.equal(out_host[i][:r_bytes].view(torch.float32).view(B, k), cs.cpu()) and
+                    torch.equal(out_host[i][r_bytes:].view(torch.int32).view(B, k), cd.cpu())):
+                raise RuntimeError(f"end-to-end pipeline ({pr_x.last_schedule}) result differs from the serial call")
+        if world > 1:
+            t_ = torch.tensor([ms_], device=dev)
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+            ms_ = float(t_.item())
+        return ms_, segments
+
+    # The host-buffer path is bound by the 3.2 MB H2D copy per step (PCIe), so what counts there is a short dependency chain behind each
+    # copy, not SM residency: when the device-resident loop runs on the SM partition, the whole-call `batches` schedule is measured as
+    # well and the faster of the two is reported (both are listed in e2e.by_schedule).
+    e2e_cands = [(schedule, pr)]
+    if schedule == "partitioned":
+        e2e_cands.append(("batches", PipelinedRetriever(stores, schedule="batches", depth=n_pipe, launch_priorities=True).reserve(B, K, k, flags)))
+    e2e_by = {name: measure_e2e(p_) for name, p_ in e2e_cands}
+    e2e_sched = min(e2e_by, key=lambda n_: e2e_by[n_][0])
+    e2e_ms, e2e_segments = e2e_by[e2e_sched]
+    e2e_steps = e2e_steps_box[0]
     e2e_qps = e2e_steps * B * world / (e2e_ms * 1e-3)
 
     if rank != 0:
@@ -725,8 +744,10 @@ def main():
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": q_bytes + b_bytes, "d2h_bytes_per_step": 2 * r_bytes, "steps": e2e_steps,
                 "segments_ms_per_step": [round(x / e2e_steps, 5) for x in e2e_segments], "estimator": "median of 7 timed segments",
                 "copies_alone": {k_: round(v_, 2) for k_, v_ in pcie.items()},
+                "schedule": e2e_sched + (" + launch priorities" if e2e_sched == "batches" and schedule == "partitioned" else ""),
+                "by_schedule": {n_: {"value": e2e_steps * B * world / (v_[0] * 1e-3), "ms_per_step": v_[0] / e2e_steps} for n_, v_ in e2e_by.items()},
                 "pipeline": "PipelinedRetriever.submit_host: pinned host buffers, per step one H2D copy (q + beams) and one D2H copy (scores + docids), "
-                            "one copy stream per direction, 4 staging slots"},
+                            f"one copy stream per direction, {n_pipe + 1} staging slots"},
         "roofline": roofline, "cpu_baseline": cpu,
         "path": {"simt_items": int(stats["simt_items"]), "umma_tiles": int(stats["umma_tiles"]), "clusters_touched": int(stats["clusters_touched"])},
     }

@@ -1,5 +1,5 @@
 #!/bin/bash
-# Round 2 iteration call: variant / p2p tests, parity suite, smoke, A/B against the round-1 tree, the bench with its autotune, ncu captures.
+# Round 2 iteration call: variant / p2p tests, parity suite, smoke, A/B against a second checkout in _r1/ (if present), the bench with its autotune, ncu captures.
 mkdir -p gpurun_out
 show() { python - "$1" <<'PY'
 import json, sys
@@ -15,7 +15,7 @@ PY
 timeout 700 python -m pytest tests/test_gpu_pipeline.py tests/test_gpu_sharded_p2p.py -q --timeout 150 > gpurun_out/r02_pytest_pipeline.log 2>&1; tail -15 gpurun_out/r02_pytest_pipeline.log
 timeout 900 python -m pytest tests -m gpu -q --timeout 300 --deselect tests/test_gpu_pipeline.py --deselect tests/test_gpu_sharded_p2p.py > gpurun_out/r02_pytest_gpu.log 2>&1; tail -6 gpurun_out/r02_pytest_gpu.log
 timeout 200 python __graft_entry__.py smoke > gpurun_out/r02_smoke.log 2>&1; tail -2 gpurun_out/r02_smoke.log
-(cd _r1 && timeout 300 python bench.py --no-cpu-baseline --launch-priorities off --schedule batches > ../gpurun_out/ab_r1.json 2> ../gpurun_out/ab_r1.err); show gpurun_out/ab_r1.json
+[ -d _r1 ] && (cd _r1 && timeout 300 python bench.py --no-cpu-baseline --launch-priorities off --schedule batches > ../gpurun_out/ab_r1.json 2> ../gpurun_out/ab_r1.err); show gpurun_out/ab_r1.json
 timeout 300 python bench.py --no-cpu-baseline --no-autotune --schedule batches > gpurun_out/ab_cur.json 2> gpurun_out/ab_cur.err; show gpurun_out/ab_cur.json
 timeout 500 python bench.py > gpurun_out/r02_bench_default.json 2> gpurun_out/r02_bench_default.err; tail -c 800 gpurun_out/r02_bench_default.err; show gpurun_out/r02_bench_default.json
 NCU="ncu --clock-control none --cache-control none"

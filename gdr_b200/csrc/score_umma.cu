@@ -13,8 +13,9 @@
 // reads the A tile from shared memory once for all three (SS-mode MMAs are bound by the 128 B/clk smem
 // read of A, measured: three N=32 MMAs per K step were MIO-throttled); the epilogue adds the three TMEM
 // column groups.  Every product bf16 x bf16 is exact in fp32, so the result matches an fp32 dot product to
-// accumulation-order noise.  The kernel is still HBM-bound: per tile it moves 128 x 768 x 2 B = 196 KB of
-// embeddings and issues 12 x 4 MMAs of 128 x 96 x 16.
+// accumulation-order noise.  Per tile the kernel moves 128 x 768 x 2 B = 196 KB of embeddings and issues 12 x 4 MMAs of
+// 128 x 96 x 16; it reaches 0.77 of the HBM peak on the whole device, but what bounds it is the per-K-block choreography and the
+// per-launch fill / drain, not the byte stream (tools/probe_umma_limits.py; score_umma_x2.cu).
 //
 // Warp roles (320 threads, one persistent CTA per SM, tiles claimed one at a time from a global counter):
 //   warp 0       TMA producer: A tiles of the store (L2 evict-first hint), 6-stage ring shared with B (96 KB of A in flight per SM)

@@ -310,16 +310,18 @@ def autotune(args, local_rank):
     default (`batches`) stays if nothing beats it by > 3 %.  All timings / failures are reported in config.launch_autotune."""
     cands = [("batches", dict(schedule="batches", pipeline=5))]
     if args.workload == "cfg2" and args.path == "auto":
-        cands += [("fused_140", dict(schedule="fused", fused_groups=5, fused_ctas=140)),
-                  ("fused64_140", dict(schedule="fused", fused_groups=9, fused_ctas=140))]
-    cands.append(("batches_priorities", dict(schedule="batches", pipeline=5, launch_priorities="on")))
-    if args.workload == "cfg2" and args.path == "auto":     # SM partition (green contexts): inversion + top-k on a small SM set, scoring on the rest
-        # measured, us per step: one 6-stage scoring CTA per SM: 40 SMs -> 52.3, 48 -> 48.4, 56 -> 50.6, 64 -> 52.7, 72 -> 55.1;
-        # two 4-stage scoring CTAs per SM (k_score_umma_x2): 48 -> 45.7, 56 -> 44.3, 64 -> 45.6, 72 -> 47.5
+        # Candidates in the order of how they measured (the time budget cuts the tail, not the head).  SM partition (green contexts):
+        # inversion + top-k on a small SM set, scoring on the rest; us per step: one 6-stage scoring CTA per SM: 40 SMs -> 52.3,
+        # 48 -> 48.4, 56 -> 50.6, 64 -> 52.7, 72 -> 55.1; two 4-stage CTAs per SM (k_score_umma_x2): 48 -> 45.7, 56 -> 44.3, 64 -> 45.6, 72 -> 47.5
         cands += [("partitioned_56x2", dict(schedule="partitioned", pipeline=5, small_sms=56, ctas_per_sm=2)),
+                  ("batches_priorities", dict(schedule="batches", pipeline=5, launch_priorities="on")),
                   ("partitioned_48x2", dict(schedule="partitioned", pipeline=5, small_sms=48, ctas_per_sm=2)),
                   ("partitioned_64x2", dict(schedule="partitioned", pipeline=5, small_sms=64, ctas_per_sm=2)),
-                  ("partitioned_48", dict(schedule="partitioned", pipeline=5, small_sms=48, ctas_per_sm=1))]
+                  ("fused_140", dict(schedule="fused", fused_groups=5, fused_ctas=140)),
+                  ("partitioned_48", dict(schedule="partitioned", pipeline=5, small_sms=48, ctas_per_sm=1)),
+                  ("fused64_140", dict(schedule="fused", fused_groups=9, fused_ctas=140))]
+    else:
+        cands.append(("batches_priorities", dict(schedule="batches", pipeline=5, launch_priorities="on")))
     report, best, t_start = {}, None, time.time()
     for name, opt in cands:
         if time.time() - t_start > 240:

@@ -232,7 +232,7 @@ def test_bench_launch_autotune_decision(monkeypatch):
     import bench
 
     args = argparse.Namespace(workload="cfg2", path="auto", schedule="auto", replicas=0)
-    names = ("batches", "fused_140", "fused64_140", "batches_priorities", "partitioned_56x2", "partitioned_48x2", "partitioned_64x2", "partitioned_48")
+    names = ("batches", "partitioned_56x2", "batches_priorities", "partitioned_48x2", "partitioned_64x2", "fused_140", "partitioned_48", "fused64_140")
     expect = {"fused_140": ("fused", "5", "140"), "fused64_140": ("fused", "9", "140")}
     expect_part = {"partitioned_56x2": ("56", "2"), "partitioned_48x2": ("48", "2"), "partitioned_64x2": ("64", "2"), "partitioned_48": ("48", "1")}
     seen = []

@@ -8,10 +8,14 @@ this module keeps them in flight; it is the schedule `bench.py` times and the on
   batch ahead on a second stream.  Three scratch sets (= three store handles over the same device arrays): launch i scores
   into set i % 3 and reads set (i-1) % 3, the inversion of batch i+1 fills set (i+1) % 3.
 * `batches` (every other shape): whole `gdr_score_topk` calls round-robin on `depth` streams, one handle each, so the
-  latency-bound inversion and top-k kernels of one batch hide under the HBM-bound scoring kernel of its neighbours.
+  latency-bound inversion and top-k kernels of one batch hide under the scoring kernel of its neighbours.
 * `partitioned` (opt-in; tcgen05 shapes): the SMs are split into two disjoint sets (CUDA green contexts, `SmPartition`): the
   inversion and the top-k of every batch run on streams of the small set, the scoring kernels on streams of the big set, so the
   two sides do not compete for residency on the same SMs.  Same handles / scratch sets as `batches`.
+
+Which one (cfg2 on a B200, us per 1,024-query step, inputs on the device): partitioned 41-46, batches with launch priorities 51,
+fused 53-54, batches 54 — `bench.py` measures them and picks; 'auto' keeps the static rule fused-where-eligible-else-batches.  Behind
+host-to-device copies (`submit_host`) the step is bound by the copy and `batches` is the fastest (66 vs 73 us for `partitioned`).
 
 Contract: `submit()` returns a `Ticket`; the ticket's outputs are complete, in stream order on the stream that calls it, after
 `ticket.wait()` (which needs two further `submit()`s or a `flush()` to have been issued: in the fused schedule `submit(i)`

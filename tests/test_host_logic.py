@@ -125,6 +125,20 @@ def test_cabi_library_loads_and_exports_every_declared_symbol():
     assert lib.gdr_last_error() is not None
 
 
+def test_cabi_argument_checks_need_no_gpu():
+    """Bad arguments are refused with a status code and a message before any CUDA call (include/gdr_b200.h: errors are integer
+    status codes, never aborts): the SM partition, the handle options and the batch call on a null handle."""
+    import ctypes
+    lib = _cabi.lib()
+    h = ctypes.c_void_p()
+    assert lib.gdr_partition_create(ctypes.byref(h), 4, 1, 1) == -1 and b"small_sms" in lib.gdr_last_error()
+    assert lib.gdr_partition_create(ctypes.byref(h), 56, 0, 5) == -1 and h.value is None
+    assert lib.gdr_partition_create(None, 56, 2, 5) == -1
+    assert lib.gdr_partition_stream(None, 0, 0) is None and lib.gdr_partition_destroy(None) == 0
+    assert lib.gdr_store_set_option(None, _cabi.OPTIONS["umma_ctas_per_sm"], 2) == -1
+    assert lib.gdr_score_topk(None, None, None, None, None, 1, 1, 1, 0, 1, 0, None, None, None) == -1 and b"null" in lib.gdr_last_error()
+
+
 def test_no_cpu_fallback_in_product_path():
     """The product refuses CPU tensors instead of silently computing elsewhere."""
     with pytest.raises(ValueError):

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Per-source-line instruction counts and stall samples of one kernel from an ncu report.
 
-    python tools/ncu_by_line.py <report.ncu-rep> <object.o> <mangled kernel name> [top N]
+    python tools/ncu_by_line.py <report.ncu-rep> <object.o> <kernel name, plain or mangled> [top N]
 
 ncu's CSV source page is per SASS instruction; the line table comes from `nvdisasm -g` on the same object (built with
 -lineinfo), matched by instruction offset.  Lines are reported as file:line with warp-level instructions executed, the share
@@ -24,7 +24,9 @@ def line_table(obj, kernel):
     table, cur, inside = {}, ("?", 0), False
     for ln in out.splitlines():
         if ln.startswith("\t.section") or ln.startswith("//-----"):
-            inside = (".text." + kernel) in ln if ".text." in ln else False
+            # a plain name (k_topk_fast) matches its Itanium-mangled section (.text._ZN3gdr11k_topk_fastE...): length-prefixed identifier
+            key = kernel if kernel.startswith("_Z") else f"{len(kernel)}{kernel}E"
+            inside = (key in ln) if ".text." in ln else False
             continue
         if not inside:
             continue
@@ -42,8 +44,8 @@ def main():
     rep, obj, kernel = sys.argv[1:4]
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
     table = line_table(obj, kernel)
-    short = re.sub(r"^_ZN3gdr\d+", "", kernel)
-    short = re.match(r"[A-Za-z_0-9]+", short).group(0) if re.match(r"[A-Za-z_0-9]+", short) else kernel
+    m = re.match(r"^_ZN3gdr(\d+)", kernel)
+    short = kernel[m.end():m.end() + int(m.group(1))] if m else kernel          # the identifier inside a mangled name, or the plain name
     txt = subprocess.run(["ncu", "-i", rep, "--kernel-name", "regex:" + os.environ.get("NCU_KERNEL", short), "--page", "source", "--csv"],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
